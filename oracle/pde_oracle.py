@@ -1,0 +1,429 @@
+"""CPU oracle: NumPy restatement of pde-opt's time-stepping hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``pde_opt_b200/`` imports this module; it is
+used by ``tests/``, by ``__graft_entry__.smoke()`` and by ``bench.py``'s CPU-baseline /
+``--impl reference`` legs as the checker and the timed CPU arm, never as the product.
+
+Why a restatement: the reference (``/root/reference``, acoh64/pde-opt) is pure Python on
+jax / diffrax / equinox, none of which is installed in this image (no network), so the
+reference itself cannot be imported.  Every function below cites the reference lines it
+restates.  Third-party arithmetic the reference delegates to and that is *not* under
+/root/reference:
+
+* diffrax >= 0.7.0 (pyproject.toml:18, unpinned): constant-step loop, end clipping and
+  ``SaveAt(ts)`` linear interpolation.  Restated in :func:`constant_step_schedule` and
+  :func:`integrate` from the published algorithm (diffrax/_integrate.py).
+* jax >= 0.6.2 ``jnp.fft.fftn/ifftn`` (pyproject.toml:16): restated with ``numpy.fft``
+  (pocketfft; float32 -> complex64 is preserved by NumPy 2.x).
+
+Pinning: this oracle passes the reference's own known-answer tests (tests/test_oracle_kat.py
+re-runs tests/test_solvers.py:21-61 and :107-205, tests/test_rhs_convergence.py:14-77,
+tests/test_functions.py:22-61 of the reference against it) and reproduces the surviving
+fixture notebooks/reference.npy.  At the north-star tolerances (1e-5 one step, 1e-3 after
+1000 steps) the reference has no golden vectors of its own: PARITY IS PINNED BY THE KATS
+ONLY ("parity unpinned" beyond 1e-3 in the sense of the task statement).
+
+All arithmetic runs in the dtype of the state (float32 in -> float32/complex64 arithmetic).
+"""
+
+from __future__ import annotations
+
+import dataclasses
+import math
+from typing import Callable, Optional, Sequence, Tuple
+
+import numpy as np
+
+# --------------------------------------------------------------------------------------
+# Domain  (reference: pde_opt/numerics/domains.py:16-64)
+# --------------------------------------------------------------------------------------
+
+
+@dataclasses.dataclass
+class Domain:
+    points: Tuple[int, ...]
+    box: Tuple[Tuple[float, float], ...]
+    units: str = "dimensionless"
+
+    def __post_init__(self):
+        # domains.py:29-34
+        self.dx = tuple((hi - lo) / n for (lo, hi), n in zip(self.box, self.points))
+        self.L = tuple((hi - lo) for (lo, hi) in self.box)
+
+    def axes(self, dtype=np.float64):
+        # domains.py:36-42  (cell-centred)
+        return tuple(
+            np.linspace(lo + h / 2, hi - h / 2, num=n).astype(dtype)
+            for (lo, hi), n, h in zip(self.box, self.points, self.dx)
+        )
+
+    def fft_axes(self, dtype=np.float64):
+        # domains.py:44-47  cycles / length
+        return tuple(np.fft.fftfreq(n, h).astype(dtype) for n, h in zip(self.points, self.dx))
+
+    def mesh(self, dtype=np.float64):
+        return tuple(np.meshgrid(*self.axes(dtype), indexing="ij"))  # domains.py:54-56
+
+    def fft_mesh(self, dtype=np.float64):
+        return tuple(np.meshgrid(*self.fft_axes(dtype), indexing="ij"))  # domains.py:58-60
+
+
+def _cdtype(dtype):
+    return np.complex64 if np.dtype(dtype) == np.float32 else np.complex128
+
+
+# --------------------------------------------------------------------------------------
+# Periodic stencils  (reference: pde_opt/numerics/utils/derivatives.py:8-66)
+# --------------------------------------------------------------------------------------
+
+
+def lap_2nd(u, h):
+    """derivatives.py:8-21 (2-D and 3-D)."""
+    out = None
+    for ax, hh in enumerate(h):
+        t = (np.roll(u, -1, ax) - 2 * u + np.roll(u, 1, ax)) / u.dtype.type(hh) ** 2
+        out = t if out is None else out + t
+    return out
+
+
+def grad_c2f(a, h, ax):  # derivatives.py:24-36
+    return (np.roll(a, -1, ax) - a) / a.dtype.type(h)
+
+
+def avg_c2f(a, ax):  # derivatives.py:39-51
+    return a.dtype.type(0.5) * (a + np.roll(a, -1, ax))
+
+
+def div_f2c(F, h, ax):  # derivatives.py:54-66
+    return (F - np.roll(F, 1, ax)) / F.dtype.type(h)
+
+
+# --------------------------------------------------------------------------------------
+# Pointwise closure families
+# --------------------------------------------------------------------------------------
+
+
+def mu_double_well(c):  # tests/test_solvers.py:36  lambda c: c**3 - c
+    return c**3 - c
+
+
+def mu_log(c, omega=3.0):  # notebooks/optimize_nn_script.py:33
+    t = c.dtype.type
+    return np.log(c / (t(1.0) - c)) + t(omega) * (t(1.0) - t(2.0) * c)
+
+
+def legendre_expansion(params, x):
+    """functions/legendre.py:12-34 (three-term recurrence, inputs in [-1,1])."""
+    t = x.dtype.type
+    params = np.asarray(params, dtype=x.dtype)
+    result = params[0] * np.ones_like(x)
+    deg = len(params) - 1
+    if deg >= 1:
+        result = result + params[1] * x
+    p_prev = np.ones_like(x)
+    p_curr = x
+    for n in range(2, deg + 1):
+        p_next = (t(2 * n - 1) * x * p_curr - t(n - 1) * p_prev) / t(n)
+        result = result + params[n] * p_next
+        p_prev, p_curr = p_curr, p_next
+    return result
+
+
+def D_legendre(params, c):  # functions/legendre.py:37-53
+    t = c.dtype.type
+    return np.exp(legendre_expansion(params, t(2.0) * c - t(1.0)))
+
+
+def mu_legendre(params, c, prior: Optional[Callable] = None):  # functions/legendre.py:56-74
+    t = c.dtype.type
+    r = legendre_expansion(params, t(2.0) * c - t(1.0))
+    if prior is not None:
+        r = r + prior(c)
+    return r
+
+
+def prior_log(c):  # docs/notebooks/optimization_3D.ipynb cell 15: log(x/(1-x))
+    return np.log(c / (c.dtype.type(1.0) - c))
+
+
+# --------------------------------------------------------------------------------------
+# Equations
+# --------------------------------------------------------------------------------------
+
+
+class CahnHilliardPeriodic:
+    """CahnHilliard2DPeriodic / 3DPeriodic (cahn_hilliard.py:30-109, :112-200)."""
+
+    def __init__(self, domain, kappa, mu, D, derivs="fd", dtype=np.float32, forcing=None):
+        self.domain, self.kappa, self.mu, self.D, self.derivs = domain, kappa, mu, D, derivs
+        self.dtype = np.dtype(dtype)
+        self.forcing = forcing  # optional additive field in mu (our control definition)
+        ct = _cdtype(dtype)
+        ks = domain.fft_mesh(dtype)
+        # cahn_hilliard.py:65-74: (2*pi*i*k)**2 summed, squared, times kappa
+        self.two_pi_i_k = [(ct(2j) * ct(np.pi) * k.astype(ct)) for k in ks]
+        self.two_pi_i_k_2 = sum(q**2 for q in self.two_pi_i_k)
+        self.two_pi_i_k_4 = self.two_pi_i_k_2**2
+        self.fourier_symbol = (ct(kappa) * self.two_pi_i_k_4).astype(ct)
+        self.fft, self.ifft = np.fft.fftn, np.fft.ifftn
+        if derivs not in ("fd", "fourier"):
+            raise ValueError(f"Invalid derivative type: {derivs}")
+        self.rhs = self.rhs_fd if derivs == "fd" else self.rhs_fourier
+
+    def _mu_h(self, u):
+        m = self.mu(u)
+        if self.forcing is not None:
+            m = m + self.forcing.astype(u.dtype)
+        return m
+
+    def rhs_fd(self, state, t=0.0):  # cahn_hilliard.py:89-109 / :177-200
+        h = self.domain.dx
+        tt = state.dtype.type
+        mu = self._mu_h(state) - tt(self.kappa) * lap_2nd(state, h)
+        Du = self.D(state)
+        out = None
+        for ax, hh in enumerate(h):
+            F = avg_c2f(Du, ax) * grad_c2f(mu, hh, ax)
+            d = div_f2c(F, hh, ax)
+            out = d if out is None else out + d
+        return out
+
+    def rhs_fourier(self, state, t=0.0):  # cahn_hilliard.py:82-87 / :165-175
+        ct = _cdtype(state.dtype)
+        sh = self.fft(state).astype(ct)
+        tmp = self.fft(self._mu_h(state)).astype(ct) - ct(self.kappa) * self.two_pi_i_k_2 * sh
+        acc = 0
+        Du = self.D(state)
+        for q in self.two_pi_i_k:
+            acc = acc + q * self.fft(Du * self.ifft(q * tmp).astype(ct)).astype(ct)
+        return self.ifft(acc).real.astype(state.dtype)
+
+
+class AllenCahn2DPeriodic:
+    """allen_cahn.py:26-84.  ``fourier_symbol`` is *our* definition: the
+    reference class has none; sigma = -kappa*(2 pi i k)^2 = kappa (2 pi)^2 |k|^2."""
+
+    def __init__(self, domain, kappa, mu, R, derivs="fd", dtype=np.float32):
+        self.domain, self.kappa, self.mu, self.R, self.derivs = domain, kappa, mu, R, derivs
+        ct = _cdtype(dtype)
+        ks = domain.fft_mesh(dtype)
+        self.two_pi_i_k = [(ct(2j) * ct(np.pi) * k.astype(ct)) for k in ks]
+        self.two_pi_i_k_2 = sum(q**2 for q in self.two_pi_i_k)
+        self.fourier_symbol = (-ct(kappa) * self.two_pi_i_k_2).astype(ct)
+        self.fft, self.ifft = np.fft.fftn, np.fft.ifftn
+        self.rhs = self.rhs_fd if derivs == "fd" else self.rhs_fourier
+
+    def rhs_fd(self, state, t=0.0):  # allen_cahn.py:81-84
+        tt = state.dtype.type
+        mu = self.mu(state) - tt(self.kappa) * lap_2nd(state, self.domain.dx)
+        return -self.R(state) * mu
+
+    def rhs_fourier(self, state, t=0.0):  # allen_cahn.py:74-79
+        ct = _cdtype(state.dtype)
+        sh = self.fft(state).astype(ct)
+        mu = self.ifft(self.fft(self.mu(state)).astype(ct) - ct(self.kappa) * self.two_pi_i_k_2 * sh)
+        return -self.R(state) * mu.real.astype(state.dtype)
+
+
+class AdvectionDiffusion2D:
+    """Recovered equation (absent from the reference tree, imported by
+    notebooks/run_advection_diffusion.ipynb cell 0): du/dt = -div(v u) + D lap(u) with
+    Fourier-spectral derivatives; v = p0 * grad exp(-r^2/(2 p1)) about ``centre``
+    (notebook cell 2).  IMEX symbol sigma = D (2 pi)^2 |k|^2 (our definition, A = 1)."""
+
+    def __init__(self, domain, velocity, D, dtype=np.float32):
+        self.domain, self.velocity, self.Dc = domain, velocity, D
+        ct = _cdtype(dtype)
+        ks = domain.fft_mesh(dtype)
+        self.two_pi_i_k = [(ct(2j) * ct(np.pi) * k.astype(ct)) for k in ks]
+        self.two_pi_i_k_2 = sum(q**2 for q in self.two_pi_i_k)
+        self.fourier_symbol = (-ct(D) * self.two_pi_i_k_2).astype(ct)
+        self.fft, self.ifft = np.fft.fftn, np.fft.ifftn
+        self.xm, self.ym = domain.mesh(dtype)
+
+    def rhs(self, state, t=0.0):
+        ct = _cdtype(state.dtype)
+        vx, vy = self.velocity(t, self.xm, self.ym)
+        vx = np.asarray(vx, dtype=state.dtype)
+        vy = np.asarray(vy, dtype=state.dtype)
+        uh = self.fft(state).astype(ct)
+        fx = self.fft(vx * state).astype(ct)
+        fy = self.fft(vy * state).astype(ct)
+        spec = -(self.two_pi_i_k[0] * fx + self.two_pi_i_k[1] * fy) + ct(self.Dc) * self.two_pi_i_k_2 * uh
+        return self.ifft(spec).real.astype(state.dtype)
+
+
+def gaussian_velocity(p, centre):
+    """notebooks/run_advection_diffusion.ipynb cell 2 (``advection``)."""
+
+    def v(t, xs, ys):
+        xi, yi = centre(t) if callable(centre) else centre
+        tt = xs.dtype.type
+        r2 = ((xs - tt(xi)) ** 2 + (ys - tt(yi)) ** 2) / tt(2.0 * p[1])
+        e = np.exp(-r2)
+        return tt(p[0]) * (-(xs - tt(xi)) / tt(p[1]) * e), tt(p[0]) * (-(ys - tt(yi)) / tt(p[1]) * e)
+
+    return v
+
+
+class GPE2DTSControl:
+    """gross_pitaevskii.py:18-81.  State layout [N,N,2] (re,im)."""
+
+    def __init__(self, domain, k, e, lights, trap_factor=1.0, dtype=np.float32, kinetic=False):
+        self.domain, self.k, self.e, self.lights, self.trap_factor = domain, k, e, lights, trap_factor
+        ct = _cdtype(dtype)
+        self.dx = domain.dx[0]  # :51
+        ks = domain.fft_mesh(dtype)
+        tp = [(ct(2j) * ct(np.pi) * kk.astype(ct)) for kk in ks]
+        self.two_pi_i_k_2 = sum(q**2 for q in tp)
+        self.fft, self.ifft = np.fft.fftn, np.fft.ifftn
+        self.xmesh, self.ymesh = domain.mesh(dtype)
+        # :62  A_term = 0.5j * two_pi_i_k_2 * 0.0 (kinetic term disabled as shipped);
+        # kinetic=True gives the physical 0.5j*(2 pi i k)^2 variant used by our extra cases.
+        self.A_term = (ct(0.5j) * self.two_pi_i_k_2 * ct(1.0 if kinetic else 0.0)).astype(ct)
+
+    def B_terms(self, state, t=0.0):  # :67-75
+        ct = _cdtype(state.dtype)
+        tt = state.dtype.type
+        psi = state[..., 0].astype(ct) + ct(1j) * state[..., 1].astype(ct)
+        ctrl = self.lights(t, self.xmesh, self.ymesh)
+        ctrl = np.asarray(ctrl, dtype=state.dtype)
+        tmp = (
+            ct(-0.5j) * ct(self.trap_factor) * ((tt(1 + self.e)) * self.xmesh**2 + tt(1 - self.e) * self.ymesh**2).astype(ct)
+            - ct(1j) * ctrl.astype(ct)
+            - ct(self.k) * ct(1j) * (np.abs(psi) ** 2).astype(ct)
+        )
+        return np.stack([tmp.real, tmp.imag], axis=-1).astype(state.dtype)
+
+    rhs = B_terms  # :77-81
+
+
+# --------------------------------------------------------------------------------------
+# Steppers  (reference: pde_opt/numerics/solvers.py)
+# --------------------------------------------------------------------------------------
+
+
+def sifs_step(rhs, y0, t0, t1, A, fourier_symbol, with_error=False):
+    """SemiImplicitFourierSpectral.step, solvers.py:56-70."""
+    ct = _cdtype(y0.dtype)
+    dt = y0.dtype.type(t1 - t0)  # :58
+    f0 = rhs(y0, t0)  # :59
+    tmp = ct(1.0) + ct(A) * ct(dt) * fourier_symbol.astype(ct)  # :62
+    y1 = y0 + dt * np.fft.ifftn(np.fft.fftn(f0).astype(ct) / tmp).real.astype(y0.dtype)  # :63
+    if with_error:
+        return y1, y1 - (y0 + dt * f0)  # :61,:65
+    return y1
+
+
+def strang_step(b_terms, y0, t0, t1, A_term, dx, time_scale):
+    """StrangSplitting.step, solvers.py:99-122 (b evaluated at y0; global renormalisation)."""
+    ct = _cdtype(y0.dtype)
+    tt = y0.dtype.type
+    dt = ct(tt(t1 - t0)) * ct(time_scale)  # :101
+    psi = y0[..., 0].astype(ct) + ct(1j) * y0[..., 1].astype(ct)  # :103
+    eA = np.exp(A_term.astype(ct) * ct(0.5) * dt)  # :105
+    tmp = np.fft.ifftn(np.fft.fftn(psi).astype(ct) * eA).astype(ct)  # :107-108
+    b = b_terms(y0, t0)  # :109
+    tmp = tmp * np.exp((b[..., 0].astype(ct) + ct(1j) * b[..., 1].astype(ct)) * dt)  # :110
+    tmp = tmp / np.sqrt(np.sum(np.abs(tmp) ** 2) * tt(dx) ** 2).astype(tt)  # :111
+    tmp = np.fft.fftn(tmp).astype(ct) * eA  # :112-113
+    y1 = np.fft.ifftn(tmp).astype(ct)  # :114
+    return np.stack([y1.real, y1.imag], axis=-1).astype(y0.dtype)  # :115
+
+
+# --------------------------------------------------------------------------------------
+# diffrax constant-step driver (third-party; restated from diffrax/_integrate.py)
+# --------------------------------------------------------------------------------------
+
+
+def constant_step_schedule(t0, t1, dt0, dtype=np.float32, max_steps=1_000_000):
+    """Times visited by ``diffeqsolve(..., ConstantStepSize())``.
+
+    diffrax keeps ``tprev, tnext`` in the working precision; after each step
+    ``tprev <- tnext`` and ``tnext <- tnext + (tnext - tprev)`` (ConstantStepSize returns the
+    same step length measured in floating point), then ``tnext`` is clipped:
+    ``tnext = where(tnext > t1 - tol, t1, tnext)`` with tol = 1e-6 (float32) / 1e-10 (float64)
+    (``_clip_to_end``).  Returns the array of step boundaries ``[t_0, ..., t_n]`` with t_n == t1.
+    """
+    tt = np.dtype(dtype).type
+    tol = tt(1e-6) if np.dtype(dtype) == np.float32 else tt(1e-10)
+    t0, t1, dt0 = tt(t0), tt(t1), tt(dt0)
+    ts = [t0]
+    tprev, tnext = t0, tt(t0 + dt0)
+    if tnext > t1 - tol:
+        tnext = t1
+    n = 0
+    while tprev < t1 and n < max_steps:
+        ts.append(tnext)
+        step = tt(tnext - tprev)
+        tprev = tnext
+        tnext = tt(tprev + step)
+        if tnext > t1 - tol:
+            tnext = t1
+        n += 1
+    return np.asarray(ts, dtype=dtype)
+
+
+def integrate(step_fn, y0, t0, t1, dt0, save_ts=None, max_steps=1_000_000):
+    """Constant-step solve.  ``step_fn(y, ta, tb) -> y``.  ``save_ts=None`` mimics
+    ``SaveAt(t1=True)`` (pde_env.py:301) and returns ys[-1:]; otherwise ``SaveAt(ts=...)``
+    (pde_model.py:129) with LocalLinearInterpolation between step end points
+    (solvers.py:48,66)."""
+    dtype = y0.dtype
+    ts = constant_step_schedule(t0, t1, dt0, dtype, max_steps)
+    y = y0
+    if save_ts is None:
+        for a, b in zip(ts[:-1], ts[1:]):
+            y = step_fn(y, a, b)
+        return y[None]
+    save_ts = np.asarray(save_ts, dtype=dtype)
+    out = np.empty((len(save_ts),) + y0.shape, dtype=dtype)
+    si = 0
+    while si < len(save_ts) and save_ts[si] <= ts[0]:
+        out[si] = y0
+        si += 1
+    for a, b in zip(ts[:-1], ts[1:]):
+        y1 = step_fn(y, a, b)
+        while si < len(save_ts) and save_ts[si] <= b:
+            # LocalLinearInterpolation.evaluate: y0 + (y1-y0) * (t - t0)/(t1 - t0)
+            w = dtype.type((save_ts[si] - a) / (b - a))
+            out[si] = y + (y1 - y) * w
+            si += 1
+        y = y1
+    while si < len(save_ts):
+        out[si] = y
+        si += 1
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# Convenience: batched fused rollouts used by the parity tests / CPU baseline
+# --------------------------------------------------------------------------------------
+
+
+def ch2d_rollout(u0, n, h, kappa, A, dts, mu, D, forcing=None):
+    """K = len(dts) SIFS steps of the FD Cahn-Hilliard equation on one env (float32 in/out)."""
+    dom = Domain((n, n), ((0.0, n * h), (0.0, n * h)))
+    eq = CahnHilliardPeriodic(dom, kappa, mu, D, "fd", u0.dtype, forcing=forcing)
+    y, t = u0, u0.dtype.type(0)
+    for dt in dts:
+        y = sifs_step(eq.rhs, y, t, t + u0.dtype.type(dt), A, eq.fourier_symbol)
+        t = t + u0.dtype.type(dt)
+    return y
+
+
+def quantise_obs(u, lo=0.0, hi=1.0):
+    """uint8 observation (pde_env.py:118-126 Box(0,255,(1,*points),uint8)); the mapping
+    state -> obs is a user callback in the reference; ours: round(clip((u-lo)/(hi-lo))*255)."""
+    x = np.clip((u - u.dtype.type(lo)) / u.dtype.type(hi - lo), 0, 1) * u.dtype.type(255.0)
+    return np.rint(x).astype(np.uint8)[None]
+
+
+def initialize_Psi(N, width=100, vortexnumber=0):
+    """utils/initialization_utils.py:11-34 (Gaussian blob, optional vortex phase)."""
+    i, j = np.meshgrid(np.arange(N), np.arange(N), indexing="ij")
+    psi = np.exp(-(((i - N // 2) / width) ** 2.0) - ((j - N // 2) / width) ** 2.0).astype(complex)
+    if vortexnumber:
+        phi = vortexnumber * np.arctan2((i - N // 2), (j - N // 2))
+        psi = psi * np.exp(1.0j * np.mod(phi, 2 * np.pi))
+    return psi
