@@ -1,0 +1,139 @@
+/* pdeopt_b200 — C ABI of the B200-native time-stepping hot path of acoh64/pde-opt.
+ *
+ * The reference has no FFI: its "plugin API" is two Python protocols (a diffrax
+ * AbstractSolver and an equation dataclass).  Each entry point below names the reference
+ * code it replaces (paths relative to the reference root):
+ *
+ *   pdeopt_sifs_step_batched      K fused calls of SemiImplicitFourierSpectral.step
+ *                                 (pde_opt/numerics/solvers.py:56-70) with
+ *                                 CahnHilliard2DPeriodic.rhs_fd (equations/cahn_hilliard.py:89-109)
+ *                                 or AllenCahn2DPeriodic.rhs_fd (equations/allen_cahn.py:81-84)
+ *                                 as the vector field, i.e. the body of the diffeqsolve loop
+ *                                 driven from pde_env.py:293-303 / pde_model.py:120-134,
+ *                                 plus the observation / reward callbacks of
+ *                                 PDEEnv.step (pde_env.py:305-309) as a fused epilogue.
+ *   pdeopt_sifs_step_batched_host same, host buffers in / out (H2D + D2H inside the call).
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types.  Pointers named *_dev are CUDA
+ * device pointers on the current device, *_host are host pointers.  `stream` is a
+ * cudaStream_t passed as void* (NULL = legacy default stream).  Every function returns a
+ * pdeopt_status and never throws; pdeopt_last_error() describes the last failure on the
+ * calling thread.  No hidden allocation after plan creation.  A plan may be used from one
+ * thread at a time.  There is no CPU fallback: without a CUDA device every compute entry
+ * point returns PDEOPT_ERR_CUDA.
+ */
+#ifndef PDEOPT_B200_H
+#define PDEOPT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDEOPT_ABI_VERSION 1
+#define PDEOPT_MAX_COEF 16
+#define PDEOPT_MAX_FUSED_STEPS 64 /* per launch; callers loop for longer rollouts */
+#define PDEOPT_MAX_TABLES 2       /* distinct step lengths per launch */
+#define PDEOPT_NCTRL 8            /* floats per environment in the control block */
+
+typedef enum {
+  PDEOPT_OK = 0,
+  PDEOPT_ERR_INVALID = 1,     /* bad argument */
+  PDEOPT_ERR_UNSUPPORTED = 2, /* valid request the library has no kernel for */
+  PDEOPT_ERR_CUDA = 3         /* CUDA runtime failure (incl. no device) */
+} pdeopt_status;
+
+typedef enum {
+  PDEOPT_CH2D = 0, /* CahnHilliard2DPeriodic, cahn_hilliard.py:30-109 */
+  PDEOPT_AC2D = 1, /* AllenCahn2DPeriodic,    allen_cahn.py:26-84    */
+  PDEOPT_AD2D = 2, /* advection-diffusion (recovered)      */
+  PDEOPT_GPE2D = 3 /* GPE2DTSControl,         gross_pitaevskii.py:18-81 */
+} pdeopt_kind;
+
+typedef enum { PDEOPT_DERIVS_FD = 0, PDEOPT_DERIVS_FOURIER = 1 } pdeopt_derivs;
+
+/* Pointwise closure families for mu_h(c). */
+typedef enum {
+  PDEOPT_MU_DOUBLE_WELL = 0,     /* c^3 - c                          (tests/test_solvers.py:36) */
+  PDEOPT_MU_LOG = 1,             /* log(c/(1-c)) + w(1-2c), w=coef[0] (notebooks/optimize_nn_script.py:33) */
+  PDEOPT_MU_LEGENDRE = 2,        /* P(2c-1)                          (functions/legendre.py:56-74, no prior) */
+  PDEOPT_MU_LEGENDRE_LOGPRIOR = 3 /* P(2c-1) + log(c/(1-c))          (same, prior_fn = log(x/(1-x))) */
+} pdeopt_mu_family;
+
+/* Pointwise closure families for the mobility D(c) / reaction rate R(c). */
+typedef enum {
+  PDEOPT_MOB_CONST = 0,       /* coef[0]            (ones_like, 0.15*ones) */
+  PDEOPT_MOB_DEGENERATE = 1,  /* c(1-c)                                   */
+  PDEOPT_MOB_ONE_PLUS_SQ = 2, /* 1 + c^2            (tests/test_rhs_convergence.py:22,55) */
+  PDEOPT_MOB_LEGENDRE_EXP = 3 /* exp(P(2c-1))       (functions/legendre.py:37-53) */
+} pdeopt_mob_family;
+
+/* Control block layout, PDEOPT_NCTRL floats per environment (our definition of the
+ * user callbacks update_control_value / update_control_parameter, pde_env.py:274-286):
+ *   [0] mu scalar offset added to coef[0] of the mu family (e.g. the interaction w)
+ *   [1] amplitude, [2] x0, [3] y0, [4] width s of an additive Gaussian bump in mu:
+ *       amp * exp(-((x-x0)^2 + (y-y0)^2) / (2 s^2)), x/y the cell-centred axes
+ *   [5..7] reserved (0). */
+
+typedef struct {
+  int32_t kind;   /* pdeopt_kind */
+  int32_t derivs; /* pdeopt_derivs */
+  int32_t nx, ny; /* collocation points per axis (axis 0 = x = slow index) */
+  double lo_x, lo_y; /* lower box bounds (for the cell-centred axes used by the control bump) */
+  double hx, hy;  /* grid spacings, Domain.dx (domains.py:29-32) */
+  double kappa;   /* gradient-energy coefficient */
+  int32_t mu_family, mu_ncoef;
+  double mu_coef[PDEOPT_MAX_COEF];
+  int32_t mob_family, mob_ncoef;
+  double mob_coef[PDEOPT_MAX_COEF];
+} pdeopt_plan_desc;
+
+typedef struct pdeopt_plan pdeopt_plan;
+
+int pdeopt_abi_version(void);
+const char* pdeopt_last_error(void);
+
+/* Validates the description and selects kernels.  Needs no device. */
+pdeopt_status pdeopt_plan_create(const pdeopt_plan_desc* desc, pdeopt_plan** out);
+pdeopt_status pdeopt_plan_destroy(pdeopt_plan* plan);
+
+/* Number of floats of one folded inverse-denominator table for this plan:
+ * (nx/2+1)*(ny/2+1).  Entry [i][j] = (1/(nx*ny)) / (1 + A*dt*symbol[i][j]), i<=nx/2, j<=ny/2,
+ * i.e. solvers.py:62 with the inverse-FFT normalisation folded in; the symbol of the
+ * SIFS-compatible equations is real and even in each wavenumber, so one quadrant suffices. */
+int64_t pdeopt_table_len(const pdeopt_plan* plan);
+
+/* K = ksteps fused IMEX steps on `batch` independent environments.
+ *   y0_dev, y1_dev : [batch][nx][ny] float32 (may alias)
+ *   dt_host        : [ksteps] step lengths (t1 - t0 of each step, solvers.py:58)
+ *   tables_dev     : [ntab][pdeopt_table_len] folded inverse denominators
+ *   tab_idx_host   : [ksteps] which table each step uses (NULL = all 0)
+ *   ctrl_dev       : [batch][PDEOPT_NCTRL] control block or NULL
+ *   obs_dev        : [batch][nx][ny] uint8 observation of y1 or NULL:
+ *                    rint(clamp((y1-obs_lo)/(obs_hi-obs_lo),0,1)*255)   (pde_env.py:118-126)
+ *   reward_dev     : [batch][2] (mean, variance) of y1 or NULL          (pde_env.py:309)
+ */
+pdeopt_status pdeopt_sifs_step_batched(pdeopt_plan* plan, const float* y0_dev, float* y1_dev, int32_t batch,
+                                       int32_t ksteps, const float* dt_host, const float* tables_dev,
+                                       int32_t ntab, const int32_t* tab_idx_host, const float* ctrl_dev,
+                                       uint8_t* obs_dev, float obs_lo, float obs_hi, float* reward_dev,
+                                       void* stream);
+
+/* Same with HOST buffers: copies y0/ctrl/tables in, runs, copies y1/obs/reward out, and
+ * synchronises the stream before returning.  Scratch device memory is owned by the plan
+ * (grown on first use, reused afterwards). */
+pdeopt_status pdeopt_sifs_step_batched_host(pdeopt_plan* plan, const float* y0_host, float* y1_host,
+                                            int32_t batch, int32_t ksteps, const float* dt_host,
+                                            const float* tables_host, int32_t ntab,
+                                            const int32_t* tab_idx_host, const float* ctrl_host,
+                                            uint8_t* obs_host, float obs_lo, float obs_hi, float* reward_host,
+                                            void* stream);
+
+/* Number of kernels this library has launched in this process (bench.py "gpu_launches"). */
+int64_t pdeopt_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDEOPT_B200_H */

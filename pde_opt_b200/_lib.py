@@ -1,0 +1,91 @@
+"""ctypes binding of libpdeopt_b200.so (the C ABI declared in include/pdeopt_b200.h).
+
+The product path has no CPU fallback: if the shared library is missing, loading raises
+instead of silently degrading."""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpdeopt_b200.so")
+
+MAX_COEF = 16
+MAX_FUSED_STEPS = 64
+MAX_TABLES = 2
+NCTRL = 8
+
+OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
+KIND_CH2D, KIND_AC2D, KIND_AD2D, KIND_GPE2D = 0, 1, 2, 3
+DERIVS_FD, DERIVS_FOURIER = 0, 1
+
+
+class PlanDesc(ctypes.Structure):
+    _fields_ = [
+        ("kind", ctypes.c_int32),
+        ("derivs", ctypes.c_int32),
+        ("nx", ctypes.c_int32),
+        ("ny", ctypes.c_int32),
+        ("lo_x", ctypes.c_double),
+        ("lo_y", ctypes.c_double),
+        ("hx", ctypes.c_double),
+        ("hy", ctypes.c_double),
+        ("kappa", ctypes.c_double),
+        ("mu_family", ctypes.c_int32),
+        ("mu_ncoef", ctypes.c_int32),
+        ("mu_coef", ctypes.c_double * MAX_COEF),
+        ("mob_family", ctypes.c_int32),
+        ("mob_ncoef", ctypes.c_int32),
+        ("mob_coef", ctypes.c_double * MAX_COEF),
+    ]
+
+
+class PdeOptError(RuntimeError):
+    pass
+
+
+_lib = None
+
+EXPORTS = [
+    "pdeopt_abi_version",
+    "pdeopt_last_error",
+    "pdeopt_plan_create",
+    "pdeopt_plan_destroy",
+    "pdeopt_table_len",
+    "pdeopt_sifs_step_batched",
+    "pdeopt_sifs_step_batched_host",
+    "pdeopt_launch_count",
+]
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PdeOptError(
+            f"{LIB_PATH} is missing: build it with `python -m pde_opt_b200.build` "
+            "(there is no CPU fallback for the stepping path)"
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_float
+    lib.pdeopt_abi_version.restype = ctypes.c_int
+    lib.pdeopt_last_error.restype = ctypes.c_char_p
+    lib.pdeopt_plan_create.argtypes = [ctypes.POINTER(PlanDesc), ctypes.POINTER(vp)]
+    lib.pdeopt_plan_create.restype = ctypes.c_int
+    lib.pdeopt_plan_destroy.argtypes = [vp]
+    lib.pdeopt_plan_destroy.restype = ctypes.c_int
+    lib.pdeopt_table_len.argtypes = [vp]
+    lib.pdeopt_table_len.restype = ctypes.c_int64
+    sig = [vp, vp, vp, i32, i32, vp, vp, i32, vp, vp, vp, f32, f32, vp, vp]
+    lib.pdeopt_sifs_step_batched.argtypes = sig
+    lib.pdeopt_sifs_step_batched.restype = ctypes.c_int
+    lib.pdeopt_sifs_step_batched_host.argtypes = sig
+    lib.pdeopt_sifs_step_batched_host.restype = ctypes.c_int
+    lib.pdeopt_launch_count.restype = ctypes.c_int64
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != OK:
+        msg = load().pdeopt_last_error().decode()
+        raise PdeOptError(f"pdeopt status {status}: {msg}")

@@ -1,0 +1,67 @@
+// Pointwise closure families for mu_h(c), D(c), R(c).
+//
+// The reference takes arbitrary Python callables for `mu`, `D`, `R`
+// (equations/cahn_hilliard.py:50-53, allen_cahn.py:47-50); callables cannot cross a C ABI,
+// so the families that the reference's tests, notebooks and docs actually use are
+// enumerated here and evaluated inside the fused kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace pdeopt {
+
+enum : int { MU_DOUBLE_WELL = 0, MU_LOG = 1, MU_LEGENDRE = 2, MU_LEGENDRE_LOGPRIOR = 3, MU_RUNTIME = -1 };
+enum : int { MOB_CONST = 0, MOB_DEGENERATE = 1, MOB_ONE_PLUS_SQ = 2, MOB_LEGENDRE_EXP = 3, MOB_RUNTIME = -1 };
+
+struct PointwiseParams {
+  int mu_family, mu_ncoef;
+  float mu_coef[16];
+  int mob_family, mob_ncoef;
+  float mob_coef[16];
+};
+
+// functions/legendre.py:19-34: three-term recurrence on x in [-1,1].
+__device__ __forceinline__ float legendre_eval(const float* __restrict__ coef, int ncoef, float x) {
+  float result = coef[0];
+  if (ncoef > 1) result = fmaf(coef[1], x, result);
+  float p_prev = 1.0f, p_curr = x;
+  for (int n = 2; n < ncoef; ++n) {
+    float p_next = (float(2 * n - 1) * x * p_curr - float(n - 1) * p_prev) / float(n);
+    result = fmaf(coef[n], p_next, result);
+    p_prev = p_curr;
+    p_curr = p_next;
+  }
+  return result;
+}
+
+// log(c/(1-c)): one MUFU.RCP-based division and one MUFU.LG2.
+__device__ __forceinline__ float logit(float c) { return __logf(__fdividef(c, 1.0f - c)); }
+
+template <int MU>
+__device__ __forceinline__ float mu_h(float c, const PointwiseParams& pw, float w_off) {
+  const int fam = (MU == MU_RUNTIME) ? pw.mu_family : MU;
+  if (fam == MU_DOUBLE_WELL) {
+    return c * c * c - c;  // tests/test_solvers.py:36
+  } else if (fam == MU_LOG) {
+    return logit(c) + (pw.mu_coef[0] + w_off) * (1.0f - 2.0f * c);  // optimize_nn_script.py:33
+  } else if (fam == MU_LEGENDRE) {
+    return legendre_eval(pw.mu_coef, pw.mu_ncoef, 2.0f * c - 1.0f);  // legendre.py:68-73
+  } else {
+    return legendre_eval(pw.mu_coef, pw.mu_ncoef, 2.0f * c - 1.0f) + logit(c);
+  }
+}
+
+template <int MOB>
+__device__ __forceinline__ float mob(float c, const PointwiseParams& pw) {
+  const int fam = (MOB == MOB_RUNTIME) ? pw.mob_family : MOB;
+  if (fam == MOB_CONST) {
+    return pw.mob_coef[0];
+  } else if (fam == MOB_DEGENERATE) {
+    return (1.0f - c) * c;
+  } else if (fam == MOB_ONE_PLUS_SQ) {
+    return 1.0f + c * c;  // test_rhs_convergence.py:22,55
+  } else {
+    return __expf(legendre_eval(pw.mob_coef, pw.mob_ncoef, 2.0f * c - 1.0f));  // legendre.py:48-53
+  }
+}
+
+}  // namespace pdeopt

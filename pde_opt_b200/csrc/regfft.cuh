@@ -1,0 +1,150 @@
+// In-register power-of-two FFTs on float2 arrays with compile-time twiddles.
+//
+// Building block of the fused in-SMEM spectral steppers: every pass of the 2-D transform
+// is a set of small DFTs held entirely in one thread's registers (fully unrolled, all
+// indices compile-time so the array lives in registers).  Forward transforms are
+// decimation-in-frequency (natural order in, bit-reversed order out); inverse transforms
+// are decimation-in-time (bit-reversed in, natural out), so a forward/inverse pair needs no
+// reordering and a spectral multiplier is simply applied in bit-reversed positions.
+//
+// Replaces jnp.fft.fftn / ifftn as called from the reference's
+// pde_opt/numerics/solvers.py:63 and :107-114 (XLA library FFT there).
+//
+// The header is host-compilable (tests/test_regfft_host.py builds it with g++).
+#pragma once
+#include <type_traits>
+
+#if defined(__CUDACC__)
+#define PDEOPT_HD __host__ __device__ __forceinline__
+#else
+#define PDEOPT_HD inline
+#ifndef PDEOPT_HOST_FLOAT2
+#define PDEOPT_HOST_FLOAT2
+struct float2 {
+  float x, y;
+};
+static inline float2 make_float2(float a, float b) {
+  float2 r;
+  r.x = a;
+  r.y = b;
+  return r;
+}
+#endif
+#endif
+
+namespace pdeopt {
+
+// ---- compile-time sin/cos (Taylor on [-pi, pi], double precision) ----------------------
+constexpr double kPi = 3.14159265358979323846264338327950288;
+
+constexpr double cx_sin(double x) {
+  double x2 = x * x, term = x, sum = x;
+  for (int i = 1; i < 16; ++i) {
+    term *= -x2 / double((2 * i) * (2 * i + 1));
+    sum += term;
+  }
+  return sum;
+}
+constexpr double cx_cos(double x) {
+  double x2 = x * x, term = 1.0, sum = 1.0;
+  for (int i = 1; i < 16; ++i) {
+    term *= -x2 / double((2 * i - 1) * (2 * i));
+    sum += term;
+  }
+  return sum;
+}
+
+// w_N^J = exp(-2 pi i J / N) (forward) ; conjugate for the inverse.
+template <int N, int J>
+struct Tw {
+  static constexpr float re = float(cx_cos(2.0 * kPi * double(J) / double(N)));
+  static constexpr float im = float(-cx_sin(2.0 * kPi * double(J) / double(N)));
+};
+
+template <int LOG2N>
+constexpr int brev(int k) {
+  int r = 0;
+  for (int b = 0; b < LOG2N; ++b) r |= ((k >> b) & 1) << (LOG2N - 1 - b);
+  return r;
+}
+
+constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n >> 1); }
+
+PDEOPT_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+PDEOPT_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+PDEOPT_HD float2 cmul(float2 a, float2 w) {
+  return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
+}
+PDEOPT_HD float2 cmulc(float2 a, float2 w) {  // a * conj(w)
+  return make_float2(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y);
+}
+
+// (a) * w_N^J, with the trivial and 8th-root cases specialised at compile time.
+template <int N, int J, bool INV>
+PDEOPT_HD float2 mul_tw(float2 a) {
+  constexpr int Jm = ((J % N) + N) % N;
+  if constexpr (Jm == 0) {
+    return a;
+  } else if constexpr (Jm * 4 == N) {  // -i (fwd) / +i (inv)
+    return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+  } else if constexpr (Jm * 2 == N) {
+    return make_float2(-a.x, -a.y);
+  } else if constexpr (Jm * 4 == 3 * N) {
+    return INV ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x);
+  } else if constexpr (Jm * 8 == N) {  // (1 - i)/sqrt2 fwd
+    constexpr float s = 0.70710678118654752440f;
+    return INV ? make_float2((a.x - a.y) * s, (a.x + a.y) * s) : make_float2((a.x + a.y) * s, (a.y - a.x) * s);
+  } else if constexpr (Jm * 8 == 3 * N) {  // (-1 - i)/sqrt2 fwd
+    constexpr float s = 0.70710678118654752440f;
+    return INV ? make_float2(-(a.x + a.y) * s, (a.x - a.y) * s) : make_float2((a.y - a.x) * s, -(a.x + a.y) * s);
+  } else {
+    constexpr float wr = Tw<N, Jm>::re;
+    constexpr float wi = INV ? -Tw<N, Jm>::im : Tw<N, Jm>::im;
+    return make_float2(a.x * wr - a.y * wi, a.x * wi + a.y * wr);
+  }
+}
+
+template <int I, int E, class F>
+PDEOPT_HD void static_for(F&& f) {
+  if constexpr (I < E) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, E>(static_cast<F&&>(f));
+  }
+}
+
+// Decimation in frequency, in place on x[0], x[S], ..., x[(N-1)S].
+// Natural order in; position p (units of S) holds X[brev(p)] on return.
+template <int N, int S, bool INV>
+struct Dif {
+  static PDEOPT_HD void run(float2* x) {
+    if constexpr (N >= 2) {
+      static_for<0, N / 2>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        float2 a = x[j * S], b = x[(j + N / 2) * S];
+        x[j * S] = cadd(a, b);
+        x[(j + N / 2) * S] = mul_tw<N, j, INV>(csub(a, b));
+      });
+      Dif<N / 2, S, INV>::run(x);
+      Dif<N / 2, S, INV>::run(x + (N / 2) * S);
+    }
+  }
+};
+
+// Decimation in time, in place.  Position p holds x[brev(p)] on entry; natural order out.
+template <int N, int S, bool INV>
+struct Dit {
+  static PDEOPT_HD void run(float2* x) {
+    if constexpr (N >= 2) {
+      Dit<N / 2, S, INV>::run(x);
+      Dit<N / 2, S, INV>::run(x + (N / 2) * S);
+      static_for<0, N / 2>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        float2 a = x[j * S], b = mul_tw<N, j, INV>(x[(j + N / 2) * S]);
+        x[j * S] = cadd(a, b);
+        x[(j + N / 2) * S] = csub(a, b);
+      });
+    }
+  }
+};
+
+}  // namespace pdeopt

@@ -1,0 +1,652 @@
+// Fused K-step semi-implicit Fourier-spectral stepper for 128x128 real fields (sm_100a).
+//
+// Replaces, for one launch, K iterations of the diffeqsolve loop body of the reference:
+//   SemiImplicitFourierSpectral.step        pde_opt/numerics/solvers.py:56-70
+//   CahnHilliard2DPeriodic.rhs_fd           pde_opt/numerics/equations/cahn_hilliard.py:89-109
+//   AllenCahn2DPeriodic.rhs_fd              pde_opt/numerics/equations/allen_cahn.py:81-84
+//   stencils                                pde_opt/numerics/utils/derivatives.py:8-66
+// and the observation/reward callbacks of PDEEnv.step (pde_opt/pde_env.py:305-309).
+//
+// Design (DESIGN.md has the full derivation):
+//  * one CTA (512 threads) owns TWO environments packed as one complex field z = u_a + i u_b.
+//    The IMEX multiplier 1/(1 + A dt sigma(k)) is real and even, i.e. a real convolution
+//    kernel, so filtering z filters u_a and u_b independently: one complex 128x128 FFT pair
+//    serves two environments with no Hermitian untangling.
+//  * the field never leaves the SM for K steps: 128 KB of shared memory holds it in the
+//    "natural" (spatial) layout for the finite-difference RHS and doubles as the exchange
+//    buffer of the FFT; the state y that the update y1 = y0 + dt*g needs is parked in
+//    tensor memory (TMEM, 64 columns per thread) because registers hold the FFT data.
+//  * the 2-D FFT is three register passes (radix 32 | 4x8 | 16x2, all twiddles compile-time
+//    except 10 per-thread inter-pass twiddles) with two shared-memory exchanges each way;
+//    all exchange patterns are bank-conflict free (tools/fft_decomp_model.py proves it).
+//  * the RHS marches down 8 rows per warp with a rolling register window; column
+//    neighbours come from warp shuffles (a warp spans a whole periodic row).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pointwise.cuh"
+#include "regfft.cuh"
+
+namespace pdeopt {
+
+constexpr int kN = 128;
+constexpr int kThreads = 512;
+constexpr int kTabDim = 65;
+constexpr int kTabLen = kTabDim * kTabDim;
+constexpr int kMaxK = 64;
+constexpr int kMaxTab = 2;
+constexpr int kNCtrl = 8;
+
+enum : int { EQ_CH = 0, EQ_AC = 1 };
+
+struct SifsParams {
+  const float* y0;
+  float* y1;
+  int batch;
+  int ksteps;
+  const float* tables;  // [ntab][kTabLen]
+  int ntab;
+  const float* ctrl;  // [batch][kNCtrl] or null
+  uint8_t* obs;       // [batch][128][128] or null
+  float obs_lo, obs_scale;
+  float* reward;  // [batch][2] or null
+  float* park;    // global parking scratch (only when built with PDEOPT_PARK_GLOBAL)
+  float inv_hx, inv_hy, inv_hx2, inv_hy2, kappa;
+  float lo_x, lo_y, hx, hy;
+  PointwiseParams pw;
+  float dt[kMaxK];
+  uint8_t tab[kMaxK];
+};
+
+// ---- shared-memory layouts (validated in tools/fft_decomp_model.py) ----------------------
+__device__ __forceinline__ int nat_idx(int r, int c) {
+  const int c1 = (c >> 1) & 1;
+  int pos = (c & 1) | ((c >> 2) << 1) | (c1 << 6);
+  pos ^= ((r & 3) << 1) ^ (c1 << 3);
+  return r * kN + pos;
+}
+__device__ __forceinline__ int ex_idx(int k1c, int rho, int q) {
+  return ((k1c * 32 + (rho >> 2)) * 16) + ((((rho & 3) ^ ((k1c >> 2) & 3))) << 2) + (q ^ (k1c & 3));
+}
+
+// ---- TMEM parking of the state (64 x 32-bit columns per thread) --------------------------
+#ifndef PDEOPT_PARK_GLOBAL
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float2 (&v)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "f"(v[0].x), "f"(v[0].y), "f"(v[1].x), "f"(v[1].y), "f"(v[2].x), "f"(v[2].y), "f"(v[3].x), "f"(v[3].y),
+      "f"(v[4].x), "f"(v[4].y), "f"(v[5].x), "f"(v[5].y), "f"(v[6].x), "f"(v[6].y), "f"(v[7].x), "f"(v[7].y)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float2 (&v)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y), "=f"(v[2].x), "=f"(v[2].y), "=f"(v[3].x), "=f"(v[3].y),
+        "=f"(v[4].x), "=f"(v[4].y), "=f"(v[5].x), "=f"(v[5].y), "=f"(v[6].x), "=f"(v[6].y), "=f"(v[7].x), "=f"(v[7].y)
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+#endif
+
+struct Park {
+#ifndef PDEOPT_PARK_GLOBAL
+  uint32_t taddr;
+#else
+  float2* g;  // [32][512] per CTA, element-major so a warp's accesses coalesce
+#endif
+  __device__ __forceinline__ void store(int chunk, const float2 (&v)[8]) const {
+#ifndef PDEOPT_PARK_GLOBAL
+    tmem_st16(taddr + chunk * 16, v);
+#else
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[(chunk * 8 + i) * kThreads + threadIdx.x] = v[i];
+#endif
+  }
+  __device__ __forceinline__ void load(int chunk, float2 (&v)[8]) const {
+#ifndef PDEOPT_PARK_GLOBAL
+    tmem_ld16(taddr + chunk * 16, v);
+#else
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = g[(chunk * 8 + i) * kThreads + threadIdx.x];
+#endif
+  }
+  __device__ __forceinline__ void fence_store() const {
+#ifndef PDEOPT_PARK_GLOBAL
+    tmem_wait_st();
+#endif
+  }
+};
+
+// ---- small helpers ------------------------------------------------------------------------
+__device__ __forceinline__ float2 shfl2(float2 v, int src) {
+  return make_float2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+__device__ __forceinline__ float2 f2scale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+
+// One row of the natural layout for the S (stencil) mapping: lane l owns columns 4l..4l+3.
+__device__ __forceinline__ void load_row(const float2* __restrict__ W, int r, int lane, float2 (&v)[4]) {
+  const int p0 = r * kN + ((2 * lane) ^ ((r & 3) << 1));
+  const float4 a = *reinterpret_cast<const float4*>(W + p0);
+  const float4 b = *reinterpret_cast<const float4*>(W + (p0 ^ 8) + 64);
+  v[0] = make_float2(a.x, a.y);
+  v[1] = make_float2(a.z, a.w);
+  v[2] = make_float2(b.x, b.y);
+  v[3] = make_float2(b.z, b.w);
+}
+__device__ __forceinline__ void store_row(float2* __restrict__ W, int r, int lane, const float2 (&v)[4]) {
+  const int p0 = r * kN + ((2 * lane) ^ ((r & 3) << 1));
+  *reinterpret_cast<float4*>(W + p0) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+  *reinterpret_cast<float4*>(W + (p0 ^ 8) + 64) = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
+}
+
+struct EnvCtrl {
+  float2 w_off;  // per-env offset of the mu scalar (a, b)
+  bool has_bump;
+};
+
+// ---- RHS phase: W (natural layout) holds u on entry and f0 = rhs(u) on return ------------
+template <int EQ, int MU, int MOB>
+__device__ __forceinline__ void rhs_phase(float2* __restrict__ W, const SifsParams& p, const EnvCtrl& ec,
+                                          const float2* __restrict__ gx, const float2* __restrict__ gy) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r0 = warp * 8;
+  const int lm1 = (lane + 31) & 31, lp1 = (lane + 1) & 31;
+
+  // Halo rows are read before anybody overwrites them with f0.
+  float2 hm2[4], hm1[4], hp8[4], hp9[4];
+  load_row(W, (r0 + kN - 1) & (kN - 1), lane, hm1);
+  load_row(W, (r0 + 8) & (kN - 1), lane, hp8);
+  if (EQ == EQ_CH) {
+    load_row(W, (r0 + kN - 2) & (kN - 1), lane, hm2);
+    load_row(W, (r0 + 9) & (kN - 1), lane, hp9);
+  }
+  __syncthreads();
+
+  float2 gyv[4];
+  if (ec.has_bump) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) gyv[j] = gy[4 * lane + j];
+  }
+
+  // mu and mobility of one row from its three-row neighbourhood.
+  auto mu_row = [&](int rho, const float2 (&um)[4], const float2 (&u0)[4], const float2 (&up)[4], float2 (&mu)[4],
+                    float2 (&D)[4]) {
+    const float2 uL = shfl2(u0[3], lm1), uR = shfl2(u0[0], lp1);
+    float2 gxr = make_float2(0.f, 0.f);
+    if (ec.has_bump) gxr = gx[rho & (kN - 1)];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 left = (j == 0) ? uL : u0[j - 1];
+      const float2 right = (j == 3) ? uR : u0[j + 1];
+      float2 lap;
+      lap.x = ((up[j].x - 2.0f * u0[j].x) + um[j].x) * p.inv_hx2 + ((right.x - 2.0f * u0[j].x) + left.x) * p.inv_hy2;
+      lap.y = ((up[j].y - 2.0f * u0[j].y) + um[j].y) * p.inv_hx2 + ((right.y - 2.0f * u0[j].y) + left.y) * p.inv_hy2;
+      float ma = mu_h<MU>(u0[j].x, p.pw, ec.w_off.x), mb = mu_h<MU>(u0[j].y, p.pw, ec.w_off.y);
+      if (ec.has_bump) {
+        ma = fmaf(gxr.x, gyv[j].x, ma);
+        mb = fmaf(gxr.y, gyv[j].y, mb);
+      }
+      mu[j] = make_float2(ma - p.kappa * lap.x, mb - p.kappa * lap.y);
+      D[j] = make_float2(mob<MOB>(u0[j].x, p.pw), mob<MOB>(u0[j].y, p.pw));
+    }
+  };
+
+  if (EQ == EQ_AC) {
+    // f = -R(u) * mu   (allen_cahn.py:81-84)
+    float2 um[4], u0[4], up[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) um[j] = hm1[j];
+    load_row(W, r0, lane, u0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < 7) {
+        load_row(W, r0 + i + 1, lane, up);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) up[j] = hp8[j];
+      }
+      float2 mu[4], R[4], f[4];
+      mu_row(r0 + i, um, u0, up, mu, R);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) f[j] = make_float2(-R[j].x * mu[j].x, -R[j].y * mu[j].y);
+      store_row(W, r0 + i, lane, f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        um[j] = u0[j];
+        u0[j] = up[j];
+      }
+    }
+    return;
+  }
+
+  // Cahn-Hilliard: f = div( D_face * grad_face(mu) )   (cahn_hilliard.py:89-109)
+  float2 um[4], u0[4], up[4];
+  float2 mu_p[4], D_p[4], fx_old[4], divy_p[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    um[j] = hm2[j];
+    u0[j] = hm1[j];
+  }
+  load_row(W, r0, lane, up);
+  // it = -1 .. 8  <->  rho = r0 + it : compute mu/D of row rho, emit f of row rho-1.
+#pragma unroll
+  for (int it = -1; it <= 8; ++it) {
+    float2 mu[4], D[4];
+    mu_row(r0 + it + kN, um, u0, up, mu, D);
+    float2 divy[4];
+    if (it >= 0 && it <= 7) {
+      const float2 muR = shfl2(mu[0], lp1), DR = shfl2(D[0], lp1);
+      float2 fy[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 mr = (j == 3) ? muR : mu[j + 1];
+        const float2 dr = (j == 3) ? DR : D[j + 1];
+        fy[j].x = (0.5f * (D[j].x + dr.x)) * ((mr.x - mu[j].x) * p.inv_hy);
+        fy[j].y = (0.5f * (D[j].y + dr.y)) * ((mr.y - mu[j].y) * p.inv_hy);
+      }
+      const float2 fyL = shfl2(fy[3], lm1);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 fl = (j == 0) ? fyL : fy[j - 1];
+        divy[j] = make_float2((fy[j].x - fl.x) * p.inv_hy, (fy[j].y - fl.y) * p.inv_hy);
+      }
+    }
+    if (it >= 0) {
+      float2 fx[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        fx[j].x = (0.5f * (D_p[j].x + D[j].x)) * ((mu[j].x - mu_p[j].x) * p.inv_hx);
+        fx[j].y = (0.5f * (D_p[j].y + D[j].y)) * ((mu[j].y - mu_p[j].y) * p.inv_hx);
+      }
+      if (it >= 1) {
+        float2 f[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          f[j].x = (fx[j].x - fx_old[j].x) * p.inv_hx + divy_p[j].x;
+          f[j].y = (fx[j].y - fx_old[j].y) * p.inv_hx + divy_p[j].y;
+        }
+        store_row(W, r0 + it - 1, lane, f);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) fx_old[j] = fx[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      mu_p[j] = mu[j];
+      D_p[j] = D[j];
+      if (it >= 0 && it <= 7) divy_p[j] = divy[j];
+      um[j] = u0[j];
+      u0[j] = up[j];
+    }
+    // next "up" row: rho + 2 = r0 + it + 2
+    if (it + 2 <= 7) {
+      load_row(W, r0 + it + 2, lane, up);
+    } else if (it + 2 == 8) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) up[j] = hp8[j];
+    } else if (it + 2 == 9) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) up[j] = hp9[j];
+    }
+  }
+}
+
+// ---- FFT passes ---------------------------------------------------------------------------
+// P1: thread (r, n2c) owns c = 4*n1c + n2c, n1c = 0..31.
+struct P1Map {
+  int r, n2c;
+  __device__ __forceinline__ P1Map() {
+    const int t = threadIdx.x;
+    n2c = t & 3;
+    r = ((t >> 2) & 3) | ((t >> 4) << 2);
+  }
+};
+// P2: thread (k1c, n2r) owns (q, hi) with rho = 16*hi + n2r.
+struct P2Map {
+  int k1c, n2r;
+  __device__ __forceinline__ P2Map() {
+    const int t = threadIdx.x;
+    k1c = (t & 3) | (((t >> 4) & 7) << 2);
+    n2r = ((t >> 2) & 3) | (((t >> 7) & 3) << 2);
+  }
+};
+// P3: thread (k1r, k1c, k2c_t) owns n2r = 0..15 and k2c = b | (k2c_t << 1), b = 0,1.
+struct P3Map {
+  int k1r, k1c, k2ct;
+  __device__ __forceinline__ P3Map() {
+    const int t = threadIdx.x;
+    k1c = t & 31;
+    k2ct = (t >> 5) & 1;
+    k1r = t >> 6;
+  }
+};
+
+__device__ __forceinline__ void p1_gather_nat(const float2* __restrict__ W, const P1Map& m, float2 (&x)[32]) {
+#pragma unroll
+  for (int n = 0; n < 32; ++n) x[n] = W[nat_idx(m.r, 4 * n + m.n2c)];
+}
+__device__ __forceinline__ void p1_scatter_nat(float2* __restrict__ W, const P1Map& m, const float2 (&x)[32]) {
+#pragma unroll
+  for (int n = 0; n < 32; ++n) W[nat_idx(m.r, 4 * n + m.n2c)] = x[n];
+}
+
+// Forward: natural f0 in W  ->  spectrum (x multiplier) -> inverse -> g in registers (P1 map).
+// tw: 128-entry table of w_128^e in shared memory; mt: folded multiplier table in shared memory.
+__device__ __forceinline__ void spectral_filter(float2* __restrict__ W, const float2* __restrict__ tw,
+                                                const float* __restrict__ mt, const P1Map& m1, float2 (&x)[32]) {
+  const P2Map m2;
+  const P3Map m3;
+  // ---- P1 forward: 32-point DFT over n1c ----
+  p1_gather_nat(W, m1, x);
+  __syncthreads();  // everybody has read f0 before the buffer is reused as exchange space
+  Dif<32, 1, false>::run(x);
+  static_for<0, 32>([&](auto pc) {
+    constexpr int pp = decltype(pc)::value;
+    W[ex_idx(brev<5>(pp), m1.r, m1.n2c)] = x[pp];
+  });
+  __syncthreads();
+  // ---- P2 forward: twiddle, 4-point DFT over n2c, 8-point DFT over n1r, twiddle ----
+  {
+    float2 twc[4], twr[8];
+#pragma unroll
+    for (int q = 1; q < 4; ++q) twc[q] = tw[(q * m2.k1c) & 127];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) twr[k] = tw[(k * m2.n2r) & 127];
+    // v[q*8 + hi]
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int hi = 0; hi < 8; ++hi) x[q * 8 + hi] = W[ex_idx(m2.k1c, 16 * hi + m2.n2r, q)];
+#pragma unroll
+    for (int q = 1; q < 4; ++q)
+#pragma unroll
+      for (int hi = 0; hi < 8; ++hi) x[q * 8 + hi] = cmul(x[q * 8 + hi], twc[q]);
+    static_for<0, 8>([&](auto hc) { Dif<4, 8, false>::run(x + decltype(hc)::value); });
+    static_for<0, 4>([&](auto qc) { Dif<8, 1, false>::run(x + 8 * decltype(qc)::value); });
+    // position (pq, pr) holds k2c = brev2(pq), k1r = brev3(pr)
+    static_for<0, 4>([&](auto qc) {
+      constexpr int pq = decltype(qc)::value;
+      static_for<0, 8>([&](auto rc) {
+        constexpr int pr = decltype(rc)::value;
+        constexpr int k1r = brev<3>(pr);
+        float2 v = x[pq * 8 + pr];
+        if constexpr (k1r != 0) v = cmul(v, twr[k1r]);
+        W[ex_idx(m2.k1c, 16 * k1r + m2.n2r, brev<2>(pq))] = v;
+      });
+    });
+  }
+  __syncthreads();
+  // ---- P3: 16-point DFT over n2r, multiplier, inverse 16-point ----
+  {
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int n = 0; n < 16; ++n) x[b * 16 + n] = W[ex_idx(m3.k1c, 16 * m3.k1r + n, b | (m3.k2ct << 1))];
+    Dif<16, 1, false>::run(x);
+    Dif<16, 1, false>::run(x + 16);
+    static_for<0, 2>([&](auto bc) {
+      constexpr int b = decltype(bc)::value;
+      const int kc = m3.k1c + 32 * (b | (m3.k2ct << 1));
+      const int fc = kc <= 64 ? kc : 128 - kc;
+      static_for<0, 16>([&](auto pc) {
+        constexpr int pp = decltype(pc)::value;
+        const int kr = m3.k1r + 8 * brev<4>(pp);
+        const int fr = kr <= 64 ? kr : 128 - kr;
+        const float mval = mt[fr * kTabDim + fc];
+        x[b * 16 + pp] = make_float2(x[b * 16 + pp].x * mval, x[b * 16 + pp].y * mval);
+      });
+    });
+    Dit<16, 1, true>::run(x);
+    Dit<16, 1, true>::run(x + 16);
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int n = 0; n < 16; ++n) W[ex_idx(m3.k1c, 16 * m3.k1r + n, b | (m3.k2ct << 1))] = x[b * 16 + n];
+  }
+  __syncthreads();
+  // ---- P2 inverse ----
+  {
+    float2 twc[4], twr[8];
+#pragma unroll
+    for (int q = 1; q < 4; ++q) twc[q] = tw[(q * m2.k1c) & 127];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) twr[k] = tw[(k * m2.n2r) & 127];
+    static_for<0, 4>([&](auto qc) {
+      constexpr int pq = decltype(qc)::value;
+      static_for<0, 8>([&](auto rc) {
+        constexpr int pr = decltype(rc)::value;
+        constexpr int k1r = brev<3>(pr);
+        float2 v = W[ex_idx(m2.k1c, 16 * k1r + m2.n2r, brev<2>(pq))];
+        if constexpr (k1r != 0) v = cmulc(v, twr[k1r]);
+        x[pq * 8 + pr] = v;
+      });
+    });
+    static_for<0, 4>([&](auto qc) { Dit<8, 1, true>::run(x + 8 * decltype(qc)::value); });
+    static_for<0, 8>([&](auto hc) { Dit<4, 8, true>::run(x + decltype(hc)::value); });
+#pragma unroll
+    for (int q = 1; q < 4; ++q)
+#pragma unroll
+      for (int hi = 0; hi < 8; ++hi) x[q * 8 + hi] = cmulc(x[q * 8 + hi], twc[q]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int hi = 0; hi < 8; ++hi) W[ex_idx(m2.k1c, 16 * hi + m2.n2r, q)] = x[q * 8 + hi];
+  }
+  __syncthreads();
+  // ---- P1 inverse ----
+  static_for<0, 32>([&](auto pc) {
+    constexpr int pp = decltype(pc)::value;
+    x[pp] = W[ex_idx(brev<5>(pp), m1.r, m1.n2c)];
+  });
+  Dit<32, 1, true>::run(x);
+}
+
+// ---- block reductions for the reward epilogue -----------------------------------------------
+__device__ __forceinline__ float2 block_sum2(float2 v, float2* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+    v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) {
+    s.x += red[w].x;
+    s.y += red[w].y;
+  }
+  return s;
+}
+
+struct __align__(16) SifsSmem {
+  float2 W[kN * kN];
+  float tab[kMaxTab][kTabLen + 3];
+  float2 tw[128];
+  float2 gx[kN], gy[kN];
+  float2 red[kThreads / 32];
+  uint32_t tmem_base;
+};
+
+template <int EQ, int MU, int MOB>
+__global__ void __launch_bounds__(kThreads, 1) sifs128_kernel(const __grid_constant__ SifsParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SifsSmem& S = *reinterpret_cast<SifsSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int env_a = 2 * blockIdx.x;
+  const int env_b = (env_a + 1 < p.batch) ? env_a + 1 : env_a;  // odd batch: duplicate the last env
+  const bool b_valid = env_a + 1 < p.batch;
+
+  // ---- setup: TMEM, tables, twiddles, control ----
+  Park park;
+#ifndef PDEOPT_PARK_GLOBAL
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(
+        (uint32_t)__cvta_generic_to_shared(&S.tmem_base)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+#endif
+  for (int i = tid; i < p.ntab * kTabLen; i += kThreads) S.tab[i / kTabLen][i % kTabLen] = p.tables[i];
+  if (tid < 128) {
+    float s, c;
+    sincospif(-2.0f * float(tid) / 128.0f, &s, &c);
+    S.tw[tid] = make_float2(c, s);
+  }
+  EnvCtrl ec;
+  ec.w_off = make_float2(0.f, 0.f);
+  ec.has_bump = false;
+  if (p.ctrl != nullptr) {
+    const float* ca = p.ctrl + (size_t)env_a * kNCtrl;
+    const float* cb = p.ctrl + (size_t)env_b * kNCtrl;
+    ec.w_off = make_float2(ca[0], cb[0]);
+    ec.has_bump = true;
+    if (tid < 2 * kN) {
+      // separable Gaussian bump amp*exp(-(x-x0)^2/(2s^2)) * exp(-(y-y0)^2/(2s^2)); amp folded into gx
+      const int i = tid & (kN - 1);
+      const bool isx = tid < kN;
+      float2 out;
+      {
+        const float pos = isx ? (p.lo_x + (i + 0.5f) * p.hx) : (p.lo_y + (i + 0.5f) * p.hy);
+        const float da = pos - (isx ? ca[2] : ca[3]), db = pos - (isx ? cb[2] : cb[3]);
+        const float ia = 0.5f / (ca[4] * ca[4]), ib = 0.5f / (cb[4] * cb[4]);
+        out.x = (ca[1] != 0.f ? expf(-da * da * ia) : 0.f) * (isx ? ca[1] : 1.0f);
+        out.y = (cb[1] != 0.f ? expf(-db * db * ib) : 0.f) * (isx ? cb[1] : 1.0f);
+      }
+      if (isx) S.gx[i] = out; else S.gy[i] = out;
+    }
+  }
+#ifndef PDEOPT_PARK_GLOBAL
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+#endif
+  __syncthreads();
+#ifndef PDEOPT_PARK_GLOBAL
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  park.taddr = S.tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * 64u;
+#else
+  park.g = reinterpret_cast<float2*>(p.park) + (size_t)blockIdx.x * 32 * kThreads;
+#endif
+
+  // ---- prologue: y0 of both envs -> natural layout (S mapping: warp = 8 rows, lane = 4 cols) ----
+  {
+    const float* ya = p.y0 + (size_t)env_a * kN * kN;
+    const float* yb = p.y0 + (size_t)env_b * kN * kN;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = warp * 8 + i;
+      const float4 a = *reinterpret_cast<const float4*>(ya + r * kN + 4 * lane);
+      const float4 b = *reinterpret_cast<const float4*>(yb + r * kN + 4 * lane);
+      float2 v[4] = {make_float2(a.x, b.x), make_float2(a.y, b.y), make_float2(a.z, b.z), make_float2(a.w, b.w)};
+      store_row(S.W, r, lane, v);
+    }
+  }
+  __syncthreads();
+  const P1Map m1;
+  float2 x[32];
+  p1_gather_nat(S.W, m1, x);
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    float2 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = x[ch * 8 + i];
+    park.store(ch, v);
+  }
+  park.fence_store();
+  __syncthreads();
+
+  // ---- K fused steps ----
+  for (int k = 0; k < p.ksteps; ++k) {
+    rhs_phase<EQ, MU, MOB>(S.W, p, ec, S.gx, S.gy);
+    __syncthreads();
+    spectral_filter(S.W, S.tw, S.tab[p.tab[k]], m1, x);
+    const float dt = p.dt[k];
+    // y1 = y0 + dt * g   (solvers.py:63); y0 comes back from the parking space
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      float2 v[8];
+      park.load(ch, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[i].x = fmaf(dt, x[ch * 8 + i].x, v[i].x);
+        v[i].y = fmaf(dt, x[ch * 8 + i].y, v[i].y);
+        x[ch * 8 + i] = v[i];
+      }
+      park.store(ch, v);
+    }
+    park.fence_store();
+    __syncthreads();  // all exchange-layout reads are done before the natural layout is rewritten
+    p1_scatter_nat(S.W, m1, x);
+    __syncthreads();
+  }
+
+  // ---- epilogue: y1 to global (coalesced), optional uint8 observation and (mean, var) ----
+  {
+    float* ya = p.y1 + (size_t)env_a * kN * kN;
+    float* yb = p.y1 + (size_t)env_b * kN * kN;
+    float2 sum = make_float2(0.f, 0.f);
+    float2 rows[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = warp * 8 + i;
+      load_row(S.W, r, lane, rows[i]);
+      const float2* v = rows[i];
+      *reinterpret_cast<float4*>(ya + r * kN + 4 * lane) = make_float4(v[0].x, v[1].x, v[2].x, v[3].x);
+      if (b_valid) *reinterpret_cast<float4*>(yb + r * kN + 4 * lane) = make_float4(v[0].y, v[1].y, v[2].y, v[3].y);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sum.x += v[j].x;
+        sum.y += v[j].y;
+      }
+      if (p.obs != nullptr) {
+        uint32_t pa = 0, pb = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float qa = rintf(__saturatef((v[j].x - p.obs_lo) * p.obs_scale) * 255.0f);
+          const float qb = rintf(__saturatef((v[j].y - p.obs_lo) * p.obs_scale) * 255.0f);
+          pa |= (uint32_t)qa << (8 * j);
+          pb |= (uint32_t)qb << (8 * j);
+        }
+        *reinterpret_cast<uint32_t*>(p.obs + (size_t)env_a * kN * kN + r * kN + 4 * lane) = pa;
+        if (b_valid) *reinterpret_cast<uint32_t*>(p.obs + (size_t)env_b * kN * kN + r * kN + 4 * lane) = pb;
+      }
+    }
+    if (p.reward != nullptr) {
+      const float inv_n = 1.0f / float(kN * kN);
+      const float2 tot = block_sum2(sum, S.red);
+      const float2 mean = make_float2(tot.x * inv_n, tot.y * inv_n);
+      float2 sq = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float da = rows[i][j].x - mean.x, db = rows[i][j].y - mean.y;
+          sq.x = fmaf(da, da, sq.x);
+          sq.y = fmaf(db, db, sq.y);
+        }
+      const float2 tsq = block_sum2(sq, S.red);
+      if (tid == 0) {
+        p.reward[2 * env_a] = mean.x;
+        p.reward[2 * env_a + 1] = tsq.x * inv_n;
+        if (b_valid) {
+          p.reward[2 * env_b] = mean.y;
+          p.reward[2 * env_b + 1] = tsq.y * inv_n;
+        }
+      }
+    }
+  }
+#ifndef PDEOPT_PARK_GLOBAL
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(S.tmem_base));
+  }
+#endif
+}
+
+}  // namespace pdeopt

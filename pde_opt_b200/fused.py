@@ -1,0 +1,131 @@
+"""Thin torch-facing wrapper over the C ABI (device pointers + stream in, status out).
+
+torch is used for device memory and streams only; all arithmetic of the stepping path
+happens inside libpdeopt_b200.so."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+MU_FAMILIES = {"double_well": 0, "log": 1, "legendre": 2, "legendre_logprior": 3}
+MOB_FAMILIES = {"const": 0, "degenerate": 1, "one_plus_sq": 2, "legendre_exp": 3}
+
+
+def fold_symbol(symbol):
+    """Quadrant [nx/2+1, ny/2+1] of a SIFS fourier_symbol (cahn_hilliard.py:74), after checking
+    that it is real and even in each wavenumber (so that the quadrant determines it)."""
+    s = np.asarray(symbol)
+    nx, ny = s.shape
+    if np.iscomplexobj(s):
+        if np.abs(s.imag).max() > 1e-6 * max(1.0, np.abs(s.real).max()):
+            raise ValueError("fourier_symbol must be real for the fused SIFS path")
+        s = s.real
+    full_even = np.allclose(s[1:, :], s[1:, :][::-1, :], rtol=1e-5) and np.allclose(s[:, 1:], s[:, 1:][:, ::-1], rtol=1e-5)
+    if not full_even:
+        raise ValueError("fourier_symbol must be even in each wavenumber for the fused SIFS path")
+    return np.ascontiguousarray(s[: nx // 2 + 1, : ny // 2 + 1]).astype(np.float32)
+
+
+def inverse_denominator(symbol_quadrant, A, dt, npts):
+    """(1/npts) / (1 + A*dt*symbol) in float32, mirroring solvers.py:62 (`1.0 + A*dt*symbol`)."""
+    adt = np.float32(np.float32(A) * np.float32(dt))
+    tmp = np.float32(1.0) + adt * symbol_quadrant.astype(np.float32)
+    return ((np.float32(1.0) / tmp) * np.float32(1.0 / npts)).astype(np.float32)
+
+
+class SifsPlan:
+    """One fused-stepper plan: equation kind, grid, pointwise families (pdeopt_plan_create)."""
+
+    def __init__(self, kind, nx, ny, lo, h, kappa, mu=("double_well", ()), mob=("const", (1.0,)), derivs="fd"):
+        lib = _lib.load()
+        d = _lib.PlanDesc()
+        d.kind = {"ch2d": _lib.KIND_CH2D, "ac2d": _lib.KIND_AC2D}[kind]
+        d.derivs = {"fd": _lib.DERIVS_FD, "fourier": _lib.DERIVS_FOURIER}[derivs]
+        d.nx, d.ny = nx, ny
+        d.lo_x, d.lo_y = float(lo[0]), float(lo[1])
+        d.hx, d.hy = float(h[0]), float(h[1])
+        d.kappa = float(kappa)
+        d.mu_family = MU_FAMILIES[mu[0]]
+        d.mu_ncoef = len(mu[1])
+        for i, c in enumerate(mu[1]):
+            d.mu_coef[i] = float(c)
+        d.mob_family = MOB_FAMILIES[mob[0]]
+        d.mob_ncoef = len(mob[1])
+        for i, c in enumerate(mob[1]):
+            d.mob_coef[i] = float(c)
+        self._h = ctypes.c_void_p()
+        _lib.check(lib.pdeopt_plan_create(ctypes.byref(d), ctypes.byref(self._h)))
+        self.nx, self.ny = nx, ny
+        self.table_len = int(lib.pdeopt_table_len(self._h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.load().pdeopt_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @staticmethod
+    def _ptr(t):
+        return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p()
+
+    def step(self, y0, dts, tables, tab_idx=None, ctrl=None, obs=None, obs_range=(0.0, 1.0), reward=None, out=None):
+        """K = len(dts) fused steps on y0 [B, nx, ny] float32 CUDA.  Returns y1 (out or new)."""
+        lib = _lib.load()
+        assert y0.is_cuda and y0.dtype == torch.float32 and y0.is_contiguous()
+        B = y0.shape[0]
+        assert tuple(y0.shape[1:]) == (self.nx, self.ny)
+        y1 = out if out is not None else torch.empty_like(y0)
+        dts = np.ascontiguousarray(np.asarray(dts, dtype=np.float32))
+        K = len(dts)
+        assert tables.is_cuda and tables.dtype == torch.float32 and tables.is_contiguous()
+        ntab = tables.numel() // self.table_len
+        idx = None
+        if tab_idx is not None:
+            idx = np.ascontiguousarray(np.asarray(tab_idx, dtype=np.int32))
+        stream = torch.cuda.current_stream(y0.device).cuda_stream
+        done = 0
+        src = y0
+        while done < K:
+            k = min(_lib.MAX_FUSED_STEPS, K - done)
+            last = done + k == K
+            st = lib.pdeopt_sifs_step_batched(
+                self._h, self._ptr(src), self._ptr(y1), B, k,
+                dts[done:].ctypes.data_as(ctypes.c_void_p),
+                self._ptr(tables), ntab,
+                idx[done:].ctypes.data_as(ctypes.c_void_p) if idx is not None else ctypes.c_void_p(),
+                self._ptr(ctrl),
+                self._ptr(obs) if last else ctypes.c_void_p(),
+                float(obs_range[0]), float(obs_range[1]),
+                self._ptr(reward) if last else ctypes.c_void_p(),
+                ctypes.c_void_p(stream),
+            )
+            _lib.check(st)
+            src = y1
+            done += k
+        return y1
+
+    def step_host(self, y0, dts, tables, tab_idx=None, ctrl=None, obs=None, obs_range=(0.0, 1.0), reward=None, out=None):
+        """Same through pdeopt_sifs_step_batched_host: numpy (ideally pinned) buffers in/out."""
+        lib = _lib.load()
+        B = y0.shape[0]
+        y1 = out if out is not None else np.empty_like(y0)
+        dts = np.ascontiguousarray(np.asarray(dts, dtype=np.float32))
+        K = len(dts)
+        assert K <= _lib.MAX_FUSED_STEPS
+        ntab = tables.size // self.table_len
+        idx = np.ascontiguousarray(np.asarray(tab_idx, dtype=np.int32)) if tab_idx is not None else None
+
+        def p(a):
+            return a.ctypes.data_as(ctypes.c_void_p) if a is not None else ctypes.c_void_p()
+
+        stream = torch.cuda.current_stream().cuda_stream
+        st = lib.pdeopt_sifs_step_batched_host(
+            self._h, p(y0), p(y1), B, K, p(dts), p(tables), ntab, p(idx), p(ctrl), p(obs),
+            float(obs_range[0]), float(obs_range[1]), p(reward), ctypes.c_void_p(stream),
+        )
+        _lib.check(st)
+        return y1

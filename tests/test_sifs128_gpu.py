@@ -1,0 +1,158 @@
+"""GPU parity of the fused 128x128 SIFS kernels against the NumPy oracle (through the C ABI)."""
+import numpy as np
+import pytest
+
+from oracle import pde_oracle as O
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+N = 128
+H = 0.01
+KAPPA = 0.002
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b.astype(np.float64)) / np.linalg.norm(b.astype(np.float64)))
+
+
+def make_ic(B, seed0=0, centre=0.5):
+    return np.stack(
+        [np.clip(centre + 0.01 * np.random.default_rng(seed0 + i).normal(size=(N, N)), 0.0, 1.0) for i in range(B)]
+    ).astype(np.float32)
+
+
+def oracle_eq(kind, mu, D):
+    dom = O.Domain((N, N), ((-N * H / 2, N * H / 2),) * 2)
+    if kind == "ch2d":
+        return O.CahnHilliardPeriodic(dom, KAPPA, mu, D, "fd", np.float32)
+    return O.AllenCahn2DPeriodic(dom, KAPPA, mu, D, "fd", np.float32)
+
+
+CASES = {
+    "log_degenerate": (("log", (3.0,)), ("degenerate", ()), lambda c: O.mu_log(c, 3.0), lambda c: (1 - c) * c, 0.5),
+    "log_const": (("log", (3.0,)), ("const", (1.0,)), lambda c: O.mu_log(c, 3.0), lambda c: np.ones_like(c), 0.5),
+    "dw_const": (("double_well", ()), ("const", (1.0,)), O.mu_double_well, lambda c: np.ones_like(c), 0.0),
+    "dw_1psq": (("double_well", ()), ("one_plus_sq", ()), O.mu_double_well, lambda c: 1 + c * c, 0.0),
+}
+
+
+def run_gpu(kind, mu, mob, y0, dts, A):
+    from pde_opt_b200.fused import SifsPlan, fold_symbol, inverse_denominator
+
+    plan = SifsPlan(kind, N, N, (-N * H / 2, -N * H / 2), (H, H), KAPPA, mu, mob)
+    eq = oracle_eq(kind, O.mu_double_well, lambda c: c)
+    quad = fold_symbol(eq.fourier_symbol)
+    uniq = sorted(set(np.float32(d) for d in dts))
+    assert len(uniq) <= 2
+    tabs = np.stack([inverse_denominator(quad, A, d, N * N) for d in uniq]).astype(np.float32)
+    idx = [uniq.index(np.float32(d)) for d in dts]
+    yd = torch.from_numpy(y0).cuda()
+    out = plan.step(yd, dts, torch.from_numpy(tabs).cuda().contiguous(), idx)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_ch_one_step(case):
+    mu, mob, mu_f, D_f, centre = CASES[case]
+    y0 = make_ic(5, 0, centre)  # odd batch exercises the duplicated last env
+    dt = 1e-6
+    got = run_gpu("ch2d", mu, mob, y0, [dt], 0.5)
+    eq = oracle_eq("ch2d", mu_f, D_f)
+    for b in range(y0.shape[0]):
+        ref = O.sifs_step(eq.rhs, y0[b], np.float32(0), np.float32(dt), 0.5, eq.fourier_symbol)
+        assert rel_l2(got[b], ref) <= 1e-5, (case, b)
+        # the increment itself (not masked by |y0|) must agree to fp32 FFT accuracy
+        assert rel_l2(got[b] - y0[b], ref - y0[b]) <= 2e-3, (case, b)
+
+
+def test_ch_k16_two_step_lengths():
+    mu, mob, mu_f, D_f, centre = CASES["log_degenerate"]
+    y0 = make_ic(4, 10, centre)
+    dts = [1e-6] * 15 + [5e-7]
+    got = run_gpu("ch2d", mu, mob, y0, dts, 0.5)
+    eq = oracle_eq("ch2d", mu_f, D_f)
+    for b in range(4):
+        y, t = y0[b], np.float32(0)
+        for d in dts:
+            y = O.sifs_step(eq.rhs, y, t, t + np.float32(d), 0.5, eq.fourier_symbol)
+            t = t + np.float32(d)
+        assert rel_l2(got[b], y) <= 1e-5
+
+
+def test_ch_1000_steps():
+    mu, mob, mu_f, D_f, centre = CASES["log_degenerate"]
+    y0 = make_ic(2, 20, centre)
+    dts = [1e-6] * 1000
+    got = run_gpu("ch2d", mu, mob, y0, dts, 0.5)
+    eq = oracle_eq("ch2d", mu_f, D_f)
+    for b in range(2):
+        y, t = y0[b], np.float32(0)
+        for d in dts:
+            y = O.sifs_step(eq.rhs, y, t, t + np.float32(d), 0.5, eq.fourier_symbol)
+            t = t + np.float32(d)
+        assert rel_l2(got[b], y) <= 1e-3
+        assert np.isfinite(got[b]).all()
+
+
+def test_ac_steps():
+    y0 = make_ic(3, 30, 0.0)
+    dts = [5e-6] * 8
+    from pde_opt_b200.fused import SifsPlan, fold_symbol, inverse_denominator
+
+    eq = oracle_eq("ac2d", O.mu_double_well, lambda c: np.ones_like(c))
+    plan = SifsPlan("ac2d", N, N, (-N * H / 2,) * 2, (H, H), KAPPA, ("double_well", ()), ("const", (1.0,)))
+    quad = fold_symbol(eq.fourier_symbol)
+    tabs = inverse_denominator(quad, 1.0, dts[0], N * N)[None]
+    out = plan.step(torch.from_numpy(y0).cuda(), dts, torch.from_numpy(tabs).cuda().contiguous())
+    got = out.cpu().numpy()
+    for b in range(3):
+        y, t = y0[b], np.float32(0)
+        for d in dts:
+            y = O.sifs_step(eq.rhs, y, t, t + np.float32(d), 1.0, eq.fourier_symbol)
+            t = t + np.float32(d)
+        assert rel_l2(got[b], y) <= 1e-5
+        assert rel_l2(got[b] - y0[b], y - y0[b]) <= 2e-3
+
+
+def test_obs_reward_and_control():
+    from pde_opt_b200.fused import SifsPlan, fold_symbol, inverse_denominator
+
+    mu, mob, _, D_f, centre = CASES["log_degenerate"]
+    B = 4
+    y0 = make_ic(B, 40, centre)
+    dom = O.Domain((N, N), ((-N * H / 2, N * H / 2),) * 2)
+    X, Y = dom.mesh(np.float32)
+    ctrl = np.zeros((B, 8), np.float32)
+    ctrl[:, 0] = [0.0, 0.25, -0.5, 0.1]
+    ctrl[:, 1] = [0.0, 0.5, 1.0, -0.7]
+    ctrl[:, 2] = [0.0, 0.1, -0.2, 0.3]
+    ctrl[:, 3] = [0.0, -0.3, 0.2, 0.05]
+    ctrl[:, 4] = [0.1, 0.1, 0.05, 0.2]
+    dts = [1e-6] * 4
+    plan = SifsPlan("ch2d", N, N, (-N * H / 2,) * 2, (H, H), KAPPA, mu, mob)
+    eq0 = oracle_eq("ch2d", O.mu_double_well, D_f)
+    tabs = inverse_denominator(fold_symbol(eq0.fourier_symbol), 0.5, dts[0], N * N)[None]
+    obs = torch.empty((B, N, N), dtype=torch.uint8, device="cuda")
+    rew = torch.empty((B, 2), dtype=torch.float32, device="cuda")
+    out = plan.step(
+        torch.from_numpy(y0).cuda(), dts, torch.from_numpy(tabs).cuda().contiguous(),
+        ctrl=torch.from_numpy(ctrl).cuda(), obs=obs, obs_range=(0.0, 1.0), reward=rew,
+    )
+    got, obs, rew = out.cpu().numpy(), obs.cpu().numpy(), rew.cpu().numpy()
+    for b in range(B):
+        w = 3.0 + ctrl[b, 0]
+        bump = ctrl[b, 1] * np.exp(-((X - ctrl[b, 2]) ** 2 + (Y - ctrl[b, 3]) ** 2) / (2 * ctrl[b, 4] ** 2))
+        eq = O.CahnHilliardPeriodic(dom, KAPPA, lambda c: O.mu_log(c, w), D_f, "fd", np.float32, forcing=bump.astype(np.float32))
+        y, t = y0[b], np.float32(0)
+        for d in dts:
+            y = O.sifs_step(eq.rhs, y, t, t + np.float32(d), 0.5, eq.fourier_symbol)
+            t = t + np.float32(d)
+        assert rel_l2(got[b], y) <= 1e-5
+        assert rel_l2(got[b] - y0[b], y - y0[b]) <= 2e-3
+        ref_obs = O.quantise_obs(got[b])[0]
+        assert np.abs(obs[b].astype(int) - ref_obs.astype(int)).max() <= 1
+        assert (obs[b] == ref_obs).mean() > 0.999
+        np.testing.assert_allclose(rew[b, 0], got[b].astype(np.float64).mean(), rtol=1e-5)
+        np.testing.assert_allclose(rew[b, 1], got[b].astype(np.float64).var(), rtol=1e-4)
