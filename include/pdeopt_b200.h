@@ -33,8 +33,7 @@ extern "C" {
 
 #define PDEOPT_ABI_VERSION 1
 #define PDEOPT_MAX_COEF 16
-#define PDEOPT_MAX_FUSED_STEPS 64 /* per launch; callers loop for longer rollouts */
-#define PDEOPT_MAX_TABLES 2       /* distinct step lengths per launch */
+#define PDEOPT_MAX_FUSED_STEPS 512 /* per launch; callers loop for longer rollouts */
 #define PDEOPT_NCTRL 8            /* floats per environment in the control block */
 
 typedef enum {
@@ -98,37 +97,52 @@ const char* pdeopt_last_error(void);
 pdeopt_status pdeopt_plan_create(const pdeopt_plan_desc* desc, pdeopt_plan** out);
 pdeopt_status pdeopt_plan_destroy(pdeopt_plan* plan);
 
-/* Number of floats of one folded inverse-denominator table for this plan:
- * (nx/2+1)*(ny/2+1).  Entry [i][j] = (1/(nx*ny)) / (1 + A*dt*symbol[i][j]), i<=nx/2, j<=ny/2,
- * i.e. solvers.py:62 with the inverse-FFT normalisation folded in; the symbol of the
- * SIFS-compatible equations is real and even in each wavenumber, so one quadrant suffices. */
+/* Number of floats of the folded symbol table for this plan: (nx/2+1)*(ny/2+1).
+ * Entry [i][j] = A * fourier_symbol[i][j] for i <= nx/2, j <= ny/2 (A = the solver's splitting
+ * constant, solvers.py:34,62).  The symbol of the SIFS-compatible equations is real and even in
+ * each wavenumber, so one quadrant determines it.  The kernel forms 1/(1 + dt*A*symbol) per step
+ * from the step's own dt, because diffrax's float32 time accumulation makes dt differ by ulps
+ * from step to step. */
 int64_t pdeopt_table_len(const pdeopt_plan* plan);
 
 /* K = ksteps fused IMEX steps on `batch` independent environments.
  *   y0_dev, y1_dev : [batch][nx][ny] float32 (may alias)
  *   dt_host        : [ksteps] step lengths (t1 - t0 of each step, solvers.py:58)
- *   tables_dev     : [ntab][pdeopt_table_len] folded inverse denominators
- *   tab_idx_host   : [ksteps] which table each step uses (NULL = all 0)
+ *   symbol_dev     : [pdeopt_table_len] folded A*symbol table
  *   ctrl_dev       : [batch][PDEOPT_NCTRL] control block or NULL
  *   obs_dev        : [batch][nx][ny] uint8 observation of y1 or NULL:
  *                    rint(clamp((y1-obs_lo)/(obs_hi-obs_lo),0,1)*255)   (pde_env.py:118-126)
  *   reward_dev     : [batch][2] (mean, variance) of y1 or NULL          (pde_env.py:309)
  */
 pdeopt_status pdeopt_sifs_step_batched(pdeopt_plan* plan, const float* y0_dev, float* y1_dev, int32_t batch,
-                                       int32_t ksteps, const float* dt_host, const float* tables_dev,
-                                       int32_t ntab, const int32_t* tab_idx_host, const float* ctrl_dev,
-                                       uint8_t* obs_dev, float obs_lo, float obs_hi, float* reward_dev,
-                                       void* stream);
+                                       int32_t ksteps, const float* dt_host, const float* symbol_dev,
+                                       const float* ctrl_dev, uint8_t* obs_dev, float obs_lo, float obs_hi,
+                                       float* reward_dev, void* stream);
 
-/* Same with HOST buffers: copies y0/ctrl/tables in, runs, copies y1/obs/reward out, and
+/* eq.rhs(state, t) for `batch` states (CahnHilliard2DPeriodic.rhs_fd, cahn_hilliard.py:89-109;
+ * AllenCahn2DPeriodic.rhs_fd, allen_cahn.py:81-84): f_dev[b] = rhs(y_dev[b]).  May alias. */
+pdeopt_status pdeopt_rhs_batched(pdeopt_plan* plan, const float* y_dev, float* f_dev, int32_t batch,
+                                 const float* ctrl_dev, void* stream);
+
+/* One SemiImplicitFourierSpectral.step (solvers.py:56-70) with an externally evaluated vector
+ * field f0 = terms.vf(t0, y0, args) (the unfused path for mu/D closures outside the enumerated
+ * families): y1 = y0 + dt * Re ifft( fft(f0) / (1 + dt*A*symbol) ). */
+pdeopt_status pdeopt_sifs_filter_batched(pdeopt_plan* plan, const float* y0_dev, const float* f0_dev, float* y1_dev,
+                                         int32_t batch, float dt, const float* symbol_dev, void* stream);
+
+/* Same with HOST buffers: copies y0/ctrl/symbol in, runs, copies y1/obs/reward out, and
  * synchronises the stream before returning.  Scratch device memory is owned by the plan
  * (grown on first use, reused afterwards). */
 pdeopt_status pdeopt_sifs_step_batched_host(pdeopt_plan* plan, const float* y0_host, float* y1_host,
                                             int32_t batch, int32_t ksteps, const float* dt_host,
-                                            const float* tables_host, int32_t ntab,
-                                            const int32_t* tab_idx_host, const float* ctrl_host,
+                                            const float* symbol_host, const float* ctrl_host,
                                             uint8_t* obs_host, float obs_lo, float obs_hi, float* reward_host,
                                             void* stream);
+
+/* Measured FP32 CUDA-core peak of the current device in TFLOP/s (dependent FFMA chains, 16-way
+ * ILP, all SMs, best of 4 timed launches): the denominator the fused path's roofline fraction is
+ * quoted against (MEASURED_PEAKS.json has no FP32 entry). */
+pdeopt_status pdeopt_measure_fp32_peak(double* tflops_out, void* stream);
 
 /* Number of kernels this library has launched in this process (bench.py "gpu_launches"). */
 int64_t pdeopt_launch_count(void);

@@ -9,8 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libpdeopt_b200.so")
 
 MAX_COEF = 16
-MAX_FUSED_STEPS = 64
-MAX_TABLES = 2
+MAX_FUSED_STEPS = 512
 NCTRL = 8
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
@@ -52,6 +51,9 @@ EXPORTS = [
     "pdeopt_table_len",
     "pdeopt_sifs_step_batched",
     "pdeopt_sifs_step_batched_host",
+    "pdeopt_rhs_batched",
+    "pdeopt_sifs_filter_batched",
+    "pdeopt_measure_fp32_peak",
     "pdeopt_launch_count",
 ]
 
@@ -75,11 +77,17 @@ def load():
     lib.pdeopt_plan_destroy.restype = ctypes.c_int
     lib.pdeopt_table_len.argtypes = [vp]
     lib.pdeopt_table_len.restype = ctypes.c_int64
-    sig = [vp, vp, vp, i32, i32, vp, vp, i32, vp, vp, vp, f32, f32, vp, vp]
+    sig = [vp, vp, vp, i32, i32, vp, vp, vp, vp, f32, f32, vp, vp]
     lib.pdeopt_sifs_step_batched.argtypes = sig
     lib.pdeopt_sifs_step_batched.restype = ctypes.c_int
     lib.pdeopt_sifs_step_batched_host.argtypes = sig
     lib.pdeopt_sifs_step_batched_host.restype = ctypes.c_int
+    lib.pdeopt_rhs_batched.argtypes = [vp, vp, vp, i32, vp, vp]
+    lib.pdeopt_rhs_batched.restype = ctypes.c_int
+    lib.pdeopt_sifs_filter_batched.argtypes = [vp, vp, vp, vp, i32, f32, vp, vp]
+    lib.pdeopt_sifs_filter_batched.restype = ctypes.c_int
+    lib.pdeopt_measure_fp32_peak.argtypes = [ctypes.POINTER(ctypes.c_double), vp]
+    lib.pdeopt_measure_fp32_peak.restype = ctypes.c_int
     lib.pdeopt_launch_count.restype = ctypes.c_int64
     _lib = lib
     return lib

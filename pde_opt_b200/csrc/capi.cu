@@ -84,15 +84,16 @@ static cudaError_t launch(const SifsParams& p, int grid, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-extern "C" pdeopt_status pdeopt_sifs_step_batched(pdeopt_plan* plan, const float* y0_dev, float* y1_dev, int32_t batch,
-                                                  int32_t ksteps, const float* dt_host, const float* tables_dev,
-                                                  int32_t ntab, const int32_t* tab_idx_host, const float* ctrl_dev,
-                                                  uint8_t* obs_dev, float obs_lo, float obs_hi, float* reward_dev,
-                                                  void* stream) {
-  if (!plan || !y0_dev || !y1_dev || !dt_host || !tables_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
+static pdeopt_status sifs_launch(pdeopt_plan* plan, int mode, const float* f0_dev, const float* y0_dev, float* y1_dev,
+                                 int32_t batch, int32_t ksteps, const float* dt_host, const float* symbol_dev,
+                                 const float* ctrl_dev, uint8_t* obs_dev, float obs_lo, float obs_hi,
+                                 float* reward_dev, void* stream) {
+  if (!plan || !y0_dev || !y1_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
+  if (mode != MODE_RHS_ONLY && (!dt_host || !symbol_dev)) return fail(PDEOPT_ERR_INVALID, "null argument");
+  if (mode == MODE_GIVEN_F && (!f0_dev || ksteps != 1)) return fail(PDEOPT_ERR_INVALID, "given-f mode needs f0 and ksteps == 1");
+  if (mode == MODE_RHS_ONLY) ksteps = 1;
   if (batch <= 0) return fail(PDEOPT_ERR_INVALID, "batch must be positive");
-  if (ksteps <= 0 || ksteps > PDEOPT_MAX_FUSED_STEPS) return fail(PDEOPT_ERR_INVALID, "ksteps must be in [1, 64]");
-  if (ntab <= 0 || ntab > PDEOPT_MAX_TABLES) return fail(PDEOPT_ERR_INVALID, "ntab must be 1 or 2");
+  if (ksteps <= 0 || ksteps > PDEOPT_MAX_FUSED_STEPS) return fail(PDEOPT_ERR_INVALID, "ksteps must be in [1, 512]");
   if (obs_dev && !(obs_hi > obs_lo)) return fail(PDEOPT_ERR_INVALID, "obs_hi must exceed obs_lo");
   const pdeopt_plan_desc& d = plan->d;
   SifsParams p;
@@ -101,13 +102,14 @@ extern "C" pdeopt_status pdeopt_sifs_step_batched(pdeopt_plan* plan, const float
   p.y1 = y1_dev;
   p.batch = batch;
   p.ksteps = ksteps;
-  p.tables = tables_dev;
-  p.ntab = ntab;
+  p.symbol = (mode == MODE_RHS_ONLY) ? nullptr : symbol_dev;
   p.ctrl = ctrl_dev;
   p.obs = obs_dev;
   p.obs_lo = obs_lo;
   p.obs_scale = obs_dev ? 1.0f / (obs_hi - obs_lo) : 0.f;
   p.reward = reward_dev;
+  p.mode = mode;
+  p.f0 = f0_dev;
   p.inv_hx = (float)(1.0 / d.hx);
   p.inv_hy = (float)(1.0 / d.hy);
   p.inv_hx2 = (float)(1.0 / (d.hx * d.hx));
@@ -125,12 +127,7 @@ extern "C" pdeopt_status pdeopt_sifs_step_batched(pdeopt_plan* plan, const float
     p.pw.mu_coef[i] = (float)d.mu_coef[i];
     p.pw.mob_coef[i] = (float)d.mob_coef[i];
   }
-  for (int k = 0; k < ksteps; ++k) {
-    p.dt[k] = dt_host[k];
-    const int t = tab_idx_host ? tab_idx_host[k] : 0;
-    if (t < 0 || t >= ntab) return fail(PDEOPT_ERR_INVALID, "tab_idx out of range");
-    p.tab[k] = (uint8_t)t;
-  }
+  for (int k = 0; k < ksteps && mode != MODE_RHS_ONLY; ++k) p.dt[k] = dt_host[k];
   const int grid = (batch + 1) / 2;
   cudaStream_t st = (cudaStream_t)stream;
 #ifdef PDEOPT_PARK_GLOBAL
@@ -163,18 +160,37 @@ extern "C" pdeopt_status pdeopt_sifs_step_batched(pdeopt_plan* plan, const float
   return PDEOPT_OK;
 }
 
+extern "C" pdeopt_status pdeopt_sifs_step_batched(pdeopt_plan* plan, const float* y0_dev, float* y1_dev, int32_t batch,
+                                                  int32_t ksteps, const float* dt_host, const float* symbol_dev,
+                                                  const float* ctrl_dev, uint8_t* obs_dev, float obs_lo, float obs_hi,
+                                                  float* reward_dev, void* stream) {
+  return sifs_launch(plan, MODE_FUSED, nullptr, y0_dev, y1_dev, batch, ksteps, dt_host, symbol_dev, ctrl_dev, obs_dev,
+                     obs_lo, obs_hi, reward_dev, stream);
+}
+
+extern "C" pdeopt_status pdeopt_rhs_batched(pdeopt_plan* plan, const float* y_dev, float* f_dev, int32_t batch,
+                                            const float* ctrl_dev, void* stream) {
+  return sifs_launch(plan, MODE_RHS_ONLY, nullptr, y_dev, f_dev, batch, 1, nullptr, nullptr, ctrl_dev, nullptr, 0.f, 1.f,
+                     nullptr, stream);
+}
+
+extern "C" pdeopt_status pdeopt_sifs_filter_batched(pdeopt_plan* plan, const float* y0_dev, const float* f0_dev,
+                                                    float* y1_dev, int32_t batch, float dt, const float* symbol_dev,
+                                                    void* stream) {
+  return sifs_launch(plan, MODE_GIVEN_F, f0_dev, y0_dev, y1_dev, batch, 1, &dt, symbol_dev, nullptr, nullptr, 0.f, 1.f,
+                     nullptr, stream);
+}
+
 extern "C" pdeopt_status pdeopt_sifs_step_batched_host(pdeopt_plan* plan, const float* y0_host, float* y1_host,
                                                        int32_t batch, int32_t ksteps, const float* dt_host,
-                                                       const float* tables_host, int32_t ntab,
-                                                       const int32_t* tab_idx_host, const float* ctrl_host,
+                                                       const float* symbol_host, const float* ctrl_host,
                                                        uint8_t* obs_host, float obs_lo, float obs_hi,
                                                        float* reward_host, void* stream) {
-  if (!plan || !y0_host || !y1_host || !dt_host || !tables_host) return fail(PDEOPT_ERR_INVALID, "null argument");
+  if (!plan || !y0_host || !y1_host || !dt_host || !symbol_host) return fail(PDEOPT_ERR_INVALID, "null argument");
   if (batch <= 0) return fail(PDEOPT_ERR_INVALID, "batch must be positive");
-  if (ntab <= 0 || ntab > PDEOPT_MAX_TABLES) return fail(PDEOPT_ERR_INVALID, "ntab must be 1 or 2");
   const size_t npts = (size_t)plan->d.nx * plan->d.ny;
   const size_t y_bytes = (size_t)batch * npts * sizeof(float);
-  const size_t tab_bytes = (size_t)ntab * pdeopt_table_len(plan) * sizeof(float);
+  const size_t tab_bytes = (size_t)pdeopt_table_len(plan) * sizeof(float);
   const size_t ctrl_bytes = (size_t)batch * PDEOPT_NCTRL * sizeof(float);
   const size_t obs_bytes = (size_t)batch * npts;
   const size_t rew_bytes = (size_t)batch * 2 * sizeof(float);
@@ -195,9 +211,9 @@ extern "C" pdeopt_status pdeopt_sifs_step_batched_host(pdeopt_plan* plan, const 
   float* rew_dev = (float*)(base + al(y_bytes) + al(tab_bytes) + al(ctrl_bytes) + al(obs_bytes));
   cudaStream_t st = (cudaStream_t)stream;
   CUDA_TRY(cudaMemcpyAsync(y_dev, y0_host, y_bytes, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(tab_dev, tables_host, tab_bytes, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(tab_dev, symbol_host, tab_bytes, cudaMemcpyHostToDevice, st));
   if (ctrl_host) CUDA_TRY(cudaMemcpyAsync(ctrl_dev, ctrl_host, ctrl_bytes, cudaMemcpyHostToDevice, st));
-  pdeopt_status s = pdeopt_sifs_step_batched(plan, y_dev, y_dev, batch, ksteps, dt_host, tab_dev, ntab, tab_idx_host,
+  pdeopt_status s = pdeopt_sifs_step_batched(plan, y_dev, y_dev, batch, ksteps, dt_host, tab_dev,
                                              ctrl_host ? ctrl_dev : nullptr, obs_host ? obs_dev : nullptr, obs_lo,
                                              obs_hi, reward_host ? rew_dev : nullptr, stream);
   if (s != PDEOPT_OK) return s;
@@ -205,5 +221,53 @@ extern "C" pdeopt_status pdeopt_sifs_step_batched_host(pdeopt_plan* plan, const 
   if (obs_host) CUDA_TRY(cudaMemcpyAsync(obs_host, obs_dev, obs_bytes, cudaMemcpyDeviceToHost, st));
   if (reward_host) CUDA_TRY(cudaMemcpyAsync(reward_host, rew_dev, rew_bytes, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
+  return PDEOPT_OK;
+}
+
+// ---- measured FP32 peak (FFMA chains), the denominator of the fused path's roofline ----------
+__global__ void __launch_bounds__(512) fma_peak_kernel(float* out, int iters) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = 1.0f + threadIdx.x * 1e-6f + i;
+  const float b = 0.9999f, c = 1e-4f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], b, c);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" pdeopt_status pdeopt_measure_fp32_peak(double* tflops_out, void* stream) {
+  if (!tflops_out) return fail(PDEOPT_ERR_INVALID, "null argument");
+  int dev = 0, nsm = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = nsm * 4, iters = 8192;
+  float* out = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&out, sizeof(float) * grid * 512));
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CUDA_TRY(cudaEventRecord(e0, st));
+    fma_peak_kernel<<<grid, 512, 0, st>>>(out, iters);
+    CUDA_TRY(cudaEventRecord(e1, st));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    const double flop = 2.0 * 16.0 * iters * 512.0 * grid;
+    const double tf = flop / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+    g_launches.fetch_add(1);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  *tflops_out = best;
   return PDEOPT_OK;
 }

@@ -34,29 +34,29 @@ constexpr int kN = 128;
 constexpr int kThreads = 512;
 constexpr int kTabDim = 65;
 constexpr int kTabLen = kTabDim * kTabDim;
-constexpr int kMaxK = 64;
-constexpr int kMaxTab = 2;
+constexpr int kMaxK = 512;
 constexpr int kNCtrl = 8;
 
 enum : int { EQ_CH = 0, EQ_AC = 1 };
+enum : int { MODE_FUSED = 0, MODE_RHS_ONLY = 1, MODE_GIVEN_F = 2 };
 
 struct SifsParams {
   const float* y0;
   float* y1;
   int batch;
   int ksteps;
-  const float* tables;  // [ntab][kTabLen]
-  int ntab;
+  const float* symbol;  // [kTabLen] folded A*sigma(|kx|,|ky|) (solvers.py:62), or null in rhs-only mode
   const float* ctrl;  // [batch][kNCtrl] or null
   uint8_t* obs;       // [batch][128][128] or null
   float obs_lo, obs_scale;
   float* reward;  // [batch][2] or null
   float* park;    // global parking scratch (only when built with PDEOPT_PARK_GLOBAL)
+  const float* f0;  // MODE_GIVEN_F: externally evaluated vector field [batch][128][128]
+  int mode;         // MODE_FUSED / MODE_RHS_ONLY / MODE_GIVEN_F
   float inv_hx, inv_hy, inv_hx2, inv_hy2, kappa;
   float lo_x, lo_y, hx, hy;
   PointwiseParams pw;
   float dt[kMaxK];
-  uint8_t tab[kMaxK];
 };
 
 // ---- shared-memory layouts (validated in tools/fft_decomp_model.py) ----------------------
@@ -339,7 +339,8 @@ __device__ __forceinline__ void p1_scatter_nat(float2* __restrict__ W, const P1M
 // Forward: natural f0 in W  ->  spectrum (x multiplier) -> inverse -> g in registers (P1 map).
 // tw: 128-entry table of w_128^e in shared memory; mt: folded multiplier table in shared memory.
 __device__ __forceinline__ void spectral_filter(float2* __restrict__ W, const float2* __restrict__ tw,
-                                                const float* __restrict__ mt, const P1Map& m1, float2 (&x)[32]) {
+                                                const float* __restrict__ mt, float dt, const P1Map& m1,
+                                                float2 (&x)[32]) {
   const P2Map m2;
   const P3Map m3;
   // ---- P1 forward: 32-point DFT over n1c ----
@@ -398,7 +399,8 @@ __device__ __forceinline__ void spectral_filter(float2* __restrict__ W, const fl
         constexpr int pp = decltype(pc)::value;
         const int kr = m3.k1r + 8 * brev<4>(pp);
         const int fr = kr <= 64 ? kr : 128 - kr;
-        const float mval = mt[fr * kTabDim + fc];
+        // 1/(N^2 (1 + A dt sigma)): solvers.py:62-63 with the inverse-FFT scale folded in
+        const float mval = __fdividef(1.0f / float(kN * kN), fmaf(dt, mt[fr * kTabDim + fc], 1.0f));
         x[b * 16 + pp] = make_float2(x[b * 16 + pp].x * mval, x[b * 16 + pp].y * mval);
       });
     });
@@ -469,7 +471,7 @@ __device__ __forceinline__ float2 block_sum2(float2 v, float2* red) {
 
 struct __align__(16) SifsSmem {
   float2 W[kN * kN];
-  float tab[kMaxTab][kTabLen + 3];
+  float tab[kTabLen + 3];
   float2 tw[128];
   float2 gx[kN], gy[kN];
   float2 red[kThreads / 32];
@@ -494,7 +496,8 @@ __global__ void __launch_bounds__(kThreads, 1) sifs128_kernel(const __grid_const
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
 #endif
-  for (int i = tid; i < p.ntab * kTabLen; i += kThreads) S.tab[i / kTabLen][i % kTabLen] = p.tables[i];
+  if (p.symbol != nullptr)
+    for (int i = tid; i < kTabLen; i += kThreads) S.tab[i] = p.symbol[i];
   if (tid < 128) {
     float s, c;
     sincospif(-2.0f * float(tid) / 128.0f, &s, &c);
@@ -562,11 +565,30 @@ __global__ void __launch_bounds__(kThreads, 1) sifs128_kernel(const __grid_const
   __syncthreads();
 
   // ---- K fused steps ----
-  for (int k = 0; k < p.ksteps; ++k) {
+  if (p.mode == MODE_RHS_ONLY) {
+    // eq.rhs(state, t): emit f0 = rhs(y0) instead of stepping (cahn_hilliard.py:89-109).
     rhs_phase<EQ, MU, MOB>(S.W, p, ec, S.gx, S.gy);
     __syncthreads();
-    spectral_filter(S.W, S.tw, S.tab[p.tab[k]], m1, x);
+  }
+  for (int k = 0; k < ((p.mode == MODE_RHS_ONLY) ? 0 : p.ksteps); ++k) {
+    if (p.mode == MODE_GIVEN_F) {
+      // unfused vector field (terms.vf evaluated by the caller, solvers.py:59): load f0 instead
+      const float* fa = p.f0 + (size_t)env_a * kN * kN;
+      const float* fb = p.f0 + (size_t)env_b * kN * kN;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = warp * 8 + i;
+        const float4 a = *reinterpret_cast<const float4*>(fa + r * kN + 4 * lane);
+        const float4 b = *reinterpret_cast<const float4*>(fb + r * kN + 4 * lane);
+        float2 v[4] = {make_float2(a.x, b.x), make_float2(a.y, b.y), make_float2(a.z, b.z), make_float2(a.w, b.w)};
+        store_row(S.W, r, lane, v);
+      }
+    } else {
+      rhs_phase<EQ, MU, MOB>(S.W, p, ec, S.gx, S.gy);
+    }
+    __syncthreads();
     const float dt = p.dt[k];
+    spectral_filter(S.W, S.tw, S.tab, dt, m1, x);
     // y1 = y0 + dt * g   (solvers.py:63); y0 comes back from the parking space
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {

@@ -1,0 +1,4 @@
+from .base_eq import BaseEquation, TimeSplittingEquation
+from .phase_field import AllenCahn2DPeriodic, CahnHilliard2DPeriodic
+
+__all__ = ["BaseEquation", "TimeSplittingEquation", "CahnHilliard2DPeriodic", "AllenCahn2DPeriodic"]

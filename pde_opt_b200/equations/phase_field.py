@@ -1,0 +1,127 @@
+"""Cahn-Hilliard and Allen-Cahn equations on periodic 2-D grids.
+
+Mirror of pde_opt/numerics/equations/cahn_hilliard.py:30-109 and allen_cahn.py:26-84: same
+dataclass fields, same class-level `fft / ifft / fourier_symbol` attributes (the solver
+compatibility check is a class-level hasattr, pde_opt/utils.py:23-25), same symbols.
+`rhs(state, t)` runs the fused-kernel RHS (pdeopt_rhs_batched) on CUDA tensors."""
+import dataclasses
+from typing import Any, Callable, Optional
+
+import numpy as np
+
+from ..domains import Domain
+from ..functions import Closure, recognize
+from .base_eq import BaseEquation
+
+
+def _fft_marker(*a, **k):
+    raise NotImplementedError(
+        "fft/ifft are performed inside the fused CUDA kernels; this attribute only marks solver compatibility"
+    )
+
+
+def _symbols(domain):
+    kx, ky = domain.fft_mesh()
+    two_pi_i_kx = (2j * np.pi * kx).astype(np.complex64)
+    two_pi_i_ky = (2j * np.pi * ky).astype(np.complex64)
+    k2 = two_pi_i_kx**2 + two_pi_i_ky**2
+    return two_pi_i_kx, two_pi_i_ky, k2
+
+
+class _PhaseField2D(BaseEquation):
+    _kind = None
+
+    def _setup(self, mob_name):
+        if self.derivs not in ("fd", "fourier"):
+            raise ValueError(f"Invalid derivative type: {self.derivs}")
+        self.two_pi_i_kx, self.two_pi_i_ky, self.two_pi_i_k_2 = _symbols(self.domain)
+        self.fft, self.ifft = _fft_marker, _fft_marker
+        self._mu_c = recognize(self.mu, "mu")
+        self._mob_c = recognize(getattr(self, mob_name), "mob")
+        self._plan = None
+        self.control = None  # optional [B, 8] control block (see include/pdeopt_b200.h)
+
+    @property
+    def fused(self):
+        """True when mu and the mobility are enumerated families and derivs == 'fd'."""
+        return self._mu_c is not None and self._mob_c is not None and self.derivs == "fd"
+
+    def plan(self):
+        if self._plan is None:
+            if not self.fused:
+                raise NotImplementedError(
+                    "no fused kernel for this equation (non-enumerated mu/D closure or derivs='fourier'); "
+                    "use the unfused solver path"
+                )
+            from ..fused import SifsPlan
+
+            nx, ny = self.domain.points
+            self._plan = SifsPlan(
+                self._kind, nx, ny, (self.domain.box[0][0], self.domain.box[1][0]), self.domain.dx, self.kappa,
+                self._mu_c.descriptor(), self._mob_c.descriptor(), self.derivs,
+            )
+        return self._plan
+
+    def rhs(self, state, t=0.0):
+        """eq.rhs(state, t) on CUDA float32 tensors, [nx,ny] or [B,nx,ny]."""
+        import ctypes
+
+        import torch
+
+        from .. import _lib
+
+        single = state.dim() == 2
+        y = state.unsqueeze(0) if single else state
+        y = y.contiguous()
+        out = torch.empty_like(y)
+        plan = self.plan()
+        st = _lib.load().pdeopt_rhs_batched(
+            plan._h, ctypes.c_void_p(y.data_ptr()), ctypes.c_void_p(out.data_ptr()), y.shape[0],
+            ctypes.c_void_p(self.control.data_ptr()) if self.control is not None else ctypes.c_void_p(),
+            ctypes.c_void_p(torch.cuda.current_stream(y.device).cuda_stream),
+        )
+        _lib.check(st)
+        return out[0] if single else out
+
+
+@dataclasses.dataclass
+class CahnHilliard2DPeriodic(_PhaseField2D):
+    """du/dt = div(D(u) grad(mu)), mu = mu_h(u) - kappa lap(u)  (cahn_hilliard.py:30-109)."""
+
+    domain: Domain
+    kappa: float
+    mu: Any
+    D: Any
+    derivs: str = "fd"
+    fft = None
+    ifft = None
+    fourier_symbol = None
+    _kind = "ch2d"
+
+    def __post_init__(self):
+        self._setup("D")
+        self.two_pi_i_k_4 = self.two_pi_i_k_2**2
+        self.fourier_symbol = (np.complex64(self.kappa) * self.two_pi_i_k_4).astype(np.complex64)  # :74
+
+
+@dataclasses.dataclass
+class AllenCahn2DPeriodic(_PhaseField2D):
+    """du/dt = -R(u) mu  (allen_cahn.py:26-84).
+
+    The reference class defines no `fourier_symbol` (so it cannot be paired with
+    SemiImplicitFourierSpectral there); BASELINE config 1 needs one, so we define
+    sigma = -kappa (2 pi i k)^2 = kappa (2 pi)^2 |k|^2, the stiff linear part for R == 1."""
+
+    domain: Domain
+    kappa: float
+    mu: Any
+    R: Any
+    derivs: str = "fd"
+    fft = None
+    ifft = None
+    fourier_symbol = None
+    _kind = "ac2d"
+
+    def __post_init__(self):
+        self._setup("R")
+        self.fourier_symbol = (-np.complex64(self.kappa) * self.two_pi_i_k_2).astype(np.complex64)

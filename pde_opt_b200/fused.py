@@ -13,26 +13,29 @@ MU_FAMILIES = {"double_well": 0, "log": 1, "legendre": 2, "legendre_logprior": 3
 MOB_FAMILIES = {"const": 0, "degenerate": 1, "one_plus_sq": 2, "legendre_exp": 3}
 
 
-def fold_symbol(symbol):
-    """Quadrant [nx/2+1, ny/2+1] of a SIFS fourier_symbol (cahn_hilliard.py:74), after checking
-    that it is real and even in each wavenumber (so that the quadrant determines it)."""
+def fold_symbol(symbol, A=1.0):
+    """Quadrant [nx/2+1, ny/2+1] of A * fourier_symbol (cahn_hilliard.py:74, solvers.py:62),
+    after checking that the symbol is real and even in each wavenumber (so that the quadrant
+    determines it).  float32, C-contiguous."""
     s = np.asarray(symbol)
     nx, ny = s.shape
     if np.iscomplexobj(s):
         if np.abs(s.imag).max() > 1e-6 * max(1.0, np.abs(s.real).max()):
             raise ValueError("fourier_symbol must be real for the fused SIFS path")
         s = s.real
-    full_even = np.allclose(s[1:, :], s[1:, :][::-1, :], rtol=1e-5) and np.allclose(s[:, 1:], s[:, 1:][:, ::-1], rtol=1e-5)
-    if not full_even:
+    even = np.allclose(s[1:, :], s[1:, :][::-1, :], rtol=1e-5) and np.allclose(s[:, 1:], s[:, 1:][:, ::-1], rtol=1e-5)
+    if not even:
         raise ValueError("fourier_symbol must be even in each wavenumber for the fused SIFS path")
-    return np.ascontiguousarray(s[: nx // 2 + 1, : ny // 2 + 1]).astype(np.float32)
+    q = s[: nx // 2 + 1, : ny // 2 + 1].astype(np.float32)
+    return np.ascontiguousarray(np.float32(A) * q)
 
 
-def inverse_denominator(symbol_quadrant, A, dt, npts):
-    """(1/npts) / (1 + A*dt*symbol) in float32, mirroring solvers.py:62 (`1.0 + A*dt*symbol`)."""
-    adt = np.float32(np.float32(A) * np.float32(dt))
-    tmp = np.float32(1.0) + adt * symbol_quadrant.astype(np.float32)
-    return ((np.float32(1.0) / tmp) * np.float32(1.0 / npts)).astype(np.float32)
+def _ptr(t):
+    if t is None:
+        return ctypes.c_void_p()
+    if isinstance(t, np.ndarray):
+        return t.ctypes.data_as(ctypes.c_void_p)
+    return ctypes.c_void_p(t.data_ptr())
 
 
 class SifsPlan:
@@ -68,12 +71,9 @@ class SifsPlan:
         except Exception:
             pass
 
-    @staticmethod
-    def _ptr(t):
-        return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p()
-
-    def step(self, y0, dts, tables, tab_idx=None, ctrl=None, obs=None, obs_range=(0.0, 1.0), reward=None, out=None):
-        """K = len(dts) fused steps on y0 [B, nx, ny] float32 CUDA.  Returns y1 (out or new)."""
+    def step(self, y0, dts, symbol, ctrl=None, obs=None, obs_range=(0.0, 1.0), reward=None, out=None):
+        """K = len(dts) fused steps on y0 [B, nx, ny] float32 CUDA (pdeopt_sifs_step_batched).
+        `symbol` is the folded A*symbol table on the device.  Returns y1 (out or new)."""
         lib = _lib.load()
         assert y0.is_cuda and y0.dtype == torch.float32 and y0.is_contiguous()
         B = y0.shape[0]
@@ -81,51 +81,47 @@ class SifsPlan:
         y1 = out if out is not None else torch.empty_like(y0)
         dts = np.ascontiguousarray(np.asarray(dts, dtype=np.float32))
         K = len(dts)
-        assert tables.is_cuda and tables.dtype == torch.float32 and tables.is_contiguous()
-        ntab = tables.numel() // self.table_len
-        idx = None
-        if tab_idx is not None:
-            idx = np.ascontiguousarray(np.asarray(tab_idx, dtype=np.int32))
-        stream = torch.cuda.current_stream(y0.device).cuda_stream
-        done = 0
-        src = y0
+        assert symbol.is_cuda and symbol.dtype == torch.float32 and symbol.numel() == self.table_len
+        stream = ctypes.c_void_p(torch.cuda.current_stream(y0.device).cuda_stream)
+        done, src = 0, y0
         while done < K:
             k = min(_lib.MAX_FUSED_STEPS, K - done)
             last = done + k == K
             st = lib.pdeopt_sifs_step_batched(
-                self._h, self._ptr(src), self._ptr(y1), B, k,
-                dts[done:].ctypes.data_as(ctypes.c_void_p),
-                self._ptr(tables), ntab,
-                idx[done:].ctypes.data_as(ctypes.c_void_p) if idx is not None else ctypes.c_void_p(),
-                self._ptr(ctrl),
-                self._ptr(obs) if last else ctypes.c_void_p(),
-                float(obs_range[0]), float(obs_range[1]),
-                self._ptr(reward) if last else ctypes.c_void_p(),
-                ctypes.c_void_p(stream),
+                self._h, _ptr(src), _ptr(y1), B, k, _ptr(dts[done:]), _ptr(symbol), _ptr(ctrl),
+                _ptr(obs) if last else None, float(obs_range[0]), float(obs_range[1]),
+                _ptr(reward) if last else None, stream,
             )
             _lib.check(st)
             src = y1
             done += k
         return y1
 
-    def step_host(self, y0, dts, tables, tab_idx=None, ctrl=None, obs=None, obs_range=(0.0, 1.0), reward=None, out=None):
-        """Same through pdeopt_sifs_step_batched_host: numpy (ideally pinned) buffers in/out."""
+    def filter(self, y0, f0, dt, symbol, out=None):
+        """One step with an externally evaluated vector field (pdeopt_sifs_filter_batched)."""
         lib = _lib.load()
-        B = y0.shape[0]
+        y1 = out if out is not None else torch.empty_like(y0)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(y0.device).cuda_stream)
+        _lib.check(lib.pdeopt_sifs_filter_batched(self._h, _ptr(y0), _ptr(f0), _ptr(y1), y0.shape[0], float(dt), _ptr(symbol), stream))
+        return y1
+
+    def rhs(self, y, ctrl=None, out=None):
+        lib = _lib.load()
+        f = out if out is not None else torch.empty_like(y)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(y.device).cuda_stream)
+        _lib.check(lib.pdeopt_rhs_batched(self._h, _ptr(y), _ptr(f), y.shape[0], _ptr(ctrl), stream))
+        return f
+
+    def step_host(self, y0, dts, symbol, ctrl=None, obs=None, obs_range=(0.0, 1.0), reward=None, out=None):
+        """Same through pdeopt_sifs_step_batched_host: NumPy (ideally pinned) buffers in/out."""
+        lib = _lib.load()
         y1 = out if out is not None else np.empty_like(y0)
         dts = np.ascontiguousarray(np.asarray(dts, dtype=np.float32))
-        K = len(dts)
-        assert K <= _lib.MAX_FUSED_STEPS
-        ntab = tables.size // self.table_len
-        idx = np.ascontiguousarray(np.asarray(tab_idx, dtype=np.int32)) if tab_idx is not None else None
-
-        def p(a):
-            return a.ctypes.data_as(ctypes.c_void_p) if a is not None else ctypes.c_void_p()
-
-        stream = torch.cuda.current_stream().cuda_stream
+        assert len(dts) <= _lib.MAX_FUSED_STEPS
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         st = lib.pdeopt_sifs_step_batched_host(
-            self._h, p(y0), p(y1), B, K, p(dts), p(tables), ntab, p(idx), p(ctrl), p(obs),
-            float(obs_range[0]), float(obs_range[1]), p(reward), ctypes.c_void_p(stream),
+            self._h, _ptr(y0), _ptr(y1), y0.shape[0], len(dts), _ptr(dts), _ptr(symbol), _ptr(ctrl), _ptr(obs),
+            float(obs_range[0]), float(obs_range[1]), _ptr(reward), stream,
         )
         _lib.check(st)
         return y1

@@ -1,0 +1,137 @@
+"""Steppers.  Mirror of pde_opt/numerics/solvers.py: same class names, constructor fields,
+`required_equation_attrs` protocol and `step(...)` signature / return tuple, with the
+arithmetic running in the fused sm_100a kernels.
+
+Differences a user can see (documented, not hidden):
+* arrays are torch CUDA float32 tensors, optionally with a leading batch axis;
+* `terms` is this module's ODETerm.  `ODETerm(eq)` (an equation object) takes the fused path;
+  `ODETerm(callable)` evaluates the vector field first (solvers.py:59) and filters it in a
+  second launch (the path for closures outside the enumerated families);
+* `y_error` (solvers.py:61,65) is only materialised when the solver is built with
+  `with_error=True` (only adaptive controllers consume it; the reference's drivers use
+  ConstantStepSize)."""
+import dataclasses
+from typing import Any, Callable, Optional
+
+import numpy as np
+import torch
+
+from .fused import SifsPlan, fold_symbol
+
+
+class RESULTS:
+    """Subset of diffrax.RESULTS used on this path."""
+    successful = 0
+    max_steps_reached = 1
+
+
+class ODETerm:
+    """Stand-in for diffrax.ODETerm: wraps f(t, y, args) or an equation object."""
+
+    def __init__(self, vector_field):
+        self.equation = vector_field if hasattr(vector_field, "rhs") and not callable(vector_field) else None
+        self.vector_field = vector_field
+
+    def vf(self, t, y, args=None):
+        if self.equation is not None:
+            return self.equation.rhs(y, t)
+        return self.vector_field(t, y, args)
+
+
+class LocalLinearInterpolation:
+    """diffrax.LocalLinearInterpolation: y0 + (y1 - y0) * (t - t0) / (t1 - t0)."""
+
+    def __init__(self, t0, t1, y0, y1):
+        self.t0, self.t1, self.y0, self.y1 = t0, t1, y0, y1
+
+    def evaluate(self, t):
+        w = (np.float32(t) - np.float32(self.t0)) / (np.float32(self.t1) - np.float32(self.t0))
+        return self.y0 + (self.y1 - self.y0) * float(w)
+
+
+@dataclasses.dataclass
+class SemiImplicitFourierSpectral:
+    """y1 = y0 + dt * Re ifft( fft(f(y0)) / (1 + A dt symbol) )   (solvers.py:23-73)."""
+
+    A: float
+    fourier_symbol: Any
+    fft: Optional[Callable] = None
+    ifft: Optional[Callable] = None
+    with_error: bool = False
+
+    required_equation_attrs = ["fourier_symbol", "fft", "ifft"]  # solvers.py:42
+    term_structure = ODETerm
+    interpolation_cls = LocalLinearInterpolation
+
+    def __post_init__(self):
+        self._quad = fold_symbol(self.fourier_symbol, self.A)
+        self._sym_dev = {}
+        self._filter_plan = None
+
+    def order(self, terms):
+        return 1
+
+    def init(self, terms, t0, t1, y0, args):
+        return None
+
+    def func(self, terms, t0, y0, args):
+        return terms.vf(t0, y0, args)
+
+    def symbol_on(self, device):
+        key = str(device)
+        if key not in self._sym_dev:
+            self._sym_dev[key] = torch.from_numpy(self._quad).to(device)
+        return self._sym_dev[key]
+
+    def _plan_for(self, terms, shape):
+        eq = getattr(terms, "equation", None)
+        if eq is not None and getattr(eq, "fused", False):
+            return eq.plan(), eq
+        if self._filter_plan is None:
+            nx, ny = shape
+            self._filter_plan = SifsPlan("ch2d", nx, ny, (0.0, 0.0), (1.0, 1.0), 0.0)
+        return self._filter_plan, None
+
+    def step(self, terms, t0, t1, y0, args=None, solver_state=None, made_jump=False):
+        del solver_state, made_jump
+        dt = np.float32(np.float32(t1) - np.float32(t0))  # solvers.py:58 in the working precision
+        single = y0.dim() == 2
+        y = (y0.unsqueeze(0) if single else y0).contiguous()
+        plan, eq = self._plan_for(terms, tuple(y.shape[-2:]))
+        sym = self.symbol_on(y.device)
+        f0 = None
+        if eq is not None:
+            y1 = plan.step(y, [dt], sym, ctrl=eq.control)
+        else:
+            f0 = terms.vf(t0, y0, args)
+            f0 = (f0.unsqueeze(0) if single else f0).contiguous()
+            y1 = plan.filter(y, f0, dt, sym)
+        y_error = None
+        if self.with_error:
+            if f0 is None:
+                f0 = plan.rhs(y, ctrl=eq.control)
+            y_error = y1 - (y + float(dt) * f0)  # solvers.py:61,65
+            y_error = y_error[0] if single else y_error
+        y1 = y1[0] if single else y1
+        dense_info = dict(y0=y0, y1=y1)
+        return y1, y_error, dense_info, None, RESULTS.successful
+
+    def rollout(self, terms, times, y0, ctrl=None, obs=None, obs_range=(0.0, 1.0), reward=None, out=None):
+        """All steps between consecutive entries of `times` (host array, working precision) in as
+        few launches as possible: the K-fused form of the diffeqsolve loop body."""
+        times = np.asarray(times, dtype=np.float32)
+        dts = (times[1:] - times[:-1]).astype(np.float32)
+        single = y0.dim() == 2
+        y = (y0.unsqueeze(0) if single else y0).contiguous()
+        plan, eq = self._plan_for(terms, tuple(y.shape[-2:]))
+        sym = self.symbol_on(y.device)
+        if eq is not None:
+            c = ctrl if ctrl is not None else eq.control
+            y1 = plan.step(y, dts, sym, ctrl=c, obs=obs, obs_range=obs_range, reward=reward, out=out)
+        else:
+            y1 = y
+            for k, dt in enumerate(dts):
+                f0 = terms.vf(times[k], y1[0] if single else y1, None)
+                f0 = (f0.unsqueeze(0) if single else f0).contiguous()
+                y1 = plan.filter(y1, f0, dt, sym)
+        return y1[0] if single else y1

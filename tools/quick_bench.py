@@ -2,7 +2,7 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from pde_opt_b200.fused import SifsPlan, inverse_denominator
+from pde_opt_b200.fused import SifsPlan
 
 N, H, KAPPA = 128, 0.01, 0.002
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
@@ -13,7 +13,7 @@ plan = SifsPlan("ch2d", N, N, (-N * H / 2,) * 2, (H, H), KAPPA, mu, mob)
 k = np.fft.fftfreq(N, H)[: N // 2 + 1]
 k2 = (2 * np.pi) ** 2 * (k[:, None] ** 2 + k[None, :] ** 2)
 quad = (KAPPA * k2 ** 2).astype(np.float32)
-tab = torch.from_numpy(inverse_denominator(quad, 0.5, 1e-6, N * N)[None]).cuda().contiguous()
+tab = torch.from_numpy(np.ascontiguousarray(0.5 * quad)).cuda()
 g = torch.Generator(device="cuda").manual_seed(0)
 y = (0.5 + 0.01 * torch.randn((B, N, N), device="cuda", generator=g)).clamp(0, 1).contiguous()
 out = torch.empty_like(y)
