@@ -1,0 +1,143 @@
+"""CPU tests of the host-side mirror of the reference API and of the C-ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import pde_oracle as O
+from pde_opt_b200 import Domain, check_equation_solver_compatibility, prepare_solver_params
+from pde_opt_b200 import _lib, functions, schedule
+from pde_opt_b200.equations import AllenCahn2DPeriodic, CahnHilliard2DPeriodic
+from pde_opt_b200.fused import fold_symbol
+from pde_opt_b200.solvers import SemiImplicitFourierSpectral
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def dom(n=128, h=0.01):
+    return Domain((n, n), ((-n * h / 2, n * h / 2),) * 2, "dimensionless")
+
+
+def test_domain_matches_oracle():
+    d, o = dom(64, 0.02), O.Domain((64, 64), ((-0.64, 0.64),) * 2)
+    assert d.dx == o.dx and d.L == o.L
+    for a, b in zip(d.axes(), o.axes()):
+        np.testing.assert_array_equal(a, b)
+    for a, b in zip(d.fft_mesh(), o.fft_mesh()):
+        np.testing.assert_array_equal(a, b)
+    assert d.mesh()[0][3, 5] == d.axes()[0][3] and d.mesh()[1][3, 5] == d.axes()[1][5]  # indexing="ij"
+
+
+def test_symbols_match_oracle():
+    d = dom()
+    eq = CahnHilliard2DPeriodic(d, 0.002, functions.DoubleWell(), functions.ConstantMobility(1.0))
+    oeq = O.CahnHilliardPeriodic(O.Domain((128, 128), ((-0.64, 0.64),) * 2), 0.002, O.mu_double_well, lambda c: c, "fd", np.float32)
+    np.testing.assert_allclose(eq.fourier_symbol, oeq.fourier_symbol, rtol=2e-6)
+    ac = AllenCahn2DPeriodic(d, 0.002, functions.DoubleWell(), functions.ConstantMobility(1.0))
+    oac = O.AllenCahn2DPeriodic(O.Domain((128, 128), ((-0.64, 0.64),) * 2), 0.002, O.mu_double_well, lambda c: c, "fd", np.float32)
+    np.testing.assert_allclose(ac.fourier_symbol, oac.fourier_symbol, rtol=2e-6)
+    q = fold_symbol(eq.fourier_symbol, 0.5)
+    assert q.shape == (65, 65) and q.dtype == np.float32
+    np.testing.assert_allclose(q, 0.5 * eq.fourier_symbol.real[:65, :65], rtol=1e-6)
+
+
+def test_fold_symbol_rejects_non_even_or_complex():
+    s = np.ones((8, 8), np.complex64)
+    s[1, 2] = 5.0
+    with pytest.raises(ValueError):
+        fold_symbol(s)
+    s = np.ones((8, 8), np.complex64) * (1 + 1j)
+    with pytest.raises(ValueError):
+        fold_symbol(s)
+
+
+def test_solver_equation_protocol():
+    """pde_opt/utils.py:6-53: class-level hasattr check and by-name attribute injection."""
+    check_equation_solver_compatibility(SemiImplicitFourierSpectral, CahnHilliard2DPeriodic)
+    check_equation_solver_compatibility(SemiImplicitFourierSpectral, AllenCahn2DPeriodic)
+
+    class NoSymbol:
+        fft = None
+        ifft = None
+
+    with pytest.raises(ValueError, match="fourier_symbol"):
+        check_equation_solver_compatibility(SemiImplicitFourierSpectral, NoSymbol)
+    eq = CahnHilliard2DPeriodic(dom(), 0.002, lambda c: c**3 - c, lambda c: 0 * c + 1.0)
+    params = prepare_solver_params(SemiImplicitFourierSpectral, {"A": 0.5}, eq)
+    assert set(params) == {"A", "fourier_symbol", "fft", "ifft"}
+    s = SemiImplicitFourierSpectral(**params)
+    assert s.order(None) == 1 and s.init(None, 0, 1, None, None) is None
+    assert SemiImplicitFourierSpectral.required_equation_attrs == ["fourier_symbol", "fft", "ifft"]
+    with pytest.raises(ValueError):
+        CahnHilliard2DPeriodic(dom(), 0.002, lambda c: c, lambda c: c, derivs="nope")
+
+
+def test_closure_recognition():
+    r = functions.recognize
+    assert r(lambda c: c**3 - c, "mu").family == "double_well"
+    m = r(lambda c: np.log(c / (1.0 - c)) + 2.5 * (1.0 - 2.0 * c), "mu")
+    assert m.family == "log" and abs(m.coef[0] - 2.5) < 1e-9
+    assert r(lambda c: np.ones_like(c), "mob").descriptor() == ("const", (1.0,))
+    assert r(lambda c: 0.15 * np.ones_like(c), "mob").descriptor() == ("const", (0.15,))
+    assert r(lambda c: (1 - c) * c, "mob").family == "degenerate"
+    assert r(lambda c: 1 + c**2, "mob").family == "one_plus_sq"
+    assert r(lambda c: np.sin(c), "mu") is None
+    eq = CahnHilliard2DPeriodic(dom(), 0.002, lambda c: np.sin(c), lambda c: 0 * c + 1.0)
+    assert not eq.fused
+    with pytest.raises(NotImplementedError):
+        eq.plan()
+    # closures evaluate like the oracle's
+    c = np.linspace(0.05, 0.95, 11)
+    np.testing.assert_allclose(functions.LogRegular(3.0)(c), O.mu_log(c, 3.0))
+    p = np.array([0.3, -0.2, 0.5, 0.1])
+    np.testing.assert_allclose(functions.DiffusionLegendrePolynomials(p)(c), O.D_legendre(p, c))
+    np.testing.assert_allclose(functions.ChemicalPotentialLegendrePolynomials(p, "log")(c), O.mu_legendre(p, c, O.prior_log))
+
+
+@pytest.mark.parametrize("args", [(0.0, 0.05, 1e-4, np.float32), (0.0, 0.02, 1e-6, np.float32), (0.0, 1.0, 0.3, np.float64)])
+def test_schedule_matches_oracle(args):
+    a = schedule.constant_step_times(*args)
+    b = O.constant_step_schedule(*args)
+    np.testing.assert_array_equal(a, b)
+    assert a[-1] == np.dtype(args[3]).type(args[1])
+    assert (schedule.step_lengths(a) > 0).all()
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The shared library loads and exports every function include/pdeopt_b200.h declares."""
+    hdr = open(os.path.join(ROOT, "include", "pdeopt_b200.h")).read()
+    declared = set(re.findall(r"\b(pdeopt_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"pdeopt_plan_desc"}
+    assert declared, "header parse failed"
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert set(_lib.EXPORTS) == declared
+    assert lib.pdeopt_abi_version() == 1
+
+
+def test_plan_validation_without_gpu():
+    lib = _lib.load()
+    d = _lib.PlanDesc()
+    d.kind, d.derivs, d.nx, d.ny, d.hx, d.hy, d.kappa = _lib.KIND_CH2D, _lib.DERIVS_FD, 128, 128, 0.01, 0.01, 0.002
+    h = ctypes.c_void_p()
+    assert lib.pdeopt_plan_create(ctypes.byref(d), ctypes.byref(h)) == _lib.OK
+    assert lib.pdeopt_table_len(h) == 65 * 65
+    assert lib.pdeopt_plan_destroy(h) == _lib.OK
+    d.nx = 100
+    assert lib.pdeopt_plan_create(ctypes.byref(d), ctypes.byref(h)) == _lib.ERR_UNSUPPORTED
+    assert b"128x128" in lib.pdeopt_last_error()
+    d.nx, d.hx = 128, -1.0
+    assert lib.pdeopt_plan_create(ctypes.byref(d), ctypes.byref(h)) == _lib.ERR_INVALID
+    d.hx, d.mu_family = 0.01, 9
+    assert lib.pdeopt_plan_create(ctypes.byref(d), ctypes.byref(h)) == _lib.ERR_INVALID
+    assert lib.pdeopt_plan_create(None, ctypes.byref(h)) == _lib.ERR_INVALID
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libpdeopt_b200.so")
+    with pytest.raises(_lib.PdeOptError, match="no CPU fallback"):
+        _lib.load()
