@@ -36,6 +36,7 @@ A_SPLIT = 0.5
 DT = 1e-6
 K_FUSED = 16
 ENVS_PER_GPU = 4096
+CPU_SAMPLE_ENVS_PER_CORE = 768  # ~10 s of CPU work per core for the cpu_baseline leg
 OMEGA = 3.0
 FLOP_PER_POINT = 70 + 35 + 1 + 2  # BASELINE.md section 3, log potential: 108 flop / grid point / numeric step
 BYTES_PER_ENV_LAUNCH = 2 * 4 * N * N  # one read + one write of the state per launch (K fused steps)
@@ -328,7 +329,7 @@ def run_ours(args):
     if rank == 0:
         cpu_value, cores, cpu_wall = (None, None, None)
         if world == 1 and not args.no_cpu_baseline:
-            cpu_value, cores, cpu_wall = cpu_arm(envs_per_core=64, nsteps=K_FUSED)
+            cpu_value, cores, cpu_wall = cpu_arm(envs_per_core=CPU_SAMPLE_ENVS_PER_CORE, nsteps=K_FUSED)
         line = {
             "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -354,7 +355,7 @@ def run_ours(args):
         }
         if cpu_value is not None:
             line["cpu_baseline"] = {"value": cpu_value, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                                    "sample": f"{cores * 64} envs x {K_FUSED} numeric steps, NumPy restatement of the reference (oracle/), {cpu_wall:.1f} s"}
+                                    "sample": f"{cores * CPU_SAMPLE_ENVS_PER_CORE} envs x {K_FUSED} numeric steps, NumPy restatement of the reference (oracle/), {cpu_wall:.1f} s"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -7,6 +7,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "regfft.cuh"
+
 namespace pdeopt {
 
 enum : int { MU_DOUBLE_WELL = 0, MU_LOG = 1, MU_LEGENDRE = 2, MU_LEGENDRE_LOGPRIOR = 3, MU_RUNTIME = -1 };
@@ -61,6 +63,36 @@ __device__ __forceinline__ float mob(float c, const PointwiseParams& pw) {
     return 1.0f + c * c;  // test_rhs_convergence.py:22,55
   } else {
     return __expf(legendre_eval(pw.mob_coef, pw.mob_ncoef, 2.0f * c - 1.0f));  // legendre.py:48-53
+  }
+}
+
+// ---- packed (two environments per register pair) evaluation -------------------------------
+__device__ __forceinline__ float lg2_fast(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+
+// mu_h(c) and mobility D(c) for the (a, b) pair held in one float2.  `w` is the per-env value of
+// the first mu coefficient (family coefficient + control offset).
+template <int MU, int MOB>
+__device__ __forceinline__ void mu_mob_pair(float2 c, const PointwiseParams& pw, float2 w_off, float2& mu, float2& D) {
+  if constexpr (MU == MU_LOG && (MOB == MOB_DEGENERATE || MOB == MOB_CONST)) {
+    const float2 s = sub2(splat2(1.0f), c);                                 // 1 - c
+    const float2 l = sub2(make_float2(lg2_fast(c.x), lg2_fast(c.y)),        // log2(c) - log2(1-c)
+                          make_float2(lg2_fast(s.x), lg2_fast(s.y)));
+    const float2 t = fma2(c, splat2(-2.0f), splat2(1.0f));                  // 1 - 2c
+    const float2 w = add2(splat2(pw.mu_coef[0]), w_off);
+    mu = fma2(l, splat2(0.69314718055994531f), mul2(w, t));
+    D = (MOB == MOB_DEGENERATE) ? mul2(s, c) : splat2(pw.mob_coef[0]);
+  } else if constexpr (MU == MU_DOUBLE_WELL && (MOB == MOB_CONST || MOB == MOB_ONE_PLUS_SQ)) {
+    const float2 c2 = mul2(c, c);
+    mu = sub2(mul2(c2, c), c);  // c^3 - c
+    D = (MOB == MOB_CONST) ? splat2(pw.mob_coef[0]) : add2(splat2(1.0f), c2);
+  } else {
+    mu = make_float2(mu_h<MU>(c.x, pw, w_off.x), mu_h<MU>(c.y, pw, w_off.y));
+    D = make_float2(mob<MOB>(c.x, pw), mob<MOB>(c.y, pw));
   }
 }
 

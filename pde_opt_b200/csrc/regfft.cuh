@@ -70,8 +70,47 @@ constexpr int brev(int k) {
 
 constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n >> 1); }
 
-PDEOPT_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-PDEOPT_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Packed two-lane FP32 arithmetic (sm_100 add/sub/mul/fma .f32x2: one issue slot, both lanes).
+// A complex add is exactly one packed add; on the host the scalar form is used.
+#if defined(__CUDA_ARCH__) && !defined(PDEOPT_NO_F32X2)
+__device__ __forceinline__ unsigned long long pk2(float2 a) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+  return r;
+}
+__device__ __forceinline__ float2 unpk2(unsigned long long u) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(u));
+  return r;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)));
+  return unpk2(r);
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)));
+  return unpk2(r);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)));
+  return unpk2(r);
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)), "l"(pk2(c)));
+  return unpk2(r);
+}
+#else
+PDEOPT_HD float2 add2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+PDEOPT_HD float2 sub2(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+PDEOPT_HD float2 mul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+PDEOPT_HD float2 fma2(float2 a, float2 b, float2 c) { return make_float2(a.x * b.x + c.x, a.y * b.y + c.y); }
+#endif
+PDEOPT_HD float2 cadd(float2 a, float2 b) { return add2(a, b); }
+PDEOPT_HD float2 csub(float2 a, float2 b) { return sub2(a, b); }
 PDEOPT_HD float2 cmul(float2 a, float2 w) {
   return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
 }

@@ -151,6 +151,10 @@ struct EnvCtrl {
 };
 
 // ---- RHS phase: W (natural layout) holds u on entry and f0 = rhs(u) on return ------------
+// All arithmetic is packed f32x2 over the (env a, env b) pair.  Relative to the reference's
+// expression order (cahn_hilliard.py:89-109) the constant factors 1/2, 1/hx, 1/hy are
+// collected into cx = 1/(2 hx^2), cy = 1/(2 hy^2): f = cx*(Gx - Gx_prev) + cy*(Gy - Gy_left)
+// with G = (D + D_next) * (mu_next - mu); identical in exact arithmetic, a few ulp in float32.
 template <int EQ, int MU, int MOB>
 __device__ __forceinline__ void rhs_phase(float2* __restrict__ W, const SifsParams& p, const EnvCtrl& ec,
                                           const float2* __restrict__ gx, const float2* __restrict__ gy) {
@@ -173,6 +177,7 @@ __device__ __forceinline__ void rhs_phase(float2* __restrict__ W, const SifsPara
 #pragma unroll
     for (int j = 0; j < 4; ++j) gyv[j] = gy[4 * lane + j];
   }
+  const float2 ihx2 = splat2(p.inv_hx2), ihy2 = splat2(p.inv_hy2), mkappa = splat2(-p.kappa), m2 = splat2(-2.0f);
 
   // mu and mobility of one row from its three-row neighbourhood.
   auto mu_row = [&](int rho, const float2 (&um)[4], const float2 (&u0)[4], const float2 (&up)[4], float2 (&mu)[4],
@@ -184,16 +189,14 @@ __device__ __forceinline__ void rhs_phase(float2* __restrict__ W, const SifsPara
     for (int j = 0; j < 4; ++j) {
       const float2 left = (j == 0) ? uL : u0[j - 1];
       const float2 right = (j == 3) ? uR : u0[j + 1];
-      float2 lap;
-      lap.x = ((up[j].x - 2.0f * u0[j].x) + um[j].x) * p.inv_hx2 + ((right.x - 2.0f * u0[j].x) + left.x) * p.inv_hy2;
-      lap.y = ((up[j].y - 2.0f * u0[j].y) + um[j].y) * p.inv_hx2 + ((right.y - 2.0f * u0[j].y) + left.y) * p.inv_hy2;
-      float ma = mu_h<MU>(u0[j].x, p.pw, ec.w_off.x), mb = mu_h<MU>(u0[j].y, p.pw, ec.w_off.y);
-      if (ec.has_bump) {
-        ma = fmaf(gxr.x, gyv[j].x, ma);
-        mb = fmaf(gxr.y, gyv[j].y, mb);
-      }
-      mu[j] = make_float2(ma - p.kappa * lap.x, mb - p.kappa * lap.y);
-      D[j] = make_float2(mob<MOB>(u0[j].x, p.pw), mob<MOB>(u0[j].y, p.pw));
+      // derivatives.py:8-12: (u[i+1] - 2u + u[i-1])/hx^2 + (u[j+1] - 2u + u[j-1])/hy^2
+      const float2 dxx = add2(fma2(u0[j], m2, up[j]), um[j]);
+      const float2 dyy = add2(fma2(u0[j], m2, right), left);
+      const float2 lap = fma2(dyy, ihy2, mul2(dxx, ihx2));
+      float2 mh;
+      mu_mob_pair<MU, MOB>(u0[j], p.pw, ec.w_off, mh, D[j]);
+      if (ec.has_bump) mh = fma2(gxr, gyv[j], mh);
+      mu[j] = fma2(lap, mkappa, mh);
     }
   };
 
@@ -214,7 +217,7 @@ __device__ __forceinline__ void rhs_phase(float2* __restrict__ W, const SifsPara
       float2 mu[4], R[4], f[4];
       mu_row(r0 + i, um, u0, up, mu, R);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) f[j] = make_float2(-R[j].x * mu[j].x, -R[j].y * mu[j].y);
+      for (int j = 0; j < 4; ++j) f[j] = mul2(mul2(R[j], splat2(-1.0f)), mu[j]);
       store_row(W, r0 + i, lane, f);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -226,8 +229,9 @@ __device__ __forceinline__ void rhs_phase(float2* __restrict__ W, const SifsPara
   }
 
   // Cahn-Hilliard: f = div( D_face * grad_face(mu) )   (cahn_hilliard.py:89-109)
+  const float2 cx = splat2(0.5f * p.inv_hx * p.inv_hx), cy = splat2(0.5f * p.inv_hy * p.inv_hy);
   float2 um[4], u0[4], up[4];
-  float2 mu_p[4], D_p[4], fx_old[4], divy_p[4];
+  float2 mu_p[4], D_p[4], gx_old[4], dy_p[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     um[j] = hm2[j];
@@ -239,48 +243,38 @@ __device__ __forceinline__ void rhs_phase(float2* __restrict__ W, const SifsPara
   for (int it = -1; it <= 8; ++it) {
     float2 mu[4], D[4];
     mu_row(r0 + it + kN, um, u0, up, mu, D);
-    float2 divy[4];
+    float2 dy[4];
     if (it >= 0 && it <= 7) {
       const float2 muR = shfl2(mu[0], lp1), DR = shfl2(D[0], lp1);
-      float2 fy[4];
+      float2 g[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 mr = (j == 3) ? muR : mu[j + 1];
         const float2 dr = (j == 3) ? DR : D[j + 1];
-        fy[j].x = (0.5f * (D[j].x + dr.x)) * ((mr.x - mu[j].x) * p.inv_hy);
-        fy[j].y = (0.5f * (D[j].y + dr.y)) * ((mr.y - mu[j].y) * p.inv_hy);
+        g[j] = mul2(add2(D[j], dr), sub2(mr, mu[j]));
       }
-      const float2 fyL = shfl2(fy[3], lm1);
+      const float2 gL = shfl2(g[3], lm1);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 fl = (j == 0) ? fyL : fy[j - 1];
-        divy[j] = make_float2((fy[j].x - fl.x) * p.inv_hy, (fy[j].y - fl.y) * p.inv_hy);
-      }
+      for (int j = 0; j < 4; ++j) dy[j] = sub2(g[j], (j == 0) ? gL : g[j - 1]);
     }
     if (it >= 0) {
-      float2 fx[4];
+      float2 gxn[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        fx[j].x = (0.5f * (D_p[j].x + D[j].x)) * ((mu[j].x - mu_p[j].x) * p.inv_hx);
-        fx[j].y = (0.5f * (D_p[j].y + D[j].y)) * ((mu[j].y - mu_p[j].y) * p.inv_hx);
-      }
+      for (int j = 0; j < 4; ++j) gxn[j] = mul2(add2(D_p[j], D[j]), sub2(mu[j], mu_p[j]));
       if (it >= 1) {
         float2 f[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          f[j].x = (fx[j].x - fx_old[j].x) * p.inv_hx + divy_p[j].x;
-          f[j].y = (fx[j].y - fx_old[j].y) * p.inv_hx + divy_p[j].y;
-        }
+        for (int j = 0; j < 4; ++j) f[j] = fma2(sub2(gxn[j], gx_old[j]), cx, mul2(dy_p[j], cy));
         store_row(W, r0 + it - 1, lane, f);
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) fx_old[j] = fx[j];
+      for (int j = 0; j < 4; ++j) gx_old[j] = gxn[j];
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       mu_p[j] = mu[j];
       D_p[j] = D[j];
-      if (it >= 0 && it <= 7) divy_p[j] = divy[j];
+      if (it >= 0 && it <= 7) dy_p[j] = dy[j];
       um[j] = u0[j];
       u0[j] = up[j];
     }
@@ -401,7 +395,7 @@ __device__ __forceinline__ void spectral_filter(float2* __restrict__ W, const fl
         const int fr = kr <= 64 ? kr : 128 - kr;
         // 1/(N^2 (1 + A dt sigma)): solvers.py:62-63 with the inverse-FFT scale folded in
         const float mval = __fdividef(1.0f / float(kN * kN), fmaf(dt, mt[fr * kTabDim + fc], 1.0f));
-        x[b * 16 + pp] = make_float2(x[b * 16 + pp].x * mval, x[b * 16 + pp].y * mval);
+        x[b * 16 + pp] = mul2(x[b * 16 + pp], splat2(mval));
       });
     });
     Dit<16, 1, true>::run(x);
@@ -596,8 +590,7 @@ __global__ void __launch_bounds__(kThreads, 1) sifs128_kernel(const __grid_const
       park.load(ch, v);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        v[i].x = fmaf(dt, x[ch * 8 + i].x, v[i].x);
-        v[i].y = fmaf(dt, x[ch * 8 + i].y, v[i].y);
+        v[i] = fma2(x[ch * 8 + i], splat2(dt), v[i]);
         x[ch * 8 + i] = v[i];
       }
       park.store(ch, v);

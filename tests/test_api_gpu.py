@@ -101,7 +101,8 @@ def test_pde_model_solve_saveat_interpolation():
     ysb = model.solve(params, torch.from_numpy(yb).cuda(), ts[:3], {"A": 0.5}, dt0=1e-6).cpu().numpy()
     ys8 = model.solve(params, torch.from_numpy(yb[0]).cuda(), ts[:3], {"A": 0.5}, dt0=1e-6).cpu().numpy()
     assert tuple(ysb.shape) == (3, 2, N, N)
-    np.testing.assert_allclose(ysb[:, 0], ys8, rtol=0, atol=1e-7)
+    # two environments share one complex FFT, so a trajectory depends on its batch partner at the ulp level
+    np.testing.assert_allclose(ysb[:, 0], ys8, rtol=0, atol=2e-6)
 
 
 def test_pde_model_incompatible_pair_raises():
