@@ -321,68 +321,128 @@ struct P3Map {
   }
 };
 
-__device__ __forceinline__ void p1_gather_nat(const float2* __restrict__ W, const P1Map& m, float2 (&x)[32]) {
-#pragma unroll
-  for (int n = 0; n < 32; ++n) x[n] = W[nat_idx(m.r, 4 * n + m.n2c)];
+// Shared-memory accesses of the FFT passes: a per-thread base register XORed with a compile-time
+// constant (one LOP3) plus a compile-time immediate offset, so no per-element index arithmetic.
+// `a` is a shared-window BYTE address; the buffer is 1024-byte aligned so XORs of low bits commute
+// with the base.
+template <int OFF>
+__device__ __forceinline__ float2 lds64(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(a), "n"(OFF));
+  return v;
 }
-__device__ __forceinline__ void p1_scatter_nat(float2* __restrict__ W, const P1Map& m, const float2 (&x)[32]) {
-#pragma unroll
-  for (int n = 0; n < 32; ++n) W[nat_idx(m.r, 4 * n + m.n2c)] = x[n];
+template <int OFF>
+__device__ __forceinline__ void sts64(uint32_t a, float2 v) {
+  asm volatile("st.shared.v2.f32 [%0+%1], {%2, %3};" ::"r"(a), "n"(OFF), "f"(v.x), "f"(v.y) : "memory");
+}
+
+// natural layout, P1 map: element(r, c = 4n + n2c) = (row_base + tbn) ^ (n << 1)   [elements]
+__device__ __forceinline__ uint32_t p1_nat_base(uint32_t wbase, const P1Map& m) {
+  const int c1 = m.n2c >> 1;
+  const int tbn = (m.n2c & 1) | (c1 << 6) | ((m.r & 3) << 1) | (c1 << 3);
+  return wbase + (uint32_t)(m.r * kN + tbn) * 8u;
+}
+__device__ __forceinline__ void p1_gather_nat(uint32_t nb, float2 (&x)[32]) {
+  static_for<0, 8>([&](auto lc) {
+    constexpr int lo = decltype(lc)::value;
+    const uint32_t a = nb ^ (uint32_t)(lo << 4);  // (n & 7) << 1 elements = << 4 bytes
+    static_for<0, 4>([&](auto hc) {
+      constexpr int hi = decltype(hc)::value;
+      x[hi * 8 + lo] = lds64<hi * 8 * 2 * 8>(a);  // (n >> 3) << 4 elements
+    });
+  });
+}
+__device__ __forceinline__ void p1_scatter_nat(uint32_t nb, const float2 (&x)[32]) {
+  static_for<0, 8>([&](auto lc) {
+    constexpr int lo = decltype(lc)::value;
+    const uint32_t a = nb ^ (uint32_t)(lo << 4);
+    static_for<0, 4>([&](auto hc) {
+      constexpr int hi = decltype(hc)::value;
+      sts64<hi * 8 * 2 * 8>(a, x[hi * 8 + lo]);
+    });
+  });
+}
+// exchange layout, P1 map: element(k1c, r, n2c) = (tb1 ^ Clo(k1c)) + 512 k1c, Clo = k1c & 15
+__device__ __forceinline__ uint32_t p1_ex_base(uint32_t wbase, const P1Map& m) {
+  return wbase + (uint32_t)((m.r >> 2) * 16 + ((m.r & 3) << 2) + m.n2c) * 8u;
 }
 
 // Forward: natural f0 in W  ->  spectrum (x multiplier) -> inverse -> g in registers (P1 map).
-// tw: 128-entry table of w_128^e in shared memory; mt: folded multiplier table in shared memory.
-__device__ __forceinline__ void spectral_filter(float2* __restrict__ W, const float2* __restrict__ tw,
+// tw: 128-entry table of w_128^e in shared memory; mt: folded A*symbol table in shared memory.
+__device__ __forceinline__ void spectral_filter(uint32_t wbase, const float2* __restrict__ tw,
                                                 const float* __restrict__ mt, float dt, const P1Map& m1,
                                                 float2 (&x)[32]) {
   const P2Map m2;
   const P3Map m3;
+  const uint32_t nb = p1_nat_base(wbase, m1);
+  const uint32_t e1 = p1_ex_base(wbase, m1);
+  // P2: element(k1c, 16 hi + n2r, q) = tb2 + (q ^ (k1c & 3)) + 64 hi
+  const uint32_t tb2 = wbase + (uint32_t)(m2.k1c * 512 + (m2.n2r >> 2) * 16 + (((m2.n2r & 3) ^ ((m2.k1c >> 2) & 3)) << 2)) * 8u;
+  // P3: element(k1c, 16 k1r + n, k2c = b | k2ct << 1) = base3 ^ (((n & 3) << 2) | b) + 16 (n >> 2)
+  const uint32_t tb3 = wbase + (uint32_t)(m3.k1c * 512 + m3.k1r * 64 + ((((m3.k1c >> 2) & 3)) << 2) +
+                                          (((m3.k2ct << 1) ^ (m3.k1c & 2))) + (m3.k1c & 1)) * 8u;
+
   // ---- P1 forward: 32-point DFT over n1c ----
-  p1_gather_nat(W, m1, x);
+  p1_gather_nat(nb, x);
   __syncthreads();  // everybody has read f0 before the buffer is reused as exchange space
   Dif<32, 1, false>::run(x);
-  static_for<0, 32>([&](auto pc) {
-    constexpr int pp = decltype(pc)::value;
-    W[ex_idx(brev<5>(pp), m1.r, m1.n2c)] = x[pp];
+  static_for<0, 16>([&](auto cc) {
+    constexpr int clo = decltype(cc)::value;  // k1c & 15
+    const uint32_t a = e1 ^ (uint32_t)(clo * 8);
+    sts64<clo * 512 * 8>(a, x[brev<5>(clo)]);
+    sts64<(clo + 16) * 512 * 8>(a, x[brev<5>(clo + 16)]);
   });
   __syncthreads();
   // ---- P2 forward: twiddle, 4-point DFT over n2c, 8-point DFT over n1r, twiddle ----
   {
-    float2 twc[4], twr[8];
+    static_for<0, 4>([&](auto qc) {
+      constexpr int q = decltype(qc)::value;
+      const uint32_t a = tb2 + (uint32_t)((q ^ (m2.k1c & 3)) * 8);
+      static_for<0, 8>([&](auto hc) {
+        constexpr int hi = decltype(hc)::value;
+        x[q * 8 + hi] = lds64<hi * 64 * 8>(a);
+      });
+    });
 #pragma unroll
-    for (int q = 1; q < 4; ++q) twc[q] = tw[(q * m2.k1c) & 127];
+    for (int q = 1; q < 4; ++q) {
+      const float2 w = tw[(q * m2.k1c) & 127];
 #pragma unroll
-    for (int k = 1; k < 8; ++k) twr[k] = tw[(k * m2.n2r) & 127];
-    // v[q*8 + hi]
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-      for (int hi = 0; hi < 8; ++hi) x[q * 8 + hi] = W[ex_idx(m2.k1c, 16 * hi + m2.n2r, q)];
-#pragma unroll
-    for (int q = 1; q < 4; ++q)
-#pragma unroll
-      for (int hi = 0; hi < 8; ++hi) x[q * 8 + hi] = cmul(x[q * 8 + hi], twc[q]);
+      for (int hi = 0; hi < 8; ++hi) x[q * 8 + hi] = cmul(x[q * 8 + hi], w);
+    }
     static_for<0, 8>([&](auto hc) { Dif<4, 8, false>::run(x + decltype(hc)::value); });
     static_for<0, 4>([&](auto qc) { Dif<8, 1, false>::run(x + 8 * decltype(qc)::value); });
     // position (pq, pr) holds k2c = brev2(pq), k1r = brev3(pr)
+    static_for<1, 8>([&](auto rc) {
+      constexpr int pr = decltype(rc)::value;
+      const float2 w = tw[(brev<3>(pr) * m2.n2r) & 127];
+      static_for<0, 4>([&](auto qc) {
+        constexpr int pq = decltype(qc)::value;
+        x[pq * 8 + pr] = cmul(x[pq * 8 + pr], w);
+      });
+    });
     static_for<0, 4>([&](auto qc) {
       constexpr int pq = decltype(qc)::value;
+      const uint32_t a = tb2 + (uint32_t)((brev<2>(pq) ^ (m2.k1c & 3)) * 8);
       static_for<0, 8>([&](auto rc) {
         constexpr int pr = decltype(rc)::value;
-        constexpr int k1r = brev<3>(pr);
-        float2 v = x[pq * 8 + pr];
-        if constexpr (k1r != 0) v = cmul(v, twr[k1r]);
-        W[ex_idx(m2.k1c, 16 * k1r + m2.n2r, brev<2>(pq))] = v;
+        sts64<brev<3>(pr) * 64 * 8>(a, x[pq * 8 + pr]);
       });
     });
   }
   __syncthreads();
   // ---- P3: 16-point DFT over n2r, multiplier, inverse 16-point ----
   {
-#pragma unroll
-    for (int b = 0; b < 2; ++b)
-#pragma unroll
-      for (int n = 0; n < 16; ++n) x[b * 16 + n] = W[ex_idx(m3.k1c, 16 * m3.k1r + n, b | (m3.k2ct << 1))];
+    static_for<0, 2>([&](auto bc) {
+      constexpr int b = decltype(bc)::value;
+      static_for<0, 4>([&](auto mc) {
+        constexpr int mm = decltype(mc)::value;
+        const uint32_t a = tb3 ^ (uint32_t)(((mm << 2) | b) * 8);
+        static_for<0, 4>([&](auto hc) {
+          constexpr int nh = decltype(hc)::value;
+          x[b * 16 + nh * 4 + mm] = lds64<nh * 16 * 8>(a);
+        });
+      });
+    });
     Dif<16, 1, false>::run(x);
     Dif<16, 1, false>::run(x + 16);
     static_for<0, 2>([&](auto bc) {
@@ -400,45 +460,61 @@ __device__ __forceinline__ void spectral_filter(float2* __restrict__ W, const fl
     });
     Dit<16, 1, true>::run(x);
     Dit<16, 1, true>::run(x + 16);
-#pragma unroll
-    for (int b = 0; b < 2; ++b)
-#pragma unroll
-      for (int n = 0; n < 16; ++n) W[ex_idx(m3.k1c, 16 * m3.k1r + n, b | (m3.k2ct << 1))] = x[b * 16 + n];
+    static_for<0, 2>([&](auto bc) {
+      constexpr int b = decltype(bc)::value;
+      static_for<0, 4>([&](auto mc) {
+        constexpr int mm = decltype(mc)::value;
+        const uint32_t a = tb3 ^ (uint32_t)(((mm << 2) | b) * 8);
+        static_for<0, 4>([&](auto hc) {
+          constexpr int nh = decltype(hc)::value;
+          sts64<nh * 16 * 8>(a, x[b * 16 + nh * 4 + mm]);
+        });
+      });
+    });
   }
   __syncthreads();
   // ---- P2 inverse ----
   {
-    float2 twc[4], twr[8];
-#pragma unroll
-    for (int q = 1; q < 4; ++q) twc[q] = tw[(q * m2.k1c) & 127];
-#pragma unroll
-    for (int k = 1; k < 8; ++k) twr[k] = tw[(k * m2.n2r) & 127];
     static_for<0, 4>([&](auto qc) {
       constexpr int pq = decltype(qc)::value;
+      const uint32_t a = tb2 + (uint32_t)((brev<2>(pq) ^ (m2.k1c & 3)) * 8);
       static_for<0, 8>([&](auto rc) {
         constexpr int pr = decltype(rc)::value;
-        constexpr int k1r = brev<3>(pr);
-        float2 v = W[ex_idx(m2.k1c, 16 * k1r + m2.n2r, brev<2>(pq))];
-        if constexpr (k1r != 0) v = cmulc(v, twr[k1r]);
-        x[pq * 8 + pr] = v;
+        x[pq * 8 + pr] = lds64<brev<3>(pr) * 64 * 8>(a);
+      });
+    });
+    static_for<1, 8>([&](auto rc) {
+      constexpr int pr = decltype(rc)::value;
+      const float2 w = tw[(brev<3>(pr) * m2.n2r) & 127];
+      static_for<0, 4>([&](auto qc) {
+        constexpr int pq = decltype(qc)::value;
+        x[pq * 8 + pr] = cmulc(x[pq * 8 + pr], w);
       });
     });
     static_for<0, 4>([&](auto qc) { Dit<8, 1, true>::run(x + 8 * decltype(qc)::value); });
     static_for<0, 8>([&](auto hc) { Dit<4, 8, true>::run(x + decltype(hc)::value); });
 #pragma unroll
-    for (int q = 1; q < 4; ++q)
+    for (int q = 1; q < 4; ++q) {
+      const float2 w = tw[(q * m2.k1c) & 127];
 #pragma unroll
-      for (int hi = 0; hi < 8; ++hi) x[q * 8 + hi] = cmulc(x[q * 8 + hi], twc[q]);
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-      for (int hi = 0; hi < 8; ++hi) W[ex_idx(m2.k1c, 16 * hi + m2.n2r, q)] = x[q * 8 + hi];
+      for (int hi = 0; hi < 8; ++hi) x[q * 8 + hi] = cmulc(x[q * 8 + hi], w);
+    }
+    static_for<0, 4>([&](auto qc) {
+      constexpr int q = decltype(qc)::value;
+      const uint32_t a = tb2 + (uint32_t)((q ^ (m2.k1c & 3)) * 8);
+      static_for<0, 8>([&](auto hc) {
+        constexpr int hi = decltype(hc)::value;
+        sts64<hi * 64 * 8>(a, x[q * 8 + hi]);
+      });
+    });
   }
   __syncthreads();
   // ---- P1 inverse ----
-  static_for<0, 32>([&](auto pc) {
-    constexpr int pp = decltype(pc)::value;
-    x[pp] = W[ex_idx(brev<5>(pp), m1.r, m1.n2c)];
+  static_for<0, 16>([&](auto cc) {
+    constexpr int clo = decltype(cc)::value;
+    const uint32_t a = e1 ^ (uint32_t)(clo * 8);
+    x[brev<5>(clo)] = lds64<clo * 512 * 8>(a);
+    x[brev<5>(clo + 16)] = lds64<(clo + 16) * 512 * 8>(a);
   });
   Dit<32, 1, true>::run(x);
 }
@@ -463,7 +539,7 @@ __device__ __forceinline__ float2 block_sum2(float2 v, float2* red) {
   return s;
 }
 
-struct __align__(16) SifsSmem {
+struct __align__(1024) SifsSmem {
   float2 W[kN * kN];
   float tab[kTabLen + 3];
   float2 tw[128];
@@ -474,7 +550,7 @@ struct __align__(16) SifsSmem {
 
 template <int EQ, int MU, int MOB>
 __global__ void __launch_bounds__(kThreads, 1) sifs128_kernel(const __grid_constant__ SifsParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   SifsSmem& S = *reinterpret_cast<SifsSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int env_a = 2 * blockIdx.x;
@@ -546,8 +622,10 @@ __global__ void __launch_bounds__(kThreads, 1) sifs128_kernel(const __grid_const
   }
   __syncthreads();
   const P1Map m1;
+  const uint32_t wbase = (uint32_t)__cvta_generic_to_shared(S.W);
+  const uint32_t nbase = p1_nat_base(wbase, m1);
   float2 x[32];
-  p1_gather_nat(S.W, m1, x);
+  p1_gather_nat(nbase, x);
 #pragma unroll
   for (int ch = 0; ch < 4; ++ch) {
     float2 v[8];
@@ -582,7 +660,7 @@ __global__ void __launch_bounds__(kThreads, 1) sifs128_kernel(const __grid_const
     }
     __syncthreads();
     const float dt = p.dt[k];
-    spectral_filter(S.W, S.tw, S.tab, dt, m1, x);
+    spectral_filter(wbase, S.tw, S.tab, dt, m1, x);
     // y1 = y0 + dt * g   (solvers.py:63); y0 comes back from the parking space
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
@@ -597,7 +675,7 @@ __global__ void __launch_bounds__(kThreads, 1) sifs128_kernel(const __grid_const
     }
     park.fence_store();
     __syncthreads();  // all exchange-layout reads are done before the natural layout is rewritten
-    p1_scatter_nat(S.W, m1, x);
+    p1_scatter_nat(nbase, x);
     __syncthreads();
   }
 
