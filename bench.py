@@ -40,6 +40,9 @@ CPU_SAMPLE_ENVS_PER_CORE = 768  # ~10 s of CPU work per core for the cpu_baselin
 OMEGA = 3.0
 FLOP_PER_POINT = 70 + 35 + 1 + 2  # BASELINE.md section 3, log potential: 108 flop / grid point / numeric step
 BYTES_PER_ENV_LAUNCH = 2 * 4 * N * N  # one read + one write of the state per launch (K fused steps)
+# dram__bytes_read.sum + dram__bytes_write.sum of one sifs128_kernel launch of this exact config
+# (ncu --set full, profiles/ncu_raw_r1_bench_4096x16.txt): 269.1 MB + 283.6 MB
+NCU_DRAM_BYTES_PER_LAUNCH = 552.7e6
 
 
 def make_ic(env_index):
@@ -343,7 +346,8 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {
                 "bound": "fp32", "achieved": achieved_tf, "peak": float(peak_tf.value), "unit": "TFLOP/s",
-                "frac": achieved_tf / float(peak_tf.value) if peak_tf.value else None, "traffic": None,
+                "frac": achieved_tf / float(peak_tf.value) if peak_tf.value else None,
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                 "kernel": "pdeopt::sifs128_kernel<CH, MU_LOG, MOB_DEGENERATE>",
                 "how": f"{FLOP_PER_POINT} algorithmic flop/grid-point/step (BASELINE.md s3) x 16384 points x {B} envs x {K_FUSED} steps per launch / "
                        "CUDA-event launch time; peak = FFMA-chain peak measured live on this GPU (pdeopt_measure_fp32_peak); "
