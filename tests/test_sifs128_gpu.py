@@ -29,11 +29,25 @@ def oracle_eq(kind, mu, D):
     return O.AllenCahn2DPeriodic(dom, KAPPA, mu, D, "fd", np.float32)
 
 
+LEG_MU = (0.1, 2.5, -0.3, 0.8, 0.05)
+LEG_D = (-0.5, 0.3, -0.2)
+
 CASES = {
     "log_degenerate": (("log", (3.0,)), ("degenerate", ()), lambda c: O.mu_log(c, 3.0), lambda c: (1 - c) * c, 0.5),
     "log_const": (("log", (3.0,)), ("const", (1.0,)), lambda c: O.mu_log(c, 3.0), lambda c: np.ones_like(c), 0.5),
     "dw_const": (("double_well", ()), ("const", (1.0,)), O.mu_double_well, lambda c: np.ones_like(c), 0.0),
     "dw_1psq": (("double_well", ()), ("one_plus_sq", ()), O.mu_double_well, lambda c: 1 + c * c, 0.0),
+    # runtime-switch kernel: Legendre closures (functions/legendre.py:37-74)
+    "legendre_logprior_exp": (
+        ("legendre_logprior", LEG_MU), ("legendre_exp", LEG_D),
+        lambda c: O.mu_legendre(np.asarray(LEG_MU, np.float32), c, O.prior_log),
+        lambda c: O.D_legendre(np.asarray(LEG_D, np.float32), c), 0.5,
+    ),
+    "legendre_const": (
+        ("legendre", LEG_MU), ("const", (0.15,)),
+        lambda c: O.mu_legendre(np.asarray(LEG_MU, np.float32), c, None), lambda c: 0.15 * np.ones_like(c), 0.5,
+    ),
+    "log_1psq": (("log", (2.5,)), ("one_plus_sq", ()), lambda c: O.mu_log(c, 2.5), lambda c: 1 + c * c, 0.5),
 }
 
 
