@@ -10,6 +10,7 @@
 
 #include "../../include/pdeopt_b200.h"
 #include "sifs128.cuh"
+#include "sifs_generic.cuh"
 
 using namespace pdeopt;
 
@@ -45,7 +46,15 @@ extern "C" pdeopt_status pdeopt_plan_create(const pdeopt_plan_desc* desc, pdeopt
   if (desc->kind != PDEOPT_CH2D && desc->kind != PDEOPT_AC2D)
     return fail(PDEOPT_ERR_UNSUPPORTED, "sifs: only CH2D / AC2D plans are implemented");
   if (desc->derivs != PDEOPT_DERIVS_FD) return fail(PDEOPT_ERR_UNSUPPORTED, "sifs: only derivs='fd' is implemented");
-  if (desc->nx != 128 || desc->ny != 128) return fail(PDEOPT_ERR_UNSUPPORTED, "sifs: only 128x128 grids are implemented");
+  {
+    auto pow2 = [](int v) { return v >= 1 && (v & (v - 1)) == 0; };
+    const bool tuned = desc->nx == 128 && desc->ny == 128;
+    const bool generic = pow2(desc->nx) && pow2(desc->ny) && (int64_t)desc->nx * desc->ny <= kGenMaxPts &&
+                         (int64_t)desc->nx * desc->ny >= 2;
+    if (!tuned && !generic)
+      return fail(PDEOPT_ERR_UNSUPPORTED,
+                  "sifs: grids must be 128x128 (tuned kernel) or powers of two with nx*ny <= 8192 (generic kernel)");
+  }
   if (!(desc->hx > 0) || !(desc->hy > 0)) return fail(PDEOPT_ERR_INVALID, "grid spacing must be positive");
   if (desc->mu_family < 0 || desc->mu_family > 3) return fail(PDEOPT_ERR_INVALID, "unknown mu family");
   if (desc->mob_family < 0 || desc->mob_family > 3) return fail(PDEOPT_ERR_INVALID, "unknown mobility family");
@@ -130,6 +139,37 @@ static pdeopt_status sifs_launch(pdeopt_plan* plan, int mode, const float* f0_de
   for (int k = 0; k < ksteps && mode != MODE_RHS_ONLY; ++k) p.dt[k] = dt_host[k];
   const int grid = (batch + 1) / 2;
   cudaStream_t st = (cudaStream_t)stream;
+  if (!(d.nx == 128 && d.ny == 128)) {
+    GenParams gp;
+    gp.s = p;
+    gp.nx = d.nx;
+    gp.ny = d.ny;
+    gp.lognx = ilog2(d.nx);
+    gp.logny = ilog2(d.ny);
+    const size_t smem = gen_smem_bytes(d.nx, d.ny);
+    cudaError_t ge;
+    if (d.kind == PDEOPT_AC2D) {
+      static bool attr = false;
+      if (!attr) {
+        ge = cudaFuncSetAttribute(sifs_generic_kernel<EQ_AC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (ge != cudaSuccess) return fail(PDEOPT_ERR_CUDA, cudaGetErrorString(ge));
+        attr = true;
+      }
+      sifs_generic_kernel<EQ_AC><<<grid, kGenThreads, smem, st>>>(gp);
+    } else {
+      static bool attr = false;
+      if (!attr) {
+        ge = cudaFuncSetAttribute(sifs_generic_kernel<EQ_CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (ge != cudaSuccess) return fail(PDEOPT_ERR_CUDA, cudaGetErrorString(ge));
+        attr = true;
+      }
+      sifs_generic_kernel<EQ_CH><<<grid, kGenThreads, smem, st>>>(gp);
+    }
+    ge = cudaGetLastError();
+    if (ge != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(ge));
+    g_launches.fetch_add(1);
+    return PDEOPT_OK;
+  }
 #ifdef PDEOPT_PARK_GLOBAL
   {
     const size_t need = (size_t)grid * 32 * kThreads * sizeof(float2);

@@ -129,6 +129,13 @@ def test_plan_validation_without_gpu():
     d.nx = 100
     assert lib.pdeopt_plan_create(ctypes.byref(d), ctypes.byref(h)) == _lib.ERR_UNSUPPORTED
     assert b"128x128" in lib.pdeopt_last_error()
+    d.nx, d.ny = 256, 256  # too large for the single-CTA kernels
+    assert lib.pdeopt_plan_create(ctypes.byref(d), ctypes.byref(h)) == _lib.ERR_UNSUPPORTED
+    d.nx, d.ny = 64, 64
+    assert lib.pdeopt_plan_create(ctypes.byref(d), ctypes.byref(h)) == _lib.OK
+    assert lib.pdeopt_table_len(h) == 33 * 33
+    lib.pdeopt_plan_destroy(h)
+    d.ny = 128
     d.nx, d.hx = 128, -1.0
     assert lib.pdeopt_plan_create(ctypes.byref(d), ctypes.byref(h)) == _lib.ERR_INVALID
     d.hx, d.mu_family = 0.01, 9
