@@ -13,6 +13,8 @@
  *                                 plus the observation / reward callbacks of
  *                                 PDEEnv.step (pde_env.py:305-309) as a fused epilogue.
  *   pdeopt_sifs_step_batched_host same, host buffers in / out (H2D + D2H inside the call).
+ *   pdeopt_strang_step_batched    K fused calls of StrangSplitting.step (solvers.py:99-122) with
+ *                                 GPE2DTSControl.B_terms (equations/gross_pitaevskii.py:67-75).
  *
  * Conventions: plain pointers and sizes, no C++/torch types.  Pointers named *_dev are CUDA
  * device pointers on the current device, *_host are host pointers.  `stream` is a
@@ -129,6 +131,29 @@ pdeopt_status pdeopt_rhs_batched(pdeopt_plan* plan, const float* y_dev, float* f
  * families): y1 = y0 + dt * Re ifft( fft(f0) / (1 + dt*A*symbol) ). */
 pdeopt_status pdeopt_sifs_filter_batched(pdeopt_plan* plan, const float* y0_dev, const float* f0_dev, float* y1_dev,
                                          int32_t batch, float dt, const float* symbol_dev, void* stream);
+
+/* GPE2DTSControl (gross_pitaevskii.py:18-81) geometry and constants. */
+typedef struct {
+  int32_t nx, ny;
+  double lo_x, lo_y, hx, hy; /* Domain box lower bounds and spacings; dx of solvers.py:111 is hx */
+  double k;                  /* interaction strength */
+  double e;                  /* trap ellipticity */
+  double trap_factor;
+} pdeopt_gpe_desc;
+
+/* K = ksteps fused calls of StrangSplitting.step (solvers.py:99-122) with GPE2DTSControl.B_terms
+ * (gross_pitaevskii.py:67-75) evaluated at y0 inside the kernel, on `batch` wavefunctions.
+ *   y0_dev, y1_dev : [batch][nx][ny][2] float32 (re, im) (may alias)
+ *   a_term_dev     : [(nx/2+1)*(ny/2+1)][2] float32, the (kx>=0, ky>=0) quadrant of the complex
+ *                    A_term (must be even in each wavenumber), or NULL when A_term is identically
+ *                    zero as shipped (gross_pitaevskii.py:62) — the FFT round trips are then skipped
+ *   ts_re, ts_im   : time_scale (solvers.py:90), e.g. (0,-1) for imaginary time
+ *   ctrl_dev       : [batch][PDEOPT_NCTRL] or NULL; [1] amp [2] x0 [3] y0 [4] width of a Gaussian
+ *                    `lights` spot amp*exp(-((x-x0)^2+(y-y0)^2)/(2 width^2)) (gross_pitaevskii.py:61,72) */
+pdeopt_status pdeopt_strang_step_batched(const pdeopt_gpe_desc* desc, const float* y0_dev, float* y1_dev,
+                                         int32_t batch, int32_t ksteps, const float* dt_host,
+                                         const float* a_term_dev, float ts_re, float ts_im, const float* ctrl_dev,
+                                         void* stream);
 
 /* Same with HOST buffers: copies y0/ctrl/symbol in, runs, copies y1/obs/reward out, and
  * synchronises the stream before returning.  Scratch device memory is owned by the plan

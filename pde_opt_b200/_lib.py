@@ -37,6 +37,20 @@ class PlanDesc(ctypes.Structure):
     ]
 
 
+class GpeDesc(ctypes.Structure):
+    _fields_ = [
+        ("nx", ctypes.c_int32),
+        ("ny", ctypes.c_int32),
+        ("lo_x", ctypes.c_double),
+        ("lo_y", ctypes.c_double),
+        ("hx", ctypes.c_double),
+        ("hy", ctypes.c_double),
+        ("k", ctypes.c_double),
+        ("e", ctypes.c_double),
+        ("trap_factor", ctypes.c_double),
+    ]
+
+
 class PdeOptError(RuntimeError):
     pass
 
@@ -53,6 +67,7 @@ EXPORTS = [
     "pdeopt_sifs_step_batched_host",
     "pdeopt_rhs_batched",
     "pdeopt_sifs_filter_batched",
+    "pdeopt_strang_step_batched",
     "pdeopt_measure_fp32_peak",
     "pdeopt_launch_count",
 ]
@@ -86,6 +101,8 @@ def load():
     lib.pdeopt_rhs_batched.restype = ctypes.c_int
     lib.pdeopt_sifs_filter_batched.argtypes = [vp, vp, vp, vp, i32, f32, vp, vp]
     lib.pdeopt_sifs_filter_batched.restype = ctypes.c_int
+    lib.pdeopt_strang_step_batched.argtypes = [ctypes.POINTER(GpeDesc), vp, vp, i32, i32, vp, vp, f32, f32, vp, vp]
+    lib.pdeopt_strang_step_batched.restype = ctypes.c_int
     lib.pdeopt_measure_fp32_peak.argtypes = [ctypes.POINTER(ctypes.c_double), vp]
     lib.pdeopt_measure_fp32_peak.restype = ctypes.c_int
     lib.pdeopt_launch_count.restype = ctypes.c_int64

@@ -27,11 +27,10 @@
 
 #include "pointwise.cuh"
 #include "regfft.cuh"
+#include "fft128.cuh"
 
 namespace pdeopt {
 
-constexpr int kN = 128;
-constexpr int kThreads = 512;
 constexpr int kTabDim = 65;
 constexpr int kTabLen = kTabDim * kTabDim;
 constexpr int kMaxK = 512;
@@ -58,17 +57,6 @@ struct SifsParams {
   PointwiseParams pw;
   float dt[kMaxK];
 };
-
-// ---- shared-memory layouts (validated in tools/fft_decomp_model.py) ----------------------
-__device__ __forceinline__ int nat_idx(int r, int c) {
-  const int c1 = (c >> 1) & 1;
-  int pos = (c & 1) | ((c >> 2) << 1) | (c1 << 6);
-  pos ^= ((r & 3) << 1) ^ (c1 << 3);
-  return r * kN + pos;
-}
-__device__ __forceinline__ int ex_idx(int k1c, int rho, int q) {
-  return ((k1c * 32 + (rho >> 2)) * 16) + ((((rho & 3) ^ ((k1c >> 2) & 3))) << 2) + (q ^ (k1c & 3));
-}
 
 // ---- TMEM parking of the state (64 x 32-bit columns per thread) --------------------------
 #ifndef PDEOPT_PARK_GLOBAL
@@ -291,232 +279,25 @@ __device__ __forceinline__ void rhs_phase(float2* __restrict__ W, const SifsPara
   }
 }
 
-// ---- FFT passes ---------------------------------------------------------------------------
-// P1: thread (r, n2c) owns c = 4*n1c + n2c, n1c = 0..31.
-struct P1Map {
-  int r, n2c;
-  __device__ __forceinline__ P1Map() {
-    const int t = threadIdx.x;
-    n2c = t & 3;
-    r = ((t >> 2) & 3) | ((t >> 4) << 2);
-  }
-};
-// P2: thread (k1c, n2r) owns (q, hi) with rho = 16*hi + n2r.
-struct P2Map {
-  int k1c, n2r;
-  __device__ __forceinline__ P2Map() {
-    const int t = threadIdx.x;
-    k1c = (t & 3) | (((t >> 4) & 7) << 2);
-    n2r = ((t >> 2) & 3) | (((t >> 7) & 3) << 2);
-  }
-};
-// P3: thread (k1r, k1c, k2c_t) owns n2r = 0..15 and k2c = b | (k2c_t << 1), b = 0,1.
-struct P3Map {
-  int k1r, k1c, k2ct;
-  __device__ __forceinline__ P3Map() {
-    const int t = threadIdx.x;
-    k1c = t & 31;
-    k2ct = (t >> 5) & 1;
-    k1r = t >> 6;
-  }
-};
-
-// Shared-memory accesses of the FFT passes: a per-thread base register XORed with a compile-time
-// constant (one LOP3) plus a compile-time immediate offset, so no per-element index arithmetic.
-// `a` is a shared-window BYTE address; the buffer is 1024-byte aligned so XORs of low bits commute
-// with the base.
-template <int OFF>
-__device__ __forceinline__ float2 lds64(uint32_t a) {
-  float2 v;
-  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(a), "n"(OFF));
-  return v;
-}
-template <int OFF>
-__device__ __forceinline__ void sts64(uint32_t a, float2 v) {
-  asm volatile("st.shared.v2.f32 [%0+%1], {%2, %3};" ::"r"(a), "n"(OFF), "f"(v.x), "f"(v.y) : "memory");
-}
-
-// natural layout, P1 map: element(r, c = 4n + n2c) = (row_base + tbn) ^ (n << 1)   [elements]
-__device__ __forceinline__ uint32_t p1_nat_base(uint32_t wbase, const P1Map& m) {
-  const int c1 = m.n2c >> 1;
-  const int tbn = (m.n2c & 1) | (c1 << 6) | ((m.r & 3) << 1) | (c1 << 3);
-  return wbase + (uint32_t)(m.r * kN + tbn) * 8u;
-}
-__device__ __forceinline__ void p1_gather_nat(uint32_t nb, float2 (&x)[32]) {
-  static_for<0, 8>([&](auto lc) {
-    constexpr int lo = decltype(lc)::value;
-    const uint32_t a = nb ^ (uint32_t)(lo << 4);  // (n & 7) << 1 elements = << 4 bytes
-    static_for<0, 4>([&](auto hc) {
-      constexpr int hi = decltype(hc)::value;
-      x[hi * 8 + lo] = lds64<hi * 8 * 2 * 8>(a);  // (n >> 3) << 4 elements
-    });
-  });
-}
-__device__ __forceinline__ void p1_scatter_nat(uint32_t nb, const float2 (&x)[32]) {
-  static_for<0, 8>([&](auto lc) {
-    constexpr int lo = decltype(lc)::value;
-    const uint32_t a = nb ^ (uint32_t)(lo << 4);
-    static_for<0, 4>([&](auto hc) {
-      constexpr int hi = decltype(hc)::value;
-      sts64<hi * 8 * 2 * 8>(a, x[hi * 8 + lo]);
-    });
-  });
-}
-// exchange layout, P1 map: element(k1c, r, n2c) = (tb1 ^ Clo(k1c)) + 512 k1c, Clo = k1c & 15
-__device__ __forceinline__ uint32_t p1_ex_base(uint32_t wbase, const P1Map& m) {
-  return wbase + (uint32_t)((m.r >> 2) * 16 + ((m.r & 3) << 2) + m.n2c) * 8u;
-}
-
-// Forward: natural f0 in W  ->  spectrum (x multiplier) -> inverse -> g in registers (P1 map).
-// tw: 128-entry table of w_128^e in shared memory; mt: folded A*symbol table in shared memory.
-__device__ __forceinline__ void spectral_filter(uint32_t wbase, const float2* __restrict__ tw,
-                                                const float* __restrict__ mt, float dt, const P1Map& m1,
-                                                float2 (&x)[32]) {
-  const P2Map m2;
-  const P3Map m3;
-  const uint32_t nb = p1_nat_base(wbase, m1);
-  const uint32_t e1 = p1_ex_base(wbase, m1);
-  // P2: element(k1c, 16 hi + n2r, q) = tb2 + (q ^ (k1c & 3)) + 64 hi
-  const uint32_t tb2 = wbase + (uint32_t)(m2.k1c * 512 + (m2.n2r >> 2) * 16 + (((m2.n2r & 3) ^ ((m2.k1c >> 2) & 3)) << 2)) * 8u;
-  // P3: element(k1c, 16 k1r + n, k2c = b | k2ct << 1) = base3 ^ (((n & 3) << 2) | b) + 16 (n >> 2)
-  const uint32_t tb3 = wbase + (uint32_t)(m3.k1c * 512 + m3.k1r * 64 + ((((m3.k1c >> 2) & 3)) << 2) +
-                                          (((m3.k2ct << 1) ^ (m3.k1c & 2))) + (m3.k1c & 1)) * 8u;
-
-  // ---- P1 forward: 32-point DFT over n1c ----
-  p1_gather_nat(nb, x);
+// ---- spectral filter: f0 (natural layout in W) -> g = Re ifft(fft(f0) / (1 + dt A sigma)) --------
+__device__ __forceinline__ void spectral_filter(const Fft128& F, const float* __restrict__ mt, float dt, float2 (&x)[32]) {
+  p1_gather_nat(F.nb, x);
   __syncthreads();  // everybody has read f0 before the buffer is reused as exchange space
-  Dif<32, 1, false>::run(x);
-  static_for<0, 16>([&](auto cc) {
-    constexpr int clo = decltype(cc)::value;  // k1c & 15
-    const uint32_t a = e1 ^ (uint32_t)(clo * 8);
-    sts64<clo * 512 * 8>(a, x[brev<5>(clo)]);
-    sts64<(clo + 16) * 512 * 8>(a, x[brev<5>(clo + 16)]);
+  F.forward(x);
+  static_for<0, 2>([&](auto bc) {
+    constexpr int b = decltype(bc)::value;
+    const int kc = F.p3_kc(b);
+    const int fc = kc <= 64 ? kc : 128 - kc;
+    static_for<0, 16>([&](auto pc) {
+      constexpr int pp = decltype(pc)::value;
+      const int kr = F.p3_kr(pp);
+      const int fr = kr <= 64 ? kr : 128 - kr;
+      // 1/(N^2 (1 + A dt sigma)): solvers.py:62-63 with the inverse-FFT scale folded in
+      const float mval = __fdividef(1.0f / float(kN * kN), fmaf(dt, mt[fr * kTabDim + fc], 1.0f));
+      x[b * 16 + pp] = mul2(x[b * 16 + pp], splat2(mval));
+    });
   });
-  __syncthreads();
-  // ---- P2 forward: twiddle, 4-point DFT over n2c, 8-point DFT over n1r, twiddle ----
-  {
-    static_for<0, 4>([&](auto qc) {
-      constexpr int q = decltype(qc)::value;
-      const uint32_t a = tb2 + (uint32_t)((q ^ (m2.k1c & 3)) * 8);
-      static_for<0, 8>([&](auto hc) {
-        constexpr int hi = decltype(hc)::value;
-        x[q * 8 + hi] = lds64<hi * 64 * 8>(a);
-      });
-    });
-#pragma unroll
-    for (int q = 1; q < 4; ++q) {
-      const float2 w = tw[(q * m2.k1c) & 127];
-#pragma unroll
-      for (int hi = 0; hi < 8; ++hi) x[q * 8 + hi] = cmul(x[q * 8 + hi], w);
-    }
-    static_for<0, 8>([&](auto hc) { Dif<4, 8, false>::run(x + decltype(hc)::value); });
-    static_for<0, 4>([&](auto qc) { Dif<8, 1, false>::run(x + 8 * decltype(qc)::value); });
-    // position (pq, pr) holds k2c = brev2(pq), k1r = brev3(pr)
-    static_for<1, 8>([&](auto rc) {
-      constexpr int pr = decltype(rc)::value;
-      const float2 w = tw[(brev<3>(pr) * m2.n2r) & 127];
-      static_for<0, 4>([&](auto qc) {
-        constexpr int pq = decltype(qc)::value;
-        x[pq * 8 + pr] = cmul(x[pq * 8 + pr], w);
-      });
-    });
-    static_for<0, 4>([&](auto qc) {
-      constexpr int pq = decltype(qc)::value;
-      const uint32_t a = tb2 + (uint32_t)((brev<2>(pq) ^ (m2.k1c & 3)) * 8);
-      static_for<0, 8>([&](auto rc) {
-        constexpr int pr = decltype(rc)::value;
-        sts64<brev<3>(pr) * 64 * 8>(a, x[pq * 8 + pr]);
-      });
-    });
-  }
-  __syncthreads();
-  // ---- P3: 16-point DFT over n2r, multiplier, inverse 16-point ----
-  {
-    static_for<0, 2>([&](auto bc) {
-      constexpr int b = decltype(bc)::value;
-      static_for<0, 4>([&](auto mc) {
-        constexpr int mm = decltype(mc)::value;
-        const uint32_t a = tb3 ^ (uint32_t)(((mm << 2) | b) * 8);
-        static_for<0, 4>([&](auto hc) {
-          constexpr int nh = decltype(hc)::value;
-          x[b * 16 + nh * 4 + mm] = lds64<nh * 16 * 8>(a);
-        });
-      });
-    });
-    Dif<16, 1, false>::run(x);
-    Dif<16, 1, false>::run(x + 16);
-    static_for<0, 2>([&](auto bc) {
-      constexpr int b = decltype(bc)::value;
-      const int kc = m3.k1c + 32 * (b | (m3.k2ct << 1));
-      const int fc = kc <= 64 ? kc : 128 - kc;
-      static_for<0, 16>([&](auto pc) {
-        constexpr int pp = decltype(pc)::value;
-        const int kr = m3.k1r + 8 * brev<4>(pp);
-        const int fr = kr <= 64 ? kr : 128 - kr;
-        // 1/(N^2 (1 + A dt sigma)): solvers.py:62-63 with the inverse-FFT scale folded in
-        const float mval = __fdividef(1.0f / float(kN * kN), fmaf(dt, mt[fr * kTabDim + fc], 1.0f));
-        x[b * 16 + pp] = mul2(x[b * 16 + pp], splat2(mval));
-      });
-    });
-    Dit<16, 1, true>::run(x);
-    Dit<16, 1, true>::run(x + 16);
-    static_for<0, 2>([&](auto bc) {
-      constexpr int b = decltype(bc)::value;
-      static_for<0, 4>([&](auto mc) {
-        constexpr int mm = decltype(mc)::value;
-        const uint32_t a = tb3 ^ (uint32_t)(((mm << 2) | b) * 8);
-        static_for<0, 4>([&](auto hc) {
-          constexpr int nh = decltype(hc)::value;
-          sts64<nh * 16 * 8>(a, x[b * 16 + nh * 4 + mm]);
-        });
-      });
-    });
-  }
-  __syncthreads();
-  // ---- P2 inverse ----
-  {
-    static_for<0, 4>([&](auto qc) {
-      constexpr int pq = decltype(qc)::value;
-      const uint32_t a = tb2 + (uint32_t)((brev<2>(pq) ^ (m2.k1c & 3)) * 8);
-      static_for<0, 8>([&](auto rc) {
-        constexpr int pr = decltype(rc)::value;
-        x[pq * 8 + pr] = lds64<brev<3>(pr) * 64 * 8>(a);
-      });
-    });
-    static_for<1, 8>([&](auto rc) {
-      constexpr int pr = decltype(rc)::value;
-      const float2 w = tw[(brev<3>(pr) * m2.n2r) & 127];
-      static_for<0, 4>([&](auto qc) {
-        constexpr int pq = decltype(qc)::value;
-        x[pq * 8 + pr] = cmulc(x[pq * 8 + pr], w);
-      });
-    });
-    static_for<0, 4>([&](auto qc) { Dit<8, 1, true>::run(x + 8 * decltype(qc)::value); });
-    static_for<0, 8>([&](auto hc) { Dit<4, 8, true>::run(x + decltype(hc)::value); });
-#pragma unroll
-    for (int q = 1; q < 4; ++q) {
-      const float2 w = tw[(q * m2.k1c) & 127];
-#pragma unroll
-      for (int hi = 0; hi < 8; ++hi) x[q * 8 + hi] = cmulc(x[q * 8 + hi], w);
-    }
-    static_for<0, 4>([&](auto qc) {
-      constexpr int q = decltype(qc)::value;
-      const uint32_t a = tb2 + (uint32_t)((q ^ (m2.k1c & 3)) * 8);
-      static_for<0, 8>([&](auto hc) {
-        constexpr int hi = decltype(hc)::value;
-        sts64<hi * 64 * 8>(a, x[q * 8 + hi]);
-      });
-    });
-  }
-  __syncthreads();
-  // ---- P1 inverse ----
-  static_for<0, 16>([&](auto cc) {
-    constexpr int clo = decltype(cc)::value;
-    const uint32_t a = e1 ^ (uint32_t)(clo * 8);
-    x[brev<5>(clo)] = lds64<clo * 512 * 8>(a);
-    x[brev<5>(clo + 16)] = lds64<(clo + 16) * 512 * 8>(a);
-  });
-  Dit<32, 1, true>::run(x);
+  F.inverse(x);
 }
 
 // ---- block reductions for the reward epilogue -----------------------------------------------
@@ -621,11 +402,9 @@ __global__ void __launch_bounds__(kThreads, 1) sifs128_kernel(const __grid_const
     }
   }
   __syncthreads();
-  const P1Map m1;
-  const uint32_t wbase = (uint32_t)__cvta_generic_to_shared(S.W);
-  const uint32_t nbase = p1_nat_base(wbase, m1);
+  const Fft128 F((uint32_t)__cvta_generic_to_shared(S.W), S.tw);
   float2 x[32];
-  p1_gather_nat(nbase, x);
+  p1_gather_nat(F.nb, x);
 #pragma unroll
   for (int ch = 0; ch < 4; ++ch) {
     float2 v[8];
@@ -660,7 +439,7 @@ __global__ void __launch_bounds__(kThreads, 1) sifs128_kernel(const __grid_const
     }
     __syncthreads();
     const float dt = p.dt[k];
-    spectral_filter(wbase, S.tw, S.tab, dt, m1, x);
+    spectral_filter(F, S.tab, dt, x);
     // y1 = y0 + dt * g   (solvers.py:63); y0 comes back from the parking space
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
@@ -675,7 +454,7 @@ __global__ void __launch_bounds__(kThreads, 1) sifs128_kernel(const __grid_const
     }
     park.fence_store();
     __syncthreads();  // all exchange-layout reads are done before the natural layout is rewritten
-    p1_scatter_nat(nbase, x);
+    p1_scatter_nat(F.nb, x);
     __syncthreads();
   }
 

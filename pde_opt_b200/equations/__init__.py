@@ -1,4 +1,5 @@
 from .base_eq import BaseEquation, TimeSplittingEquation
+from .gross_pitaevskii import GPE2DTSControl
 from .phase_field import AllenCahn2DPeriodic, CahnHilliard2DPeriodic
 
-__all__ = ["BaseEquation", "TimeSplittingEquation", "CahnHilliard2DPeriodic", "AllenCahn2DPeriodic"]
+__all__ = ["BaseEquation", "TimeSplittingEquation", "CahnHilliard2DPeriodic", "AllenCahn2DPeriodic", "GPE2DTSControl"]

@@ -116,6 +116,19 @@ class DiffusionLegendrePolynomials(Closure):
         return _lib(c).exp(_legendre(self.coef, 2.0 * c - 1.0))
 
 
+class GaussianLight:
+    """`lights(t, x, y)` control field of GPE2DTSControl (gross_pitaevskii.py:61,72) as a Gaussian
+    spot amp * exp(-((x-x0)^2 + (y-y0)^2) / (2 width^2)); the enumerated form the fused Strang
+    kernel evaluates."""
+
+    def __init__(self, amp, x0, y0, width):
+        self.amp, self.x0, self.y0, self.width = float(amp), float(x0), float(y0), float(width)
+
+    def __call__(self, t, x, y):
+        m = _lib(x)
+        return self.amp * m.exp(-((x - self.x0) ** 2 + (y - self.y0) ** 2) / (2.0 * self.width**2))
+
+
 _PROBE = np.array([0.07, 0.19, 0.33, 0.5, 0.61, 0.78, 0.93])
 
 

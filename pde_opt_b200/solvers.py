@@ -135,3 +135,92 @@ class SemiImplicitFourierSpectral:
                 f0 = (f0.unsqueeze(0) if single else f0).contiguous()
                 y1 = plan.filter(y1, f0, dt, sym)
         return y1[0] if single else y1
+
+
+def fold_complex_even(a):
+    """(kx>=0, ky>=0) quadrant of a complex array that is even in each wavenumber, as float32
+    [(nx/2+1)*(ny/2+1), 2]; None when the array is identically zero."""
+    a = np.asarray(a)
+    if not np.any(a):
+        return None
+    nx, ny = a.shape
+    if not (np.allclose(a[1:, :], a[1:, :][::-1, :], rtol=1e-5) and np.allclose(a[:, 1:], a[:, 1:][:, ::-1], rtol=1e-5)):
+        raise ValueError("A_term must be even in each wavenumber for the fused Strang path")
+    q = a[: nx // 2 + 1, : ny // 2 + 1].astype(np.complex64)
+    return np.ascontiguousarray(np.stack([q.real, q.imag], -1).astype(np.float32)).reshape(-1, 2)
+
+
+@dataclasses.dataclass
+class StrangSplitting:
+    """Strang split-step method with global renormalisation (solvers.py:76-125)."""
+
+    A_term: Any
+    dx: float
+    fft: Optional[Callable] = None
+    ifft: Optional[Callable] = None
+    time_scale: complex = 1.0
+
+    required_equation_attrs = ["A_term", "dx", "fft", "ifft"]  # solvers.py:84
+    term_structure = ODETerm
+    interpolation_cls = LocalLinearInterpolation
+
+    def __post_init__(self):
+        self._a_host = fold_complex_even(self.A_term)
+        self._a_dev = {}
+
+    def order(self, terms):
+        return 1
+
+    def init(self, terms, t0, t1, y0, args):
+        return None
+
+    def func(self, terms, t0, y0, args):
+        return NotImplementedError  # solvers.py:124-125 (sic)
+
+    def _a_on(self, device):
+        if self._a_host is None:
+            return None
+        key = str(device)
+        if key not in self._a_dev:
+            self._a_dev[key] = torch.from_numpy(self._a_host).to(device)
+        return self._a_dev[key]
+
+    def rollout(self, terms, times, y0, ctrl=None, out=None, **_):
+        import ctypes
+
+        from . import _lib
+
+        eq = getattr(terms, "equation", None)
+        if eq is None or not getattr(eq, "fused", False):
+            raise NotImplementedError(
+                "StrangSplitting needs ODETerm(equation) with an enumerated `lights` (none or GaussianLight)"
+            )
+        times = np.asarray(times, dtype=np.float32)
+        dts = np.ascontiguousarray((times[1:] - times[:-1]).astype(np.float32))
+        single = y0.dim() == 3
+        y = (y0.unsqueeze(0) if single else y0).contiguous()
+        assert y.is_cuda and y.dtype == torch.float32 and y.shape[-1] == 2
+        y1 = out if out is not None else torch.empty_like(y)
+        a = self._a_on(y.device)
+        c = ctrl if ctrl is not None else (eq.control_block(y.shape[0], y.device) if eq._light.amp != 0.0 else None)
+        ts = complex(self.time_scale)
+        desc = eq.gpe_desc()
+        lib = _lib.load()
+        stream = ctypes.c_void_p(torch.cuda.current_stream(y.device).cuda_stream)
+        done, src = 0, y
+        while done < len(dts):
+            k = min(_lib.MAX_FUSED_STEPS, len(dts) - done)
+            st = lib.pdeopt_strang_step_batched(
+                ctypes.byref(desc), ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(y1.data_ptr()), y.shape[0], k,
+                dts[done:].ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(a.data_ptr()) if a is not None else None,
+                float(ts.real), float(ts.imag), ctypes.c_void_p(c.data_ptr()) if c is not None else None, stream,
+            )
+            _lib.check(st)
+            src = y1
+            done += k
+        return y1[0] if single else y1
+
+    def step(self, terms, t0, t1, y0, args=None, solver_state=None, made_jump=False):
+        del solver_state, made_jump
+        y1 = self.rollout(terms, np.asarray([t0, t1], dtype=np.float32), y0)
+        return y1, None, dict(y0=y0, y1=y1), None, RESULTS.successful
