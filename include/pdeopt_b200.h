@@ -13,6 +13,9 @@
  *                                 plus the observation / reward callbacks of
  *                                 PDEEnv.step (pde_env.py:305-309) as a fused epilogue.
  *   pdeopt_sifs_step_batched_host same, host buffers in / out (H2D + D2H inside the call).
+ *   pdeopt_ad_rollout_fwd / _bwd  K fused steps of the recovered advection-diffusion equation and the
+ *                                 hand-written adjoint of the rollout (custom_vjp; replaces diffrax's
+ *                                 reverse-mode through diffeqsolve, pde_model.py:226-323).
  *   pdeopt_strang_step_batched    K fused calls of StrangSplitting.step (solvers.py:99-122) with
  *                                 GPE2DTSControl.B_terms (equations/gross_pitaevskii.py:67-75).
  *
@@ -154,6 +157,43 @@ pdeopt_status pdeopt_strang_step_batched(const pdeopt_gpe_desc* desc, const floa
                                          int32_t batch, int32_t ksteps, const float* dt_host,
                                          const float* a_term_dev, float ts_re, float ts_im, const float* ctrl_dev,
                                          void* stream);
+
+/* Advection-diffusion (recovered equation; notebooks/run_advection_diffusion.ipynb
+ * cells 0-2): du/dt = -div(v u) + D lap(u), spectral derivatives, v = p0 grad exp(-r^2/(2 p1))
+ * about a controlled centre, stepped by SemiImplicitFourierSpectral.step (solvers.py:56-70). */
+typedef struct {
+  int32_t nx, ny;
+  double lo_x, lo_y, hx, hy;
+} pdeopt_ad_desc;
+
+/* Floats in the spectral table block of an advection-diffusion rollout:
+ *   [ (nx/2+1)*(ny/2+1) ]  A * fourier_symbol quadrant (IMEX denominator, solvers.py:62)
+ *   [ (nx/2+1)*(ny/2+1) ]  D (2 pi)^2 |k|^2 quadrant = -(D * two_pi_i_k_2).real (explicit diffusion)
+ *   [ nx ] imag(two_pi_i_kx) along axis 0 with the Nyquist entry set to 0
+ *   [ ny ] imag(two_pi_i_ky) along axis 1 with the Nyquist entry set to 0 */
+int64_t pdeopt_ad_tables_len(const pdeopt_ad_desc* desc);
+
+/* K = ksteps fused IMEX steps of the advection-diffusion equation (the diffeqsolve loop body
+ * driven from pde_env.py:293-303 / pde_model.py:120-134) on `batch` environments.
+ *   ctrl_dev : [batch][nseg][4] (cx, cy, p0, p1): velocity parameters, piecewise constant over
+ *              `hold` numeric steps; local step k uses segment min((step0 + k)/hold, nseg-1)
+ *   traj_dev : NULL, or where the state at the START of local step k is saved for the adjoint:
+ *              traj_dev[k*traj_stride + b*nx*ny ...] (traj_stride in floats)                  */
+pdeopt_status pdeopt_ad_rollout_fwd(const pdeopt_ad_desc* desc, const float* y0_dev, float* y1_dev, int32_t batch,
+                                    int32_t ksteps, const float* dt_host, const float* tables_dev,
+                                    const float* ctrl_dev, int32_t nseg, int32_t hold, int32_t step0,
+                                    float* traj_dev, int64_t traj_stride, void* stream);
+
+/* Discrete adjoint of the same K steps (the hand-written custom_vjp of the rollout; replaces
+ * reverse-mode differentiation through diffeqsolve, pde_model.py:226-323):
+ *   lam1_dev  : [batch][nx][ny] cotangent of the state after the K steps
+ *   lam0_dev  : [batch][nx][ny] cotangent of the state before them (may alias lam1_dev)
+ *   gctrl_dev : [batch][nseg][4] cotangent of ctrl_dev, ACCUMULATED (+=); zero it before the
+ *               first call of a backward sweep                                                 */
+pdeopt_status pdeopt_ad_rollout_bwd(const pdeopt_ad_desc* desc, const float* traj_dev, int64_t traj_stride,
+                                    const float* lam1_dev, float* lam0_dev, int32_t batch, int32_t ksteps,
+                                    const float* dt_host, const float* tables_dev, const float* ctrl_dev,
+                                    int32_t nseg, int32_t hold, int32_t step0, float* gctrl_dev, void* stream);
 
 /* Same with HOST buffers: copies y0/ctrl/symbol in, runs, copies y1/obs/reward out, and
  * synchronises the stream before returning.  Scratch device memory is owned by the plan

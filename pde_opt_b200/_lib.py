@@ -51,6 +51,17 @@ class GpeDesc(ctypes.Structure):
     ]
 
 
+class AdDesc(ctypes.Structure):
+    _fields_ = [
+        ("nx", ctypes.c_int32),
+        ("ny", ctypes.c_int32),
+        ("lo_x", ctypes.c_double),
+        ("lo_y", ctypes.c_double),
+        ("hx", ctypes.c_double),
+        ("hy", ctypes.c_double),
+    ]
+
+
 class PdeOptError(RuntimeError):
     pass
 
@@ -68,6 +79,9 @@ EXPORTS = [
     "pdeopt_rhs_batched",
     "pdeopt_sifs_filter_batched",
     "pdeopt_strang_step_batched",
+    "pdeopt_ad_tables_len",
+    "pdeopt_ad_rollout_fwd",
+    "pdeopt_ad_rollout_bwd",
     "pdeopt_measure_fp32_peak",
     "pdeopt_launch_count",
 ]
@@ -103,6 +117,13 @@ def load():
     lib.pdeopt_sifs_filter_batched.restype = ctypes.c_int
     lib.pdeopt_strang_step_batched.argtypes = [ctypes.POINTER(GpeDesc), vp, vp, i32, i32, vp, vp, f32, f32, vp, vp]
     lib.pdeopt_strang_step_batched.restype = ctypes.c_int
+    i64 = ctypes.c_int64
+    lib.pdeopt_ad_tables_len.argtypes = [ctypes.POINTER(AdDesc)]
+    lib.pdeopt_ad_tables_len.restype = ctypes.c_int64
+    lib.pdeopt_ad_rollout_fwd.argtypes = [ctypes.POINTER(AdDesc), vp, vp, i32, i32, vp, vp, vp, i32, i32, i32, vp, i64, vp]
+    lib.pdeopt_ad_rollout_fwd.restype = ctypes.c_int
+    lib.pdeopt_ad_rollout_bwd.argtypes = [ctypes.POINTER(AdDesc), vp, i64, vp, vp, i32, i32, vp, vp, vp, i32, i32, i32, vp, vp]
+    lib.pdeopt_ad_rollout_bwd.restype = ctypes.c_int
     lib.pdeopt_measure_fp32_peak.argtypes = [ctypes.POINTER(ctypes.c_double), vp]
     lib.pdeopt_measure_fp32_peak.restype = ctypes.c_int
     lib.pdeopt_launch_count.restype = ctypes.c_int64

@@ -129,6 +129,25 @@ class GaussianLight:
         return self.amp * m.exp(-((x - self.x0) ** 2 + (y - self.y0) ** 2) / (2.0 * self.width**2))
 
 
+class GaussianVelocity:
+    """`advection(t, x, y)` of notebooks/run_advection_diffusion.ipynb cell 2: the velocity field
+    v = p0 * grad exp(-((x-cx)^2 + (y-cy)^2) / (2 p1)) about the centre (cx, cy); the enumerated
+    form the fused advection-diffusion kernels evaluate.  (cx, cy, p0, p1) is the control block
+    of one control segment."""
+
+    def __init__(self, p0, p1, centre=(0.0, 0.0)):
+        self.p0, self.p1 = float(p0), float(p1)
+        self.centre = (float(centre[0]), float(centre[1]))
+
+    def __call__(self, t, x, y):
+        m = _lib(x)
+        e = m.exp(-((x - self.centre[0]) ** 2 + (y - self.centre[1]) ** 2) / (2.0 * self.p1))
+        return self.p0 * (-(x - self.centre[0]) / self.p1 * e), self.p0 * (-(y - self.centre[1]) / self.p1 * e)
+
+    def control_row(self):
+        return (self.centre[0], self.centre[1], self.p0, self.p1)
+
+
 _PROBE = np.array([0.07, 0.19, 0.33, 0.5, 0.61, 0.78, 0.93])
 
 

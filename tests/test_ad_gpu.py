@@ -1,0 +1,145 @@
+"""Advection-diffusion: fused forward kernel vs the NumPy oracle, hand-written adjoint vs
+torch.autograd on the float64 oracle twin (BASELINE config 4; north-star tolerance 1e-4)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ad_torch_oracle as TO
+from oracle import pde_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+N, H, DCOEF = 128, 0.02, 0.1
+BOX = ((-N * H / 2, N * H / 2),) * 2
+
+
+def _eq():
+    from pde_opt_b200 import Domain
+    from pde_opt_b200.equations import AdvectionDiffusion2D
+    from pde_opt_b200.functions import GaussianVelocity
+
+    return AdvectionDiffusion2D(Domain((N, N), BOX, "dimensionless"), GaussianVelocity(0.1, 0.01), DCOEF)
+
+
+def _y0(B, seed=0):
+    return np.stack([0.5 + 0.01 * np.random.default_rng(seed + i).normal(size=(N, N)) for i in range(B)]).astype(np.float32)
+
+
+def _ctrl(B, nseg, seed=1):
+    rng = np.random.default_rng(seed)
+    c = np.empty((B, nseg, 4), np.float32)
+    c[..., 0] = rng.uniform(-0.5, 0.5, (B, nseg))
+    c[..., 1] = rng.uniform(-0.5, 0.5, (B, nseg))
+    c[..., 2] = rng.uniform(0.05, 0.2, (B, nseg))
+    c[..., 3] = rng.uniform(0.01, 0.05, (B, nseg))
+    return c
+
+
+def _oracle_rollout(y0, ctrl, dts, hold):
+    dom = O.Domain((N, N), BOX)
+    out = np.empty_like(y0)
+    for b in range(y0.shape[0]):
+        y, t = y0[b], np.float32(0)
+        for k, dt in enumerate(dts):
+            s = min(k // hold, ctrl.shape[1] - 1)
+            cx, cy, p0, p1 = (float(v) for v in ctrl[b, s])
+            eq = O.AdvectionDiffusion2D(dom, O.gaussian_velocity((p0, p1), (cx, cy)), DCOEF, np.float32)
+            y = O.sifs_step(eq.rhs, y, t, t + np.float32(dt), 1.0, eq.fourier_symbol)
+            t = t + np.float32(dt)
+        out[b] = y
+    return out
+
+
+def _rel(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b.astype(np.float64)) / np.linalg.norm(b.astype(np.float64)))
+
+
+@pytest.mark.parametrize("B,K,nseg", [(2, 1, 1), (3, 16, 4), (1, 7, 7)])
+def test_forward_matches_oracle(B, K, nseg):
+    from pde_opt_b200.adjoint import ad_rollout
+
+    eq = _eq()
+    y0, ctrl = _y0(B), _ctrl(B, nseg)
+    times = (np.arange(K + 1, dtype=np.float32) * np.float32(1e-4)).astype(np.float32)
+    dts = times[1:] - times[:-1]
+    hold = -(-K // nseg)
+    got = ad_rollout(eq, torch.from_numpy(y0).cuda(), torch.from_numpy(ctrl).cuda(), times, hold=hold).cpu().numpy()
+    want = _oracle_rollout(y0, ctrl, dts, hold)
+    assert _rel(got, want) <= 1e-5  # north star: 1e-5 after one step
+    # the increment itself (y1 - y0 is tiny next to y0, so test it separately)
+    assert _rel(got - y0, want - y0) <= 2e-3
+
+
+def test_forward_500_steps():
+    from pde_opt_b200.adjoint import ad_rollout
+
+    eq = _eq()
+    B, K, nseg = 2, 500, 10
+    y0, ctrl = _y0(B, 7), _ctrl(B, nseg, 3)
+    times = (np.arange(K + 1, dtype=np.float32) * np.float32(1e-4)).astype(np.float32)
+    got = ad_rollout(eq, torch.from_numpy(y0).cuda(), torch.from_numpy(ctrl).cuda(), times, hold=50).cpu().numpy()
+    want = _oracle_rollout(y0, ctrl, times[1:] - times[:-1], 50)
+    assert _rel(got, want) <= 1e-3  # north star: 1e-3 after 1000 steps
+    assert _rel(got - y0, want - y0) <= 5e-3
+
+
+def test_rhs_matches_oracle():
+    eq = _eq()
+    y0 = _y0(2, 11)
+    f = eq.rhs(torch.from_numpy(y0).cuda()).cpu().numpy()
+    dom = O.Domain((N, N), BOX)
+    oeq = O.AdvectionDiffusion2D(dom, O.gaussian_velocity((0.1, 0.01), (0.0, 0.0)), DCOEF, np.float64)
+    for b in range(2):
+        want = oeq.rhs(y0[b].astype(np.float64))
+        assert _rel(f[b], want) <= 5e-3  # (y1-y0)/dt in float32: cancellation-limited
+
+
+@pytest.mark.parametrize("checkpoint_every", [None, 8])
+def test_adjoint_matches_autograd(checkpoint_every):
+    from pde_opt_b200.adjoint import ad_rollout
+
+    eq = _eq()
+    B, K, nseg = 3, 24, 3
+    y0, ctrl = _y0(B, 21), _ctrl(B, nseg, 5)
+    times = (np.arange(K + 1, dtype=np.float32) * np.float32(1e-4)).astype(np.float32)
+    dts = (times[1:] - times[:-1]).astype(np.float64)
+    wgt = np.random.default_rng(9).normal(size=(B, N, N)).astype(np.float32)
+
+    yg = torch.from_numpy(y0).cuda().requires_grad_(True)
+    cg = torch.from_numpy(ctrl).cuda().requires_grad_(True)
+    yT = ad_rollout(eq, yg, cg, times, hold=8, checkpoint_every=checkpoint_every)
+    loss = (yT * torch.from_numpy(wgt).cuda()).sum() + 0.5 * (yT**2).mean()
+    loss.backward()
+
+    yr = torch.from_numpy(y0.astype(np.float64)).requires_grad_(True)
+    cr = torch.from_numpy(ctrl.astype(np.float64)).requires_grad_(True)
+    yTr = TO.rollout(yr, cr, dts, (N, N), BOX, DCOEF, 1.0, hold=8)
+    lr = (yTr * torch.from_numpy(wgt.astype(np.float64))).sum() + 0.5 * (yTr**2).mean()
+    lr.backward()
+
+    assert abs(loss.item() - lr.item()) <= 1e-5 * abs(lr.item())
+    assert _rel(yg.grad.cpu().numpy(), yr.grad.numpy()) <= 1e-4
+    gc, gr = cg.grad.cpu().numpy(), cr.grad.numpy()
+    for j, name in enumerate(("cx", "cy", "p0", "p1")):
+        assert _rel(gc[..., j], gr[..., j]) <= 1e-4, name
+
+
+def test_adjoint_mean_square_loss_long():
+    """SURVEY C4 loss (mean u^2 at T) over a longer rollout crossing the 512-step launch limit."""
+    from pde_opt_b200.adjoint import ad_rollout
+
+    eq = _eq()
+    B, K, nseg = 2, 600, 6
+    y0, ctrl = _y0(B, 31), _ctrl(B, nseg, 8)
+    times = (np.arange(K + 1, dtype=np.float32) * np.float32(1e-4)).astype(np.float32)
+    dts = (times[1:] - times[:-1]).astype(np.float64)
+    yg = torch.from_numpy(y0).cuda().requires_grad_(True)
+    cg = torch.from_numpy(ctrl).cuda().requires_grad_(True)
+    loss = (ad_rollout(eq, yg, cg, times, hold=100) ** 2).mean()
+    loss.backward()
+    yr = torch.from_numpy(y0.astype(np.float64)).requires_grad_(True)
+    cr = torch.from_numpy(ctrl.astype(np.float64)).requires_grad_(True)
+    lr = (TO.rollout(yr, cr, dts, (N, N), BOX, DCOEF, 1.0, hold=100) ** 2).mean()
+    lr.backward()
+    assert _rel(yg.grad.cpu().numpy(), yr.grad.numpy()) <= 1e-4
+    assert _rel(cg.grad.cpu().numpy(), cr.grad.numpy()) <= 1e-3  # float32 sums over 600 steps

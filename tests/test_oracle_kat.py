@@ -160,3 +160,42 @@ def test_saveat_interpolation_endpoints():
     y0 = np.zeros((4,), np.float64)
     ys = O.integrate(lambda y, a, b: y + (b - a), y0, 0.0, 1.0, 0.3, save_ts=[0.0, 0.45, 1.0])
     np.testing.assert_allclose(ys[:, 0], [0.0, 0.45, 1.0], atol=1e-12)
+
+
+def test_torch_gradient_oracle_matches_numpy_oracle_and_finite_differences():
+    """The torch float64 twin used as the gradient oracle (stand-in for jax.grad) reproduces the
+    NumPy oracle's forward rollout and its autograd gradients agree with central differences."""
+    import torch
+
+    from oracle import ad_torch_oracle as TO
+
+    n, h, D = 32, 0.04, 0.1
+    box = ((-n * h / 2, n * h / 2),) * 2
+    rng = np.random.default_rng(0)
+    y0 = 0.5 + 0.01 * rng.normal(size=(1, n, n))
+    ctrl = np.array([[[0.1, -0.2, 0.1, 0.02], [-0.1, 0.15, 0.15, 0.03]]])
+    dts = np.full(6, 1e-3)
+    dom = O.Domain((n, n), box)
+    y = y0[0]
+    for k, dt in enumerate(dts):
+        cx, cy, p0, p1 = ctrl[0, min(k // 3, 1)]
+        eq = O.AdvectionDiffusion2D(dom, O.gaussian_velocity((p0, p1), (cx, cy)), D, np.float64)
+        y = O.sifs_step(eq.rhs, y, 0.0, dt, 1.0, eq.fourier_symbol)
+    yt = torch.from_numpy(y0).requires_grad_(True)
+    ct = torch.from_numpy(ctrl).requires_grad_(True)
+    out = TO.rollout(yt, ct, dts, (n, n), box, D, 1.0, hold=3)
+    assert np.allclose(out.detach().numpy()[0], y, rtol=1e-12, atol=1e-14)
+    loss = (out**2).mean()
+    loss.backward()
+
+    def f(c):
+        with torch.no_grad():
+            return float((TO.rollout(torch.from_numpy(y0), torch.from_numpy(c), dts, (n, n), box, D, 1.0, hold=3) ** 2).mean())
+
+    for idx in [(0, 0, 0), (0, 1, 1), (0, 0, 2), (0, 1, 3)]:
+        eps = 1e-6
+        cp, cm = ctrl.copy(), ctrl.copy()
+        cp[idx] += eps
+        cm[idx] -= eps
+        fd = (f(cp) - f(cm)) / (2 * eps)
+        assert abs(fd - float(ct.grad[idx])) <= 1e-5 * max(abs(fd), 1e-12) + 1e-14
