@@ -195,6 +195,78 @@ pdeopt_status pdeopt_ad_rollout_bwd(const pdeopt_ad_desc* desc, const float* tra
                                     const float* dt_host, const float* tables_dev, const float* ctrl_dev,
                                     int32_t nseg, int32_t hold, int32_t step0, float* gctrl_dev, void* stream);
 
+/* ---- line-FFT engine (replaces jnp.fft.fftn / ifftn for fields that do not fit one SM; call sites
+ * cahn_hilliard.py:156-157, gross_pitaevskii.py:58-59, solvers.py:63,:107-114) ------------------ */
+
+/* Addressing of a batch of lines, strides in ELEMENTS of the addressed array:
+ *   offset(line, idx) = (line / n_inner) * outer + (line % n_inner) * inner
+ *                     + (idx / chunk) * hi + (idx % chunk) * lo
+ * chunk == n gives plain strided lines; chunk < n is the packed layout of the slab all-to-all. */
+typedef struct {
+  int64_t n_lines, n_inner, outer, inner;
+  int32_t chunk, reserved;
+  int64_t hi, lo;
+} pdeopt_line_geom;
+
+/* Frequency index held at storage position `pos` after a forward transform of length n (the
+ * transforms leave spectra in digit-reversed position order; -1 on bad arguments). */
+int32_t pdeopt_fft_pos_to_freq(int32_t n, int32_t pos);
+
+/* n-point transforms (n a power of two in [8, 512]) of gin->n_lines lines: forward (natural in,
+ * position order out) or inverse (position order in, natural out, unnormalised), times `scale`.
+ * in_dev is complex64, or float32 when in_real != 0; out_dev is complex64.  May run in place. */
+pdeopt_status pdeopt_fft_lines(const void* in_dev, void* out_dev, int32_t n, const pdeopt_line_geom* gin,
+                               const pdeopt_line_geom* gout, int32_t inverse, int32_t in_real, float scale, void* stream);
+
+/* Forward transform, multiply by scale / (1 + dt * sym), inverse transform, along one axis in one
+ * pass (solvers.py:62-63 on the last-transformed axis).  sym_dev: float32 A*fourier_symbol in
+ * position order, addressed by gsym like the data by g. */
+pdeopt_status pdeopt_fft_lines_imex(const void* in_dev, void* out_dev, int32_t n, const pdeopt_line_geom* g,
+                                    const float* sym_dev, const pdeopt_line_geom* gsym, float dt, float scale,
+                                    void* stream);
+
+/* Inverse transform of the last axis fused with the update y1 = y0 + dt * Re(.) (solvers.py:63). */
+pdeopt_status pdeopt_fft_lines_inv_update(const void* spec_dev, int32_t n, const pdeopt_line_geom* gin,
+                                          const float* y0_dev, float* y1_dev, const pdeopt_line_geom* gout, float dt,
+                                          void* stream);
+
+/* ---- CahnHilliard3DPeriodic (cahn_hilliard.py:112-200) ---------------------------------------- */
+typedef struct {
+  int32_t nx, ny, nz; /* nx = planes held by this rank in slab mode */
+  double hx, hy, hz, kappa;
+  int32_t mu_family, mu_ncoef;
+  double mu_coef[PDEOPT_MAX_COEF];
+  int32_t mob_family, mob_ncoef;
+  double mob_coef[PDEOPT_MAX_COEF];
+} pdeopt_ch3d_desc;
+
+/* rhs_fd (cahn_hilliard.py:177-200) of `batch` periodic 3-D fields u_dev [batch][nx][ny][nz] ->
+ * f_dev.  Slab mode (batch == 1): halo_lo_dev [2][ny][nz] = planes x = -2, -1 and halo_hi_dev
+ * [2][ny][nz] = planes nx, nx+1 of the neighbouring ranks; NULL = periodic on this rank.
+ * mu_work_dev: scratch [batch][nx+2][ny][nz]. */
+pdeopt_status pdeopt_ch3d_rhs(const pdeopt_ch3d_desc* desc, const float* u_dev, const float* halo_lo_dev,
+                              const float* halo_hi_dev, float* mu_work_dev, float* f_dev, int32_t batch, void* stream);
+
+int64_t pdeopt_ch3d_work_floats(const pdeopt_ch3d_desc* desc, int32_t batch);
+
+/* ksteps calls of SemiImplicitFourierSpectral.step (solvers.py:56-70) with
+ * CahnHilliard3DPeriodic.rhs_fd on `batch` whole domains (single GPU).  symbol_pos_dev: float32
+ * [nx][ny][nz] A*fourier_symbol in position order on every axis; work_dev: pdeopt_ch3d_work_floats. */
+pdeopt_status pdeopt_ch3d_step(const pdeopt_ch3d_desc* desc, const float* y0_dev, float* y1_dev, int32_t batch,
+                               int32_t ksteps, const float* dt_host, const float* symbol_pos_dev, float* work_dev,
+                               void* stream);
+
+/* ---- StrangSplitting.step on grids that do not fit one SM (256x256 complex64; any nx, ny powers of
+ * two in [32, 512]): multi-kernel path on the line-FFT engine, state resident in L2.
+ *   a_term_full_dev : [nx][ny][2] complex A_term in natural (fftfreq) order, or NULL when it is
+ *                     identically zero (gross_pitaevskii.py:62)
+ *   work_dev        : pdeopt_strang_lines_work_floats(nx, ny, batch) floats of scratch        */
+int64_t pdeopt_strang_lines_work_floats(int32_t nx, int32_t ny, int32_t batch);
+pdeopt_status pdeopt_strang_lines_step_batched(const pdeopt_gpe_desc* desc, const float* y0_dev, float* y1_dev,
+                                               int32_t batch, int32_t ksteps, const float* dt_host,
+                                               const float* a_term_full_dev, float ts_re, float ts_im,
+                                               const float* ctrl_dev, float* work_dev, void* stream);
+
 /* Same with HOST buffers: copies y0/ctrl/symbol in, runs, copies y1/obs/reward out, and
  * synchronises the stream before returning.  Scratch device memory is owned by the plan
  * (grown on first use, reused afterwards). */

@@ -62,6 +62,39 @@ class AdDesc(ctypes.Structure):
     ]
 
 
+class LineGeom(ctypes.Structure):
+    """pdeopt_line_geom: offset(line, idx) = (line // n_inner)*outer + (line % n_inner)*inner
+    + (idx // chunk)*hi + (idx % chunk)*lo, in elements."""
+    _fields_ = [
+        ("n_lines", ctypes.c_int64),
+        ("n_inner", ctypes.c_int64),
+        ("outer", ctypes.c_int64),
+        ("inner", ctypes.c_int64),
+        ("chunk", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("hi", ctypes.c_int64),
+        ("lo", ctypes.c_int64),
+    ]
+
+
+class Ch3dDesc(ctypes.Structure):
+    _fields_ = [
+        ("nx", ctypes.c_int32),
+        ("ny", ctypes.c_int32),
+        ("nz", ctypes.c_int32),
+        ("hx", ctypes.c_double),
+        ("hy", ctypes.c_double),
+        ("hz", ctypes.c_double),
+        ("kappa", ctypes.c_double),
+        ("mu_family", ctypes.c_int32),
+        ("mu_ncoef", ctypes.c_int32),
+        ("mu_coef", ctypes.c_double * MAX_COEF),
+        ("mob_family", ctypes.c_int32),
+        ("mob_ncoef", ctypes.c_int32),
+        ("mob_coef", ctypes.c_double * MAX_COEF),
+    ]
+
+
 class PdeOptError(RuntimeError):
     pass
 
@@ -82,6 +115,15 @@ EXPORTS = [
     "pdeopt_ad_tables_len",
     "pdeopt_ad_rollout_fwd",
     "pdeopt_ad_rollout_bwd",
+    "pdeopt_fft_pos_to_freq",
+    "pdeopt_fft_lines",
+    "pdeopt_fft_lines_imex",
+    "pdeopt_fft_lines_inv_update",
+    "pdeopt_ch3d_rhs",
+    "pdeopt_ch3d_work_floats",
+    "pdeopt_ch3d_step",
+    "pdeopt_strang_lines_work_floats",
+    "pdeopt_strang_lines_step_batched",
     "pdeopt_measure_fp32_peak",
     "pdeopt_launch_count",
 ]
@@ -124,6 +166,26 @@ def load():
     lib.pdeopt_ad_rollout_fwd.restype = ctypes.c_int
     lib.pdeopt_ad_rollout_bwd.argtypes = [ctypes.POINTER(AdDesc), vp, i64, vp, vp, i32, i32, vp, vp, vp, i32, i32, i32, vp, vp]
     lib.pdeopt_ad_rollout_bwd.restype = ctypes.c_int
+    gp = ctypes.POINTER(LineGeom)
+    lib.pdeopt_fft_pos_to_freq.argtypes = [i32, i32]
+    lib.pdeopt_fft_pos_to_freq.restype = ctypes.c_int32
+    lib.pdeopt_fft_lines.argtypes = [vp, vp, i32, gp, gp, i32, i32, f32, vp]
+    lib.pdeopt_fft_lines.restype = ctypes.c_int
+    lib.pdeopt_fft_lines_imex.argtypes = [vp, vp, i32, gp, vp, gp, f32, f32, vp]
+    lib.pdeopt_fft_lines_imex.restype = ctypes.c_int
+    lib.pdeopt_fft_lines_inv_update.argtypes = [vp, i32, gp, vp, vp, gp, f32, vp]
+    lib.pdeopt_fft_lines_inv_update.restype = ctypes.c_int
+    c3 = ctypes.POINTER(Ch3dDesc)
+    lib.pdeopt_ch3d_rhs.argtypes = [c3, vp, vp, vp, vp, vp, i32, vp]
+    lib.pdeopt_ch3d_rhs.restype = ctypes.c_int
+    lib.pdeopt_ch3d_work_floats.argtypes = [c3, i32]
+    lib.pdeopt_ch3d_work_floats.restype = ctypes.c_int64
+    lib.pdeopt_ch3d_step.argtypes = [c3, vp, vp, i32, i32, vp, vp, vp, vp]
+    lib.pdeopt_ch3d_step.restype = ctypes.c_int
+    lib.pdeopt_strang_lines_work_floats.argtypes = [i32, i32, i32]
+    lib.pdeopt_strang_lines_work_floats.restype = ctypes.c_int64
+    lib.pdeopt_strang_lines_step_batched.argtypes = [ctypes.POINTER(GpeDesc), vp, vp, i32, i32, vp, vp, f32, f32, vp, vp, vp]
+    lib.pdeopt_strang_lines_step_batched.restype = ctypes.c_int
     lib.pdeopt_measure_fp32_peak.argtypes = [ctypes.POINTER(ctypes.c_double), vp]
     lib.pdeopt_measure_fp32_peak.restype = ctypes.c_int
     lib.pdeopt_launch_count.restype = ctypes.c_int64

@@ -1,0 +1,97 @@
+// C ABI: advection-diffusion rollout and adjoint (see include/pdeopt_b200.h).
+#include "capi_common.h"
+#include "ad128.cuh"
+using namespace pdeopt;
+
+// ---- advection-diffusion rollout and its adjoint ------------------------------------------------
+static pdeopt_status ad_fill(AdParams& p, const pdeopt_ad_desc* desc, int32_t batch, int32_t ksteps,
+                             const float* dt_host, const float* tables_dev, const float* ctrl_dev, int32_t nseg,
+                             int32_t hold, int32_t step0) {
+  if (!desc || !dt_host || !tables_dev || !ctrl_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
+  if (desc->nx != 128 || desc->ny != 128)
+    return fail(PDEOPT_ERR_UNSUPPORTED, "advection-diffusion: only 128x128 grids are implemented");
+  if (batch <= 0) return fail(PDEOPT_ERR_INVALID, "batch must be positive");
+  if (ksteps <= 0 || ksteps > PDEOPT_MAX_FUSED_STEPS) return fail(PDEOPT_ERR_INVALID, "ksteps must be in [1, 512]");
+  if (nseg <= 0 || hold <= 0 || step0 < 0) return fail(PDEOPT_ERR_INVALID, "bad control segmentation");
+  if (!(desc->hx > 0) || !(desc->hy > 0)) return fail(PDEOPT_ERR_INVALID, "grid spacing must be positive");
+  std::memset(&p, 0, sizeof(p));
+  p.batch = batch;
+  p.ksteps = ksteps;
+  p.tabA = tables_dev;
+  p.tabL = tables_dev + kTabLen;
+  p.kx = tables_dev + 2 * kTabLen;
+  p.ky = tables_dev + 2 * kTabLen + kN;
+  p.ctrl = ctrl_dev;
+  p.nseg = nseg;
+  p.hold = hold;
+  p.step0 = step0;
+  p.lo_x = (float)desc->lo_x;
+  p.lo_y = (float)desc->lo_y;
+  p.hx = (float)desc->hx;
+  p.hy = (float)desc->hy;
+  for (int k = 0; k < ksteps; ++k) p.dt[k] = dt_host[k];
+  return PDEOPT_OK;
+}
+
+extern "C" int64_t pdeopt_ad_tables_len(const pdeopt_ad_desc* desc) {
+  if (!desc) return 0;
+  return 2 * (int64_t)(desc->nx / 2 + 1) * (desc->ny / 2 + 1) + desc->nx + desc->ny;
+}
+
+extern "C" pdeopt_status pdeopt_ad_rollout_fwd(const pdeopt_ad_desc* desc, const float* y0_dev, float* y1_dev,
+                                               int32_t batch, int32_t ksteps, const float* dt_host,
+                                               const float* tables_dev, const float* ctrl_dev, int32_t nseg,
+                                               int32_t hold, int32_t step0, float* traj_dev, int64_t traj_stride,
+                                               void* stream) {
+  if (!y0_dev || !y1_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
+#ifdef PDEOPT_PARK_GLOBAL
+  return fail(PDEOPT_ERR_UNSUPPORTED, "advection-diffusion: PDEOPT_PARK_GLOBAL builds are not supported");
+#endif
+  AdParams p;
+  pdeopt_status s = ad_fill(p, desc, batch, ksteps, dt_host, tables_dev, ctrl_dev, nseg, hold, step0);
+  if (s != PDEOPT_OK) return s;
+  p.y0 = y0_dev;
+  p.y1 = y1_dev;
+  p.traj = traj_dev;
+  p.traj_stride = traj_stride;
+  static bool attr = false;
+  if (!attr) {
+    CUDA_TRY(cudaFuncSetAttribute(ad128_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AdSmem)));
+    attr = true;
+  }
+  ad128_fwd_kernel<<<(batch + 1) / 2, kThreads, sizeof(AdSmem), (cudaStream_t)stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+  g_launches.fetch_add(1);
+  return PDEOPT_OK;
+}
+
+extern "C" pdeopt_status pdeopt_ad_rollout_bwd(const pdeopt_ad_desc* desc, const float* traj_dev, int64_t traj_stride,
+                                               const float* lam1_dev, float* lam0_dev, int32_t batch, int32_t ksteps,
+                                               const float* dt_host, const float* tables_dev, const float* ctrl_dev,
+                                               int32_t nseg, int32_t hold, int32_t step0, float* gctrl_dev,
+                                               void* stream) {
+  if (!traj_dev || !lam1_dev || !lam0_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
+#ifdef PDEOPT_PARK_GLOBAL
+  return fail(PDEOPT_ERR_UNSUPPORTED, "advection-diffusion: PDEOPT_PARK_GLOBAL builds are not supported");
+#endif
+  AdParams p;
+  pdeopt_status s = ad_fill(p, desc, batch, ksteps, dt_host, tables_dev, ctrl_dev, nseg, hold, step0);
+  if (s != PDEOPT_OK) return s;
+  p.y0 = lam1_dev;
+  p.y1 = lam0_dev;
+  p.traj_in = traj_dev;
+  p.traj_stride = traj_stride;
+  p.gctrl = gctrl_dev;
+  static bool attr = false;
+  if (!attr) {
+    CUDA_TRY(cudaFuncSetAttribute(ad128_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AdSmem)));
+    attr = true;
+  }
+  ad128_bwd_kernel<<<(batch + 1) / 2, kThreads, sizeof(AdSmem), (cudaStream_t)stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+  g_launches.fetch_add(1);
+  return PDEOPT_OK;
+}
+

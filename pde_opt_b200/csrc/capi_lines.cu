@@ -1,0 +1,246 @@
+// C ABI: line-FFT engine, 3-D Cahn-Hilliard, Strang on large grids (see include/pdeopt_b200.h).
+#include "capi_common.h"
+#include "linefft.cuh"
+#include "ch3d.cuh"
+#include "strang_lines.cuh"
+using namespace pdeopt;
+
+// ---- line-FFT engine, 3-D Cahn-Hilliard, Strang on large grids ---------------------------------
+static LineGeom to_geom(const pdeopt_line_geom* g) {
+  LineGeom r;
+  r.n_lines = g->n_lines;
+  r.n_inner = g->n_inner;
+  r.outer = g->outer;
+  r.inner = g->inner;
+  r.chunk = g->chunk;
+  r.hi = g->hi;
+  r.lo = g->lo;
+  return r;
+}
+static bool geom_ok(const pdeopt_line_geom* g, int n) {
+  return g && g->n_lines > 0 && g->n_inner > 0 && g->chunk > 0 && g->chunk <= n && n % g->chunk == 0;
+}
+static bool lf_size_ok(int n) { return n >= 8 && n <= 512 && (n & (n - 1)) == 0; }
+
+extern "C" int32_t pdeopt_fft_pos_to_freq(int32_t n, int32_t pos) {
+  if (!lf_size_ok(n) || pos < 0 || pos >= n) return -1;
+  return line_pos_to_freq(n, pos);
+}
+
+template <int MODE, bool CONTIG, class L, class M, class S>
+static cudaError_t lf_run(int n, long long n_lines, L ld, M mid, S st, cudaStream_t stream) {
+  PDEOPT_LF_DISPATCH(n, return (lf_launch<LFN, MODE, CONTIG>(n_lines, ld, mid, st, stream)));
+  return cudaSuccess;
+}
+
+extern "C" pdeopt_status pdeopt_fft_lines(const void* in_dev, void* out_dev, int32_t n, const pdeopt_line_geom* gin,
+                                          const pdeopt_line_geom* gout, int32_t inverse, int32_t in_real, float scale,
+                                          void* stream) {
+  if (!in_dev || !out_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
+  if (!lf_size_ok(n)) return fail(PDEOPT_ERR_UNSUPPORTED, "fft_lines: n must be a power of two in [8, 512]");
+  if (!geom_ok(gin, n) || !geom_ok(gout, n) || gin->n_lines != gout->n_lines) return fail(PDEOPT_ERR_INVALID, "bad line geometry");
+  const LineGeom gi = to_geom(gin), go = to_geom(gout);
+  const bool contig = gi.lo == 1 && go.lo == 1 && gi.chunk == n && go.chunk == n;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  LfStoreCScaled sto{(float2*)out_dev, go, scale};
+#define PDEOPT_RUN(MODE, LOADER)                                                                   \
+  e = contig ? lf_run<MODE, true>(n, gi.n_lines, LOADER, LfMidNone{}, sto, st)                     \
+             : lf_run<MODE, false>(n, gi.n_lines, LOADER, LfMidNone{}, sto, st)
+  if (in_real) {
+    LfLoadReal ld{(const float*)in_dev, gi};
+    if (inverse) { PDEOPT_RUN(LF_INV, ld); } else { PDEOPT_RUN(LF_FWD, ld); }
+  } else {
+    LfLoadC ld{(const float2*)in_dev, gi};
+    if (inverse) { PDEOPT_RUN(LF_INV, ld); } else { PDEOPT_RUN(LF_FWD, ld); }
+  }
+#undef PDEOPT_RUN
+  if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("fft_lines: ") + cudaGetErrorString(e));
+  g_launches.fetch_add(1);
+  return PDEOPT_OK;
+}
+
+extern "C" pdeopt_status pdeopt_fft_lines_imex(const void* in_dev, void* out_dev, int32_t n, const pdeopt_line_geom* g,
+                                               const float* sym_dev, const pdeopt_line_geom* gsym, float dt, float scale,
+                                               void* stream) {
+  if (!in_dev || !out_dev || !sym_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
+  if (!lf_size_ok(n)) return fail(PDEOPT_ERR_UNSUPPORTED, "fft_lines: n must be a power of two in [8, 512]");
+  if (!geom_ok(g, n) || !geom_ok(gsym, n)) return fail(PDEOPT_ERR_INVALID, "bad line geometry");
+  const LineGeom gg = to_geom(g);
+  LfLoadC ld{(const float2*)in_dev, gg};
+  LfMidImex mid{sym_dev, to_geom(gsym), dt, scale};
+  LfStoreC sto{(float2*)out_dev, gg};
+  cudaError_t e = (gg.lo == 1 && gg.chunk == n) ? lf_run<LF_FWD_MUL_INV, true>(n, gg.n_lines, ld, mid, sto, (cudaStream_t)stream)
+                                                : lf_run<LF_FWD_MUL_INV, false>(n, gg.n_lines, ld, mid, sto, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("fft_lines_imex: ") + cudaGetErrorString(e));
+  g_launches.fetch_add(1);
+  return PDEOPT_OK;
+}
+
+extern "C" pdeopt_status pdeopt_fft_lines_inv_update(const void* spec_dev, int32_t n, const pdeopt_line_geom* gin,
+                                                     const float* y0_dev, float* y1_dev, const pdeopt_line_geom* gout,
+                                                     float dt, void* stream) {
+  if (!spec_dev || !y0_dev || !y1_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
+  if (!lf_size_ok(n)) return fail(PDEOPT_ERR_UNSUPPORTED, "fft_lines: n must be a power of two in [8, 512]");
+  if (!geom_ok(gin, n) || !geom_ok(gout, n) || gin->n_lines != gout->n_lines) return fail(PDEOPT_ERR_INVALID, "bad line geometry");
+  const LineGeom gi = to_geom(gin), go = to_geom(gout);
+  LfLoadC ld{(const float2*)spec_dev, gi};
+  LfStoreUpdate sto{y0_dev, y1_dev, go, dt};
+  const bool contig = gi.lo == 1 && go.lo == 1 && gi.chunk == n && go.chunk == n;
+  cudaError_t e = contig ? lf_run<LF_INV, true>(n, gi.n_lines, ld, LfMidNone{}, sto, (cudaStream_t)stream)
+                         : lf_run<LF_INV, false>(n, gi.n_lines, ld, LfMidNone{}, sto, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("fft_lines_inv_update: ") + cudaGetErrorString(e));
+  g_launches.fetch_add(1);
+  return PDEOPT_OK;
+}
+
+static pdeopt_status ch3d_check(const pdeopt_ch3d_desc* d, int32_t batch) {
+  if (!d) return fail(PDEOPT_ERR_INVALID, "null argument");
+  if (batch <= 0) return fail(PDEOPT_ERR_INVALID, "batch must be positive");
+  if (d->nx < 1 || d->ny < 2 || d->nz < 2) return fail(PDEOPT_ERR_INVALID, "bad grid");
+  if ((int64_t)batch * (d->nx + 2) > 65535) return fail(PDEOPT_ERR_UNSUPPORTED, "ch3d: batch * (nx + 2) must be <= 65535");
+  if (d->ny > 65535) return fail(PDEOPT_ERR_UNSUPPORTED, "ch3d: ny must be <= 65535");
+  if (!(d->hx > 0) || !(d->hy > 0) || !(d->hz > 0)) return fail(PDEOPT_ERR_INVALID, "grid spacing must be positive");
+  if (d->mu_family < 0 || d->mu_family > 3 || d->mob_family < 0 || d->mob_family > 3) return fail(PDEOPT_ERR_INVALID, "unknown closure family");
+  if (d->mu_ncoef < 0 || d->mu_ncoef > PDEOPT_MAX_COEF || d->mob_ncoef < 0 || d->mob_ncoef > PDEOPT_MAX_COEF)
+    return fail(PDEOPT_ERR_INVALID, "too many coefficients");
+  return PDEOPT_OK;
+}
+
+extern "C" pdeopt_status pdeopt_ch3d_rhs(const pdeopt_ch3d_desc* d, const float* u_dev, const float* halo_lo_dev,
+                                         const float* halo_hi_dev, float* mu_work_dev, float* f_dev, int32_t batch,
+                                         void* stream) {
+  pdeopt_status s = ch3d_check(d, batch);
+  if (s != PDEOPT_OK) return s;
+  if (!u_dev || !mu_work_dev || !f_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
+  if ((halo_lo_dev || halo_hi_dev) && batch != 1) return fail(PDEOPT_ERR_INVALID, "slab halos need batch == 1");
+  if ((halo_lo_dev == nullptr) != (halo_hi_dev == nullptr)) return fail(PDEOPT_ERR_INVALID, "give both halos or neither");
+  Ch3dParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.nx = d->nx; p.ny = d->ny; p.nz = d->nz; p.batch = batch;
+  p.u = u_dev; p.halo_lo = halo_lo_dev; p.halo_hi = halo_hi_dev; p.mu = mu_work_dev; p.f = f_dev;
+  p.inv_hx = (float)(1.0 / d->hx); p.inv_hy = (float)(1.0 / d->hy); p.inv_hz = (float)(1.0 / d->hz);
+  p.inv_hx2 = (float)(1.0 / (d->hx * d->hx)); p.inv_hy2 = (float)(1.0 / (d->hy * d->hy)); p.inv_hz2 = (float)(1.0 / (d->hz * d->hz));
+  p.kappa = (float)d->kappa;
+  p.pw.mu_family = d->mu_family; p.pw.mu_ncoef = d->mu_ncoef; p.pw.mob_family = d->mob_family; p.pw.mob_ncoef = d->mob_ncoef;
+  for (int i = 0; i < PDEOPT_MAX_COEF; ++i) { p.pw.mu_coef[i] = (float)d->mu_coef[i]; p.pw.mob_coef[i] = (float)d->mob_coef[i]; }
+  const int bx = d->nz >= 256 ? 256 : (d->nz >= 128 ? 128 : (d->nz >= 64 ? 64 : 32));
+  dim3 block(bx), g1((d->nz + bx - 1) / bx, d->ny, batch * (d->nx + 2)), g2((d->nz + bx - 1) / bx, d->ny, batch * d->nx);
+  cudaStream_t st = (cudaStream_t)stream;
+  ch3d_mu_kernel<<<g1, block, 0, st>>>(p);
+  ch3d_div_kernel<<<g2, block, 0, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("ch3d_rhs: ") + cudaGetErrorString(e));
+  g_launches.fetch_add(2);
+  return PDEOPT_OK;
+}
+
+extern "C" int64_t pdeopt_ch3d_work_floats(const pdeopt_ch3d_desc* d, int32_t batch) {
+  if (!d || batch <= 0) return 0;
+  const int64_t pl = (int64_t)d->ny * d->nz;
+  return (int64_t)batch * ((d->nx + 2) * pl + d->nx * pl + 2 * d->nx * pl);
+}
+
+extern "C" pdeopt_status pdeopt_ch3d_step(const pdeopt_ch3d_desc* d, const float* y0_dev, float* y1_dev, int32_t batch,
+                                          int32_t ksteps, const float* dt_host, const float* symbol_pos_dev,
+                                          float* work_dev, void* stream) {
+  pdeopt_status s = ch3d_check(d, batch);
+  if (s != PDEOPT_OK) return s;
+  if (!y0_dev || !y1_dev || !dt_host || !symbol_pos_dev || !work_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
+  if (ksteps <= 0) return fail(PDEOPT_ERR_INVALID, "ksteps must be positive");
+  if (!lf_size_ok(d->nx) || !lf_size_ok(d->ny) || !lf_size_ok(d->nz))
+    return fail(PDEOPT_ERR_UNSUPPORTED, "ch3d_step: nx, ny, nz must be powers of two in [8, 512]");
+  const int64_t nx = d->nx, ny = d->ny, nz = d->nz, pl = ny * nz, vol = nx * pl;
+  float* mu = work_dev;
+  float* f = mu + (int64_t)batch * (nx + 2) * pl;
+  float* W = f + (int64_t)batch * vol;  // complex [batch][nx][ny][nz]
+  pdeopt_line_geom gz{(int64_t)batch * nx * ny, 1, nz, 0, (int32_t)nz, 0, 0, 1};
+  pdeopt_line_geom gy{(int64_t)batch * nx * nz, nz, pl, 1, (int32_t)ny, 0, 0, nz};
+  pdeopt_line_geom gx{(int64_t)batch * pl, pl, vol, 1, (int32_t)nx, 0, 0, pl};
+  pdeopt_line_geom gsym = gx;
+  gsym.outer = 0;  // the symbol is shared by the batch
+  const float* src = y0_dev;
+  for (int k = 0; k < ksteps; ++k) {
+    if ((s = pdeopt_ch3d_rhs(d, src, nullptr, nullptr, mu, f, batch, stream)) != PDEOPT_OK) return s;
+    if ((s = pdeopt_fft_lines(f, W, (int32_t)nz, &gz, &gz, 0, 1, 1.0f, stream)) != PDEOPT_OK) return s;
+    if ((s = pdeopt_fft_lines(W, W, (int32_t)ny, &gy, &gy, 0, 0, 1.0f, stream)) != PDEOPT_OK) return s;
+    if ((s = pdeopt_fft_lines_imex(W, W, (int32_t)nx, &gx, symbol_pos_dev, &gsym, dt_host[k], 1.0f / (float)vol, stream)) != PDEOPT_OK) return s;
+    if ((s = pdeopt_fft_lines(W, W, (int32_t)ny, &gy, &gy, 1, 0, 1.0f, stream)) != PDEOPT_OK) return s;
+    if ((s = pdeopt_fft_lines_inv_update(W, (int32_t)nz, &gz, src, y1_dev, &gz, dt_host[k], stream)) != PDEOPT_OK) return s;
+    src = y1_dev;
+  }
+  return PDEOPT_OK;
+}
+
+extern "C" int64_t pdeopt_strang_lines_work_floats(int32_t nx, int32_t ny, int32_t batch) {
+  if (nx <= 0 || ny <= 0 || batch <= 0) return 0;
+  return 2 * (int64_t)nx * ny * batch + 2 * (int64_t)nx * ny + ((batch + 63) / 64) * 64;
+}
+
+extern "C" pdeopt_status pdeopt_strang_lines_step_batched(const pdeopt_gpe_desc* desc, const float* y0_dev, float* y1_dev,
+                                                          int32_t batch, int32_t ksteps, const float* dt_host,
+                                                          const float* a_term_full_dev, float ts_re, float ts_im,
+                                                          const float* ctrl_dev, float* work_dev, void* stream) {
+  if (!desc || !y0_dev || !y1_dev || !dt_host || !work_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
+  const int nx = desc->nx, ny = desc->ny;
+  if (!lf_size_ok(nx) || !lf_size_ok(ny) || nx < 32 || ny < 32)
+    return fail(PDEOPT_ERR_UNSUPPORTED, "strang_lines: nx, ny must be powers of two in [32, 512]");
+  if (batch <= 0) return fail(PDEOPT_ERR_INVALID, "batch must be positive");
+  if (ksteps <= 0) return fail(PDEOPT_ERR_INVALID, "ksteps must be positive");
+  if (!(desc->hx > 0) || !(desc->hy > 0)) return fail(PDEOPT_ERR_INVALID, "grid spacing must be positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t npts = (int64_t)nx * ny, total = npts * batch;
+  float2* W = (float2*)work_dev;
+  float2* etab = W + total;
+  float* norm = (float*)(etab + npts);
+  GpeLinesConst c;
+  c.nx = nx; c.ny = ny;
+  c.lo_x = (float)desc->lo_x; c.lo_y = (float)desc->lo_y; c.hx = (float)desc->hx; c.hy = (float)desc->hy;
+  c.trap = (float)desc->trap_factor; c.e = (float)desc->e; c.k_int = (float)desc->k;
+  c.ts_re = ts_re; c.ts_im = ts_im; c.ctrl = ctrl_dev;
+  const float dx2 = (float)desc->hx * (float)desc->hx;
+  const LineGeom rows{(long long)batch * nx, 1, ny, 0, ny, 0, 1};
+  const LineGeom cols{(long long)batch * ny, ny, npts, 1, nx, 0, ny};
+  const float2* src = (const float2*)y0_dev;
+  float2* dst = (float2*)y1_dev;
+  float last_dt = 0.f;
+  bool have_tab = false;
+  cudaError_t e = cudaSuccess;
+  for (int k = 0; k < ksteps && e == cudaSuccess; ++k) {
+    const float dt = dt_host[k];
+    e = cudaMemsetAsync(norm, 0, sizeof(float) * batch, st);
+    if (e != cudaSuccess) break;
+    if (a_term_full_dev == nullptr) {
+      const int bpe = (int)((npts + 16383) / 16384);
+      strang_lines_potential_kernel<<<batch * bpe, 256, 0, st>>>(src, W, norm, c, dt, bpe);
+      strang_lines_scale_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(W, dst, norm, (int)npts, dx2, total);
+      e = cudaGetLastError();
+      g_launches.fetch_add(2);
+    } else {
+      if (!have_tab || dt != last_dt) {
+        strang_lines_etab_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, st>>>((const float2*)a_term_full_dev, etab, nx, ny,
+                                                                               0.5f * dt * ts_re, 0.5f * dt * ts_im);
+        have_tab = true;
+        last_dt = dt;
+        g_launches.fetch_add(1);
+      }
+      const LfMidCTab mid{etab, ny};
+      e = lf_run<LF_FWD, true>(ny, rows.n_lines, LfLoadC{src, rows}, LfMidNone{}, LfStoreC{W, rows}, st);
+      if (e != cudaSuccess) break;
+      e = lf_run<LF_FWD_MUL_INV, false>(nx, cols.n_lines, LfLoadC{W, cols}, mid, LfStoreC{W, cols}, st);
+      if (e != cudaSuccess) break;
+      e = lf_run<LF_INV, true>(ny, rows.n_lines, LfLoadC{W, rows}, LfMidNone{}, LfStorePotential{W, src, norm, c, dt, 0.f}, st);
+      if (e != cudaSuccess) break;
+      e = lf_run<LF_FWD, true>(ny, rows.n_lines, LfLoadNormalised{W, norm, nx, ny, dx2}, LfMidNone{}, LfStoreC{W, rows}, st);
+      if (e != cudaSuccess) break;
+      e = lf_run<LF_FWD_MUL_INV, false>(nx, cols.n_lines, LfLoadC{W, cols}, mid, LfStoreC{W, cols}, st);
+      if (e != cudaSuccess) break;
+      e = lf_run<LF_INV, true>(ny, rows.n_lines, LfLoadC{W, rows}, LfMidNone{}, LfStoreC{dst, rows}, st);
+      g_launches.fetch_add(6);
+    }
+    src = dst;
+  }
+  if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("strang_lines: ") + cudaGetErrorString(e));
+  return PDEOPT_OK;
+}
+

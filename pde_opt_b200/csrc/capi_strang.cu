@@ -1,0 +1,49 @@
+// C ABI: fused 128x128 Strang split-step (see include/pdeopt_b200.h).
+#include "capi_common.h"
+#include "strang128.cuh"
+using namespace pdeopt;
+
+extern "C" pdeopt_status pdeopt_strang_step_batched(const pdeopt_gpe_desc* desc, const float* y0_dev, float* y1_dev,
+                                                    int32_t batch, int32_t ksteps, const float* dt_host,
+                                                    const float* a_term_dev, float ts_re, float ts_im,
+                                                    const float* ctrl_dev, void* stream) {
+  if (!desc || !y0_dev || !y1_dev || !dt_host) return fail(PDEOPT_ERR_INVALID, "null argument");
+  if (desc->nx != 128 || desc->ny != 128)
+    return fail(PDEOPT_ERR_UNSUPPORTED, "strang: only 128x128 grids are implemented (256x256 needs the cluster kernel)");
+  if (batch <= 0) return fail(PDEOPT_ERR_INVALID, "batch must be positive");
+  if (ksteps <= 0 || ksteps > PDEOPT_MAX_FUSED_STEPS) return fail(PDEOPT_ERR_INVALID, "ksteps must be in [1, 512]");
+  if (!(desc->hx > 0) || !(desc->hy > 0)) return fail(PDEOPT_ERR_INVALID, "grid spacing must be positive");
+  StrangParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.y0 = y0_dev;
+  p.y1 = y1_dev;
+  p.batch = batch;
+  p.ksteps = ksteps;
+  p.a_term = a_term_dev;
+  p.ts_re = ts_re;
+  p.ts_im = ts_im;
+  p.dx = (float)desc->hx;
+  p.k_int = (float)desc->k;
+  p.e = (float)desc->e;
+  p.trap = (float)desc->trap_factor;
+  p.lo_x = (float)desc->lo_x;
+  p.lo_y = (float)desc->lo_y;
+  p.hx = (float)desc->hx;
+  p.hy = (float)desc->hy;
+  p.ctrl = ctrl_dev;
+  for (int k = 0; k < ksteps; ++k) p.dt[k] = dt_host[k];
+#ifdef PDEOPT_PARK_GLOBAL
+  return fail(PDEOPT_ERR_UNSUPPORTED, "strang: PDEOPT_PARK_GLOBAL builds are not supported");
+#endif
+  static bool attr = false;
+  if (!attr) {
+    CUDA_TRY(cudaFuncSetAttribute(strang128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StrangSmem)));
+    attr = true;
+  }
+  strang128_kernel<<<batch, kThreads, sizeof(StrangSmem), (cudaStream_t)stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+  g_launches.fetch_add(1);
+  return PDEOPT_OK;
+}
+

@@ -125,3 +125,58 @@ class AllenCahn2DPeriodic(_PhaseField2D):
     def __post_init__(self):
         self._setup("R")
         self.fourier_symbol = (-np.complex64(self.kappa) * self.two_pi_i_k_2).astype(np.complex64)
+
+
+@dataclasses.dataclass
+class CahnHilliard3DPeriodic(BaseEquation):
+    """3-D Cahn-Hilliard on a periodic box (cahn_hilliard.py:112-200): same fields and class-level
+    `fft / ifft / fourier_symbol` as the reference.  Runs on the line-FFT engine (the field does not
+    fit one SM).  `fourier_symbol` is built on first use (512^3 complex64 is 1 GB on the host)."""
+
+    domain: Domain
+    kappa: float
+    mu: Any
+    D: Any
+    derivs: str = "fd"
+    fft = None
+    ifft = None
+    _kind = "ch3d"
+
+    def __post_init__(self):
+        if self.derivs not in ("fd", "fourier"):
+            raise ValueError(f"Invalid derivative type: {self.derivs}")
+        from ..linefft import fftn, ifftn
+
+        self.fft, self.ifft = fftn, ifftn
+        self._mu_c = recognize(self.mu, "mu")
+        self._mob_c = recognize(self.D, "mob")
+        self._plan = None
+        self._symbol = None
+
+    @property
+    def fourier_symbol(self):
+        if self._symbol is None:
+            kx, ky, kz = self.domain.fft_mesh()
+            t = [(2j * np.pi * k).astype(np.complex64) for k in (kx, ky, kz)]
+            k2 = t[0] ** 2 + t[1] ** 2 + t[2] ** 2  # cahn_hilliard.py:150-154
+            self._symbol = (np.complex64(self.kappa) * k2**2).astype(np.complex64)  # :158
+        return self._symbol
+
+    @property
+    def fused(self):
+        return self._mu_c is not None and self._mob_c is not None and self.derivs == "fd"
+
+    def plan(self):
+        if self._plan is None:
+            if not self.fused:
+                raise NotImplementedError("no kernel for this 3-D equation (non-enumerated mu/D closure or derivs='fourier')")
+            from ..fused import Ch3dPlan
+
+            self._plan = Ch3dPlan(self.domain.points, self.domain.dx, self.kappa, self._mu_c.descriptor(), self._mob_c.descriptor())
+        return self._plan
+
+    def rhs(self, state, t=0.0):
+        single = state.dim() == 3
+        y = (state.unsqueeze(0) if single else state).contiguous()
+        f = self.plan().rhs(y)
+        return f[0] if single else f

@@ -125,3 +125,51 @@ class SifsPlan:
         )
         _lib.check(st)
         return y1
+
+
+class Ch3dPlan:
+    """CahnHilliard3DPeriodic on the line-FFT engine (pdeopt_ch3d_rhs / pdeopt_ch3d_step)."""
+
+    def __init__(self, points, h, kappa, mu=("double_well", ()), mob=("const", (1.0,))):
+        d = _lib.Ch3dDesc()
+        d.nx, d.ny, d.nz = (int(p) for p in points)
+        d.hx, d.hy, d.hz = (float(v) for v in h)
+        d.kappa = float(kappa)
+        d.mu_family, d.mu_ncoef = MU_FAMILIES[mu[0]], len(mu[1])
+        for i, c in enumerate(mu[1]):
+            d.mu_coef[i] = float(c)
+        d.mob_family, d.mob_ncoef = MOB_FAMILIES[mob[0]], len(mob[1])
+        for i, c in enumerate(mob[1]):
+            d.mob_coef[i] = float(c)
+        self.desc = d
+        self.points = tuple(int(p) for p in points)
+        self._work = {}
+
+    def _workbuf(self, batch, device):
+        key = (batch, str(device))
+        if key not in self._work:
+            n = int(_lib.load().pdeopt_ch3d_work_floats(ctypes.byref(self.desc), batch))
+            self._work[key] = torch.empty(n, dtype=torch.float32, device=device)
+        return self._work[key]
+
+    def rhs(self, u, halo_lo=None, halo_hi=None, out=None):
+        """rhs_fd of u [B, nx, ny, nz] (cahn_hilliard.py:177-200)."""
+        lib = _lib.load()
+        assert u.is_cuda and u.dtype == torch.float32 and u.is_contiguous() and tuple(u.shape[1:]) == self.points
+        f = out if out is not None else torch.empty_like(u)
+        work = self._workbuf(u.shape[0], u.device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(u.device).cuda_stream)
+        _lib.check(lib.pdeopt_ch3d_rhs(ctypes.byref(self.desc), _ptr(u), _ptr(halo_lo), _ptr(halo_hi), _ptr(work), _ptr(f), u.shape[0], stream))
+        return f
+
+    def step(self, y0, dts, symbol_pos, out=None):
+        """len(dts) semi-implicit steps of y0 [B, nx, ny, nz]; symbol_pos: A*symbol in position order."""
+        lib = _lib.load()
+        assert y0.is_cuda and y0.dtype == torch.float32 and y0.is_contiguous() and tuple(y0.shape[1:]) == self.points
+        assert symbol_pos.is_cuda and symbol_pos.dtype == torch.float32 and tuple(symbol_pos.shape) == self.points
+        y1 = out if out is not None else torch.empty_like(y0)
+        dts = np.ascontiguousarray(np.asarray(dts, dtype=np.float32))
+        work = self._workbuf(y0.shape[0], y0.device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(y0.device).cuda_stream)
+        _lib.check(lib.pdeopt_ch3d_step(ctypes.byref(self.desc), _ptr(y0), _ptr(y1), y0.shape[0], len(dts), _ptr(dts), _ptr(symbol_pos), _ptr(work), stream))
+        return y1

@@ -64,9 +64,35 @@ class SemiImplicitFourierSpectral:
     interpolation_cls = LocalLinearInterpolation
 
     def __post_init__(self):
-        self._quad = fold_symbol(self.fourier_symbol, self.A)
+        self._is3d = np.ndim(self.fourier_symbol) == 3
+        # 2-D: folded quadrant table for the fused kernels; 3-D: position-ordered table, built lazily
+        self._quad = None if self._is3d else fold_symbol(self.fourier_symbol, self.A)
         self._sym_dev = {}
         self._filter_plan = None
+
+    def symbol_pos_on(self, device):
+        """A * fourier_symbol as float32 in the line-FFT engine's position order (3-D path)."""
+        key = ("pos", str(device))
+        if key not in self._sym_dev:
+            from .linefft import to_position_order
+
+            s = np.asarray(self.fourier_symbol)
+            if np.iscomplexobj(s):
+                if np.abs(s.imag).max() > 1e-6 * max(1.0, np.abs(s.real).max()):
+                    raise ValueError("fourier_symbol must be real for the semi-implicit path")
+                s = s.real
+            s = (np.float32(self.A) * s.astype(np.float32)).astype(np.float32)
+            self._sym_dev[key] = torch.from_numpy(np.ascontiguousarray(to_position_order(s, (0, 1, 2)))).to(device)
+        return self._sym_dev[key]
+
+    def _rollout3d(self, terms, dts, y0, out=None):
+        eq = getattr(terms, "equation", None)
+        if eq is None or getattr(eq, "_kind", None) != "ch3d" or not eq.fused:
+            raise NotImplementedError("3-D semi-implicit stepping needs ODETerm(CahnHilliard3DPeriodic) with enumerated mu / D")
+        single = y0.dim() == 3
+        y = (y0.unsqueeze(0) if single else y0).contiguous()
+        y1 = eq.plan().step(y, dts, self.symbol_pos_on(y.device), out=out)
+        return y1[0] if single else y1
 
     def order(self, terms):
         return 1
@@ -95,6 +121,12 @@ class SemiImplicitFourierSpectral:
     def step(self, terms, t0, t1, y0, args=None, solver_state=None, made_jump=False):
         del solver_state, made_jump
         dt = np.float32(np.float32(t1) - np.float32(t0))  # solvers.py:58 in the working precision
+        if self._is3d:
+            y1 = self._rollout3d(terms, [dt], y0)
+            y_error = None
+            if self.with_error:
+                y_error = y1 - (y0 + float(dt) * terms.vf(t0, y0, args))  # solvers.py:61,65
+            return y1, y_error, dict(y0=y0, y1=y1), None, RESULTS.successful
         single = y0.dim() == 2
         y = (y0.unsqueeze(0) if single else y0).contiguous()
         plan, eq = self._plan_for(terms, tuple(y.shape[-2:]))
@@ -121,6 +153,8 @@ class SemiImplicitFourierSpectral:
         few launches as possible: the K-fused form of the diffeqsolve loop body."""
         times = np.asarray(times, dtype=np.float32)
         dts = (times[1:] - times[:-1]).astype(np.float32)
+        if self._is3d:
+            return self._rollout3d(terms, dts, y0, out=out)
         single = y0.dim() == 2
         y = (y0.unsqueeze(0) if single else y0).contiguous()
         plan, eq = self._plan_for(terms, tuple(y.shape[-2:]))
@@ -165,8 +199,16 @@ class StrangSplitting:
     interpolation_cls = LocalLinearInterpolation
 
     def __post_init__(self):
-        self._a_host = fold_complex_even(self.A_term)
+        a = np.asarray(self.A_term)
+        self._fused128 = tuple(a.shape) == (128, 128)
+        # 128x128: folded quadrant for the single-CTA kernel; other grids: full table for the line path
+        self._a_host = fold_complex_even(a) if self._fused128 else None
+        self._a_full = None
+        if not self._fused128 and np.any(a):
+            q = a.astype(np.complex64)
+            self._a_full = np.ascontiguousarray(np.stack([q.real, q.imag], -1).astype(np.float32))
         self._a_dev = {}
+        self._work = {}
 
     def order(self, terms):
         return 1
@@ -207,6 +249,26 @@ class StrangSplitting:
         desc = eq.gpe_desc()
         lib = _lib.load()
         stream = ctypes.c_void_p(torch.cuda.current_stream(y.device).cuda_stream)
+        if not self._fused128:
+            # grids that do not fit one SM (256x256 complex64, BASELINE config 3): line-FFT path
+            nx, ny = int(y.shape[1]), int(y.shape[2])
+            key = (nx, ny, y.shape[0], str(y.device))
+            if key not in self._work:
+                n = int(lib.pdeopt_strang_lines_work_floats(nx, ny, y.shape[0]))
+                self._work[key] = torch.empty(n, dtype=torch.float32, device=y.device)
+            af = None
+            if self._a_full is not None:
+                if ("full", str(y.device)) not in self._a_dev:
+                    self._a_dev[("full", str(y.device))] = torch.from_numpy(self._a_full).to(y.device)
+                af = self._a_dev[("full", str(y.device))]
+            st = lib.pdeopt_strang_lines_step_batched(
+                ctypes.byref(desc), ctypes.c_void_p(y.data_ptr()), ctypes.c_void_p(y1.data_ptr()), y.shape[0], len(dts),
+                dts.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(af.data_ptr()) if af is not None else None,
+                float(ts.real), float(ts.imag), ctypes.c_void_p(c.data_ptr()) if c is not None else None,
+                ctypes.c_void_p(self._work[key].data_ptr()), stream,
+            )
+            _lib.check(st)
+            return y1[0] if single else y1
         done, src = 0, y
         while done < len(dts):
             k = min(_lib.MAX_FUSED_STEPS, len(dts) - done)
