@@ -224,14 +224,16 @@ extern "C" pdeopt_status pdeopt_strang_lines_step_batched(const pdeopt_gpe_desc*
         last_dt = dt;
         g_launches.fetch_add(1);
       }
-      const LfMidCTab mid{etab, ny};
+      LineGeom ctab = cols;
+      ctab.outer = 0;
+      const LfMidCTab mid{etab, ctab};
       e = lf_run<LF_FWD, true>(ny, rows.n_lines, LfLoadC{src, rows}, LfMidNone{}, LfStoreC{W, rows}, st);
       if (e != cudaSuccess) break;
       e = lf_run<LF_FWD_MUL_INV, false>(nx, cols.n_lines, LfLoadC{W, cols}, mid, LfStoreC{W, cols}, st);
       if (e != cudaSuccess) break;
-      e = lf_run<LF_INV, true>(ny, rows.n_lines, LfLoadC{W, rows}, LfMidNone{}, LfStorePotential{W, src, norm, c, dt, 0.f}, st);
+      e = lf_run<LF_INV, true>(ny, rows.n_lines, LfLoadC{W, rows}, LfMidNone{}, LfStorePotential{W, src, norm, c, dt, 0.f, rows}, st);
       if (e != cudaSuccess) break;
-      e = lf_run<LF_FWD, true>(ny, rows.n_lines, LfLoadNormalised{W, norm, nx, ny, dx2}, LfMidNone{}, LfStoreC{W, rows}, st);
+      e = lf_run<LF_FWD, true>(ny, rows.n_lines, LfLoadNormalised{W, norm, nx, ny, dx2, rows}, LfMidNone{}, LfStoreC{W, rows}, st);
       if (e != cudaSuccess) break;
       e = lf_run<LF_FWD_MUL_INV, false>(nx, cols.n_lines, LfLoadC{W, cols}, mid, LfStoreC{W, cols}, st);
       if (e != cudaSuccess) break;

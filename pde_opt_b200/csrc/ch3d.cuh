@@ -89,15 +89,17 @@ __global__ void __launch_bounds__(256) ch3d_div_kernel(const __grid_constant__ C
 struct LfLoadReal {  // real array -> complex with zero imaginary part
   const float* p;
   LineGeom g;
-  __device__ __forceinline__ float2 load(long long line, int idx) const { return make_float2(p[g.off(line, idx)], 0.f); }
+  __device__ __forceinline__ LineGeom gin() const { return g; }
+  __device__ __forceinline__ float2 load(long long off, long long, int) const { return make_float2(p[off], 0.f); }
 };
 // multiplier scale / (1 + dt * symbol) with the (A-folded, position-ordered) symbol laid out like the data
 struct LfMidImex {
   const float* sym;
   LineGeom g;
   float dt, scale;
-  __device__ __forceinline__ float2 apply(float2 v, long long line, int pos) const {
-    const float m = __fdividef(scale, fmaf(dt, sym[g.off(line, pos)], 1.0f));
+  __device__ __forceinline__ LineGeom gaux() const { return g; }
+  __device__ __forceinline__ float2 apply(float2 v, long long off_aux, long long, int) const {
+    const float m = __fdividef(scale, fmaf(dt, sym[off_aux], 1.0f));
     return make_float2(v.x * m, v.y * m);
   }
 };
@@ -107,10 +109,8 @@ struct LfStoreUpdate {
   float* y1;
   LineGeom g;
   float dt;
-  __device__ __forceinline__ void store(long long line, int idx, float2 v) const {
-    const long long o = g.off(line, idx);
-    y1[o] = fmaf(dt, v.x, y0[o]);
-  }
+  __device__ __forceinline__ LineGeom gout() const { return g; }
+  __device__ __forceinline__ void store(long long off, long long, int, float2 v) const { y1[off] = fmaf(dt, v.x, y0[off]); }
   __device__ __forceinline__ void flush(long long) {}
 };
 

@@ -42,132 +42,264 @@ __host__ __device__ inline int line_pos_to_freq(int n, int p) {
 
 template <int N>
 struct LineTile {
-  static constexpr int T = (N >= 512) ? 16 : 32;  // lines per tile
+  static constexpr int T = (N >= 512) ? 8 : ((N >= 256) ? 16 : 32);  // lines per tile
   static constexpr int LP = T + 1;
   static constexpr int kThreads = 256;
-  static constexpr size_t smem_bytes = sizeof(float2) * (size_t)(N * LP + N);
+  static constexpr size_t smem_bytes =
+      sizeof(float2) * (size_t)(N * LP + N) + sizeof(int) * (size_t)(3 * N) + sizeof(long long) * (size_t)(3 * T);
 };
-
-// One radix-R stage with span S on a tile.  Forward: DFT over m then twiddle w_S^{jk}; inverse:
-// conjugate twiddle then inverse DFT (exact mirror), see the derivation in DESIGN.md.
-template <int N, int R, int S, bool INV>
-__device__ __forceinline__ void lf_stage(float2* __restrict__ Sm, const float2* __restrict__ tw) {
-  if constexpr (R > 1) {
-    constexpr int T = LineTile<N>::T, LP = LineTile<N>::LP, NT = LineTile<N>::kThreads;
-    constexpr int SUB = S / R;  // distance between the R inputs of one butterfly
-    constexpr int LOG2R = ilog2(R);
-    for (int w = threadIdx.x; w < (N / R) * T; w += NT) {
-      const int line = w % T, u = w / T;
-      const int blk = u / SUB, j = u % SUB;
-      float2* base = Sm + (blk * S + j) * LP + line;
-      float2 x[R];
-      if constexpr (!INV) {
-#pragma unroll
-        for (int m = 0; m < R; ++m) x[m] = base[m * SUB * LP];
-        Dif<R, 1, false>::run(x);
-        static_for<0, R>([&](auto pc) {
-          constexpr int p = decltype(pc)::value;
-          constexpr int k = brev<LOG2R>(p);
-          float2 v = x[p];
-          if constexpr (k != 0 && SUB > 1) v = cmul(v, tw[(j * k * (N / S)) & (N - 1)]);
-          base[k * SUB * LP] = v;
-        });
-      } else {
-        static_for<0, R>([&](auto pc) {
-          constexpr int p = decltype(pc)::value;
-          constexpr int k = brev<LOG2R>(p);
-          float2 v = base[k * SUB * LP];
-          if constexpr (k != 0 && SUB > 1) v = cmulc(v, tw[(j * k * (N / S)) & (N - 1)]);
-          x[p] = v;
-        });
-        Dit<R, 1, true>::run(x);
-#pragma unroll
-        for (int m = 0; m < R; ++m) base[m * SUB * LP] = x[m];
-      }
-    }
-    __syncthreads();
-  }
-}
-
-template <int N, bool INV>
-__device__ __forceinline__ void lf_transform(float2* Sm, const float2* tw) {
-  constexpr int R1 = lf_r1(N), R2 = lf_r2(N), R3 = lf_r3(N);
-  if constexpr (!INV) {
-    lf_stage<N, R1, N, false>(Sm, tw);
-    lf_stage<N, R2, N / R1, false>(Sm, tw);
-    lf_stage<N, R3, N / R1 / R2, false>(Sm, tw);
-  } else {
-    lf_stage<N, R3, N / R1 / R2, true>(Sm, tw);
-    lf_stage<N, R2, N / R1, true>(Sm, tw);
-    lf_stage<N, R1, N, true>(Sm, tw);
-  }
-}
 
 // Line addressing (all strides in elements of the addressed array):
 //   offset(line, idx) = (line / n_inner) * outer + (line % n_inner) * inner
 //                     + (idx / chunk) * hi + (idx % chunk) * lo
 // `chunk` < N expresses the packed layout of the slab all-to-all.
+// Inside the kernel the two halves are tabulated in shared memory (per tile: T line bases; per
+// kernel: N element offsets), so an element address costs two LDS and one add, no divisions.
 struct LineGeom {
   long long n_lines;
   long long n_inner, outer, inner;
   int chunk;
   long long hi, lo;
-  __device__ __forceinline__ long long off(long long line, int idx) const {
-    return (line / n_inner) * outer + (line % n_inner) * inner + (long long)(idx / chunk) * hi + (long long)(idx % chunk) * lo;
+  __host__ __device__ __forceinline__ long long line_base(long long line) const {
+    return (line / n_inner) * outer + (line % n_inner) * inner;
   }
+  __host__ __device__ __forceinline__ long long idx_off(int idx) const {
+    return (long long)(idx / chunk) * hi + (long long)(idx % chunk) * lo;
+  }
+  __host__ __device__ __forceinline__ long long off(long long line, int idx) const { return line_base(line) + idx_off(idx); }
 };
 
 enum : int { LF_FWD = 0, LF_INV = 1, LF_FWD_MUL_INV = 2 };
 
-// Loader: float2 load(long long line, int idx) ; Mid: float2 apply(float2 v, long long line, int pos) ;
-// Storer: void store(long long line, int idx, float2 v).
-// CONTIG: elements of a line are adjacent in memory (lo == 1): a warp reads 32 consecutive idx of
-// one line; otherwise adjacent lines are adjacent in memory: a warp reads T lines at one idx.
+// Functor concepts (offsets are element offsets computed from the functor's own geometries):
+//   Loader: LineGeom gin() ;  float2 load(long long off, long long line, int idx)
+//   Mid   : LineGeom gaux();  float2 apply(float2 v, long long off_aux, long long line, int pos)
+//   Storer: LineGeom gout();  void store(long long off, long long line, int idx, float2 v) ; void flush(long long l0)
+// CONTIG: elements of a line are adjacent in memory (lo == 1): warps run along idx when they touch
+// global memory; otherwise adjacent lines are adjacent in memory and warps run across the T lines.
+//
+// The first radix stage is fused with the global loads (8 independent loads in flight per thread)
+// and the last one with the global stores, so an N = R1 R2 R3 transform makes two shared-memory
+// round trips instead of four; forward * multiplier * inverse shares the innermost stage in
+// registers (LF_FWD_MUL_INV: five stages, four round trips).
+struct LfCtx {
+  float2* Sm;
+  const float2* tw;
+  const int *io_in, *io_out, *io_aux;
+  const long long *lb_in, *lb_out, *lb_aux;
+  long long l0, n_lines;
+};
+
+template <int N, int R, int S, bool INV, bool GSRC, bool GDST, bool LANE_U, class Loader, class Storer>
+__device__ __forceinline__ void lf_stage(const LfCtx& c, Loader& ld, Storer& st) {
+  constexpr int T = LineTile<N>::T, LP = LineTile<N>::LP, NT = LineTile<N>::kThreads;
+  constexpr int SUB = S / R, NB = N / R, LOG2R = ilog2(R);
+  for (int w = threadIdx.x; w < NB * T; w += NT) {
+    const int u = LANE_U ? (w % NB) : (w / T), line = LANE_U ? (w / NB) : (w % T);
+    const int j = u % SUB, base = (u / SUB) * S + j;
+    const bool valid = c.l0 + line < c.n_lines;
+    float2 x[R];
+    if constexpr (!INV) {
+#pragma unroll
+      for (int m = 0; m < R; ++m) {
+        const int pos = base + m * SUB;
+        if constexpr (GSRC) x[m] = valid ? ld.load(c.lb_in[line] + c.io_in[pos], c.l0 + line, pos) : make_float2(0.f, 0.f);
+        else x[m] = c.Sm[pos * LP + line];
+      }
+      Dif<R, 1, false>::run(x);
+      static_for<0, R>([&](auto pc) {
+        constexpr int p = decltype(pc)::value;
+        constexpr int k = brev<LOG2R>(p);
+        float2 v = x[p];
+        if constexpr (k != 0 && SUB > 1) v = cmul(v, c.tw[(j * k * (N / S)) & (N - 1)]);
+        const int pos = base + k * SUB;
+        if constexpr (GDST) {
+          if (valid) st.store(c.lb_out[line] + c.io_out[pos], c.l0 + line, pos, v);
+        } else {
+          c.Sm[pos * LP + line] = v;
+        }
+      });
+    } else {
+      static_for<0, R>([&](auto pc) {
+        constexpr int p = decltype(pc)::value;
+        constexpr int k = brev<LOG2R>(p);
+        const int pos = base + k * SUB;
+        float2 v;
+        if constexpr (GSRC) v = valid ? ld.load(c.lb_in[line] + c.io_in[pos], c.l0 + line, pos) : make_float2(0.f, 0.f);
+        else v = c.Sm[pos * LP + line];
+        if constexpr (k != 0 && SUB > 1) v = cmulc(v, c.tw[(j * k * (N / S)) & (N - 1)]);
+        x[p] = v;
+      });
+      Dit<R, 1, true>::run(x);
+#pragma unroll
+      for (int m = 0; m < R; ++m) {
+        const int pos = base + m * SUB;
+        if constexpr (GDST) {
+          if (valid) st.store(c.lb_out[line] + c.io_out[pos], c.l0 + line, pos, x[m]);
+        } else {
+          c.Sm[pos * LP + line] = x[m];
+        }
+      }
+    }
+  }
+}
+
+// innermost stage of forward * multiplier * inverse (span == radix, no twiddles), in registers
+template <int N, int R, bool GSRC, bool GDST, bool LANE_U, class Loader, class Mid, class Storer>
+__device__ __forceinline__ void lf_stage_fmi(const LfCtx& c, Loader& ld, Mid& mid, Storer& st) {
+  constexpr int T = LineTile<N>::T, LP = LineTile<N>::LP, NT = LineTile<N>::kThreads;
+  constexpr int NB = N / R, LOG2R = ilog2(R);
+  for (int w = threadIdx.x; w < NB * T; w += NT) {
+    const int u = LANE_U ? (w % NB) : (w / T), line = LANE_U ? (w / NB) : (w % T);
+    const int base = u * R;
+    const bool valid = c.l0 + line < c.n_lines;
+    float2 x[R];
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+      if constexpr (GSRC) x[m] = valid ? ld.load(c.lb_in[line] + c.io_in[base + m], c.l0 + line, base + m) : make_float2(0.f, 0.f);
+      else x[m] = c.Sm[(base + m) * LP + line];
+    }
+    Dif<R, 1, false>::run(x);
+    static_for<0, R>([&](auto pc) {
+      constexpr int p = decltype(pc)::value;
+      constexpr int k = brev<LOG2R>(p);
+      if (valid) x[p] = mid.apply(x[p], c.lb_aux[line] + c.io_aux[base + k], c.l0 + line, base + k);
+    });
+    Dit<R, 1, true>::run(x);
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+      if constexpr (GDST) {
+        if (valid) st.store(c.lb_out[line] + c.io_out[base + m], c.l0 + line, base + m, x[m]);
+      } else {
+        c.Sm[(base + m) * LP + line] = x[m];
+      }
+    }
+  }
+}
+
 template <int N, int MODE, bool CONTIG, class Loader, class Mid, class Storer>
 __global__ void __launch_bounds__(LineTile<N>::kThreads) linefft_kernel(long long n_lines, Loader ld, Mid mid, Storer st) {
   extern __shared__ __align__(16) unsigned char lf_smem[];
   constexpr int T = LineTile<N>::T, LP = LineTile<N>::LP, NT = LineTile<N>::kThreads;
+  constexpr int R1 = lf_r1(N), R2 = lf_r2(N), R3 = lf_r3(N);
+  constexpr int NS = 1 + (R2 > 1 ? 1 : 0) + (R3 > 1 ? 1 : 0);
+  constexpr int S2 = N / R1, S3 = N / R1 / R2;
+  constexpr bool LU = CONTIG;  // lane mapping of the stages that touch global memory
   float2* Sm = reinterpret_cast<float2*>(lf_smem);
   float2* tw = Sm + N * LP;
+  long long* lb_in = reinterpret_cast<long long*>(tw + N);  // [T] line bases of the current tile
+  long long* lb_out = lb_in + T;
+  long long* lb_aux = lb_out + T;
+  int* io_in = reinterpret_cast<int*>(lb_aux + T);  // [N] element offsets within a line
+  int* io_out = io_in + N;
+  int* io_aux = io_out + N;
+  const LineGeom gi = ld.gin(), go = st.gout(), ga = mid.gaux();
   for (int i = threadIdx.x; i < N; i += NT) {
     float s, c;
     sincospif(-2.0f * float(i) / float(N), &s, &c);
     tw[i] = make_float2(c, s);
+    io_in[i] = (int)gi.idx_off(i);
+    io_out[i] = (int)go.idx_off(i);
+    io_aux[i] = (int)ga.idx_off(i);
   }
+  LfCtx c{Sm, tw, io_in, io_out, io_aux, lb_in, lb_out, lb_aux, 0, n_lines};
   for (long long tile = blockIdx.x; tile * T < n_lines; tile += gridDim.x) {
     const long long l0 = tile * T;
-    // ---- load ----
-    if constexpr (CONTIG) {
-      for (int w = threadIdx.x; w < N * T; w += NT) {
-        const int idx = w % N, line = w / N;
-        if (l0 + line < n_lines) Sm[idx * LP + line] = ld.load(l0 + line, idx);
-      }
-    } else {
-      for (int w = threadIdx.x; w < N * T; w += NT) {
-        const int line = w % T, idx = w / T;
-        if (l0 + line < n_lines) Sm[idx * LP + line] = ld.load(l0 + line, idx);
-      }
+    c.l0 = l0;
+    if (threadIdx.x < T) {
+      const long long l = l0 + threadIdx.x;
+      lb_in[threadIdx.x] = gi.line_base(l);
+      lb_out[threadIdx.x] = go.line_base(l);
+      lb_aux[threadIdx.x] = ga.line_base(l);
     }
     __syncthreads();
-    if constexpr (MODE == LF_FWD || MODE == LF_FWD_MUL_INV) lf_transform<N, false>(Sm, tw);
-    if constexpr (MODE == LF_FWD_MUL_INV) {
-      for (int w = threadIdx.x; w < N * T; w += NT) {
-        const int line = w % T, pos = w / T;
-        if (l0 + line < n_lines) Sm[pos * LP + line] = mid.apply(Sm[pos * LP + line], l0 + line, pos);
-      }
-      __syncthreads();
-    }
-    if constexpr (MODE == LF_INV || MODE == LF_FWD_MUL_INV) lf_transform<N, true>(Sm, tw);
-    // ---- store ----
-    if constexpr (CONTIG) {
+    auto copy_in = [&]() {  // contiguous lines -> tile, warps along idx
       for (int w = threadIdx.x; w < N * T; w += NT) {
         const int idx = w % N, line = w / N;
-        if (l0 + line < n_lines) st.store(l0 + line, idx, Sm[idx * LP + line]);
+        if (l0 + line < n_lines) Sm[idx * LP + line] = ld.load(lb_in[line] + io_in[idx], l0 + line, idx);
+      }
+      __syncthreads();
+    };
+    auto copy_out = [&]() {
+      __syncthreads();
+      for (int w = threadIdx.x; w < N * T; w += NT) {
+        const int idx = w % N, line = w / N;
+        if (l0 + line < n_lines) st.store(lb_out[line] + io_out[idx], l0 + line, idx, Sm[idx * LP + line]);
+      }
+    };
+    if constexpr (MODE == LF_FWD) {
+      if constexpr (!CONTIG) {
+        if constexpr (NS == 1) {
+          lf_stage<N, R1, N, false, true, true, false>(c, ld, st);
+        } else if constexpr (NS == 2) {
+          lf_stage<N, R1, N, false, true, false, false>(c, ld, st);
+          __syncthreads();
+          lf_stage<N, R2, S2, false, false, true, false>(c, ld, st);
+        } else {
+          lf_stage<N, R1, N, false, true, false, false>(c, ld, st);
+          __syncthreads();
+          lf_stage<N, R2, S2, false, false, false, false>(c, ld, st);
+          __syncthreads();
+          lf_stage<N, R3, S3, false, false, true, false>(c, ld, st);
+        }
+      } else {
+        lf_stage<N, R1, N, false, true, false, true>(c, ld, st);
+        if constexpr (NS >= 2) {
+          __syncthreads();
+          lf_stage<N, R2, S2, false, false, false, false>(c, ld, st);
+        }
+        if constexpr (NS >= 3) {
+          __syncthreads();
+          lf_stage<N, R3, S3, false, false, false, false>(c, ld, st);
+        }
+        copy_out();
+      }
+    } else if constexpr (MODE == LF_INV) {
+      if constexpr (!CONTIG) {
+        if constexpr (NS == 1) {
+          lf_stage<N, R1, N, true, true, true, false>(c, ld, st);
+        } else if constexpr (NS == 2) {
+          lf_stage<N, R2, S2, true, true, false, false>(c, ld, st);
+          __syncthreads();
+          lf_stage<N, R1, N, true, false, true, false>(c, ld, st);
+        } else {
+          lf_stage<N, R3, S3, true, true, false, false>(c, ld, st);
+          __syncthreads();
+          lf_stage<N, R2, S2, true, false, false, false>(c, ld, st);
+          __syncthreads();
+          lf_stage<N, R1, N, true, false, true, false>(c, ld, st);
+        }
+      } else {
+        copy_in();
+        if constexpr (NS >= 3) {
+          lf_stage<N, R3, S3, true, false, false, false>(c, ld, st);
+          __syncthreads();
+        }
+        if constexpr (NS >= 2) {
+          lf_stage<N, R2, S2, true, false, false, false>(c, ld, st);
+          __syncthreads();
+        }
+        lf_stage<N, R1, N, true, false, true, true>(c, ld, st);
       }
     } else {
-      for (int w = threadIdx.x; w < N * T; w += NT) {
-        const int line = w % T, idx = w / T;
-        if (l0 + line < n_lines) st.store(l0 + line, idx, Sm[idx * LP + line]);
+      if constexpr (NS == 1) {
+        lf_stage_fmi<N, R1, true, true, LU>(c, ld, mid, st);
+      } else if constexpr (NS == 2) {
+        lf_stage<N, R1, N, false, true, false, LU>(c, ld, st);
+        __syncthreads();
+        lf_stage_fmi<N, R2, false, false, false>(c, ld, mid, st);
+        __syncthreads();
+        lf_stage<N, R1, N, true, false, true, LU>(c, ld, st);
+      } else {
+        lf_stage<N, R1, N, false, true, false, LU>(c, ld, st);
+        __syncthreads();
+        lf_stage<N, R2, S2, false, false, false, false>(c, ld, st);
+        __syncthreads();
+        lf_stage_fmi<N, R3, false, false, false>(c, ld, mid, st);
+        __syncthreads();
+        lf_stage<N, R2, S2, true, false, false, false>(c, ld, st);
+        __syncthreads();
+        lf_stage<N, R1, N, true, false, true, LU>(c, ld, st);
       }
     }
     st.flush(l0);  // optional per-tile reduction hook (uniform; may contain barriers)
@@ -179,25 +311,29 @@ __global__ void __launch_bounds__(LineTile<N>::kThreads) linefft_kernel(long lon
 struct LfLoadC {  // complex array
   const float2* p;
   LineGeom g;
-  __device__ __forceinline__ float2 load(long long line, int idx) const { return p[g.off(line, idx)]; }
+  __device__ __forceinline__ LineGeom gin() const { return g; }
+  __device__ __forceinline__ float2 load(long long off, long long, int) const { return p[off]; }
 };
 struct LfStoreC {
   float2* p;
   LineGeom g;
-  __device__ __forceinline__ void store(long long line, int idx, float2 v) const { p[g.off(line, idx)] = v; }
+  __device__ __forceinline__ LineGeom gout() const { return g; }
+  __device__ __forceinline__ void store(long long off, long long, int, float2 v) const { p[off] = v; }
   __device__ __forceinline__ void flush(long long) {}
 };
 struct LfStoreCScaled {
   float2* p;
   LineGeom g;
   float scale;
-  __device__ __forceinline__ void store(long long line, int idx, float2 v) const {
-    p[g.off(line, idx)] = make_float2(v.x * scale, v.y * scale);
+  __device__ __forceinline__ LineGeom gout() const { return g; }
+  __device__ __forceinline__ void store(long long off, long long, int, float2 v) const {
+    p[off] = make_float2(v.x * scale, v.y * scale);
   }
   __device__ __forceinline__ void flush(long long) {}
 };
 struct LfMidNone {
-  __device__ __forceinline__ float2 apply(float2 v, long long, int) const { return v; }
+  __device__ __forceinline__ LineGeom gaux() const { return LineGeom{1, 1, 0, 0, 1, 0, 0}; }
+  __device__ __forceinline__ float2 apply(float2 v, long long, long long, int) const { return v; }
 };
 
 template <int N, int MODE, bool CONTIG, class Loader, class Mid, class Storer>

@@ -62,10 +62,9 @@ __device__ __forceinline__ float lf_block_sum(float v) {
 // complex multiplier table laid out like one env's field: tab[pos_row * ny + pos_col]
 struct LfMidCTab {
   const float2* tab;
-  int ny;
-  __device__ __forceinline__ float2 apply(float2 v, long long line, int pos) const {
-    return cmul(v, tab[(size_t)pos * ny + (int)(line % ny)]);
-  }
+  LineGeom g;  // the column-pass geometry with outer = 0: the table is shared by the batch
+  __device__ __forceinline__ LineGeom gaux() const { return g; }
+  __device__ __forceinline__ float2 apply(float2 v, long long off_aux, long long, int) const { return cmul(v, tab[off_aux]); }
 };
 
 // K3 storer: rows inverse done -> multiply by the potential factor (b at psi0), accumulate the norm.
@@ -76,9 +75,10 @@ struct LfStorePotential {
   GpeLinesConst c;
   float dt;
   float acc;
-  __device__ __forceinline__ void store(long long line, int idx, float2 v) {
+  LineGeom g;
+  __device__ __forceinline__ LineGeom gout() const { return g; }
+  __device__ __forceinline__ void store(long long o, long long line, int idx, float2 v) {
     const int env = (int)(line / c.nx), r = (int)(line % c.nx);
-    const long long o = line * c.ny + idx;
     const float2 w = cmul(v, gpe_potential_factor(c, env, r, idx, psi0[o], dt));
     out[o] = w;
     acc = fmaf(w.x, w.x, fmaf(w.y, w.y, acc));
@@ -96,9 +96,11 @@ struct LfLoadNormalised {
   const float* norm;
   int nx, ny;
   float dx2;
-  __device__ __forceinline__ float2 load(long long line, int idx) const {
+  LineGeom g;
+  __device__ __forceinline__ LineGeom gin() const { return g; }
+  __device__ __forceinline__ float2 load(long long off, long long line, int) const {
     const float s = rsqrtf(norm[line / nx] * dx2);
-    const float2 v = p[line * ny + idx];
+    const float2 v = p[off];
     return make_float2(v.x * s, v.y * s);
   }
 };

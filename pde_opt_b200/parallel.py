@@ -35,3 +35,159 @@ def gather_env_values(local, num_envs=None, group=None):
     parts = [out[r * bmax : r * bmax + (hi - lo)] for r, (lo, hi) in enumerate(sizes)]
     del rank
     return torch.cat(parts, dim=0)
+
+
+# --------------------------------------------------------------------------------------------------
+# Slab-decomposed 3-D Cahn-Hilliard (BASELINE config 5)
+# --------------------------------------------------------------------------------------------------
+class _DeviceBackend:
+    """The four device operations of the slab step, through the C ABI (include/pdeopt_b200.h)."""
+
+    def __init__(self, plan):
+        self.plan = plan
+
+    def rhs(self, u, halo_lo, halo_hi):
+        return self.plan.rhs(u[None], halo_lo, halo_hi)[0]
+
+    @staticmethod
+    def _stream(t):
+        import ctypes
+
+        return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+    def fft_lines(self, src, dst, n, gin, gout, inverse, in_real, scale):
+        import ctypes
+
+        from . import _lib
+
+        _lib.check(_lib.load().pdeopt_fft_lines(ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(dst.data_ptr()), n,
+                                               ctypes.byref(gin), ctypes.byref(gout), int(inverse), int(in_real), float(scale),
+                                               self._stream(src)))
+
+    def fft_lines_imex(self, buf, n, g, sym, gsym, dt, scale):
+        import ctypes
+
+        from . import _lib
+
+        _lib.check(_lib.load().pdeopt_fft_lines_imex(ctypes.c_void_p(buf.data_ptr()), ctypes.c_void_p(buf.data_ptr()), n,
+                                                    ctypes.byref(g), ctypes.c_void_p(sym.data_ptr()), ctypes.byref(gsym),
+                                                    float(dt), float(scale), self._stream(buf)))
+
+    def fft_lines_inv_update(self, spec, n, gin, y0, y1, gout, dt):
+        import ctypes
+
+        from . import _lib
+
+        _lib.check(_lib.load().pdeopt_fft_lines_inv_update(ctypes.c_void_p(spec.data_ptr()), n, ctypes.byref(gin),
+                                                          ctypes.c_void_p(y0.data_ptr()), ctypes.c_void_p(y1.data_ptr()),
+                                                          ctypes.byref(gout), float(dt), self._stream(spec)))
+
+
+class SlabCahnHilliard3D:
+    """One semi-implicit step (solvers.py:56-70) of CahnHilliard3DPeriodic.rhs_fd
+    (cahn_hilliard.py:177-200) on a single large domain sharded over ranks by x-slabs.
+
+    Rank r holds planes [r*nxl, (r+1)*nxl) of the global [Nx, Ny, Nz] field.  Per step:
+      1. ring exchange of the two boundary planes on either side (the FD RHS reaches x +- 2),
+      2. rhs_fd on the slab,
+      3. z then y line FFTs on the slab; the y pass writes straight into the packed send buffer
+         [dest][nxl][Ny/P][Nz] (chunked line geometry: no separate pack kernel),
+      4. all-to-all #1 -> [Nx][Ny/P][Nz]: x lines complete on every rank,
+      5. x pass: forward FFT, multiply by 1/(N (1 + A dt sigma)), inverse FFT in one kernel,
+      6. all-to-all #2 back (no pack needed: x-ranges are contiguous),
+      7. inverse y pass reading the packed layout, inverse z pass fused with y1 = y0 + dt g.
+    The spectrum stays in the line engine's position order throughout; the symbol table is permuted
+    once at construction.  Collectives: torch.distributed (NCCL on GPUs; gloo in the CPU tests, where
+    `backend` is an emulation of the four device operations)."""
+
+    def __init__(self, equation, A, group=None, backend=None, device=None, symbol_pos_local=None):
+        from .linefft import geom, to_position_order
+
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        P = self.world
+        self.Nx, self.Ny, self.Nz = (int(p) for p in equation.domain.points)
+        if self.Nx % P or self.Ny % P:
+            raise ValueError("Nx and Ny must be divisible by the number of ranks")
+        self.nxl, self.C = self.Nx // P, self.Ny // P
+        if self.nxl < 2:
+            raise ValueError("each slab needs at least 2 planes (halo width)")
+        nxl, C, Nx, Ny, Nz = self.nxl, self.C, self.Nx, self.Ny, self.Nz
+        self.device = device
+        if backend is None:
+            from .fused import Ch3dPlan
+
+            plan = Ch3dPlan((nxl, Ny, Nz), equation.domain.dx, equation.kappa, equation._mu_c.descriptor(), equation._mob_c.descriptor())
+            backend = _DeviceBackend(plan)
+        self.backend = backend
+        # local part of A*symbol in position order: [Nx][C][Nz] for this rank's y-chunk
+        if symbol_pos_local is None:
+            import numpy as np
+
+            s = np.asarray(equation.fourier_symbol)
+            s = (np.float32(A) * s.real.astype(np.float32)).astype(np.float32)
+            s = to_position_order(s, (0, 1, 2))[:, self.rank * C : (self.rank + 1) * C, :]
+            symbol_pos_local = torch.from_numpy(np.ascontiguousarray(s)).to(device)
+        self.sym = symbol_pos_local
+        self.scale = 1.0 / float(Nx * Ny * Nz)
+        # line geometries (elements)
+        self.g_z = geom(nxl * Ny, 1, Nz, 0, Nz, 1)
+        self.g_y = geom(nxl * Nz, Nz, Ny * Nz, 1, Ny, Nz)
+        self.g_y_packed = geom(nxl * Nz, Nz, C * Nz, 1, Ny, Nz, chunk=C, hi=nxl * C * Nz)
+        self.g_x = geom(C * Nz, C * Nz, 0, 1, Nx, C * Nz)
+        self._bufs = None
+
+    def _buffers(self, like):
+        if self._bufs is None:
+            n = self.nxl * self.Ny * self.Nz
+            mk = lambda: torch.empty(n, dtype=torch.complex64, device=like.device)
+            pl = (2, self.Ny, self.Nz)
+            self._bufs = dict(W=mk(), send=mk(), recv=mk(), lo=torch.empty(pl, dtype=like.dtype, device=like.device),
+                              hi=torch.empty(pl, dtype=like.dtype, device=like.device))
+        return self._bufs
+
+    def exchange_halos(self, u):
+        """halo_lo = last two planes of rank-1, halo_hi = first two planes of rank+1 (periodic ring)."""
+        b = self._buffers(u)
+        if self.world == 1:
+            b["lo"].copy_(u[-2:])
+            b["hi"].copy_(u[:2])
+            return b["lo"], b["hi"]
+        # one small all-gather of the four boundary planes of every rank (4 x Ny x Nz floats each);
+        # cheap next to the slab transposes and identical on NCCL and gloo
+        mine = torch.cat([u[:2], u[-2:]], 0).contiguous()
+        allb = torch.empty((self.world * 4,) + tuple(mine.shape[1:]), dtype=mine.dtype, device=mine.device)
+        dist.all_gather_into_tensor(allb, mine, group=self.group)
+        allb = allb.view((self.world, 4) + tuple(mine.shape[1:]))
+        up, down = (self.rank + 1) % self.world, (self.rank - 1) % self.world
+        b["lo"].copy_(allb[down, 2:4])
+        b["hi"].copy_(allb[up, 0:2])
+        return b["lo"], b["hi"]
+
+    def _all_to_all(self, dst, src):
+        if self.world == 1:
+            dst.copy_(src)
+        else:
+            dist.all_to_all_single(torch.view_as_real(dst), torch.view_as_real(src), group=self.group)
+
+    def step(self, u, dt, out=None):
+        """u: this rank's slab [nxl, Ny, Nz] float32; returns the slab after one step of length dt."""
+        be, b = self.backend, self._buffers(u)
+        y1 = out if out is not None else torch.empty_like(u)
+        lo, hi = self.exchange_halos(u)
+        f = be.rhs(u, lo, hi)
+        be.fft_lines(f, b["W"], self.Nz, self.g_z, self.g_z, False, True, 1.0)
+        be.fft_lines(b["W"], b["send"], self.Ny, self.g_y, self.g_y_packed, False, False, 1.0)
+        self._all_to_all(b["recv"], b["send"])
+        be.fft_lines_imex(b["recv"], self.Nx, self.g_x, self.sym, self.g_x, dt, self.scale)
+        self._all_to_all(b["send"], b["recv"])
+        be.fft_lines(b["send"], b["W"], self.Ny, self.g_y_packed, self.g_y, True, False, 1.0)
+        be.fft_lines_inv_update(b["W"], self.Nz, self.g_z, u, y1, self.g_z, dt)
+        return y1
+
+    def rollout(self, u, dts):
+        y = u
+        for dt in dts:
+            y = self.step(y, float(dt))
+        return y

@@ -176,3 +176,26 @@ def test_gpe_ground_state_fixture_is_nearly_stationary():
     for a, bb in zip(times[:-1], times[1:]):
         y = O.strang_step(oeq.B_terms, y, a, bb, oeq.A_term, oeq.dx, -1j)
     assert rel_l2(got, y) <= 2e-5
+
+
+def test_slab_path_on_one_gpu_matches_whole_domain_step():
+    """SlabCahnHilliard3D with world_size 1 (halo planes wrap on the rank, packed geometry with one
+    chunk, all-to-all = copy) must reproduce pdeopt_ch3d_step and the oracle."""
+    from pde_opt_b200.parallel import SlabCahnHilliard3D
+    from pde_opt_b200.solvers import ODETerm, SemiImplicitFourierSpectral
+
+    points = (32, 16, 64)
+    eq, oeq = _ch3d(points, 0.01, "log")
+    u = _u0(points, 1, 3)[0]
+    slab = SlabCahnHilliard3D(eq, 0.5, device="cuda")
+    y = torch.from_numpy(u).cuda()
+    for k in range(3):
+        y = slab.step(y, 1e-6)
+    solver = SemiImplicitFourierSpectral(0.5, eq.fourier_symbol, eq.fft, eq.ifft)
+    times = np.arange(4, dtype=np.float32) * np.float32(1e-6)
+    whole = solver.rollout(ODETerm(eq), times, torch.from_numpy(u).cuda()).cpu().numpy()
+    yo = u
+    for a, bb in zip(times[:-1], times[1:]):
+        yo = O.sifs_step(oeq.rhs, yo, a, bb, 0.5, oeq.fourier_symbol)
+    assert rel_l2(y.cpu().numpy(), yo) <= 1e-5
+    assert rel_l2(y.cpu().numpy() - u, whole - u) <= 1e-3
