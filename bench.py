@@ -313,6 +313,31 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = world * B * K_FUSED * e2e_steps / e2e_s
+
+    # ---- env-API view: PDEEnv keeps its state on the device (pde_env.py:234-242, 305); per env step
+    # the actions (control block) go host->device and the observation + reward come back ----
+    ctrl_dev2 = torch.empty_like(ctrl)
+    env_steps = max(3, min(args.steps, 20))
+
+    def env_api_step(src, dst):
+        ctrl_dev2.copy_(ctrl_h, non_blocking=True)
+        plan.step(src, dts, sym, ctrl=ctrl_dev2, obs=obs, obs_range=(0.0, 1.0), reward=rew, out=dst)
+        obs_h.copy_(obs, non_blocking=True)
+        rew_h.copy_(rew, non_blocking=True)
+        torch.cuda.synchronize()
+
+    env_api_step(cur, nxt)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(env_steps):
+        env_api_step(cur, nxt)
+        cur, nxt = nxt, cur
+    env_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([env_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        env_s = float(t.item())
+    env_api_value = world * B * K_FUSED * env_steps / env_s
     h2d = B * N * N * 4 + B * 8 * 4 + sym_host.nbytes
     d2h = B * N * N * 4 + B * N * N + B * 2 * 4
 
@@ -341,8 +366,12 @@ def run_ours(args):
             "grid_point_steps_per_s": value * N * N,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "pdeopt_sifs_step_batched_host (pinned host state+control in, state+obs+reward out)",
-                    "steps": e2e_steps},
+                    "api": "pdeopt_sifs_step_batched_host (pinned host state+control in, state+obs+reward out; "
+                           "chunks pipelined over 3 streams)",
+                    "steps": e2e_steps,
+                    "env_api": {"value": env_api_value, "unit": "env-steps/s", "h2d_bytes_per_step": B * 8 * 4,
+                                "d2h_bytes_per_step": B * N * N + B * 2 * 4, "steps": env_steps,
+                                "what": "state resident on the device as in PDEEnv (pde_env.py:305); pinned actions in, uint8 observation + reward out, synchronised every env step"}},
             "gpu_launches": int(launches),
             "roofline": {
                 "bound": "fp32", "achieved": achieved_tf, "peak": float(peak_tf.value), "unit": "TFLOP/s",

@@ -26,6 +26,11 @@ struct pdeopt_plan {
   float* park = nullptr;  // only used by PDEOPT_PARK_GLOBAL builds
   size_t park_bytes = 0;
   bool attr_set = false;
+  // pipeline of the host-buffer entry point
+  static constexpr int kPipe = 3;
+  cudaStream_t pipe[kPipe] = {};
+  cudaEvent_t ev_start = nullptr, ev_done[kPipe] = {};
+  bool pipe_ready = false;
 };
 
 extern "C" int pdeopt_abi_version(void) { return PDEOPT_ABI_VERSION; }
@@ -62,6 +67,13 @@ extern "C" pdeopt_status pdeopt_plan_destroy(pdeopt_plan* plan) {
   if (!plan) return PDEOPT_OK;
   if (plan->dev_scratch) cudaFree(plan->dev_scratch);
   if (plan->park) cudaFree(plan->park);
+  if (plan->pipe_ready) {
+    for (int i = 0; i < pdeopt_plan::kPipe; ++i) {
+      cudaStreamDestroy(plan->pipe[i]);
+      cudaEventDestroy(plan->ev_done[i]);
+    }
+    cudaEventDestroy(plan->ev_start);
+  }
   delete plan;
   return PDEOPT_OK;
 }
@@ -217,6 +229,9 @@ extern "C" pdeopt_status pdeopt_sifs_step_batched_host(pdeopt_plan* plan, const 
                                                        const float* symbol_host, const float* ctrl_host,
                                                        uint8_t* obs_host, float obs_lo, float obs_hi,
                                                        float* reward_host, void* stream) {
+  // Host buffers in / out.  The batch is cut into chunks that are pipelined over three internal
+  // streams (H2D of chunk c+1, kernel of chunk c and D2H of chunk c-1 overlap; PCIe is full
+  // duplex), ordered after the caller's stream and complete on return.
   if (!plan || !y0_host || !y1_host || !dt_host || !symbol_host) return fail(PDEOPT_ERR_INVALID, "null argument");
   if (batch <= 0) return fail(PDEOPT_ERR_INVALID, "batch must be positive");
   const size_t npts = (size_t)plan->d.nx * plan->d.ny;
@@ -234,6 +249,12 @@ extern "C" pdeopt_status pdeopt_sifs_step_batched_host(pdeopt_plan* plan, const 
     CUDA_TRY(cudaMalloc(&plan->dev_scratch, need));
     plan->dev_scratch_bytes = need;
   }
+  if (!plan->pipe_ready) {
+    for (int i = 0; i < pdeopt_plan::kPipe; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&plan->pipe[i], cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&plan->ev_start, cudaEventDisableTiming));
+    for (int i = 0; i < pdeopt_plan::kPipe; ++i) CUDA_TRY(cudaEventCreateWithFlags(&plan->ev_done[i], cudaEventDisableTiming));
+    plan->pipe_ready = true;
+  }
   char* base = (char*)plan->dev_scratch;
   float* y_dev = (float*)base;
   float* tab_dev = (float*)(base + al(y_bytes));
@@ -241,18 +262,34 @@ extern "C" pdeopt_status pdeopt_sifs_step_batched_host(pdeopt_plan* plan, const 
   uint8_t* obs_dev = (uint8_t*)(base + al(y_bytes) + al(tab_bytes) + al(ctrl_bytes));
   float* rew_dev = (float*)(base + al(y_bytes) + al(tab_bytes) + al(ctrl_bytes) + al(obs_bytes));
   cudaStream_t st = (cudaStream_t)stream;
-  CUDA_TRY(cudaMemcpyAsync(y_dev, y0_host, y_bytes, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(tab_dev, symbol_host, tab_bytes, cudaMemcpyHostToDevice, st));
   if (ctrl_host) CUDA_TRY(cudaMemcpyAsync(ctrl_dev, ctrl_host, ctrl_bytes, cudaMemcpyHostToDevice, st));
-  pdeopt_status s = pdeopt_sifs_step_batched(plan, y_dev, y_dev, batch, ksteps, dt_host, tab_dev,
-                                             ctrl_host ? ctrl_dev : nullptr, obs_host ? obs_dev : nullptr, obs_lo,
-                                             obs_hi, reward_host ? rew_dev : nullptr, stream);
-  if (s != PDEOPT_OK) return s;
-  CUDA_TRY(cudaMemcpyAsync(y1_host, y_dev, y_bytes, cudaMemcpyDeviceToHost, st));
-  if (obs_host) CUDA_TRY(cudaMemcpyAsync(obs_host, obs_dev, obs_bytes, cudaMemcpyDeviceToHost, st));
-  if (reward_host) CUDA_TRY(cudaMemcpyAsync(reward_host, rew_dev, rew_bytes, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord(plan->ev_start, st));
+  // chunks of an even number of environments (a CTA owns a pair), at least ~2 waves of CTAs each
+  int nchunk = batch >= 2048 ? 8 : (batch >= 512 ? 4 : 1);
+  int per = ((batch + nchunk - 1) / nchunk + 1) & ~1;
+  pdeopt_status status = PDEOPT_OK;
+  for (int c = 0, b0 = 0; b0 < batch; ++c, b0 += per) {
+    const int nb = (batch - b0 < per) ? batch - b0 : per;
+    cudaStream_t ps = plan->pipe[c % pdeopt_plan::kPipe];
+    CUDA_TRY(cudaStreamWaitEvent(ps, plan->ev_start, 0));
+    float* yc = y_dev + (size_t)b0 * npts;
+    CUDA_TRY(cudaMemcpyAsync(yc, y0_host + (size_t)b0 * npts, (size_t)nb * npts * sizeof(float), cudaMemcpyHostToDevice, ps));
+    status = pdeopt_sifs_step_batched(plan, yc, yc, nb, ksteps, dt_host, tab_dev,
+                                      ctrl_host ? ctrl_dev + (size_t)b0 * PDEOPT_NCTRL : nullptr,
+                                      obs_host ? obs_dev + (size_t)b0 * npts : nullptr, obs_lo, obs_hi,
+                                      reward_host ? rew_dev + (size_t)b0 * 2 : nullptr, (void*)ps);
+    if (status != PDEOPT_OK) break;
+    CUDA_TRY(cudaMemcpyAsync(y1_host + (size_t)b0 * npts, yc, (size_t)nb * npts * sizeof(float), cudaMemcpyDeviceToHost, ps));
+    if (obs_host) CUDA_TRY(cudaMemcpyAsync(obs_host + (size_t)b0 * npts, obs_dev + (size_t)b0 * npts, (size_t)nb * npts, cudaMemcpyDeviceToHost, ps));
+    if (reward_host) CUDA_TRY(cudaMemcpyAsync(reward_host + (size_t)b0 * 2, rew_dev + (size_t)b0 * 2, (size_t)nb * 2 * sizeof(float), cudaMemcpyDeviceToHost, ps));
+  }
+  for (int i = 0; i < pdeopt_plan::kPipe; ++i) {
+    cudaEventRecord(plan->ev_done[i], plan->pipe[i]);
+    cudaStreamWaitEvent(st, plan->ev_done[i], 0);
+  }
   CUDA_TRY(cudaStreamSynchronize(st));
-  return PDEOPT_OK;
+  return status;
 }
 
 // ---- measured FP32 peak (FFMA chains), the denominator of the fused path's roofline ----------

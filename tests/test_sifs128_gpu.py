@@ -165,3 +165,34 @@ def test_obs_reward_and_control():
         assert (obs[b] == ref_obs).mean() > 0.999
         np.testing.assert_allclose(rew[b, 0], got[b].astype(np.float64).mean(), rtol=1e-5)
         np.testing.assert_allclose(rew[b, 1], got[b].astype(np.float64).var(), rtol=1e-4)
+
+
+@pytest.mark.parametrize("B", [5, 2050])
+def test_host_buffer_entry_point_matches_device_path(B):
+    """pdeopt_sifs_step_batched_host (pipelined chunks, host buffers) == the device-pointer call,
+    bit for bit, including the observation / reward epilogue and a ragged last chunk."""
+    import torch
+
+    from pde_opt_b200.fused import SifsPlan, fold_symbol
+
+    N_, H_ = 128, 0.01
+    plan = SifsPlan("ch2d", N_, N_, (-N_ * H_ / 2,) * 2, (H_, H_), 0.002, ("log", (3.0,)), ("degenerate", ()))
+    k = np.fft.fftfreq(N_, H_)
+    k2 = -((2 * np.pi * k[:, None]) ** 2 + (2 * np.pi * k[None, :]) ** 2)
+    sym = fold_symbol((0.002 * k2**2).astype(np.complex64), 0.5)
+    rng = np.random.default_rng(B)
+    y0 = np.clip(0.5 + 0.01 * rng.normal(size=(B, N_, N_)), 0, 1).astype(np.float32)
+    ctrl = np.zeros((B, 8), np.float32)
+    ctrl[:, 0] = rng.uniform(-0.2, 0.2, B)
+    ctrl[:, 1] = rng.uniform(-0.5, 0.5, B)
+    ctrl[:, 2:4] = rng.uniform(-0.4, 0.4, (B, 2))
+    ctrl[:, 4] = rng.uniform(0.05, 0.2, B)
+    dts = [1e-6, 1e-6, 2e-6]
+    y1h, obs_h, rew_h = np.empty_like(y0), np.empty((B, N_, N_), np.uint8), np.empty((B, 2), np.float32)
+    plan.step_host(y0, dts, sym, ctrl=ctrl, obs=obs_h, reward=rew_h, out=y1h)
+    obs_d = torch.empty((B, N_, N_), dtype=torch.uint8, device="cuda")
+    rew_d = torch.empty((B, 2), dtype=torch.float32, device="cuda")
+    y1d = plan.step(torch.from_numpy(y0).cuda(), dts, torch.from_numpy(sym).cuda(), ctrl=torch.from_numpy(ctrl).cuda(), obs=obs_d, reward=rew_d)
+    np.testing.assert_array_equal(y1h, y1d.cpu().numpy())
+    np.testing.assert_array_equal(obs_h, obs_d.cpu().numpy())
+    np.testing.assert_array_equal(rew_h, rew_d.cpu().numpy())

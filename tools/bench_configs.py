@@ -165,11 +165,27 @@ def c5slab(args):
     chk = out.double().sum()
     if world > 1:
         dist.all_reduce(chk)
+    parity = None
+    if args.check:
+        # gather the slabs and compare with the whole-domain single-GPU step on rank 0
+        allo = torch.empty((world * nxl, n, n), dtype=torch.float32, device="cuda")
+        if world > 1:
+            dist.all_gather_into_tensor(allo, out)
+        else:
+            allo.copy_(out)
+        if rank == 0:
+            kfull = torch.as_tensor(kk, device="cuda")
+            k2f = (kfull[:, None, None] + kfull[None, :, None]) + kfull[None, None, :]
+            symf = (0.5 * 0.002 * k2f * k2f).contiguous()
+            ref = eq.plan().step(torch.from_numpy(full[None]).cuda(), np.asarray([1e-6], np.float32), symf)[0]
+            u0 = torch.from_numpy(full).cuda()
+            parity = {"rel_l2_state": float(((allo - ref).norm() / ref.norm()).item()),
+                      "rel_l2_increment": float((((allo - u0) - (ref - u0)).norm() / (ref - u0).norm()).item())}
     if rank == 0:
         tt = float(t.item())
         print(json.dumps({"config": f"C5 Cahn-Hilliard 3D {n}^3 slab-decomposed", "n_gpus": world, "ms_per_step": tt * 1e3,
                           "grid_point_steps_per_s": n**3 / tt, "all_to_all_MB_per_rank_per_step": 2 * nxl * n * n * 8 * (world - 1) / world / 1e6,
-                          "checksum": float(chk.item())}))
+                          "checksum": float(chk.item()), "parity_vs_single_gpu": parity}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -181,6 +197,7 @@ if __name__ == "__main__":
     ap.add_argument("--n3", type=int, default=512)
     ap.add_argument("--envs3", type=int, default=128)
     ap.add_argument("--envs4", type=int, default=512)
+    ap.add_argument("--check", action="store_true")
     a = ap.parse_args()
     todo = [a.only] if a.only else ["c3", "c4", "c5"]
     for name in todo:
