@@ -30,6 +30,7 @@
 
 #include "fft128.cuh"
 #include "sifs128.cuh"
+#include "spec_util.cuh"
 
 namespace pdeopt {
 
@@ -66,7 +67,6 @@ struct __align__(1024) AdSmem {
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
 
 // Separable velocity tables of one control segment for the (a, b) environment pair.
 __device__ __forceinline__ void ad_tables(AdSmem& S, const AdParams& p, int env_a, int env_b, int seg) {
@@ -137,17 +137,6 @@ __device__ __forceinline__ void ad_teardown(AdSmem& S) {
   if ((threadIdx.x >> 5) == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(S.tmem_base));
 }
 
-__device__ __forceinline__ void park_all(const Park& pk, const float2 (&x)[32]) {
-#pragma unroll
-  for (int ch = 0; ch < 4; ++ch) {
-    float2 v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = x[ch * 8 + i];
-    pk.store(ch, v);
-  }
-  pk.fence_store();
-}
-
 // pair field [env_a | env_b] in global memory -> natural layout in W
 __device__ __forceinline__ void ad_load_pair(float2* W, const float* ya, const float* yb) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -170,22 +159,6 @@ __device__ __forceinline__ void ad_store_pair(const float2* W, float* ya, float*
     *reinterpret_cast<float4*>(ya + r * kN + 4 * lane) = make_float4(v[0].x, v[1].x, v[2].x, v[3].x);
     if (b_valid) *reinterpret_cast<float4*>(yb + r * kN + 4 * lane) = make_float4(v[0].y, v[1].y, v[2].y, v[3].y);
   }
-}
-
-// Spectral bookkeeping for register chunk CH (registers x[CH*8 .. CH*8+7] after Fft128::forward):
-// fn(ic, kr, kc, ft) with ic the compile-time index inside the chunk, (kr, kc) the wavenumber
-// indices along axis 0 / axis 1 and ft the index into the folded (even) 65x65 tables.
-template <int CH, class Fn>
-__device__ __forceinline__ void spec_chunk(const Fft128& F, Fn&& fn) {
-  constexpr int b = CH >> 1;
-  const int kc = F.p3_kc(b);
-  const int fc = kc <= 64 ? kc : 128 - kc;
-  static_for<0, 8>([&](auto ic) {
-    constexpr int pp = (CH & 1) * 8 + decltype(ic)::value;
-    const int kr = F.p3_kr(pp);
-    const int fr = kr <= 64 ? kr : 128 - kr;
-    fn(ic, kr, kc, fr * kTabDim + fc);
-  });
 }
 
 __device__ __forceinline__ int ad_seg(const AdParams& p, int k) {

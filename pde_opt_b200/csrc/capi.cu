@@ -6,6 +6,7 @@
 #include "capi_common.h"
 #include "sifs128.cuh"
 #include "sifs_generic.cuh"
+#include "fourier128.cuh"
 
 using namespace pdeopt;
 
@@ -26,6 +27,10 @@ struct pdeopt_plan {
   float* park = nullptr;  // only used by PDEOPT_PARK_GLOBAL builds
   size_t park_bytes = 0;
   bool attr_set = false;
+  // derivs='fourier': wavenumber tables and the per-CTA scratch line
+  float* kxy = nullptr;
+  float2* fscratch = nullptr;
+  size_t fscratch_bytes = 0;
   // pipeline of the host-buffer entry point
   static constexpr int kPipe = 3;
   cudaStream_t pipe[kPipe] = {};
@@ -41,7 +46,9 @@ extern "C" pdeopt_status pdeopt_plan_create(const pdeopt_plan_desc* desc, pdeopt
   if (!desc || !out) return fail(PDEOPT_ERR_INVALID, "null argument");
   if (desc->kind != PDEOPT_CH2D && desc->kind != PDEOPT_AC2D)
     return fail(PDEOPT_ERR_UNSUPPORTED, "sifs: only CH2D / AC2D plans are implemented");
-  if (desc->derivs != PDEOPT_DERIVS_FD) return fail(PDEOPT_ERR_UNSUPPORTED, "sifs: only derivs='fd' is implemented");
+  if (desc->derivs != PDEOPT_DERIVS_FD && desc->derivs != PDEOPT_DERIVS_FOURIER) return fail(PDEOPT_ERR_INVALID, "unknown derivs");
+  if (desc->derivs == PDEOPT_DERIVS_FOURIER && !(desc->nx == 128 && desc->ny == 128))
+    return fail(PDEOPT_ERR_UNSUPPORTED, "sifs: derivs='fourier' is implemented for 128x128 grids");
   {
     auto pow2 = [](int v) { return v >= 1 && (v & (v - 1)) == 0; };
     const bool tuned = desc->nx == 128 && desc->ny == 128;
@@ -67,6 +74,8 @@ extern "C" pdeopt_status pdeopt_plan_destroy(pdeopt_plan* plan) {
   if (!plan) return PDEOPT_OK;
   if (plan->dev_scratch) cudaFree(plan->dev_scratch);
   if (plan->park) cudaFree(plan->park);
+  if (plan->kxy) cudaFree(plan->kxy);
+  if (plan->fscratch) cudaFree(plan->fscratch);
   if (plan->pipe_ready) {
     for (int i = 0; i < pdeopt_plan::kPipe; ++i) {
       cudaStreamDestroy(plan->pipe[i]);
@@ -142,6 +151,60 @@ static pdeopt_status sifs_launch(pdeopt_plan* plan, int mode, const float* f0_de
   for (int k = 0; k < ksteps && mode != MODE_RHS_ONLY; ++k) p.dt[k] = dt_host[k];
   const int grid = (batch + 1) / 2;
   cudaStream_t st = (cudaStream_t)stream;
+  if (d.derivs == PDEOPT_DERIVS_FOURIER) {
+    // pseudo-spectral right-hand sides (cahn_hilliard.py:82-87, allen_cahn.py:74-79): one env per CTA
+    if (mode == MODE_GIVEN_F) return fail(PDEOPT_ERR_INVALID, "given-f mode does not depend on derivs; use an fd plan");
+    if (obs_dev || reward_dev) return fail(PDEOPT_ERR_UNSUPPORTED, "derivs='fourier': no observation / reward epilogue");
+    if (!plan->kxy) {
+      float h[2 * kN];
+      const float two_pi = (float)6.283185307179586;  // complex64(2j) * complex64(pi)
+      for (int i = 0; i < kN; ++i) {
+        const int f = i < kN / 2 ? i : i - kN;  // numpy.fft.fftfreq ordering (Nyquist negative)
+        h[i] = two_pi * (float)((double)f / ((double)kN * d.hx));
+        h[kN + i] = two_pi * (float)((double)f / ((double)kN * d.hy));
+      }
+      CUDA_TRY(cudaMalloc((void**)&plan->kxy, sizeof(h)));
+      CUDA_TRY(cudaMemcpy(plan->kxy, h, sizeof(h), cudaMemcpyHostToDevice));
+    }
+    const size_t need = (size_t)batch * 32 * kThreads * sizeof(float2);
+    if (plan->fscratch_bytes < need) {
+      if (plan->fscratch) cudaFree(plan->fscratch);
+      plan->fscratch = nullptr;
+      plan->fscratch_bytes = 0;
+      CUDA_TRY(cudaMalloc((void**)&plan->fscratch, need));
+      plan->fscratch_bytes = need;
+    }
+    FourierParams fp;
+    std::memset(&fp, 0, sizeof(fp));
+    fp.y0 = y0_dev;
+    fp.y1 = y1_dev;
+    fp.batch = batch;
+    fp.ksteps = ksteps;
+    fp.mode = mode;
+    fp.eq = d.kind == PDEOPT_AC2D ? EQ_AC : EQ_CH;
+    fp.symbol = p.symbol;
+    fp.kx = plan->kxy;
+    fp.ky = plan->kxy + kN;
+    fp.ctrl = ctrl_dev;
+    fp.scratch = plan->fscratch;
+    fp.kappa = p.kappa;
+    fp.lo_x = p.lo_x;
+    fp.lo_y = p.lo_y;
+    fp.hx = p.hx;
+    fp.hy = p.hy;
+    fp.pw = p.pw;
+    for (int k = 0; k < ksteps && mode != MODE_RHS_ONLY; ++k) fp.dt[k] = dt_host[k];
+    static bool fattr = false;
+    if (!fattr) {
+      CUDA_TRY(cudaFuncSetAttribute(fourier128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FourierSmem)));
+      fattr = true;
+    }
+    fourier128_kernel<<<batch, kThreads, sizeof(FourierSmem), st>>>(fp);
+    cudaError_t fe = cudaGetLastError();
+    if (fe != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(fe));
+    g_launches.fetch_add(1);
+    return PDEOPT_OK;
+  }
   if (!(d.nx == 128 && d.ny == 128)) {
     GenParams gp;
     gp.s = p;

@@ -43,8 +43,11 @@ class _PhaseField2D(BaseEquation):
 
     @property
     def fused(self):
-        """True when mu and the mobility are enumerated families and derivs == 'fd'."""
-        return self._mu_c is not None and self._mob_c is not None and self.derivs == "fd"
+        """True when mu and the mobility are enumerated families and a fused kernel exists for the
+        derivative type (finite differences: every supported grid; 'fourier': 128x128)."""
+        if self._mu_c is None or self._mob_c is None:
+            return False
+        return self.derivs == "fd" or tuple(self.domain.points) == (128, 128)
 
     def plan(self):
         if self._plan is None:

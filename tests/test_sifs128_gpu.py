@@ -196,3 +196,45 @@ def test_host_buffer_entry_point_matches_device_path(B):
     np.testing.assert_array_equal(y1h, y1d.cpu().numpy())
     np.testing.assert_array_equal(obs_h, obs_d.cpu().numpy())
     np.testing.assert_array_equal(rew_h, rew_d.cpu().numpy())
+
+
+@pytest.mark.parametrize("kind", ["ch", "ac"])
+def test_rhs_fourier_and_steps_match_oracle(kind):
+    """derivs='fourier' (cahn_hilliard.py:82-87, allen_cahn.py:74-79): the complex-arithmetic fused
+    kernel against the oracle's rhs_fourier, for the RHS itself and for semi-implicit steps."""
+    import torch
+
+    from oracle import pde_oracle as O
+    from pde_opt_b200 import Domain
+    from pde_opt_b200.equations import AllenCahn2DPeriodic, CahnHilliard2DPeriodic
+    from pde_opt_b200.functions import DegenerateMobility, LogRegular, OnePlusSquare
+    from pde_opt_b200.solvers import ODETerm, SemiImplicitFourierSpectral
+
+    N_, H_ = 128, 0.01
+    box = ((-N_ * H_ / 2, N_ * H_ / 2),) * 2
+    dom, odom = Domain((N_, N_), box, "dimensionless"), O.Domain((N_, N_), box)
+    if kind == "ch":
+        eq = CahnHilliard2DPeriodic(dom, 0.002, LogRegular(3.0), DegenerateMobility(), derivs="fourier")
+        oeq = O.CahnHilliardPeriodic(odom, 0.002, lambda c: O.mu_log(c, 3.0), lambda c: (1 - c) * c, "fourier", np.float32)
+        o64 = O.CahnHilliardPeriodic(odom, 0.002, lambda c: O.mu_log(c, 3.0), lambda c: (1 - c) * c, "fourier", np.float64)
+        A, dt = 0.5, 1e-6
+    else:
+        eq = AllenCahn2DPeriodic(dom, 0.002, LogRegular(3.0), OnePlusSquare(), derivs="fourier")
+        oeq = O.AllenCahn2DPeriodic(odom, 0.002, lambda c: O.mu_log(c, 3.0), lambda c: 1 + c**2, "fourier", np.float32)
+        o64 = O.AllenCahn2DPeriodic(odom, 0.002, lambda c: O.mu_log(c, 3.0), lambda c: 1 + c**2, "fourier", np.float64)
+        A, dt = 1.0, 5e-6
+    assert eq.fused
+    y0 = np.stack([np.clip(0.5 + 0.05 * np.random.default_rng(s).normal(size=(N_, N_)), 0.05, 0.95) for s in range(3)]).astype(np.float32)
+    f = eq.rhs(torch.from_numpy(y0).cuda()).cpu().numpy()
+    for b in range(3):
+        want = o64.rhs(y0[b].astype(np.float64))
+        assert np.linalg.norm(f[b] - want) / np.linalg.norm(want) <= 5e-5
+    solver = SemiImplicitFourierSpectral(A, eq.fourier_symbol, eq.fft, eq.ifft)
+    times = (np.arange(9, dtype=np.float32) * np.float32(dt)).astype(np.float32)
+    got = solver.rollout(ODETerm(eq), times, torch.from_numpy(y0).cuda()).cpu().numpy()
+    for b in range(3):
+        y = y0[b]
+        for a, bb in zip(times[:-1], times[1:]):
+            y = O.sifs_step(oeq.rhs, y, a, bb, A, oeq.fourier_symbol)
+        assert np.linalg.norm(got[b] - y) / np.linalg.norm(y) <= 1e-5
+        assert np.linalg.norm((got[b] - y0[b]) - (y - y0[b])) / np.linalg.norm(y - y0[b]) <= 2e-3
