@@ -58,20 +58,21 @@ def _bwd(desc, traj, lam, dts, tables, ctrl, hold, step0, gctrl):
 
 class _ADRollout(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, y0, ctrl, eq, dts, tables, hold, checkpoint_every):
+    def forward(ctx, y0, ctrl, eq, dts, tables, hold, checkpoint_every, step0=0):
         desc = eq.ad_desc()
         y0c, ctrlc = y0.contiguous(), ctrl.contiguous()
         K = len(dts)
         need_grad = y0.requires_grad or ctrl.requires_grad
         y1 = torch.empty_like(y0c)
-        ctx.desc, ctx.dts, ctx.tables, ctx.hold, ctx.ckpt = desc, dts, tables, hold, checkpoint_every
+        ctx.desc, ctx.dts, ctx.tables, ctx.hold, ctx.ckpt, ctx.step0 = desc, dts, tables, hold, checkpoint_every, int(step0)
+        step0 = int(step0)
         if not need_grad:
-            _fwd(desc, y0c, y1, dts, tables, ctrlc, hold, 0, None)
+            _fwd(desc, y0c, y1, dts, tables, ctrlc, hold, step0, None)
             return y1
         if checkpoint_every is None:
             # the whole trajectory lives in HBM (500 steps x 512 envs x 64 KB = 16 GiB of 180 GB)
             traj = torch.empty((K,) + tuple(y0c.shape), dtype=torch.float32, device=y0c.device)
-            _fwd(desc, y0c, y1, dts, tables, ctrlc, hold, 0, traj)
+            _fwd(desc, y0c, y1, dts, tables, ctrlc, hold, step0, traj)
             ctx.save_for_backward(ctrlc, traj)
         else:
             S = int(checkpoint_every)
@@ -80,7 +81,7 @@ class _ADRollout(torch.autograd.Function):
             for beg in range(0, K, S):
                 cps.append(y if beg == 0 else y.clone())
                 nxt = torch.empty_like(y0c)
-                _fwd(desc, y, nxt, dts[beg : beg + S], tables, ctrlc, hold, beg, None)
+                _fwd(desc, y, nxt, dts[beg : beg + S], tables, ctrlc, hold, step0 + beg, None)
                 y = nxt
             y1 = y
             ctx.save_for_backward(ctrlc, *cps)
@@ -88,14 +89,14 @@ class _ADRollout(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gy1):
-        desc, dts, tables, hold, S = ctx.desc, ctx.dts, ctx.tables, ctx.hold, ctx.ckpt
+        desc, dts, tables, hold, S, step0 = ctx.desc, ctx.dts, ctx.tables, ctx.hold, ctx.ckpt, ctx.step0
         ctrl = ctx.saved_tensors[0]
         K = len(dts)
         lam = gy1.contiguous().clone()
         gctrl = torch.zeros_like(ctrl)
         if S is None:
             traj = ctx.saved_tensors[1]
-            _bwd(desc, traj, lam, dts, tables, ctrl, hold, 0, gctrl)
+            _bwd(desc, traj, lam, dts, tables, ctrl, hold, step0, gctrl)
         else:
             cps = ctx.saved_tensors[1:]
             seg = torch.empty((min(S, K),) + tuple(lam.shape), dtype=torch.float32, device=lam.device)
@@ -104,17 +105,19 @@ class _ADRollout(torch.autograd.Function):
             for ci in reversed(range(len(begs))):
                 beg = begs[ci]
                 d = dts[beg : beg + S]
-                _fwd(desc, cps[ci], scratch, d, tables, ctrl, hold, beg, seg)  # recompute the segment
-                _bwd(desc, seg, lam, d, tables, ctrl, hold, beg, gctrl)
-        return lam, gctrl, None, None, None, None, None
+                _fwd(desc, cps[ci], scratch, d, tables, ctrl, hold, step0 + beg, seg)  # recompute the segment
+                _bwd(desc, seg, lam, d, tables, ctrl, hold, step0 + beg, gctrl)
+        return lam, gctrl, None, None, None, None, None, None
 
 
-def ad_rollout(eq, y0, ctrl, times, hold=None, A=1.0, checkpoint_every=None):
+def ad_rollout(eq, y0, ctrl, times, hold=None, A=1.0, checkpoint_every=None, step0=0):
     """Differentiable rollout of AdvectionDiffusion2D over the step boundaries `times`.
 
     y0   : [B, nx, ny] float32 CUDA
     ctrl : [B, nseg, 4] float32 CUDA (cx, cy, p0, p1); segment s is held for `hold` numeric steps
            (default: the whole rollout divided evenly over nseg)
+    step0: index of the first step of `times` within the whole rollout (selects the control segment
+           when a rollout is issued in several calls)
     Returns the final state [B, nx, ny]; differentiable w.r.t. y0 and ctrl."""
     times = np.asarray(times, dtype=np.float32)
     dts = np.ascontiguousarray((times[1:] - times[:-1]).astype(np.float32))
@@ -124,4 +127,4 @@ def ad_rollout(eq, y0, ctrl, times, hold=None, A=1.0, checkpoint_every=None):
     if hold is None:
         hold = max(1, -(-len(dts) // ctrl.shape[1]))
     tables = eq.tables_on(y0.device, A)
-    return _ADRollout.apply(y0, ctrl, eq, dts, tables, int(hold), checkpoint_every)
+    return _ADRollout.apply(y0, ctrl, eq, dts, tables, int(hold), checkpoint_every, int(step0))

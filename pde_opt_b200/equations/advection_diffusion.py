@@ -68,10 +68,7 @@ class AdvectionDiffusion2D(BaseEquation):
         return self._tables[key]
 
     def control_block(self, batch, device, nseg=1):
-        import torch
-
-        row = torch.tensor(self.velocity.control_row(), dtype=torch.float32, device=device)
-        return row.expand(batch, nseg, 4).contiguous()
+        return self.velocity.control_block(batch, nseg, device)
 
     def rhs(self, state, t=0.0):
         """f = -div(v u) + D lap(u) on CUDA float32 tensors ([nx,ny] or [B,nx,ny]), evaluated with the

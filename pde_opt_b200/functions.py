@@ -133,19 +133,38 @@ class GaussianVelocity:
     """`advection(t, x, y)` of notebooks/run_advection_diffusion.ipynb cell 2: the velocity field
     v = p0 * grad exp(-((x-cx)^2 + (y-cy)^2) / (2 p1)) about the centre (cx, cy); the enumerated
     form the fused advection-diffusion kernels evaluate.  (cx, cy, p0, p1) is the control block
-    of one control segment."""
+    of one control segment.
+
+    p0, p1 and the centre may be Python floats or torch tensors (scalars, [B] per environment or
+    [B, nseg] per environment and control segment); tensors that require grad receive gradients
+    through the hand-written adjoint (PDEModel.mse / ad_rollout)."""
 
     def __init__(self, p0, p1, centre=(0.0, 0.0)):
-        self.p0, self.p1 = float(p0), float(p1)
-        self.centre = (float(centre[0]), float(centre[1]))
+        self.p0, self.p1 = p0, p1
+        self.centre = (centre[0], centre[1])
 
     def __call__(self, t, x, y):
         m = _lib(x)
-        e = m.exp(-((x - self.centre[0]) ** 2 + (y - self.centre[1]) ** 2) / (2.0 * self.p1))
-        return self.p0 * (-(x - self.centre[0]) / self.p1 * e), self.p0 * (-(y - self.centre[1]) / self.p1 * e)
+        cx, cy = float(self.centre[0]), float(self.centre[1])
+        p0, p1 = float(self.p0), float(self.p1)
+        e = m.exp(-((x - cx) ** 2 + (y - cy) ** 2) / (2.0 * p1))
+        return p0 * (-(x - cx) / p1 * e), p0 * (-(y - cy) / p1 * e)
 
     def control_row(self):
-        return (self.centre[0], self.centre[1], self.p0, self.p1)
+        return (float(self.centre[0]), float(self.centre[1]), float(self.p0), float(self.p1))
+
+    def control_block(self, batch, nseg, device):
+        """[batch, nseg, 4] float32 (cx, cy, p0, p1), differentiable w.r.t. tensor-valued members."""
+        import torch
+
+        cols = []
+        for v in (self.centre[0], self.centre[1], self.p0, self.p1):
+            t = v if torch.is_tensor(v) else torch.tensor(float(v))
+            t = t.to(device=device, dtype=torch.float32)
+            while t.dim() < 2:
+                t = t.unsqueeze(-1)
+            cols.append(t.expand(batch, nseg))
+        return torch.stack(cols, dim=-1).contiguous()
 
 
 _PROBE = np.array([0.07, 0.19, 0.33, 0.5, 0.61, 0.78, 0.93])

@@ -1,7 +1,8 @@
-"""PDEModel.solve — mirror of pde_opt/pde_model.py:15-136 for the stepping path.
-
-`train` / `optimize` / `residuals` (pde_model.py:138-551) sit on top of the adjoint and are
-SURVEY 8(f) "next" rows."""
+"""PDEModel — mirror of pde_opt/pde_model.py for the stepping path: `solve` (:68-136) and the
+differentiable-rollout objectives `residual_single` / `regularization` / `residuals` / `mse`
+(:138-323).  Gradients come from the hand-written adjoint kernel (pde_opt_b200/adjoint.py) through
+torch.autograd, the role jax.grad + diffrax adjoints play in the reference; the optimistix drivers
+`train` / `optimize` (:325-551) are out of scope."""
 from typing import Any, Dict
 
 import numpy as np
@@ -30,6 +31,8 @@ class PDEModel:
             raise NotImplementedError("only ConstantStepSize is implemented on the fused path")
         equation = self.equation_type(domain=self.domain, **parameters)  # :110
         solver = self.solver_type(**prepare_solver_params(self.solver_type, solver_parameters, equation))  # :112-117
+        if type(equation).__name__ == "AdvectionDiffusion2D":
+            return self._solve_differentiable(equation, solver, y0, ts, dt0, max_steps, adjoint)
         terms = ODETerm(equation)
         ts = np.asarray([float(t) for t in ts], dtype=np.float32)
         times = constant_step_times(ts[0], ts[-1], dt0, np.float32, max_steps)
@@ -60,3 +63,79 @@ class PDEModel:
             y, i_cur = y_b, j
         del truncated
         return out
+
+    # ---- differentiable rollouts (advection-diffusion + hand-written adjoint) -----------------------
+    def _solve_differentiable(self, equation, solver, y0, ts, dt0, max_steps, adjoint):
+        """solve() for AdvectionDiffusion2D: same save-time semantics, every segment an autograd node
+        whose backward is the adjoint kernel.  `adjoint` may carry `checkpoint_every` (int)."""
+        from .adjoint import ad_rollout
+
+        ts = np.asarray([float(t) for t in ts], dtype=np.float32)
+        times = constant_step_times(ts[0], ts[-1], dt0, np.float32, max_steps)
+        y = y0 if torch.is_tensor(y0) else torch.as_tensor(np.asarray(y0, dtype=np.float32))
+        y = y.to(device="cuda", dtype=torch.float32) if not y.is_cuda else y.to(torch.float32)
+        single = y.dim() == 2
+        if single:
+            y = y.unsqueeze(0)
+        ctrl = equation.control_block(y.shape[0], y.device, self._nseg(equation))
+        hold = max(1, -(-(len(times) - 1) // ctrl.shape[1]))
+        ck = getattr(adjoint, "checkpoint_every", None)
+        A = float(solver.A)
+        out, i_cur = [], 0
+        for s_ in ts:
+            j = int(np.searchsorted(times, s_, side="left"))
+            if j >= len(times):
+                out.append(torch.full_like(y, float("inf")))
+                continue
+            if j == 0 or times[j] == s_:
+                if j > i_cur:
+                    y = ad_rollout(equation, y, ctrl, times[i_cur : j + 1], hold=hold, A=A, checkpoint_every=ck, step0=i_cur)
+                    i_cur = j
+                out.append(y)
+                continue
+            if j - 1 > i_cur:
+                y = ad_rollout(equation, y, ctrl, times[i_cur:j], hold=hold, A=A, checkpoint_every=ck, step0=i_cur)
+                i_cur = j - 1
+            y_b = ad_rollout(equation, y, ctrl, times[j - 1 : j + 1], hold=hold, A=A, checkpoint_every=ck, step0=j - 1)
+            w = float(np.float32((s_ - times[j - 1]) / (times[j] - times[j - 1])))
+            out.append(y + (y_b - y) * w)  # LocalLinearInterpolation
+            y, i_cur = y_b, j
+        ys = torch.stack(out, 0)
+        return ys[:, 0] if single else ys
+
+    @staticmethod
+    def _nseg(equation):
+        v = equation.velocity
+        n = 1
+        for m in (v.centre[0], v.centre[1], v.p0, v.p1):
+            if torch.is_tensor(m) and m.dim() == 2:
+                n = max(n, m.shape[1])
+        return n
+
+    def residual_single(self, parameters, solver_parameters, y0, values, ts, adjoint=None, dt0=0.000001):
+        """values - predicted[1:] for one trajectory (pde_model.py:138-171)."""
+        pred = self.solve(parameters, y0, ts, solver_parameters, adjoint=adjoint, dt0=dt0)
+        return values - pred[1:]
+
+    def regularization(self, parameters, weights, lambda_reg):
+        """lambda * sum_i w_i p_i^2 over the weighted parameters (pde_model.py:173-224)."""
+        reg = 0.0
+        for key, w in weights.items():
+            if w is None:
+                continue
+            reg = reg + lambda_reg * (torch.as_tensor(w) * torch.as_tensor(parameters[key]) ** 2).sum()
+        return reg
+
+    def residuals(self, parameters, y0s__values, solver_parameters, ts, weights, lambda_reg, adjoint=None, dt0=0.000001):
+        """Batched residuals [batch, timepoints, *shape] and the regularisation term
+        (pde_model.py:226-272).  The batch axis is native to the kernels (no vmap)."""
+        y0s, values = y0s__values
+        pred = self.solve(parameters, y0s, ts, solver_parameters, adjoint=adjoint, dt0=dt0)  # [T, B, ...]
+        res = values - pred[1:].transpose(0, 1)
+        return res, self.regularization(parameters, weights, lambda_reg)
+
+    def mse(self, parameters, y0s__values, solver_parameters, ts, weights, lambda_reg, adjoint=None, dt0=0.000001):
+        """mean(residuals^2) + regularisation (pde_model.py:274-323); a torch scalar whose
+        `.backward()` runs the adjoint kernel."""
+        res, reg = self.residuals(parameters, y0s__values, solver_parameters, ts, weights, lambda_reg, adjoint, dt0)
+        return (res**2).mean() + reg

@@ -143,3 +143,61 @@ def test_adjoint_mean_square_loss_long():
     lr.backward()
     assert _rel(yg.grad.cpu().numpy(), yr.grad.numpy()) <= 1e-4
     assert _rel(cg.grad.cpu().numpy(), cr.grad.numpy()) <= 1e-3  # float32 sums over 600 steps
+
+
+def test_pde_model_mse_gradients_match_autograd_oracle():
+    """PDEModel.mse (pde_model.py:274-323) on the advection-diffusion equation: loss and gradients
+    w.r.t. the velocity parameters (the analogue of jax.grad(model.mse)) vs torch float64 autograd
+    on the oracle twin, with save times that fall between step boundaries (interpolated)."""
+    from pde_opt_b200 import Domain
+    from pde_opt_b200.equations import AdvectionDiffusion2D
+    from pde_opt_b200.functions import GaussianVelocity
+    from pde_opt_b200.pde_model import PDEModel
+    from pde_opt_b200.solvers import SemiImplicitFourierSpectral
+
+    B = 3
+    dom = Domain((N, N), BOX, "dimensionless")
+    model = PDEModel(AdvectionDiffusion2D, dom, SemiImplicitFourierSpectral)
+    y0 = _y0(B, 41)
+    dt0 = 1e-4
+    ts = np.asarray([0.0, 5e-4, 1.0e-3, 1.6e-3], dtype=np.float32)
+    values = (y0[:, None] + 0.001 * np.random.default_rng(2).normal(size=(B, 3, N, N))).astype(np.float32)
+    p0 = torch.tensor([0.10, 0.15, 0.08], device="cuda", requires_grad=True)
+    p1 = torch.tensor([0.02, 0.03, 0.015], device="cuda", requires_grad=True)
+    cx = torch.tensor([0.1, -0.2, 0.3], device="cuda", requires_grad=True)
+    cy = torch.tensor([-0.1, 0.25, 0.0], device="cuda", requires_grad=True)
+    params = {"velocity": GaussianVelocity(p0, p1, (cx, cy)), "D": DCOEF}
+    loss = model.mse(params, (torch.from_numpy(y0).cuda(), torch.from_numpy(values).cuda()), {"A": 1.0}, ts, {}, 0.0, dt0=dt0)
+    loss.backward()
+
+    # oracle: float64 torch twin with the same float32 time grid and interpolation
+    times = O.constant_step_schedule(ts[0], ts[-1], dt0, np.float32)
+    yr = torch.from_numpy(y0.astype(np.float64))
+    q = [torch.tensor(v.detach().cpu().numpy().astype(np.float64), requires_grad=True) for v in (cx, cy, p0, p1)]
+    ctrl = torch.stack(q, -1)[:, None, :]
+    hold = len(times) - 1
+    preds, y, i_cur = [], yr, 0
+
+    def seg(y, a, b):
+        d = (times[a + 1 : b + 1] - times[a:b]).astype(np.float64)
+        return TO.rollout(y, ctrl, d, (N, N), BOX, DCOEF, 1.0, hold=hold)
+
+    for s_ in ts:
+        j = int(np.searchsorted(times, s_, side="left"))
+        if j == 0 or times[j] == s_:
+            if j > i_cur:
+                y, i_cur = seg(y, i_cur, j), j
+            preds.append(y)
+            continue
+        if j - 1 > i_cur:
+            y, i_cur = seg(y, i_cur, j - 1), j - 1
+        yb = seg(y, j - 1, j)
+        w = float(np.float32((s_ - times[j - 1]) / (times[j] - times[j - 1])))
+        preds.append(y + (yb - y) * w)
+        y, i_cur = yb, j
+    pred = torch.stack(preds, 0)
+    lr = ((torch.from_numpy(values.astype(np.float64)) - pred[1:].transpose(0, 1)) ** 2).mean()
+    lr.backward()
+    assert abs(loss.item() - lr.item()) <= 1e-4 * abs(lr.item())
+    for got, want, name in zip((cx, cy, p0, p1), q, ("cx", "cy", "p0", "p1")):
+        assert _rel(got.grad.cpu().numpy(), want.grad.numpy()) <= 2e-4, name
