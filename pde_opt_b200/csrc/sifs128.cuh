@@ -280,7 +280,30 @@ __device__ __forceinline__ void rhs_phase(float2* __restrict__ W, const SifsPara
 }
 
 // ---- spectral filter: f0 (natural layout in W) -> g = Re ifft(fft(f0) / (1 + dt A sigma)) --------
-__device__ __forceinline__ void spectral_filter(const Fft128& F, const float* __restrict__ mt, float dt, float2 (&x)[32]) {
+// `mt` is the per-step multiplier table m[kr][fc] = 1 / (N^2 (1 + dt A sigma(|kr|, fc))) with the
+// ROW index unfolded (kr = 0..127), so that the 16 rows a thread needs (kr = k1r + 8 brev4(pp)) are
+// compile-time offsets from two per-thread base addresses: 32 LDS with immediate offsets, no index
+// arithmetic, no division in the step loop (the table is rebuilt only when dt changes).
+constexpr int kMRows = kN;
+constexpr int kMLen = kMRows * kTabDim;
+
+template <int OFF>
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(OFF));
+  return v;
+}
+
+__device__ __forceinline__ void build_multiplier(float* __restrict__ mt, const float* __restrict__ tab, float dt) {
+  // solvers.py:62-63 with the inverse-FFT scale folded in
+  for (int i = threadIdx.x; i < kMLen; i += kThreads) {
+    const int kr = i / kTabDim, fc = i - kr * kTabDim;
+    const int fr = kr <= 64 ? kr : 128 - kr;
+    mt[i] = __fdividef(1.0f / float(kN * kN), fmaf(dt, tab[fr * kTabDim + fc], 1.0f));
+  }
+}
+
+__device__ __forceinline__ void spectral_filter(const Fft128& F, uint32_t mt_saddr, float2 (&x)[32]) {
   p1_gather_nat(F.nb, x);
   __syncthreads();  // everybody has read f0 before the buffer is reused as exchange space
   F.forward(x);
@@ -288,12 +311,10 @@ __device__ __forceinline__ void spectral_filter(const Fft128& F, const float* __
     constexpr int b = decltype(bc)::value;
     const int kc = F.p3_kc(b);
     const int fc = kc <= 64 ? kc : 128 - kc;
+    const uint32_t base = mt_saddr + (uint32_t)(F.m3.k1r * kTabDim + fc) * 4u;
     static_for<0, 16>([&](auto pc) {
       constexpr int pp = decltype(pc)::value;
-      const int kr = F.p3_kr(pp);
-      const int fr = kr <= 64 ? kr : 128 - kr;
-      // 1/(N^2 (1 + A dt sigma)): solvers.py:62-63 with the inverse-FFT scale folded in
-      const float mval = __fdividef(1.0f / float(kN * kN), fmaf(dt, mt[fr * kTabDim + fc], 1.0f));
+      const float mval = lds32<brev<4>(pp) * 8 * kTabDim * 4>(base);
       x[b * 16 + pp] = mul2(x[b * 16 + pp], splat2(mval));
     });
   });
@@ -323,6 +344,7 @@ __device__ __forceinline__ float2 block_sum2(float2 v, float2* red) {
 struct __align__(1024) SifsSmem {
   float2 W[kN * kN];
   float tab[kTabLen + 3];
+  float mt[kMLen];
   float2 tw[128];
   float2 gx[kN], gy[kN];
   float2 red[kThreads / 32];
@@ -421,7 +443,15 @@ __global__ void __launch_bounds__(kThreads, 1) sifs128_kernel(const __grid_const
     rhs_phase<EQ, MU, MOB>(S.W, p, ec, S.gx, S.gy);
     __syncthreads();
   }
+  const uint32_t mt_saddr = (uint32_t)__cvta_generic_to_shared(S.mt);
+  float dt_tab = __int_as_float(0x7fc00000);  // NaN: no table yet
   for (int k = 0; k < ((p.mode == MODE_RHS_ONLY) ? 0 : p.ksteps); ++k) {
+    if (p.dt[k] != dt_tab) {
+      // rebuilt only when the step length changes; the barriers of the RHS / load phase below order
+      // these writes before the reads in spectral_filter, and the previous step's reads before them
+      dt_tab = p.dt[k];
+      build_multiplier(S.mt, S.tab, dt_tab);
+    }
     if (p.mode == MODE_GIVEN_F) {
       // unfused vector field (terms.vf evaluated by the caller, solvers.py:59): load f0 instead
       const float* fa = p.f0 + (size_t)env_a * kN * kN;
@@ -439,7 +469,7 @@ __global__ void __launch_bounds__(kThreads, 1) sifs128_kernel(const __grid_const
     }
     __syncthreads();
     const float dt = p.dt[k];
-    spectral_filter(F, S.tab, dt, x);
+    spectral_filter(F, mt_saddr, x);
     // y1 = y0 + dt * g   (solvers.py:63); y0 comes back from the parking space
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
