@@ -230,6 +230,14 @@ pdeopt_status pdeopt_fft_lines_inv_update(const void* spec_dev, int32_t n, const
                                           const float* y0_dev, float* y1_dev, const pdeopt_line_geom* gout, float dt,
                                           void* stream);
 
+/* Real contiguous lines in_dev [n_lines][n] (n_lines even) -> half spectra out_dev [n_lines][n/2+1]
+ * complex64 in NATURAL frequency order h = 0..n/2 (two real lines ride in one complex transform). */
+pdeopt_status pdeopt_fft_lines_r2c(const float* in_dev, void* out_dev, int32_t n, int64_t n_lines, void* stream);
+
+/* Inverse of the above (unnormalised) fused with y1 = y0 + dt * (.) (solvers.py:63); y0/y1 [n_lines][n]. */
+pdeopt_status pdeopt_fft_lines_c2r_update(const void* half_dev, int32_t n, int64_t n_lines, const float* y0_dev,
+                                          float* y1_dev, float dt, void* stream);
+
 /* ---- CahnHilliard3DPeriodic (cahn_hilliard.py:112-200) ---------------------------------------- */
 typedef struct {
   int32_t nx, ny, nz; /* nx = planes held by this rank in slab mode */
@@ -250,8 +258,10 @@ pdeopt_status pdeopt_ch3d_rhs(const pdeopt_ch3d_desc* desc, const float* u_dev, 
 int64_t pdeopt_ch3d_work_floats(const pdeopt_ch3d_desc* desc, int32_t batch);
 
 /* ksteps calls of SemiImplicitFourierSpectral.step (solvers.py:56-70) with
- * CahnHilliard3DPeriodic.rhs_fd on `batch` whole domains (single GPU).  symbol_pos_dev: float32
- * [nx][ny][nz] A*fourier_symbol in position order on every axis; work_dev: pdeopt_ch3d_work_floats. */
+ * CahnHilliard3DPeriodic.rhs_fd on `batch` whole domains (single GPU).  The field is real, so the
+ * z transform is real-to-half-spectrum: symbol_pos_dev is float32 [nx][ny][nz/2+1] A*fourier_symbol
+ * in position order along x and y and natural order (kz = 0..nz/2) along z;
+ * work_dev: pdeopt_ch3d_work_floats. */
 pdeopt_status pdeopt_ch3d_step(const pdeopt_ch3d_desc* desc, const float* y0_dev, float* y1_dev, int32_t batch,
                                int32_t ksteps, const float* dt_host, const float* symbol_pos_dev, float* work_dev,
                                void* stream);

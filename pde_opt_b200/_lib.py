@@ -119,6 +119,8 @@ EXPORTS = [
     "pdeopt_fft_lines",
     "pdeopt_fft_lines_imex",
     "pdeopt_fft_lines_inv_update",
+    "pdeopt_fft_lines_r2c",
+    "pdeopt_fft_lines_c2r_update",
     "pdeopt_ch3d_rhs",
     "pdeopt_ch3d_work_floats",
     "pdeopt_ch3d_step",
@@ -175,6 +177,10 @@ def load():
     lib.pdeopt_fft_lines_imex.restype = ctypes.c_int
     lib.pdeopt_fft_lines_inv_update.argtypes = [vp, i32, gp, vp, vp, gp, f32, vp]
     lib.pdeopt_fft_lines_inv_update.restype = ctypes.c_int
+    lib.pdeopt_fft_lines_r2c.argtypes = [vp, vp, i32, i64, vp]
+    lib.pdeopt_fft_lines_r2c.restype = ctypes.c_int
+    lib.pdeopt_fft_lines_c2r_update.argtypes = [vp, i32, i64, vp, vp, f32, vp]
+    lib.pdeopt_fft_lines_c2r_update.restype = ctypes.c_int
     c3 = ctypes.POINTER(Ch3dDesc)
     lib.pdeopt_ch3d_rhs.argtypes = [c3, vp, vp, vp, vp, vp, i32, vp]
     lib.pdeopt_ch3d_rhs.restype = ctypes.c_int

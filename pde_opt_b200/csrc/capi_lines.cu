@@ -94,6 +94,38 @@ extern "C" pdeopt_status pdeopt_fft_lines_inv_update(const void* spec_dev, int32
   return PDEOPT_OK;
 }
 
+extern "C" pdeopt_status pdeopt_fft_lines_r2c(const float* in_dev, void* out_dev, int32_t n, int64_t n_lines, void* stream) {
+  if (!in_dev || !out_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
+  if (!lf_size_ok(n)) return fail(PDEOPT_ERR_UNSUPPORTED, "fft_lines: n must be a power of two in [8, 512]");
+  if (n_lines <= 0 || (n_lines & 1)) return fail(PDEOPT_ERR_INVALID, "r2c needs a positive even number of lines");
+  LfIoR2C io{in_dev, (float2*)out_dev, n, n / 2 + 1};
+  cudaError_t e = cudaSuccess;
+  auto run = [&]() -> cudaError_t {
+    PDEOPT_LF_DISPATCH(n, return (lf_launch_real<LFN, false>(n_lines / 2, io, (cudaStream_t)stream)));
+    return cudaSuccess;
+  };
+  e = run();
+  if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("fft_lines_r2c: ") + cudaGetErrorString(e));
+  g_launches.fetch_add(1);
+  return PDEOPT_OK;
+}
+
+extern "C" pdeopt_status pdeopt_fft_lines_c2r_update(const void* half_dev, int32_t n, int64_t n_lines, const float* y0_dev,
+                                                     float* y1_dev, float dt, void* stream) {
+  if (!half_dev || !y0_dev || !y1_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
+  if (!lf_size_ok(n)) return fail(PDEOPT_ERR_UNSUPPORTED, "fft_lines: n must be a power of two in [8, 512]");
+  if (n_lines <= 0 || (n_lines & 1)) return fail(PDEOPT_ERR_INVALID, "c2r needs a positive even number of lines");
+  LfIoC2RUpdate io{(const float2*)half_dev, y0_dev, y1_dev, n, n / 2 + 1, dt};
+  auto run = [&]() -> cudaError_t {
+    PDEOPT_LF_DISPATCH(n, return (lf_launch_real<LFN, true>(n_lines / 2, io, (cudaStream_t)stream)));
+    return cudaSuccess;
+  };
+  cudaError_t e = run();
+  if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("fft_lines_c2r_update: ") + cudaGetErrorString(e));
+  g_launches.fetch_add(1);
+  return PDEOPT_OK;
+}
+
 static pdeopt_status ch3d_check(const pdeopt_ch3d_desc* d, int32_t batch) {
   if (!d) return fail(PDEOPT_ERR_INVALID, "null argument");
   if (batch <= 0) return fail(PDEOPT_ERR_INVALID, "batch must be positive");
@@ -127,18 +159,26 @@ extern "C" pdeopt_status pdeopt_ch3d_rhs(const pdeopt_ch3d_desc* d, const float*
   const int bx = d->nz >= 256 ? 256 : (d->nz >= 128 ? 128 : (d->nz >= 64 ? 64 : 32));
   dim3 block(bx), g1((d->nz + bx - 1) / bx, d->ny, batch * (d->nx + 2)), g2((d->nz + bx - 1) / bx, d->ny, batch * d->nx);
   cudaStream_t st = (cudaStream_t)stream;
-  ch3d_mu_kernel<<<g1, block, 0, st>>>(p);
-  ch3d_div_kernel<<<g2, block, 0, st>>>(p);
+  const int xl = d->nx % 64 == 0 ? 64 : (d->nx % 32 == 0 ? 32 : (d->nx % 16 == 0 ? 16 : (d->nx % 8 == 0 ? 8 : 0)));
+  if (xl > 0 && d->ny % kC3TY == 0 && d->nz % kC3TZ == 0 && (int64_t)batch * (d->nx / xl) <= 65535) {
+    // fused 2.5-D marching kernel: one read of u, one write of f
+    dim3 grid(d->nz / kC3TZ, d->ny / kC3TY, batch * (d->nx / xl));
+    ch3d_rhs_fused_kernel<<<grid, kC3Threads, 0, st>>>(p, xl);
+    g_launches.fetch_add(1);
+  } else {
+    ch3d_mu_kernel<<<g1, block, 0, st>>>(p);
+    ch3d_div_kernel<<<g2, block, 0, st>>>(p);
+    g_launches.fetch_add(2);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("ch3d_rhs: ") + cudaGetErrorString(e));
-  g_launches.fetch_add(2);
   return PDEOPT_OK;
 }
 
 extern "C" int64_t pdeopt_ch3d_work_floats(const pdeopt_ch3d_desc* d, int32_t batch) {
   if (!d || batch <= 0) return 0;
   const int64_t pl = (int64_t)d->ny * d->nz;
-  return (int64_t)batch * ((d->nx + 2) * pl + d->nx * pl + 2 * d->nx * pl);
+  return (int64_t)batch * ((d->nx + 2) * pl + d->nx * pl + 2 * (int64_t)d->nx * d->ny * (d->nz / 2 + 1));
 }
 
 extern "C" pdeopt_status pdeopt_ch3d_step(const pdeopt_ch3d_desc* d, const float* y0_dev, float* y1_dev, int32_t batch,
@@ -151,22 +191,22 @@ extern "C" pdeopt_status pdeopt_ch3d_step(const pdeopt_ch3d_desc* d, const float
   if (!lf_size_ok(d->nx) || !lf_size_ok(d->ny) || !lf_size_ok(d->nz))
     return fail(PDEOPT_ERR_UNSUPPORTED, "ch3d_step: nx, ny, nz must be powers of two in [8, 512]");
   const int64_t nx = d->nx, ny = d->ny, nz = d->nz, pl = ny * nz, vol = nx * pl;
+  const int64_t hp = nz / 2 + 1, hpl = ny * hp, hvol = nx * hpl;  // half spectrum along z (real field)
   float* mu = work_dev;
   float* f = mu + (int64_t)batch * (nx + 2) * pl;
-  float* W = f + (int64_t)batch * vol;  // complex [batch][nx][ny][nz]
-  pdeopt_line_geom gz{(int64_t)batch * nx * ny, 1, nz, 0, (int32_t)nz, 0, 0, 1};
-  pdeopt_line_geom gy{(int64_t)batch * nx * nz, nz, pl, 1, (int32_t)ny, 0, 0, nz};
-  pdeopt_line_geom gx{(int64_t)batch * pl, pl, vol, 1, (int32_t)nx, 0, 0, pl};
+  float* W = f + (int64_t)batch * vol;  // complex [batch][nx][ny][nz/2+1]
+  pdeopt_line_geom gy{(int64_t)batch * nx * hp, hp, hpl, 1, (int32_t)ny, 0, 0, hp};
+  pdeopt_line_geom gx{(int64_t)batch * hpl, hpl, hvol, 1, (int32_t)nx, 0, 0, hpl};
   pdeopt_line_geom gsym = gx;
   gsym.outer = 0;  // the symbol is shared by the batch
   const float* src = y0_dev;
   for (int k = 0; k < ksteps; ++k) {
     if ((s = pdeopt_ch3d_rhs(d, src, nullptr, nullptr, mu, f, batch, stream)) != PDEOPT_OK) return s;
-    if ((s = pdeopt_fft_lines(f, W, (int32_t)nz, &gz, &gz, 0, 1, 1.0f, stream)) != PDEOPT_OK) return s;
+    if ((s = pdeopt_fft_lines_r2c(f, W, (int32_t)nz, (int64_t)batch * nx * ny, stream)) != PDEOPT_OK) return s;
     if ((s = pdeopt_fft_lines(W, W, (int32_t)ny, &gy, &gy, 0, 0, 1.0f, stream)) != PDEOPT_OK) return s;
     if ((s = pdeopt_fft_lines_imex(W, W, (int32_t)nx, &gx, symbol_pos_dev, &gsym, dt_host[k], 1.0f / (float)vol, stream)) != PDEOPT_OK) return s;
     if ((s = pdeopt_fft_lines(W, W, (int32_t)ny, &gy, &gy, 1, 0, 1.0f, stream)) != PDEOPT_OK) return s;
-    if ((s = pdeopt_fft_lines_inv_update(W, (int32_t)nz, &gz, src, y1_dev, &gz, dt_host[k], stream)) != PDEOPT_OK) return s;
+    if ((s = pdeopt_fft_lines_c2r_update(W, (int32_t)nz, (int64_t)batch * nx * ny, src, y1_dev, dt_host[k], stream)) != PDEOPT_OK) return s;
     src = y1_dev;
   }
   return PDEOPT_OK;

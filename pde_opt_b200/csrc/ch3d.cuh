@@ -85,6 +85,127 @@ __global__ void __launch_bounds__(256) ch3d_div_kernel(const __grid_constant__ C
   p.f[((size_t)b * p.nx + x) * pl + o] = (fx + fy) + fz;
 }
 
+// ---- fused single-pass RHS: 2.5-D marching ----------------------------------------------------
+// One CTA owns a (y, z) tile of 16 x 64 points and marches along x for `xl` planes, so u is read
+// from HBM once (plus the tile halo, which neighbouring CTAs share through L2) and f written once:
+// ~2 field passes instead of the 5 of the two-kernel version above.  Rolling shared-memory windows:
+// three u planes (tile + halo 2) and two (mu, D) planes (tile + ring 1); the x-face flux of the
+// previous plane is carried in registers.
+constexpr int kC3TY = 16, kC3TZ = 64, kC3Threads = 256;
+constexpr int kC3UY = kC3TY + 4, kC3UZ = kC3TZ + 4, kC3UZP = 72;
+constexpr int kC3MY = kC3TY + 2, kC3MZ = kC3TZ + 2, kC3MZP = 68;
+
+struct Ch3dSmem {
+  float U[3][kC3UY][kC3UZP];
+  float2 MD[2][kC3MY][kC3MZP];
+};
+
+__global__ void __launch_bounds__(kC3Threads) ch3d_rhs_fused_kernel(const __grid_constant__ Ch3dParams p, int xl) {
+  __shared__ Ch3dSmem S;
+  const int tid = threadIdx.x;
+  const int z0 = blockIdx.x * kC3TZ, y0 = blockIdx.y * kC3TY;
+  const int nchunk = p.nx / xl;
+  const int b = blockIdx.z / nchunk, x0 = (blockIdx.z % nchunk) * xl;
+  const int ty = tid >> 4, tz = (tid & 15) * 4;  // this thread's 4 consecutive z points of row ty
+  constexpr int kULoads = (kC3UY * kC3UZ + kC3Threads - 1) / kC3Threads;  // 6
+
+  // global offsets (within a plane) of the halo-2 tile elements this thread stages
+  int goff[kULoads], soff[kULoads];
+#pragma unroll
+  for (int i = 0; i < kULoads; ++i) {
+    const int e = tid + i * kC3Threads;
+    if (e < kC3UY * kC3UZ) {
+      const int yy = e / kC3UZ, zz = e - yy * kC3UZ;
+      int gy = y0 + yy - 2, gz = z0 + zz - 2;
+      gy = gy < 0 ? gy + p.ny : (gy >= p.ny ? gy - p.ny : gy);
+      gz = gz < 0 ? gz + p.nz : (gz >= p.nz ? gz - p.nz : gz);
+      goff[i] = gy * p.nz + gz;
+      soff[i] = yy * kC3UZP + zz;
+    } else {
+      goff[i] = -1;
+      soff[i] = 0;
+    }
+  }
+  auto fetch = [&](int x, float (&r)[kULoads]) {
+    const float* pl = ch3d_plane(p, b, x);
+#pragma unroll
+    for (int i = 0; i < kULoads; ++i) r[i] = goff[i] >= 0 ? __ldg(pl + goff[i]) : 0.f;
+  };
+  auto stage = [&](int slot, const float (&r)[kULoads]) {
+    float* u = &S.U[slot][0][0];
+#pragma unroll
+    for (int i = 0; i < kULoads; ++i)
+      if (goff[i] >= 0) u[soff[i]] = r[i];
+  };
+  // (mu, D) of plane c on tile + ring 1 from U slots (c-1, c, c+1) = (sm, s0, sp)
+  auto mu_plane = [&](int sm, int s0, int sp, int md) {
+    for (int e = tid; e < kC3MY * kC3MZ; e += kC3Threads) {
+      const int yy = e / kC3MZ, zz = e - yy * kC3MZ;  // ring coordinates; U index = +1
+      const float u = S.U[s0][yy + 1][zz + 1];
+      const float lap = ((S.U[sp][yy + 1][zz + 1] - 2.0f * u) + S.U[sm][yy + 1][zz + 1]) * p.inv_hx2 +
+                        ((S.U[s0][yy + 2][zz + 1] - 2.0f * u) + S.U[s0][yy][zz + 1]) * p.inv_hy2 +
+                        ((S.U[s0][yy + 1][zz + 2] - 2.0f * u) + S.U[s0][yy + 1][zz]) * p.inv_hz2;
+      S.MD[md][yy][zz] = make_float2(mu_h<MU_RUNTIME>(u, p.pw, 0.0f) - p.kappa * lap, mob<MOB_RUNTIME>(u, p.pw));
+    }
+  };
+
+  float r[kULoads];
+  // prologue: planes x0-2, x0-1 -> slots 0, 1; plane x0 prefetched
+  fetch(x0 - 2, r);
+  stage(0, r);
+  fetch(x0 - 1, r);
+  stage(1, r);
+  fetch(x0, r);
+  float fx_prev[4] = {0.f, 0.f, 0.f, 0.f};
+  // iteration it: current plane c = x0 + it; U slots: (c-1) -> (it+1)%3 ... kept as rolling indices
+  int sm = 0, s0 = 1, sp = 2;  // slots of planes c-1, c, c+1 at it = -1 (c = x0 - 1)
+  int md_prev = 0, md_cur = 1;
+  for (int it = -1; it <= xl; ++it) {
+    const int c = x0 + it;
+    stage(sp, r);                      // plane c + 1
+    if (it < xl) fetch(c + 2, r);      // prefetch plane c + 2 while this iteration computes
+    __syncthreads();
+    mu_plane(sm, s0, sp, md_cur);
+    __syncthreads();
+    if (it >= 0) {
+      // x-face flux between planes c-1 and c, own points (cahn_hilliard.py:181-186)
+      float fx[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = S.MD[md_prev][ty + 1][tz + 1 + j], bb = S.MD[md_cur][ty + 1][tz + 1 + j];
+        fx[j] = (0.5f * (a.y + bb.y)) * ((bb.x - a.x) * p.inv_hx);
+      }
+      if (it >= 1) {
+        // f of plane c-1: x-divergence + in-plane flux divergence from the (mu, D) plane with ring
+        float out[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int yy = ty + 1, zz = tz + 1 + j;
+          const float2 m0 = S.MD[md_prev][yy][zz];
+          const float2 myp = S.MD[md_prev][yy + 1][zz], mym = S.MD[md_prev][yy - 1][zz];
+          const float2 mzp = S.MD[md_prev][yy][zz + 1], mzm = S.MD[md_prev][yy][zz - 1];
+          const float fyp = (0.5f * (m0.y + myp.y)) * ((myp.x - m0.x) * p.inv_hy);
+          const float fym = (0.5f * (mym.y + m0.y)) * ((m0.x - mym.x) * p.inv_hy);
+          const float fzp = (0.5f * (m0.y + mzp.y)) * ((mzp.x - m0.x) * p.inv_hz);
+          const float fzm = (0.5f * (mzm.y + m0.y)) * ((m0.x - mzm.x) * p.inv_hz);
+          out[j] = ((fx[j] - fx_prev[j]) * p.inv_hx + (fyp - fym) * p.inv_hy) + (fzp - fzm) * p.inv_hz;
+        }
+        float* dst = p.f + ((size_t)b * p.nx + (c - 1)) * p.ny * p.nz + (size_t)(y0 + ty) * p.nz + z0 + tz;
+        *reinterpret_cast<float4*>(dst) = make_float4(out[0], out[1], out[2], out[3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) fx_prev[j] = fx[j];
+    }
+    __syncthreads();  // all reads of U slot `sm` and MD[md_prev] done before they are overwritten
+    const int t = sm;
+    sm = s0;
+    s0 = sp;
+    sp = t;
+    md_prev ^= 1;
+    md_cur ^= 1;
+  }
+}
+
 // ---- line-FFT functors of the 3-D semi-implicit step -------------------------------------------
 struct LfLoadReal {  // real array -> complex with zero imaginary part
   const float* p;
@@ -112,6 +233,40 @@ struct LfStoreUpdate {
   __device__ __forceinline__ LineGeom gout() const { return g; }
   __device__ __forceinline__ void store(long long off, long long, int, float2 v) const { y1[off] = fmaf(dt, v.x, y0[off]); }
   __device__ __forceinline__ void flush(long long) {}
+};
+
+// real lines [n_lines][n] -> half spectra [n_lines][n/2+1]
+struct LfIoR2C {
+  const float* in;
+  float2* out;
+  int n, hp;
+  __device__ __forceinline__ float2 load_pair(long long pair, int idx) const {
+    const float* a = in + 2 * pair * n;
+    return make_float2(a[idx], a[n + idx]);
+  }
+  __device__ __forceinline__ void store_half(long long pair, int h, float2 A, float2 B) const {
+    float2* o = out + 2 * pair * hp;
+    o[h] = A;
+    o[hp + h] = B;
+  }
+};
+// half spectra -> y1 = y0 + dt * real lines   (solvers.py:63)
+struct LfIoC2RUpdate {
+  const float2* in;
+  const float* y0;
+  float* y1;
+  int n, hp;
+  float dt;
+  __device__ __forceinline__ void load_half(long long pair, int h, float2& A, float2& B) const {
+    const float2* a = in + 2 * pair * hp;
+    A = a[h];
+    B = a[hp + h];
+  }
+  __device__ __forceinline__ void store_pair(long long pair, int idx, float2 v) const {
+    const long long o = 2 * pair * n + idx;
+    y1[o] = fmaf(dt, v.x, y0[o]);
+    y1[o + n] = fmaf(dt, v.y, y0[o + n]);
+  }
 };
 
 }  // namespace pdeopt

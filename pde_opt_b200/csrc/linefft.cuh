@@ -307,6 +307,120 @@ __global__ void __launch_bounds__(LineTile<N>::kThreads) linefft_kernel(long lon
   }
 }
 
+// ---- real <-> half-spectrum transforms of contiguous lines ---------------------------------------
+// Two adjacent REAL lines a, b ride in one complex line z = a + i b (the same packing as the fused
+// 2-D kernels); the forward transform is untangled into the two half spectra
+//   A[h] = (Z[h] + conj Z[N-h]) / 2,   B[h] = (Z[h] - conj Z[N-h]) / (2i),   h = 0 .. N/2,
+// stored in NATURAL order of h (the remaining axes stay in position order), which halves the data
+// every later pass of a real field's 3-D transform has to move.  The inverse rebuilds Z from (A, B).
+struct LfNoIo {
+  __device__ __forceinline__ float2 load(long long, long long, int) const { return make_float2(0.f, 0.f); }
+  __device__ __forceinline__ void store(long long, long long, int, float2) const {}
+};
+
+template <int N>
+struct LineTileReal {
+  static constexpr int T = LineTile<N>::T;
+  static constexpr size_t smem_bytes = sizeof(float2) * (size_t)(N * (T + 1) + N) + sizeof(int) * (size_t)N;
+};
+
+// Io (forward):  float2 load_pair(long long pair, int idx) ; void store_half(long long pair, int h, float2 A, float2 B)
+// Io (inverse):  void load_half(long long pair, int h, float2& A, float2& B) ; void store_pair(long long pair, int idx, float2 v)
+template <int N, bool INV, class Io>
+__global__ void __launch_bounds__(LineTile<N>::kThreads) linefft_real_kernel(long long n_pairs, Io io) {
+  extern __shared__ __align__(16) unsigned char lf_smem[];
+  constexpr int T = LineTile<N>::T, LP = LineTile<N>::LP, NT = LineTile<N>::kThreads;
+  constexpr int R1 = lf_r1(N), R2 = lf_r2(N), R3 = lf_r3(N);
+  constexpr int S2 = N / R1, S3 = N / R1 / R2, HP = N / 2 + 1;
+  float2* Sm = reinterpret_cast<float2*>(lf_smem);
+  float2* tw = Sm + N * LP;
+  int* f2p = reinterpret_cast<int*>(tw + N);  // frequency -> storage position
+  for (int i = threadIdx.x; i < N; i += NT) {
+    float s, c;
+    sincospif(-2.0f * float(i) / float(N), &s, &c);
+    tw[i] = make_float2(c, s);
+    f2p[line_pos_to_freq(N, i)] = i;
+  }
+  LfCtx c{Sm, tw, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, n_pairs};
+  LfNoIo nio;
+  for (long long tile = blockIdx.x; tile * T < n_pairs; tile += gridDim.x) {
+    const long long l0 = tile * T;
+    c.l0 = l0;
+    __syncthreads();
+    if constexpr (!INV) {
+      for (int w = threadIdx.x; w < N * T; w += NT) {
+        const int idx = w % N, pl = w / N;
+        if (l0 + pl < n_pairs) Sm[idx * LP + pl] = io.load_pair(l0 + pl, idx);
+      }
+      __syncthreads();
+      lf_stage<N, R1, N, false, false, false, false>(c, nio, nio);
+      __syncthreads();
+      if constexpr (R2 > 1) {
+        lf_stage<N, R2, S2, false, false, false, false>(c, nio, nio);
+        __syncthreads();
+      }
+      if constexpr (R3 > 1) {
+        lf_stage<N, R3, S3, false, false, false, false>(c, nio, nio);
+        __syncthreads();
+      }
+      for (int w = threadIdx.x; w < HP * T; w += NT) {
+        const int h = w % HP, pl = w / HP;
+        if (l0 + pl < n_pairs) {
+          const float2 zk = Sm[f2p[h] * LP + pl], zn = Sm[f2p[(N - h) & (N - 1)] * LP + pl];
+          const float2 A = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+          const float2 B = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
+          io.store_half(l0 + pl, h, A, B);
+        }
+      }
+    } else {
+      for (int w = threadIdx.x; w < HP * T; w += NT) {
+        const int h = w % HP, pl = w / HP;
+        if (l0 + pl < n_pairs) {
+          float2 A, B;
+          io.load_half(l0 + pl, h, A, B);
+          // Z[h] = A + i B ;  Z[N-h] = conj(A) + i conj(B)
+          Sm[f2p[h] * LP + pl] = make_float2(A.x - B.y, A.y + B.x);
+          if (h != 0 && h != N / 2) Sm[f2p[N - h] * LP + pl] = make_float2(A.x + B.y, B.x - A.y);
+        }
+      }
+      __syncthreads();
+      if constexpr (R3 > 1) {
+        lf_stage<N, R3, S3, true, false, false, false>(c, nio, nio);
+        __syncthreads();
+      }
+      if constexpr (R2 > 1) {
+        lf_stage<N, R2, S2, true, false, false, false>(c, nio, nio);
+        __syncthreads();
+      }
+      lf_stage<N, R1, N, true, false, false, false>(c, nio, nio);
+      __syncthreads();
+      for (int w = threadIdx.x; w < N * T; w += NT) {
+        const int idx = w % N, pl = w / N;
+        if (l0 + pl < n_pairs) io.store_pair(l0 + pl, idx, Sm[idx * LP + pl]);
+      }
+    }
+  }
+}
+
+template <int N, bool INV, class Io>
+cudaError_t lf_launch_real(long long n_pairs, Io io, cudaStream_t stream) {
+  auto kern = linefft_real_kernel<N, INV, Io>;
+  constexpr size_t smem = LineTileReal<N>::smem_bytes;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  const long long tiles = (n_pairs + LineTile<N>::T - 1) / LineTile<N>::T;
+  const int per_sm = (int)((227 * 1024) / (smem + 1024));
+  long long grid = tiles;
+  const long long cap = 148LL * (per_sm > 8 ? 8 : (per_sm < 1 ? 1 : per_sm));
+  if (grid > cap) grid = cap;
+  kern<<<(unsigned)grid, LineTile<N>::kThreads, smem, stream>>>(n_pairs, io);
+  return cudaGetLastError();
+}
+
 // ---- stock functors ---------------------------------------------------------------------------
 struct LfLoadC {  // complex array
   const float2* p;

@@ -163,10 +163,12 @@ class Ch3dPlan:
         return f
 
     def step(self, y0, dts, symbol_pos, out=None):
-        """len(dts) semi-implicit steps of y0 [B, nx, ny, nz]; symbol_pos: A*symbol in position order."""
+        """len(dts) semi-implicit steps of y0 [B, nx, ny, nz]; symbol_pos: A*symbol [nx, ny, nz/2+1],
+        position order along x and y, natural kz along z (SemiImplicitFourierSpectral.symbol_pos_on)."""
         lib = _lib.load()
         assert y0.is_cuda and y0.dtype == torch.float32 and y0.is_contiguous() and tuple(y0.shape[1:]) == self.points
-        assert symbol_pos.is_cuda and symbol_pos.dtype == torch.float32 and tuple(symbol_pos.shape) == self.points
+        assert symbol_pos.is_cuda and symbol_pos.dtype == torch.float32
+        assert tuple(symbol_pos.shape) == (self.points[0], self.points[1], self.points[2] // 2 + 1)
         y1 = out if out is not None else torch.empty_like(y0)
         dts = np.ascontiguousarray(np.asarray(dts, dtype=np.float32))
         work = self._workbuf(y0.shape[0], y0.device)

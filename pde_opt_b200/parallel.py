@@ -41,7 +41,7 @@ def gather_env_values(local, num_envs=None, group=None):
 # Slab-decomposed 3-D Cahn-Hilliard (BASELINE config 5)
 # --------------------------------------------------------------------------------------------------
 class _DeviceBackend:
-    """The four device operations of the slab step, through the C ABI (include/pdeopt_b200.h)."""
+    """The device operations of the slab step, through the C ABI (include/pdeopt_b200.h)."""
 
     def __init__(self, plan):
         self.plan = plan
@@ -54,6 +54,23 @@ class _DeviceBackend:
         import ctypes
 
         return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+    def fft_r2c(self, f, dst, n, n_lines):
+        import ctypes
+
+        from . import _lib
+
+        _lib.check(_lib.load().pdeopt_fft_lines_r2c(ctypes.c_void_p(f.data_ptr()), ctypes.c_void_p(dst.data_ptr()), n, n_lines,
+                                                   self._stream(f)))
+
+    def fft_c2r_update(self, spec, n, n_lines, y0, y1, dt):
+        import ctypes
+
+        from . import _lib
+
+        _lib.check(_lib.load().pdeopt_fft_lines_c2r_update(ctypes.c_void_p(spec.data_ptr()), n, n_lines,
+                                                          ctypes.c_void_p(y0.data_ptr()), ctypes.c_void_p(y1.data_ptr()),
+                                                          float(dt), self._stream(spec)))
 
     def fft_lines(self, src, dst, n, gin, gout, inverse, in_real, scale):
         import ctypes
@@ -90,12 +107,13 @@ class SlabCahnHilliard3D:
     Rank r holds planes [r*nxl, (r+1)*nxl) of the global [Nx, Ny, Nz] field.  Per step:
       1. ring exchange of the two boundary planes on either side (the FD RHS reaches x +- 2),
       2. rhs_fd on the slab,
-      3. z then y line FFTs on the slab; the y pass writes straight into the packed send buffer
-         [dest][nxl][Ny/P][Nz] (chunked line geometry: no separate pack kernel),
-      4. all-to-all #1 -> [Nx][Ny/P][Nz]: x lines complete on every rank,
+      3. real-to-half-spectrum z transform (Hz = Nz/2+1 complex per line), then the y line FFTs; the
+         y pass writes straight into the packed send buffer [dest][nxl][Ny/P][Hz] (chunked line
+         geometry: no separate pack kernel),
+      4. all-to-all #1 -> [Nx][Ny/P][Hz]: x lines complete on every rank,
       5. x pass: forward FFT, multiply by 1/(N (1 + A dt sigma)), inverse FFT in one kernel,
       6. all-to-all #2 back (no pack needed: x-ranges are contiguous),
-      7. inverse y pass reading the packed layout, inverse z pass fused with y1 = y0 + dt g.
+      7. inverse y pass reading the packed layout, half-spectrum-to-real z pass fused with y1 = y0 + dt g.
     The spectrum stays in the line engine's position order throughout; the symbol table is permuted
     once at construction.  Collectives: torch.distributed (NCCL on GPUs; gloo in the CPU tests, where
     `backend` is an emulation of the four device operations)."""
@@ -121,26 +139,27 @@ class SlabCahnHilliard3D:
             plan = Ch3dPlan((nxl, Ny, Nz), equation.domain.dx, equation.kappa, equation._mu_c.descriptor(), equation._mob_c.descriptor())
             backend = _DeviceBackend(plan)
         self.backend = backend
-        # local part of A*symbol in position order: [Nx][C][Nz] for this rank's y-chunk
+        # local part of A*symbol: [Nx][C][Hz] for this rank's y-chunk (position order along x and y,
+        # natural kz = 0..Nz/2 along z)
+        Hz = self.Hz = Nz // 2 + 1
         if symbol_pos_local is None:
             import numpy as np
 
             s = np.asarray(equation.fourier_symbol)
             s = (np.float32(A) * s.real.astype(np.float32)).astype(np.float32)
-            s = to_position_order(s, (0, 1, 2))[:, self.rank * C : (self.rank + 1) * C, :]
+            s = to_position_order(s, (0, 1))[:, self.rank * C : (self.rank + 1) * C, :Hz]
             symbol_pos_local = torch.from_numpy(np.ascontiguousarray(s)).to(device)
         self.sym = symbol_pos_local
         self.scale = 1.0 / float(Nx * Ny * Nz)
         # line geometries (elements)
-        self.g_z = geom(nxl * Ny, 1, Nz, 0, Nz, 1)
-        self.g_y = geom(nxl * Nz, Nz, Ny * Nz, 1, Ny, Nz)
-        self.g_y_packed = geom(nxl * Nz, Nz, C * Nz, 1, Ny, Nz, chunk=C, hi=nxl * C * Nz)
-        self.g_x = geom(C * Nz, C * Nz, 0, 1, Nx, C * Nz)
+        self.g_y = geom(nxl * Hz, Hz, Ny * Hz, 1, Ny, Hz)
+        self.g_y_packed = geom(nxl * Hz, Hz, C * Hz, 1, Ny, Hz, chunk=C, hi=nxl * C * Hz)
+        self.g_x = geom(C * Hz, C * Hz, 0, 1, Nx, C * Hz)
         self._bufs = None
 
     def _buffers(self, like):
         if self._bufs is None:
-            n = self.nxl * self.Ny * self.Nz
+            n = self.nxl * self.Ny * self.Hz
             mk = lambda: torch.empty(n, dtype=torch.complex64, device=like.device)
             pl = (2, self.Ny, self.Nz)
             self._bufs = dict(W=mk(), send=mk(), recv=mk(), lo=torch.empty(pl, dtype=like.dtype, device=like.device),
@@ -177,13 +196,13 @@ class SlabCahnHilliard3D:
         y1 = out if out is not None else torch.empty_like(u)
         lo, hi = self.exchange_halos(u)
         f = be.rhs(u, lo, hi)
-        be.fft_lines(f, b["W"], self.Nz, self.g_z, self.g_z, False, True, 1.0)
+        be.fft_r2c(f, b["W"], self.Nz, self.nxl * self.Ny)
         be.fft_lines(b["W"], b["send"], self.Ny, self.g_y, self.g_y_packed, False, False, 1.0)
         self._all_to_all(b["recv"], b["send"])
         be.fft_lines_imex(b["recv"], self.Nx, self.g_x, self.sym, self.g_x, dt, self.scale)
         self._all_to_all(b["send"], b["recv"])
         be.fft_lines(b["send"], b["W"], self.Ny, self.g_y_packed, self.g_y, True, False, 1.0)
-        be.fft_lines_inv_update(b["W"], self.Nz, self.g_z, u, y1, self.g_z, dt)
+        be.fft_c2r_update(b["W"], self.Nz, self.nxl * self.Ny, u, y1, dt)
         return y1
 
     def rollout(self, u, dts):

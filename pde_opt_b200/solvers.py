@@ -71,7 +71,8 @@ class SemiImplicitFourierSpectral:
         self._filter_plan = None
 
     def symbol_pos_on(self, device):
-        """A * fourier_symbol as float32 in the line-FFT engine's position order (3-D path)."""
+        """A * fourier_symbol as float32 [nx, ny, nz/2+1]: the line-FFT engine's position order along
+        x and y, natural kz = 0..nz/2 along z (the z transform of the real field is real-to-half)."""
         key = ("pos", str(device))
         if key not in self._sym_dev:
             from .linefft import to_position_order
@@ -82,7 +83,8 @@ class SemiImplicitFourierSpectral:
                     raise ValueError("fourier_symbol must be real for the semi-implicit path")
                 s = s.real
             s = (np.float32(self.A) * s.astype(np.float32)).astype(np.float32)
-            self._sym_dev[key] = torch.from_numpy(np.ascontiguousarray(to_position_order(s, (0, 1, 2)))).to(device)
+            s = to_position_order(s, (0, 1))[:, :, : s.shape[2] // 2 + 1]
+            self._sym_dev[key] = torch.from_numpy(np.ascontiguousarray(s)).to(device)
         return self._sym_dev[key]
 
     def _rollout3d(self, terms, dts, y0, out=None):

@@ -199,3 +199,25 @@ def test_slab_path_on_one_gpu_matches_whole_domain_step():
         yo = O.sifs_step(oeq.rhs, yo, a, bb, 0.5, oeq.fourier_symbol)
     assert rel_l2(y.cpu().numpy(), yo) <= 1e-5
     assert rel_l2(y.cpu().numpy() - u, whole - u) <= 1e-3
+
+
+@pytest.mark.parametrize("n", [8, 32, 128, 512])
+def test_r2c_and_c2r_lines(n):
+    """real lines -> natural-order half spectra (two lines per complex transform) and back."""
+    import ctypes
+
+    from pde_opt_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(n)
+    L = 70  # even, not a multiple of the tile
+    x = rng.normal(size=(L, n)).astype(np.float32)
+    xd = torch.from_numpy(x).cuda()
+    half = torch.empty((L, n // 2 + 1), dtype=torch.complex64, device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.pdeopt_fft_lines_r2c(ctypes.c_void_p(xd.data_ptr()), ctypes.c_void_p(half.data_ptr()), n, L, st))
+    assert rel_l2(half.cpu().numpy(), np.fft.rfft(x.astype(np.float64), axis=1)) <= 2e-6
+    y0 = torch.from_numpy(rng.normal(size=(L, n)).astype(np.float32)).cuda()
+    y1 = torch.empty_like(y0)
+    _lib.check(lib.pdeopt_fft_lines_c2r_update(ctypes.c_void_p(half.data_ptr()), n, L, ctypes.c_void_p(y0.data_ptr()), ctypes.c_void_p(y1.data_ptr()), 0.5 / n, st))
+    assert rel_l2(y1.cpu().numpy(), y0.cpu().numpy() + 0.5 * x) <= 2e-6

@@ -43,6 +43,15 @@ class EmuBackend:
         eq = O.CahnHilliardPeriodic(dom, KAPPA, lambda c: O.mu_log(c, 3.0), lambda c: 0.15 * np.ones_like(c), "fd", np.float32)
         return torch.from_numpy(np.ascontiguousarray(eq.rhs_fd(ext)[2:-2]))
 
+    def fft_r2c(self, f, dst, n, n_lines):
+        lines = f.numpy().reshape(n_lines, n)
+        dst.numpy().ravel()[: n_lines * (n // 2 + 1)] = np.fft.rfft(lines, axis=1).astype(np.complex64).ravel()
+
+    def fft_c2r_update(self, spec, n, n_lines, y0, y1, dt):
+        half = spec.numpy().ravel()[: n_lines * (n // 2 + 1)].reshape(n_lines, n // 2 + 1)
+        g = (np.fft.irfft(half, n=n, axis=1) * n).astype(np.float32)
+        y1.numpy().reshape(n_lines, n)[:] = y0.numpy().reshape(n_lines, n) + np.float32(dt) * g
+
     def fft_lines(self, src, dst, n, gin, gout, inverse, in_real, scale):
         a = src.numpy().ravel()
         lines = a[_offsets(gin, n)].astype(np.complex64)
