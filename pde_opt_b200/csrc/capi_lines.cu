@@ -234,7 +234,7 @@ extern "C" pdeopt_status pdeopt_strang_lines_step_batched(const pdeopt_gpe_desc*
   float2* etab = W + total;
   float* norm = (float*)(etab + npts);
   GpeLinesConst c;
-  c.nx = nx; c.ny = ny;
+  c.nx = nx; c.ny = ny; c.log2nx = ilog2(nx);
   c.lo_x = (float)desc->lo_x; c.lo_y = (float)desc->lo_y; c.hx = (float)desc->hx; c.hy = (float)desc->hy;
   c.trap = (float)desc->trap_factor; c.e = (float)desc->e; c.k_int = (float)desc->k;
   c.ts_re = ts_re; c.ts_im = ts_im; c.ctrl = ctrl_dev;
@@ -273,7 +273,7 @@ extern "C" pdeopt_status pdeopt_strang_lines_step_batched(const pdeopt_gpe_desc*
       if (e != cudaSuccess) break;
       e = lf_run<LF_INV, true>(ny, rows.n_lines, LfLoadC{W, rows}, LfMidNone{}, LfStorePotential{W, src, norm, c, dt, 0.f, rows}, st);
       if (e != cudaSuccess) break;
-      e = lf_run<LF_FWD, true>(ny, rows.n_lines, LfLoadNormalised{W, norm, nx, ny, dx2, rows}, LfMidNone{}, LfStoreC{W, rows}, st);
+      e = lf_run<LF_FWD, true>(ny, rows.n_lines, LfLoadNormalised{W, norm, nx, ny, ilog2(nx), dx2, rows}, LfMidNone{}, LfStoreC{W, rows}, st);
       if (e != cudaSuccess) break;
       e = lf_run<LF_FWD_MUL_INV, false>(nx, cols.n_lines, LfLoadC{W, cols}, mid, LfStoreC{W, cols}, st);
       if (e != cudaSuccess) break;

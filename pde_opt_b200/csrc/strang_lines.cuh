@@ -21,7 +21,7 @@
 namespace pdeopt {
 
 struct GpeLinesConst {
-  int nx, ny;
+  int nx, ny, log2nx;
   float lo_x, lo_y, hx, hy;
   float trap, e, k_int;
   float ts_re, ts_im;
@@ -78,14 +78,14 @@ struct LfStorePotential {
   LineGeom g;
   __device__ __forceinline__ LineGeom gout() const { return g; }
   __device__ __forceinline__ void store(long long o, long long line, int idx, float2 v) {
-    const int env = (int)(line / c.nx), r = (int)(line % c.nx);
+    const int l32 = (int)line, env = l32 >> c.log2nx, r = l32 & (c.nx - 1);
     const float2 w = cmul(v, gpe_potential_factor(c, env, r, idx, psi0[o], dt));
     out[o] = w;
     acc = fmaf(w.x, w.x, fmaf(w.y, w.y, acc));
   }
   __device__ __forceinline__ void flush(long long l0) {
     const float t = lf_block_sum(acc);
-    if (threadIdx.x == 0) atomicAdd(norm + l0 / c.nx, t);
+    if (threadIdx.x == 0) atomicAdd(norm + (l0 >> c.log2nx), t);
     acc = 0.f;
   }
 };
@@ -94,12 +94,12 @@ struct LfStorePotential {
 struct LfLoadNormalised {
   const float2* p;
   const float* norm;
-  int nx, ny;
+  int nx, ny, log2nx;
   float dx2;
   LineGeom g;
   __device__ __forceinline__ LineGeom gin() const { return g; }
   __device__ __forceinline__ float2 load(long long off, long long line, int) const {
-    const float s = rsqrtf(norm[line / nx] * dx2);
+    const float s = rsqrtf(norm[(int)line >> log2nx] * dx2);
     const float2 v = p[off];
     return make_float2(v.x * s, v.y * s);
   }
