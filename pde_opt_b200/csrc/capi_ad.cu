@@ -1,6 +1,7 @@
 // C ABI: advection-diffusion rollout and adjoint (see include/pdeopt_b200.h).
 #include "capi_common.h"
 #include "ad128.cuh"
+#include "ad_generic.cuh"
 using namespace pdeopt;
 
 // ---- advection-diffusion rollout and its adjoint ------------------------------------------------
@@ -8,8 +9,15 @@ static pdeopt_status ad_fill(AdParams& p, const pdeopt_ad_desc* desc, int32_t ba
                              const float* dt_host, const float* tables_dev, const float* ctrl_dev, int32_t nseg,
                              int32_t hold, int32_t step0) {
   if (!desc || !dt_host || !tables_dev || !ctrl_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
-  if (desc->nx != 128 || desc->ny != 128)
-    return fail(PDEOPT_ERR_UNSUPPORTED, "advection-diffusion: only 128x128 grids are implemented");
+  {
+    auto pow2 = [](int v) { return v >= 2 && (v & (v - 1)) == 0; };
+    const bool tuned = desc->nx == 128 && desc->ny == 128;
+    const bool generic = pow2(desc->nx) && pow2(desc->ny) && (int64_t)desc->nx * desc->ny <= kGenMaxPts;
+    if (!tuned && !generic)
+      return fail(PDEOPT_ERR_UNSUPPORTED,
+                  "advection-diffusion: grids must be 128x128 (tuned kernels, with adjoint) or powers of two with "
+                  "nx*ny <= 8192 (generic forward kernel)");
+  }
   if (batch <= 0) return fail(PDEOPT_ERR_INVALID, "batch must be positive");
   if (ksteps <= 0 || ksteps > PDEOPT_MAX_FUSED_STEPS) return fail(PDEOPT_ERR_INVALID, "ksteps must be in [1, 512]");
   if (nseg <= 0 || hold <= 0 || step0 < 0) return fail(PDEOPT_ERR_INVALID, "bad control segmentation");
@@ -17,10 +25,11 @@ static pdeopt_status ad_fill(AdParams& p, const pdeopt_ad_desc* desc, int32_t ba
   std::memset(&p, 0, sizeof(p));
   p.batch = batch;
   p.ksteps = ksteps;
+  const int tl = (desc->nx / 2 + 1) * (desc->ny / 2 + 1);
   p.tabA = tables_dev;
-  p.tabL = tables_dev + kTabLen;
-  p.kx = tables_dev + 2 * kTabLen;
-  p.ky = tables_dev + 2 * kTabLen + kN;
+  p.tabL = tables_dev + tl;
+  p.kx = tables_dev + 2 * tl;
+  p.ky = tables_dev + 2 * tl + desc->nx;
   p.ctrl = ctrl_dev;
   p.nseg = nseg;
   p.hold = hold;
@@ -54,6 +63,25 @@ extern "C" pdeopt_status pdeopt_ad_rollout_fwd(const pdeopt_ad_desc* desc, const
   p.y1 = y1_dev;
   p.traj = traj_dev;
   p.traj_stride = traj_stride;
+  if (!(desc->nx == 128 && desc->ny == 128)) {
+    if (traj_dev) return fail(PDEOPT_ERR_UNSUPPORTED, "advection-diffusion: trajectory saving (adjoint) needs a 128x128 grid");
+    AdGenParams gp;
+    gp.a = p;
+    gp.nx = desc->nx;
+    gp.ny = desc->ny;
+    gp.lognx = ilog2(desc->nx);
+    gp.logny = ilog2(desc->ny);
+    static bool gattr = false;
+    if (!gattr) {
+      CUDA_TRY(cudaFuncSetAttribute(ad_generic_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+      gattr = true;
+    }
+    ad_generic_fwd_kernel<<<(batch + 1) / 2, kGenThreads, ad_gen_smem_bytes(desc->nx, desc->ny), (cudaStream_t)stream>>>(gp);
+    cudaError_t ge = cudaGetLastError();
+    if (ge != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(ge));
+    g_launches.fetch_add(1);
+    return PDEOPT_OK;
+  }
   static bool attr = false;
   if (!attr) {
     CUDA_TRY(cudaFuncSetAttribute(ad128_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AdSmem)));
@@ -72,6 +100,8 @@ extern "C" pdeopt_status pdeopt_ad_rollout_bwd(const pdeopt_ad_desc* desc, const
                                                int32_t nseg, int32_t hold, int32_t step0, float* gctrl_dev,
                                                void* stream) {
   if (!traj_dev || !lam1_dev || !lam0_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
+  if (desc && !(desc->nx == 128 && desc->ny == 128))
+    return fail(PDEOPT_ERR_UNSUPPORTED, "advection-diffusion: the adjoint kernel is implemented for 128x128 grids");
 #ifdef PDEOPT_PARK_GLOBAL
   return fail(PDEOPT_ERR_UNSUPPORTED, "advection-diffusion: PDEOPT_PARK_GLOBAL builds are not supported");
 #endif

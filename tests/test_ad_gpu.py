@@ -201,3 +201,54 @@ def test_pde_model_mse_gradients_match_autograd_oracle():
     assert abs(loss.item() - lr.item()) <= 1e-4 * abs(lr.item())
     for got, want, name in zip((cx, cy, p0, p1), q, ("cx", "cy", "p0", "p1")):
         assert _rel(got.grad.cpu().numpy(), want.grad.numpy()) <= 2e-4, name
+
+
+def test_reference_fixture_notebooks_reference_npy_on_gpu():
+    """The reference's own advection-diffusion result (notebooks/reference.npy, 64x64, t = 5; committed
+    as tests/golden/ref_advection_diffusion_64.npy) reproduced by the GPU path in float32:
+    2500 semi-implicit steps of dt = 2e-3 from the (decayed-noise) mean state."""
+    import os
+
+    from pde_opt_b200 import Domain
+    from pde_opt_b200.adjoint import ad_rollout
+    from pde_opt_b200.equations import AdvectionDiffusion2D
+    from pde_opt_b200.functions import GaussianVelocity
+
+    ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_advection_diffusion_64.npy"))
+    n, L = 64, 0.02 * 64
+    dom = Domain((n, n), ((-L / 2, L / 2), (-L / 2, L / 2)), "dimensionless")
+    eq = AdvectionDiffusion2D(dom, GaussianVelocity(0.1, 0.01, (0.4, 0.4)), 0.1)
+    y0 = torch.full((1, n, n), float(ref.mean()), dtype=torch.float32, device="cuda")
+    times = (np.arange(2501, dtype=np.float64) * 2e-3).astype(np.float32)
+    ctrl = eq.control_block(1, "cuda")
+    got = ad_rollout(eq, y0, ctrl, times)[0].cpu().numpy()
+    assert _rel(got, ref) < 2e-4
+
+
+@pytest.mark.parametrize("shape", [(64, 64), (32, 128), (16, 16)])
+def test_generic_sizes_match_oracle(shape):
+    from pde_opt_b200 import Domain
+    from pde_opt_b200.adjoint import ad_rollout
+    from pde_opt_b200.equations import AdvectionDiffusion2D
+    from pde_opt_b200.functions import GaussianVelocity
+
+    nx, ny = shape
+    box = ((-nx * H / 2, nx * H / 2), (-ny * H / 2, ny * H / 2))
+    eq = AdvectionDiffusion2D(Domain(shape, box, "dimensionless"), GaussianVelocity(0.1, 0.01), DCOEF)
+    B, K, nseg = 3, 6, 2
+    rng = np.random.default_rng(4)
+    y0 = (0.5 + 0.01 * rng.normal(size=(B,) + shape)).astype(np.float32)
+    ctrl = _ctrl(B, nseg, 6)
+    ctrl[..., :2] *= 0.3
+    times = (np.arange(K + 1, dtype=np.float32) * np.float32(1e-4)).astype(np.float32)
+    got = ad_rollout(eq, torch.from_numpy(y0).cuda(), torch.from_numpy(ctrl).cuda(), times, hold=3).cpu().numpy()
+    dom = O.Domain(shape, box)
+    for b in range(B):
+        y, t = y0[b], np.float32(0)
+        for k in range(K):
+            cx, cy, p0, p1 = (float(v) for v in ctrl[b, min(k // 3, nseg - 1)])
+            oeq = O.AdvectionDiffusion2D(dom, O.gaussian_velocity((p0, p1), (cx, cy)), DCOEF, np.float32)
+            y = O.sifs_step(oeq.rhs, y, t, t + np.float32(1e-4), 1.0, oeq.fourier_symbol)
+            t = t + np.float32(1e-4)
+        assert _rel(got[b], y) <= 1e-5
+        assert _rel(got[b] - y0[b], y - y0[b]) <= 2e-3
