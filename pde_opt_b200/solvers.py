@@ -111,6 +111,18 @@ class SemiImplicitFourierSpectral:
             self._sym_dev[key] = torch.from_numpy(self._quad).to(device)
         return self._sym_dev[key]
 
+    def _rollout_ad(self, eq, times, y0, out=None):
+        """Advection-diffusion (recovered equation): the fused forward kernel (differentiable)."""
+        from .adjoint import ad_rollout
+
+        single = y0.dim() == 2
+        y = (y0.unsqueeze(0) if single else y0).contiguous()
+        y1 = ad_rollout(eq, y, eq.control_block(y.shape[0], y.device), times, A=float(self.A))
+        if out is not None:
+            out.copy_(y1)
+            y1 = out
+        return y1[0] if single else y1
+
     def _plan_for(self, terms, shape):
         eq = getattr(terms, "equation", None)
         if eq is not None and getattr(eq, "fused", False):
@@ -123,6 +135,10 @@ class SemiImplicitFourierSpectral:
     def step(self, terms, t0, t1, y0, args=None, solver_state=None, made_jump=False):
         del solver_state, made_jump
         dt = np.float32(np.float32(t1) - np.float32(t0))  # solvers.py:58 in the working precision
+        if type(getattr(terms, "equation", None)).__name__ == "AdvectionDiffusion2D":
+            y1 = self._rollout_ad(terms.equation, np.asarray([t0, t1], dtype=np.float32), y0)
+            y_error = (y1 - (y0 + float(dt) * terms.vf(t0, y0, args))) if self.with_error else None
+            return y1, y_error, dict(y0=y0, y1=y1), None, RESULTS.successful
         if self._is3d:
             y1 = self._rollout3d(terms, [dt], y0)
             y_error = None
@@ -157,6 +173,8 @@ class SemiImplicitFourierSpectral:
         dts = (times[1:] - times[:-1]).astype(np.float32)
         if self._is3d:
             return self._rollout3d(terms, dts, y0, out=out)
+        if type(getattr(terms, "equation", None)).__name__ == "AdvectionDiffusion2D":
+            return self._rollout_ad(terms.equation, times, y0, out=out)
         single = y0.dim() == 2
         y = (y0.unsqueeze(0) if single else y0).contiguous()
         plan, eq = self._plan_for(terms, tuple(y.shape[-2:]))

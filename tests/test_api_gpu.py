@@ -184,3 +184,70 @@ def test_vec_env_matches_single_envs():
         np.testing.assert_allclose(float(reward[b]), y.astype(np.float64).var(), rtol=1e-3)
         assert (obs[b, 0].cpu().numpy() == O.quantise_obs(env.state[b].cpu().numpy())[0]).mean() > 0.999
     assert not term.any() and not trunc.any()
+
+
+def test_pde_env_with_advection_diffusion_and_gpe():
+    """PDEEnv is generic over (equation_type, solver_type) as in the reference (pde_env.py:43-61):
+    the recovered advection-diffusion equation with a moving velocity centre as the control
+    (the deleted AdvectionDiffusionEnv of notebooks/test_pde_RL.ipynb:129), and the GPE with
+    StrangSplitting."""
+    import torch
+
+    from oracle import pde_oracle as O
+    from pde_opt_b200 import Domain
+    from pde_opt_b200.equations import AdvectionDiffusion2D, GPE2DTSControl
+    from pde_opt_b200.functions import GaussianLight, GaussianVelocity
+    from pde_opt_b200.pde_env import PDEEnv
+    from pde_opt_b200.solvers import SemiImplicitFourierSpectral, StrangSplitting
+
+    n, h = 128, 0.02
+    box = ((-n * h / 2, n * h / 2),) * 2
+    dom, odom = Domain((n, n), box, "dimensionless"), O.Domain((n, n), box)
+    u0 = (0.5 + 0.01 * np.random.default_rng(0).normal(size=(n, n))).astype(np.float32)
+    env = PDEEnv(
+        AdvectionDiffusion2D, dom, SemiImplicitFourierSpectral, end_time=0.01, step_dt=0.002, numeric_dt=1e-4,
+        state_to_observation_func=lambda s: (s.clamp(0, 1) * 255).round().to(torch.uint8)[None],
+        reward_function=lambda s: float(s.var()), reset_func=lambda d, seed=None: u0,
+        reset_control_value=np.array([0.0, 0.0]), update_control_value=lambda off, old: old + np.asarray(off),
+        update_control_parameter=lambda old, new: GaussianVelocity(0.1, 0.01, (float(new[0]), float(new[1]))),
+        action_space_config={"type": "continuous", "low": -0.1, "high": 0.1, "shape": (2,)},
+        static_equation_parameters={"D": 0.1}, control_equation_parameter_name="velocity", solver_parameters={"A": 1.0},
+    )
+    obs, info = env.reset(seed=1)
+    assert obs.shape == (1, n, n) and obs.dtype == torch.uint8
+    centre, y = np.zeros(2), u0
+    for a in ([0.05, -0.02], [0.03, 0.04]):
+        obs, rew, term, trunc, info = env.step(np.asarray(a))
+        centre = centre + np.asarray(a)
+        oeq = O.AdvectionDiffusion2D(odom, O.gaussian_velocity((0.1, 0.01), tuple(centre)), 0.1, np.float32)
+        for ta, tb in zip(env._times[:-1], env._times[1:]):
+            y = O.sifs_step(oeq.rhs, y, ta, tb, 1.0, oeq.fourier_symbol)
+    got = env._state.cpu().numpy()
+    assert np.linalg.norm(got - y) / np.linalg.norm(y) <= 1e-5
+    assert not term and trunc is False
+
+    # GPE: the light amplitude is the control
+    L_ = 20.0
+    gdom = Domain((n, n), ((-L_ / 2, L_ / 2),) * 2, "dimensionless")
+    psi = np.exp(-(np.add.outer(np.linspace(-3, 3, n) ** 2, np.linspace(-3, 3, n) ** 2))).astype(np.float32)
+    psi0 = np.stack([psi, 0 * psi], -1)
+    psi0 = (psi0 / np.sqrt((psi0**2).sum() * (L_ / n) ** 2)).astype(np.float32)
+    genv = PDEEnv(
+        GPE2DTSControl, gdom, StrangSplitting, end_time=1.0, step_dt=1e-3, numeric_dt=1e-4,
+        state_to_observation_func=lambda s: ((s**2).sum(-1).clamp(0, 1) * 255).round().to(torch.uint8)[None],
+        reward_function=lambda s: float((s**2).sum(-1).max()), reset_func=lambda d, seed=None: psi0,
+        reset_control_value=0.0, update_control_value=lambda off, old: old + off,
+        update_control_parameter=lambda old, new: GaussianLight(float(new), 1.0, -1.0, 2.0),
+        action_space_config={"type": "discrete", "num_actions": 3, "action_mapping": {0: -1.0, 1: 0.0, 2: 1.0}},
+        static_equation_parameters={"k": 100.0, "e": 0.0, "trap_factor": 1.0}, control_equation_parameter_name="lights",
+        solver_parameters={"time_scale": -1j},
+    )
+    genv.reset()
+    obs, rew, term, trunc, _ = genv.step(2)
+    ogdom = O.Domain((n, n), ((-L_ / 2, L_ / 2),) * 2)
+    light = GaussianLight(1.0, 1.0, -1.0, 2.0)
+    ogeq = O.GPE2DTSControl(ogdom, 100.0, 0.0, lambda t, x, y: light(t, x, y), 1.0, np.float32)
+    yy = psi0
+    for ta, tb in zip(genv._times[:-1], genv._times[1:]):
+        yy = O.strang_step(ogeq.B_terms, yy, ta, tb, ogeq.A_term, ogeq.dx, -1j)
+    assert np.linalg.norm(genv._state.cpu().numpy() - yy) / np.linalg.norm(yy) <= 2e-5
