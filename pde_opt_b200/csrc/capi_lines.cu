@@ -18,7 +18,7 @@ static LineGeom to_geom(const pdeopt_line_geom* g) {
   return r;
 }
 static bool geom_ok(const pdeopt_line_geom* g, int n) {
-  return g && g->n_lines > 0 && g->n_inner > 0 && g->chunk > 0 && g->chunk <= n && n % g->chunk == 0;
+  return g && g->n_lines > 0 && g->n_inner > 0 && g->chunk > 0 && g->chunk <= n && (g->chunk & (g->chunk - 1)) == 0;
 }
 static bool lf_size_ok(int n) { return n >= 8 && n <= 512 && (n & (n - 1)) == 0; }
 

@@ -106,7 +106,9 @@ __global__ void __launch_bounds__(kC3Threads) ch3d_rhs_fused_kernel(const __grid
   const int z0 = blockIdx.x * kC3TZ, y0 = blockIdx.y * kC3TY;
   const int nchunk = p.nx / xl;
   const int b = blockIdx.z / nchunk, x0 = (blockIdx.z % nchunk) * xl;
-  const int ty = tid >> 4, tz = (tid & 15) * 4;  // this thread's 4 consecutive z points of row ty
+  // this thread's 4 points of row ty: z = tz + 16 j, so that the 16 lanes of a half-warp read
+  // consecutive (mu, D) pairs (stride-4 ownership made every shared-memory access 4-way conflicted)
+  const int ty = tid >> 4, tz = tid & 15;
   constexpr int kULoads = (kC3UY * kC3UZ + kC3Threads - 1) / kC3Threads;  // 6
 
   // global offsets (within a plane) of the halo-2 tile elements this thread stages
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(kC3Threads) ch3d_rhs_fused_kernel(const __grid
       float fx[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 a = S.MD[md_prev][ty + 1][tz + 1 + j], bb = S.MD[md_cur][ty + 1][tz + 1 + j];
+        const float2 a = S.MD[md_prev][ty + 1][tz + 1 + 16 * j], bb = S.MD[md_cur][ty + 1][tz + 1 + 16 * j];
         fx[j] = (0.5f * (a.y + bb.y)) * ((bb.x - a.x) * p.inv_hx);
       }
       if (it >= 1) {
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(kC3Threads) ch3d_rhs_fused_kernel(const __grid
         float out[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int yy = ty + 1, zz = tz + 1 + j;
+          const int yy = ty + 1, zz = tz + 1 + 16 * j;
           const float2 m0 = S.MD[md_prev][yy][zz];
           const float2 myp = S.MD[md_prev][yy + 1][zz], mym = S.MD[md_prev][yy - 1][zz];
           const float2 mzp = S.MD[md_prev][yy][zz + 1], mzm = S.MD[md_prev][yy][zz - 1];
@@ -191,7 +193,8 @@ __global__ void __launch_bounds__(kC3Threads) ch3d_rhs_fused_kernel(const __grid
           out[j] = ((fx[j] - fx_prev[j]) * p.inv_hx + (fyp - fym) * p.inv_hy) + (fzp - fzm) * p.inv_hz;
         }
         float* dst = p.f + ((size_t)b * p.nx + (c - 1)) * p.ny * p.nz + (size_t)(y0 + ty) * p.nz + z0 + tz;
-        *reinterpret_cast<float4*>(dst) = make_float4(out[0], out[1], out[2], out[3]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[16 * j] = out[j];
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) fx_prev[j] = fx[j];
@@ -231,7 +234,8 @@ struct LfStoreUpdate {
   LineGeom g;
   float dt;
   __device__ __forceinline__ LineGeom gout() const { return g; }
-  __device__ __forceinline__ void store(long long off, long long, int, float2 v) const { y1[off] = fmaf(dt, v.x, y0[off]); }
+  __device__ __forceinline__ float2 pre(long long off) const { return make_float2(y0[off], 0.f); }
+  __device__ __forceinline__ void store(long long off, long long, int, float2 v, float2 pre) const { y1[off] = fmaf(dt, v.x, pre.x); }
   __device__ __forceinline__ void flush(long long) {}
 };
 
@@ -262,10 +266,14 @@ struct LfIoC2RUpdate {
     A = a[h];
     B = a[hp + h];
   }
-  __device__ __forceinline__ void store_pair(long long pair, int idx, float2 v) const {
+  __device__ __forceinline__ float2 pre_pair(long long pair, int idx) const {
     const long long o = 2 * pair * n + idx;
-    y1[o] = fmaf(dt, v.x, y0[o]);
-    y1[o + n] = fmaf(dt, v.y, y0[o + n]);
+    return make_float2(y0[o], y0[o + n]);
+  }
+  __device__ __forceinline__ void store_pair(long long pair, int idx, float2 v, float2 pre) const {
+    const long long o = 2 * pair * n + idx;
+    y1[o] = fmaf(dt, v.x, pre.x);
+    y1[o + n] = fmaf(dt, v.y, pre.y);
   }
 };
 

@@ -40,14 +40,39 @@ __host__ __device__ inline int line_pos_to_freq(int n, int p) {
   return k1 + r1 * k2 + r1 * r2 * k3;
 }
 
-template <int N>
+// Tile geometry.  CT = the kernel touches CONTIGUOUS global lines (lanes run along positions in
+// its global stages); otherwise adjacent lines are adjacent in memory and lanes run across lines.
+//  * An 8-byte shared-memory access is processed per half-warp, so a layout is conflict free when
+//    the 16 lanes of a half-warp hit 16 distinct 8-byte slots modulo 16.
+//  * T >= 16 with the odd pitch LP = T + 1: a half-warp is 16 lines at one position (16 consecutive
+//    slots) or 16 consecutive positions of one line (slots 17 apart): conflict free both ways.
+//  * T = 8 (512-point strided lines, halves the tile: 6 CTAs per SM instead of 3): no padding,
+//    position index XORed with its bit 3, so that the two positions of a half-warp — neighbours, or
+//    8 apart in the span-8 stage — always land in different halves of the 16 slots.  Not usable
+//    when lanes run along positions, hence CT kernels keep T = 16.
+template <int N, bool CT>
 struct LineTile {
-  static constexpr int T = (N >= 512) ? 8 : ((N >= 256) ? 16 : 32);  // lines per tile
-  static constexpr int LP = T + 1;
+  static constexpr int T = (N >= 512 && !CT) ? 8 : ((N >= 256) ? 16 : 32);  // lines per tile
+  static constexpr bool kXor8 = (T == 8);
+  static constexpr int LP = kXor8 ? T : T + 1;
   static constexpr int kThreads = 256;
-  static constexpr size_t smem_bytes =
-      sizeof(float2) * (size_t)(N * LP + N) + sizeof(int) * (size_t)(3 * N) + sizeof(long long) * (size_t)(3 * T);
+  static constexpr size_t smem_bytes = sizeof(float2) * (size_t)(N * LP + N) + sizeof(long long) * (size_t)(3 * T);
 };
+
+// Shared-memory index of (position, line).  For the padded layouts the line index is additionally
+// XOR-swizzled with the first radix digit of the position so that accesses that run along
+// FREQUENCIES (consecutive h map to positions N/8 apart: the real <-> half-spectrum untangling) are
+// conflict free too; accesses along lines or consecutive positions are unaffected.
+template <int N, bool CT>
+__device__ __forceinline__ int lf_sidx(int pos, int line) {
+  if constexpr (LineTile<N, CT>::kXor8) {
+    return ((pos ^ ((pos >> 3) & 1)) << 3) + line;
+  } else {
+    constexpr int LP = LineTile<N, CT>::LP;
+    constexpr int SH = ilog2(N / lf_r1(N));
+    return pos * LP + (line ^ ((pos >> SH) & 7));
+  }
+}
 
 // Line addressing (all strides in elements of the addressed array):
 //   offset(line, idx) = (line / n_inner) * outer + (line % n_inner) * inner
@@ -69,12 +94,27 @@ struct LineGeom {
   __host__ __device__ __forceinline__ long long off(long long line, int idx) const { return line_base(line) + idx_off(idx); }
 };
 
+struct LfOff {  // element offset of position `pos` within a line: (pos / chunk) * hi + (pos % chunk) * lo, chunk = 2^shift
+  int shift, mask, hi, lo;
+  __device__ __forceinline__ int operator[](int pos) const { return (pos >> shift) * hi + (pos & mask) * lo; }
+};
+
+__device__ __forceinline__ LfOff lf_off(const LineGeom& g) {
+  LfOff o;
+  o.shift = 31 - __clz(g.chunk);  // chunk is a power of two (validated by the C ABI)
+  o.mask = g.chunk - 1;
+  o.hi = (int)g.hi;
+  o.lo = (int)g.lo;
+  return o;
+}
+
 enum : int { LF_FWD = 0, LF_INV = 1, LF_FWD_MUL_INV = 2 };
 
 // Functor concepts (offsets are element offsets computed from the functor's own geometries):
 //   Loader: LineGeom gin() ;  float2 load(long long off, long long line, int idx)
 //   Mid   : LineGeom gaux();  float2 apply(float2 v, long long off_aux, long long line, int pos)
-//   Storer: LineGeom gout();  void store(long long off, long long line, int idx, float2 v) ; void flush(long long l0)
+//   Storer: LineGeom gout();  float2 pre(long long off)  (the storer's own global read for that element, if any) ;
+//           void store(long long off, long long line, int idx, float2 v, float2 pre) ; void flush(long long l0)
 // CONTIG: elements of a line are adjacent in memory (lo == 1): warps run along idx when they touch
 // global memory; otherwise adjacent lines are adjacent in memory and warps run across the T lines.
 //
@@ -85,14 +125,14 @@ enum : int { LF_FWD = 0, LF_INV = 1, LF_FWD_MUL_INV = 2 };
 struct LfCtx {
   float2* Sm;
   const float2* tw;
-  const int *io_in, *io_out, *io_aux;
+  LfOff io_in, io_out, io_aux;
   const long long *lb_in, *lb_out, *lb_aux;
   long long l0, n_lines;
 };
 
-template <int N, int R, int S, bool INV, bool GSRC, bool GDST, bool LANE_U, class Loader, class Storer>
+template <int N, bool CT, int R, int S, bool INV, bool GSRC, bool GDST, bool LANE_U, class Loader, class Storer>
 __device__ __forceinline__ void lf_stage(const LfCtx& c, Loader& ld, Storer& st) {
-  constexpr int T = LineTile<N>::T, LP = LineTile<N>::LP, NT = LineTile<N>::kThreads;
+  constexpr int T = LineTile<N, CT>::T, NT = LineTile<N, CT>::kThreads;
   constexpr int SUB = S / R, NB = N / R, LOG2R = ilog2(R);
   for (int w = threadIdx.x; w < NB * T; w += NT) {
     const int u = LANE_U ? (w % NB) : (w / T), line = LANE_U ? (w / NB) : (w % T);
@@ -104,7 +144,7 @@ __device__ __forceinline__ void lf_stage(const LfCtx& c, Loader& ld, Storer& st)
       for (int m = 0; m < R; ++m) {
         const int pos = base + m * SUB;
         if constexpr (GSRC) x[m] = valid ? ld.load(c.lb_in[line] + c.io_in[pos], c.l0 + line, pos) : make_float2(0.f, 0.f);
-        else x[m] = c.Sm[pos * LP + line];
+        else x[m] = c.Sm[lf_sidx<N, CT>(pos, line)];
       }
       Dif<R, 1, false>::run(x);
       static_for<0, R>([&](auto pc) {
@@ -114,9 +154,9 @@ __device__ __forceinline__ void lf_stage(const LfCtx& c, Loader& ld, Storer& st)
         if constexpr (k != 0 && SUB > 1) v = cmul(v, c.tw[(j * k * (N / S)) & (N - 1)]);
         const int pos = base + k * SUB;
         if constexpr (GDST) {
-          if (valid) st.store(c.lb_out[line] + c.io_out[pos], c.l0 + line, pos, v);
+          if (valid) st.store(c.lb_out[line] + c.io_out[pos], c.l0 + line, pos, v, st.pre(c.lb_out[line] + c.io_out[pos]));
         } else {
-          c.Sm[pos * LP + line] = v;
+          c.Sm[lf_sidx<N, CT>(pos, line)] = v;
         }
       });
     } else {
@@ -126,7 +166,7 @@ __device__ __forceinline__ void lf_stage(const LfCtx& c, Loader& ld, Storer& st)
         const int pos = base + k * SUB;
         float2 v;
         if constexpr (GSRC) v = valid ? ld.load(c.lb_in[line] + c.io_in[pos], c.l0 + line, pos) : make_float2(0.f, 0.f);
-        else v = c.Sm[pos * LP + line];
+        else v = c.Sm[lf_sidx<N, CT>(pos, line)];
         if constexpr (k != 0 && SUB > 1) v = cmulc(v, c.tw[(j * k * (N / S)) & (N - 1)]);
         x[p] = v;
       });
@@ -135,9 +175,9 @@ __device__ __forceinline__ void lf_stage(const LfCtx& c, Loader& ld, Storer& st)
       for (int m = 0; m < R; ++m) {
         const int pos = base + m * SUB;
         if constexpr (GDST) {
-          if (valid) st.store(c.lb_out[line] + c.io_out[pos], c.l0 + line, pos, x[m]);
+          if (valid) st.store(c.lb_out[line] + c.io_out[pos], c.l0 + line, pos, x[m], st.pre(c.lb_out[line] + c.io_out[pos]));
         } else {
-          c.Sm[pos * LP + line] = x[m];
+          c.Sm[lf_sidx<N, CT>(pos, line)] = x[m];
         }
       }
     }
@@ -145,9 +185,9 @@ __device__ __forceinline__ void lf_stage(const LfCtx& c, Loader& ld, Storer& st)
 }
 
 // innermost stage of forward * multiplier * inverse (span == radix, no twiddles), in registers
-template <int N, int R, bool GSRC, bool GDST, bool LANE_U, class Loader, class Mid, class Storer>
+template <int N, bool CT, int R, bool GSRC, bool GDST, bool LANE_U, class Loader, class Mid, class Storer>
 __device__ __forceinline__ void lf_stage_fmi(const LfCtx& c, Loader& ld, Mid& mid, Storer& st) {
-  constexpr int T = LineTile<N>::T, LP = LineTile<N>::LP, NT = LineTile<N>::kThreads;
+  constexpr int T = LineTile<N, CT>::T, NT = LineTile<N, CT>::kThreads;
   constexpr int NB = N / R, LOG2R = ilog2(R);
   for (int w = threadIdx.x; w < NB * T; w += NT) {
     const int u = LANE_U ? (w % NB) : (w / T), line = LANE_U ? (w / NB) : (w % T);
@@ -157,7 +197,7 @@ __device__ __forceinline__ void lf_stage_fmi(const LfCtx& c, Loader& ld, Mid& mi
 #pragma unroll
     for (int m = 0; m < R; ++m) {
       if constexpr (GSRC) x[m] = valid ? ld.load(c.lb_in[line] + c.io_in[base + m], c.l0 + line, base + m) : make_float2(0.f, 0.f);
-      else x[m] = c.Sm[(base + m) * LP + line];
+      else x[m] = c.Sm[lf_sidx<N, CT>(base + m, line)];
     }
     Dif<R, 1, false>::run(x);
     static_for<0, R>([&](auto pc) {
@@ -169,18 +209,19 @@ __device__ __forceinline__ void lf_stage_fmi(const LfCtx& c, Loader& ld, Mid& mi
 #pragma unroll
     for (int m = 0; m < R; ++m) {
       if constexpr (GDST) {
-        if (valid) st.store(c.lb_out[line] + c.io_out[base + m], c.l0 + line, base + m, x[m]);
+        if (valid) st.store(c.lb_out[line] + c.io_out[base + m], c.l0 + line, base + m, x[m], st.pre(c.lb_out[line] + c.io_out[base + m]));
       } else {
-        c.Sm[(base + m) * LP + line] = x[m];
+        c.Sm[lf_sidx<N, CT>(base + m, line)] = x[m];
       }
     }
   }
 }
 
 template <int N, int MODE, bool CONTIG, class Loader, class Mid, class Storer>
-__global__ void __launch_bounds__(LineTile<N>::kThreads) linefft_kernel(long long n_lines, Loader ld, Mid mid, Storer st) {
+__global__ void __launch_bounds__(LineTile<N, CONTIG>::kThreads) linefft_kernel(long long n_lines, Loader ld, Mid mid, Storer st) {
   extern __shared__ __align__(16) unsigned char lf_smem[];
-  constexpr int T = LineTile<N>::T, LP = LineTile<N>::LP, NT = LineTile<N>::kThreads;
+  constexpr bool CT = CONTIG;
+  constexpr int T = LineTile<N, CT>::T, LP = LineTile<N, CT>::LP, NT = LineTile<N, CT>::kThreads;
   constexpr int R1 = lf_r1(N), R2 = lf_r2(N), R3 = lf_r3(N);
   constexpr int NS = 1 + (R2 > 1 ? 1 : 0) + (R3 > 1 ? 1 : 0);
   constexpr int S2 = N / R1, S3 = N / R1 / R2;
@@ -190,17 +231,12 @@ __global__ void __launch_bounds__(LineTile<N>::kThreads) linefft_kernel(long lon
   long long* lb_in = reinterpret_cast<long long*>(tw + N);  // [T] line bases of the current tile
   long long* lb_out = lb_in + T;
   long long* lb_aux = lb_out + T;
-  int* io_in = reinterpret_cast<int*>(lb_aux + T);  // [N] element offsets within a line
-  int* io_out = io_in + N;
-  int* io_aux = io_out + N;
   const LineGeom gi = ld.gin(), go = st.gout(), ga = mid.gaux();
+  const LfOff io_in = lf_off(gi), io_out = lf_off(go), io_aux = lf_off(ga);
   for (int i = threadIdx.x; i < N; i += NT) {
     float s, c;
     sincospif(-2.0f * float(i) / float(N), &s, &c);
     tw[i] = make_float2(c, s);
-    io_in[i] = (int)gi.idx_off(i);
-    io_out[i] = (int)go.idx_off(i);
-    io_aux[i] = (int)ga.idx_off(i);
   }
   LfCtx c{Sm, tw, io_in, io_out, io_aux, lb_in, lb_out, lb_aux, 0, n_lines};
   for (long long tile = blockIdx.x; tile * T < n_lines; tile += gridDim.x) {
@@ -214,92 +250,113 @@ __global__ void __launch_bounds__(LineTile<N>::kThreads) linefft_kernel(long lon
     }
     __syncthreads();
     auto copy_in = [&]() {  // contiguous lines -> tile, warps along idx
-      for (int w = threadIdx.x; w < N * T; w += NT) {
-        const int idx = w % N, line = w / N;
-        if (l0 + line < n_lines) Sm[idx * LP + line] = ld.load(lb_in[line] + io_in[idx], l0 + line, idx);
+      for (int w0 = threadIdx.x; w0 < N * T; w0 += 4 * NT) {
+        float2 v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int w = w0 + q * NT, idx = w % N, line = w / N;
+          v[q] = (w < N * T && l0 + line < n_lines) ? ld.load(lb_in[line] + io_in[idx], l0 + line, idx) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int w = w0 + q * NT, idx = w % N, line = w / N;
+          if (w < N * T) Sm[lf_sidx<N, CT>(idx, line)] = v[q];
+        }
       }
       __syncthreads();
     };
     auto copy_out = [&]() {
       __syncthreads();
-      for (int w = threadIdx.x; w < N * T; w += NT) {
-        const int idx = w % N, line = w / N;
-        if (l0 + line < n_lines) st.store(lb_out[line] + io_out[idx], l0 + line, idx, Sm[idx * LP + line]);
+      // the storer's own global reads (st.pre: e.g. psi0 of the potential step) are issued in
+      // batches of 4 before the dependent stores, otherwise possible aliasing serialises them
+      for (int w0 = threadIdx.x; w0 < N * T; w0 += 4 * NT) {
+        float2 pre[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int w = w0 + q * NT, idx = w % N, line = w / N;
+          pre[q] = (w < N * T && l0 + line < n_lines) ? st.pre(lb_out[line] + io_out[idx]) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int w = w0 + q * NT, idx = w % N, line = w / N;
+          if (w < N * T && l0 + line < n_lines)
+            st.store(lb_out[line] + io_out[idx], l0 + line, idx, Sm[lf_sidx<N, CT>(idx, line)], pre[q]);
+        }
       }
     };
     if constexpr (MODE == LF_FWD) {
       if constexpr (!CONTIG) {
         if constexpr (NS == 1) {
-          lf_stage<N, R1, N, false, true, true, false>(c, ld, st);
+          lf_stage<N, CT, R1, N, false, true, true, false>(c, ld, st);
         } else if constexpr (NS == 2) {
-          lf_stage<N, R1, N, false, true, false, false>(c, ld, st);
+          lf_stage<N, CT, R1, N, false, true, false, false>(c, ld, st);
           __syncthreads();
-          lf_stage<N, R2, S2, false, false, true, false>(c, ld, st);
+          lf_stage<N, CT, R2, S2, false, false, true, false>(c, ld, st);
         } else {
-          lf_stage<N, R1, N, false, true, false, false>(c, ld, st);
+          lf_stage<N, CT, R1, N, false, true, false, false>(c, ld, st);
           __syncthreads();
-          lf_stage<N, R2, S2, false, false, false, false>(c, ld, st);
+          lf_stage<N, CT, R2, S2, false, false, false, false>(c, ld, st);
           __syncthreads();
-          lf_stage<N, R3, S3, false, false, true, false>(c, ld, st);
+          lf_stage<N, CT, R3, S3, false, false, true, false>(c, ld, st);
         }
       } else {
-        lf_stage<N, R1, N, false, true, false, true>(c, ld, st);
+        lf_stage<N, CT, R1, N, false, true, false, true>(c, ld, st);
         if constexpr (NS >= 2) {
           __syncthreads();
-          lf_stage<N, R2, S2, false, false, false, false>(c, ld, st);
+          lf_stage<N, CT, R2, S2, false, false, false, false>(c, ld, st);
         }
         if constexpr (NS >= 3) {
           __syncthreads();
-          lf_stage<N, R3, S3, false, false, false, false>(c, ld, st);
+          lf_stage<N, CT, R3, S3, false, false, false, false>(c, ld, st);
         }
         copy_out();
       }
     } else if constexpr (MODE == LF_INV) {
       if constexpr (!CONTIG) {
         if constexpr (NS == 1) {
-          lf_stage<N, R1, N, true, true, true, false>(c, ld, st);
+          lf_stage<N, CT, R1, N, true, true, true, false>(c, ld, st);
         } else if constexpr (NS == 2) {
-          lf_stage<N, R2, S2, true, true, false, false>(c, ld, st);
+          lf_stage<N, CT, R2, S2, true, true, false, false>(c, ld, st);
           __syncthreads();
-          lf_stage<N, R1, N, true, false, true, false>(c, ld, st);
+          lf_stage<N, CT, R1, N, true, false, true, false>(c, ld, st);
         } else {
-          lf_stage<N, R3, S3, true, true, false, false>(c, ld, st);
+          lf_stage<N, CT, R3, S3, true, true, false, false>(c, ld, st);
           __syncthreads();
-          lf_stage<N, R2, S2, true, false, false, false>(c, ld, st);
+          lf_stage<N, CT, R2, S2, true, false, false, false>(c, ld, st);
           __syncthreads();
-          lf_stage<N, R1, N, true, false, true, false>(c, ld, st);
+          lf_stage<N, CT, R1, N, true, false, true, false>(c, ld, st);
         }
       } else {
         copy_in();
         if constexpr (NS >= 3) {
-          lf_stage<N, R3, S3, true, false, false, false>(c, ld, st);
+          lf_stage<N, CT, R3, S3, true, false, false, false>(c, ld, st);
           __syncthreads();
         }
         if constexpr (NS >= 2) {
-          lf_stage<N, R2, S2, true, false, false, false>(c, ld, st);
+          lf_stage<N, CT, R2, S2, true, false, false, false>(c, ld, st);
           __syncthreads();
         }
-        lf_stage<N, R1, N, true, false, true, true>(c, ld, st);
+        lf_stage<N, CT, R1, N, true, false, true, true>(c, ld, st);
       }
     } else {
       if constexpr (NS == 1) {
-        lf_stage_fmi<N, R1, true, true, LU>(c, ld, mid, st);
+        lf_stage_fmi<N, CT, R1, true, true, LU>(c, ld, mid, st);
       } else if constexpr (NS == 2) {
-        lf_stage<N, R1, N, false, true, false, LU>(c, ld, st);
+        lf_stage<N, CT, R1, N, false, true, false, LU>(c, ld, st);
         __syncthreads();
-        lf_stage_fmi<N, R2, false, false, false>(c, ld, mid, st);
+        lf_stage_fmi<N, CT, R2, false, false, false>(c, ld, mid, st);
         __syncthreads();
-        lf_stage<N, R1, N, true, false, true, LU>(c, ld, st);
+        lf_stage<N, CT, R1, N, true, false, true, LU>(c, ld, st);
       } else {
-        lf_stage<N, R1, N, false, true, false, LU>(c, ld, st);
+        lf_stage<N, CT, R1, N, false, true, false, LU>(c, ld, st);
         __syncthreads();
-        lf_stage<N, R2, S2, false, false, false, false>(c, ld, st);
+        lf_stage<N, CT, R2, S2, false, false, false, false>(c, ld, st);
         __syncthreads();
-        lf_stage_fmi<N, R3, false, false, false>(c, ld, mid, st);
+        lf_stage_fmi<N, CT, R3, false, false, false>(c, ld, mid, st);
         __syncthreads();
-        lf_stage<N, R2, S2, true, false, false, false>(c, ld, st);
+        lf_stage<N, CT, R2, S2, true, false, false, false>(c, ld, st);
         __syncthreads();
-        lf_stage<N, R1, N, true, false, true, LU>(c, ld, st);
+        lf_stage<N, CT, R1, N, true, false, true, LU>(c, ld, st);
       }
     }
     st.flush(l0);  // optional per-tile reduction hook (uniform; may contain barriers)
@@ -315,21 +372,23 @@ __global__ void __launch_bounds__(LineTile<N>::kThreads) linefft_kernel(long lon
 // every later pass of a real field's 3-D transform has to move.  The inverse rebuilds Z from (A, B).
 struct LfNoIo {
   __device__ __forceinline__ float2 load(long long, long long, int) const { return make_float2(0.f, 0.f); }
-  __device__ __forceinline__ void store(long long, long long, int, float2) const {}
+  __device__ __forceinline__ float2 pre(long long) const { return make_float2(0.f, 0.f); }
+  __device__ __forceinline__ void store(long long, long long, int, float2, float2) const {}
 };
 
 template <int N>
 struct LineTileReal {
-  static constexpr int T = LineTile<N>::T;
+  static constexpr int T = LineTile<N, true>::T;
   static constexpr size_t smem_bytes = sizeof(float2) * (size_t)(N * (T + 1) + N) + sizeof(int) * (size_t)N;
 };
 
 // Io (forward):  float2 load_pair(long long pair, int idx) ; void store_half(long long pair, int h, float2 A, float2 B)
-// Io (inverse):  void load_half(long long pair, int h, float2& A, float2& B) ; void store_pair(long long pair, int idx, float2 v)
+// Io (inverse):  void load_half(long long pair, int h, float2& A, float2& B) ; float2 pre_pair(long long pair, int idx) ; void store_pair(long long pair, int idx, float2 v, float2 pre)
 template <int N, bool INV, class Io>
-__global__ void __launch_bounds__(LineTile<N>::kThreads) linefft_real_kernel(long long n_pairs, Io io) {
+__global__ void __launch_bounds__(LineTile<N, true>::kThreads) linefft_real_kernel(long long n_pairs, Io io) {
   extern __shared__ __align__(16) unsigned char lf_smem[];
-  constexpr int T = LineTile<N>::T, LP = LineTile<N>::LP, NT = LineTile<N>::kThreads;
+  constexpr bool CT = true;
+  constexpr int T = LineTile<N, CT>::T, LP = LineTile<N, CT>::LP, NT = LineTile<N, CT>::kThreads;
   constexpr int R1 = lf_r1(N), R2 = lf_r2(N), R3 = lf_r3(N);
   constexpr int S2 = N / R1, S3 = N / R1 / R2, HP = N / 2 + 1;
   float2* Sm = reinterpret_cast<float2*>(lf_smem);
@@ -341,62 +400,89 @@ __global__ void __launch_bounds__(LineTile<N>::kThreads) linefft_real_kernel(lon
     tw[i] = make_float2(c, s);
     f2p[line_pos_to_freq(N, i)] = i;
   }
-  LfCtx c{Sm, tw, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, n_pairs};
+  LfCtx c{Sm, tw, LfOff{}, LfOff{}, LfOff{}, nullptr, nullptr, nullptr, 0, n_pairs};
   LfNoIo nio;
   for (long long tile = blockIdx.x; tile * T < n_pairs; tile += gridDim.x) {
     const long long l0 = tile * T;
     c.l0 = l0;
     __syncthreads();
     if constexpr (!INV) {
-      for (int w = threadIdx.x; w < N * T; w += NT) {
-        const int idx = w % N, pl = w / N;
-        if (l0 + pl < n_pairs) Sm[idx * LP + pl] = io.load_pair(l0 + pl, idx);
+      // loads issued in batches of 4 per thread before the dependent shared-memory stores
+      for (int w0 = threadIdx.x; w0 < N * T; w0 += 4 * NT) {
+        float2 v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int w = w0 + q * NT, idx = w % N, pl = w / N;
+          v[q] = (w < N * T && l0 + pl < n_pairs) ? io.load_pair(l0 + pl, idx) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int w = w0 + q * NT, idx = w % N, pl = w / N;
+          if (w < N * T) Sm[lf_sidx<N, CT>(idx, pl)] = v[q];
+        }
       }
       __syncthreads();
-      lf_stage<N, R1, N, false, false, false, false>(c, nio, nio);
+      lf_stage<N, CT, R1, N, false, false, false, false>(c, nio, nio);
       __syncthreads();
       if constexpr (R2 > 1) {
-        lf_stage<N, R2, S2, false, false, false, false>(c, nio, nio);
+        lf_stage<N, CT, R2, S2, false, false, false, false>(c, nio, nio);
         __syncthreads();
       }
       if constexpr (R3 > 1) {
-        lf_stage<N, R3, S3, false, false, false, false>(c, nio, nio);
+        lf_stage<N, CT, R3, S3, false, false, false, false>(c, nio, nio);
         __syncthreads();
       }
       for (int w = threadIdx.x; w < HP * T; w += NT) {
         const int h = w % HP, pl = w / HP;
         if (l0 + pl < n_pairs) {
-          const float2 zk = Sm[f2p[h] * LP + pl], zn = Sm[f2p[(N - h) & (N - 1)] * LP + pl];
+          const float2 zk = Sm[lf_sidx<N, CT>(f2p[h], pl)], zn = Sm[lf_sidx<N, CT>(f2p[(N - h) & (N - 1)], pl)];
           const float2 A = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
           const float2 B = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
           io.store_half(l0 + pl, h, A, B);
         }
       }
     } else {
-      for (int w = threadIdx.x; w < HP * T; w += NT) {
-        const int h = w % HP, pl = w / HP;
-        if (l0 + pl < n_pairs) {
-          float2 A, B;
-          io.load_half(l0 + pl, h, A, B);
-          // Z[h] = A + i B ;  Z[N-h] = conj(A) + i conj(B)
-          Sm[f2p[h] * LP + pl] = make_float2(A.x - B.y, A.y + B.x);
-          if (h != 0 && h != N / 2) Sm[f2p[N - h] * LP + pl] = make_float2(A.x + B.y, B.x - A.y);
+      for (int w0 = threadIdx.x; w0 < HP * T; w0 += 4 * NT) {
+        float2 A[4], B[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int w = w0 + q * NT, h = w % HP, pl = w / HP;
+          A[q] = B[q] = make_float2(0.f, 0.f);
+          if (w < HP * T && l0 + pl < n_pairs) io.load_half(l0 + pl, h, A[q], B[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int w = w0 + q * NT, h = w % HP, pl = w / HP;
+          if (w < HP * T) {
+            // Z[h] = A + i B ;  Z[N-h] = conj(A) + i conj(B)
+            Sm[lf_sidx<N, CT>(f2p[h], pl)] = make_float2(A[q].x - B[q].y, A[q].y + B[q].x);
+            if (h != 0 && h != N / 2) Sm[lf_sidx<N, CT>(f2p[N - h], pl)] = make_float2(A[q].x + B[q].y, B[q].x - A[q].y);
+          }
         }
       }
       __syncthreads();
       if constexpr (R3 > 1) {
-        lf_stage<N, R3, S3, true, false, false, false>(c, nio, nio);
+        lf_stage<N, CT, R3, S3, true, false, false, false>(c, nio, nio);
         __syncthreads();
       }
       if constexpr (R2 > 1) {
-        lf_stage<N, R2, S2, true, false, false, false>(c, nio, nio);
+        lf_stage<N, CT, R2, S2, true, false, false, false>(c, nio, nio);
         __syncthreads();
       }
-      lf_stage<N, R1, N, true, false, false, false>(c, nio, nio);
+      lf_stage<N, CT, R1, N, true, false, false, false>(c, nio, nio);
       __syncthreads();
-      for (int w = threadIdx.x; w < N * T; w += NT) {
-        const int idx = w % N, pl = w / N;
-        if (l0 + pl < n_pairs) io.store_pair(l0 + pl, idx, Sm[idx * LP + pl]);
+      for (int w0 = threadIdx.x; w0 < N * T; w0 += 4 * NT) {
+        float2 pre[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int w = w0 + q * NT, idx = w % N, pl = w / N;
+          pre[q] = (w < N * T && l0 + pl < n_pairs) ? io.pre_pair(l0 + pl, idx) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int w = w0 + q * NT, idx = w % N, pl = w / N;
+          if (w < N * T && l0 + pl < n_pairs) io.store_pair(l0 + pl, idx, Sm[lf_sidx<N, CT>(idx, pl)], pre[q]);
+        }
       }
     }
   }
@@ -412,12 +498,12 @@ cudaError_t lf_launch_real(long long n_pairs, Io io, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  const long long tiles = (n_pairs + LineTile<N>::T - 1) / LineTile<N>::T;
+  const long long tiles = (n_pairs + LineTile<N, true>::T - 1) / LineTile<N, true>::T;
   const int per_sm = (int)((227 * 1024) / (smem + 1024));
   long long grid = tiles;
   const long long cap = 148LL * (per_sm > 8 ? 8 : (per_sm < 1 ? 1 : per_sm));
   if (grid > cap) grid = cap;
-  kern<<<(unsigned)grid, LineTile<N>::kThreads, smem, stream>>>(n_pairs, io);
+  kern<<<(unsigned)grid, LineTile<N, true>::kThreads, smem, stream>>>(n_pairs, io);
   return cudaGetLastError();
 }
 
@@ -432,7 +518,8 @@ struct LfStoreC {
   float2* p;
   LineGeom g;
   __device__ __forceinline__ LineGeom gout() const { return g; }
-  __device__ __forceinline__ void store(long long off, long long, int, float2 v) const { p[off] = v; }
+  __device__ __forceinline__ float2 pre(long long) const { return make_float2(0.f, 0.f); }
+  __device__ __forceinline__ void store(long long off, long long, int, float2 v, float2) const { p[off] = v; }
   __device__ __forceinline__ void flush(long long) {}
 };
 struct LfStoreCScaled {
@@ -440,7 +527,8 @@ struct LfStoreCScaled {
   LineGeom g;
   float scale;
   __device__ __forceinline__ LineGeom gout() const { return g; }
-  __device__ __forceinline__ void store(long long off, long long, int, float2 v) const {
+  __device__ __forceinline__ float2 pre(long long) const { return make_float2(0.f, 0.f); }
+  __device__ __forceinline__ void store(long long off, long long, int, float2 v, float2) const {
     p[off] = make_float2(v.x * scale, v.y * scale);
   }
   __device__ __forceinline__ void flush(long long) {}
@@ -453,19 +541,19 @@ struct LfMidNone {
 template <int N, int MODE, bool CONTIG, class Loader, class Mid, class Storer>
 cudaError_t lf_launch(long long n_lines, Loader ld, Mid mid, Storer st, cudaStream_t stream) {
   auto kern = linefft_kernel<N, MODE, CONTIG, Loader, Mid, Storer>;
-  constexpr size_t smem = LineTile<N>::smem_bytes;
+  constexpr size_t smem = LineTile<N, CONTIG>::smem_bytes;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  const long long tiles = (n_lines + LineTile<N>::T - 1) / LineTile<N>::T;
+  const long long tiles = (n_lines + LineTile<N, CONTIG>::T - 1) / LineTile<N, CONTIG>::T;
   const int per_sm = (int)((227 * 1024) / (smem + 1024));
   long long grid = tiles;
   const long long cap = 148LL * (per_sm > 8 ? 8 : (per_sm < 1 ? 1 : per_sm));
   if (grid > cap) grid = cap;
-  kern<<<(unsigned)grid, LineTile<N>::kThreads, smem, stream>>>(n_lines, ld, mid, st);
+  kern<<<(unsigned)grid, LineTile<N, CONTIG>::kThreads, smem, stream>>>(n_lines, ld, mid, st);
   return cudaGetLastError();
 }
 

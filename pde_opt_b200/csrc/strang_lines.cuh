@@ -77,9 +77,10 @@ struct LfStorePotential {
   float acc;
   LineGeom g;
   __device__ __forceinline__ LineGeom gout() const { return g; }
-  __device__ __forceinline__ void store(long long o, long long line, int idx, float2 v) {
+  __device__ __forceinline__ float2 pre(long long o) const { return psi0[o]; }
+  __device__ __forceinline__ void store(long long o, long long line, int idx, float2 v, float2 p0) {
     const int l32 = (int)line, env = l32 >> c.log2nx, r = l32 & (c.nx - 1);
-    const float2 w = cmul(v, gpe_potential_factor(c, env, r, idx, psi0[o], dt));
+    const float2 w = cmul(v, gpe_potential_factor(c, env, r, idx, p0, dt));
     out[o] = w;
     acc = fmaf(w.x, w.x, fmaf(w.y, w.y, acc));
   }
