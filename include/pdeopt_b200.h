@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define PDEOPT_ABI_VERSION 1
+#define PDEOPT_ABI_VERSION 2
 #define PDEOPT_MAX_COEF 16
 #define PDEOPT_MAX_FUSED_STEPS 512 /* per launch; callers loop for longer rollouts */
 #define PDEOPT_NCTRL 8            /* floats per environment in the control block */
@@ -177,8 +177,10 @@ int64_t pdeopt_ad_tables_len(const pdeopt_ad_desc* desc);
  * driven from pde_env.py:293-303 / pde_model.py:120-134) on `batch` environments.
  *   ctrl_dev : [batch][nseg][4] (cx, cy, p0, p1): velocity parameters, piecewise constant over
  *              `hold` numeric steps; local step k uses segment min((step0 + k)/hold, nseg-1)
- *   traj_dev : NULL, or where the state at the START of local step k is saved for the adjoint:
- *              traj_dev[k*traj_stride + b*nx*ny ...] (traj_stride in floats)                  */
+ *   traj_dev : NULL, or where the state at the START of local step k is saved for the adjoint, at
+ *              traj_dev + k*traj_stride (traj_stride in floats, >= 2*ceil(batch/2)*nx*ny).  The
+ *              layout inside a step is internal (the kernels' register arrangement, per pair of
+ *              environments); only pdeopt_ad_rollout_bwd reads it.                              */
 pdeopt_status pdeopt_ad_rollout_fwd(const pdeopt_ad_desc* desc, const float* y0_dev, float* y1_dev, int32_t batch,
                                     int32_t ksteps, const float* dt_host, const float* tables_dev,
                                     const float* ctrl_dev, int32_t nseg, int32_t hold, int32_t step0,

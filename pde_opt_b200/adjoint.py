@@ -71,7 +71,7 @@ class _ADRollout(torch.autograd.Function):
             return y1
         if checkpoint_every is None:
             # the whole trajectory lives in HBM (500 steps x 512 envs x 64 KB = 16 GiB of 180 GB)
-            traj = torch.empty((K,) + tuple(y0c.shape), dtype=torch.float32, device=y0c.device)
+            traj = torch.empty((K, 2 * ((y0c.shape[0] + 1) // 2)) + tuple(y0c.shape[1:]), dtype=torch.float32, device=y0c.device)
             _fwd(desc, y0c, y1, dts, tables, ctrlc, hold, step0, traj)
             ctx.save_for_backward(ctrlc, traj)
         else:
@@ -99,7 +99,7 @@ class _ADRollout(torch.autograd.Function):
             _bwd(desc, traj, lam, dts, tables, ctrl, hold, step0, gctrl)
         else:
             cps = ctx.saved_tensors[1:]
-            seg = torch.empty((min(S, K),) + tuple(lam.shape), dtype=torch.float32, device=lam.device)
+            seg = torch.empty((min(S, K), 2 * ((lam.shape[0] + 1) // 2)) + tuple(lam.shape[1:]), dtype=torch.float32, device=lam.device)
             scratch = torch.empty_like(lam)
             begs = list(range(0, K, S))
             for ci in reversed(range(len(begs))):

@@ -39,7 +39,7 @@ constexpr int kAdCtrl = 4;  // (cx, cy, p0, p1) per control segment
 struct AdParams {
   const float* y0;   // fwd: [batch][128][128] initial state; bwd: cotangent of the final state
   float* y1;         // fwd: final state; bwd: cotangent of the initial state
-  float* traj;       // fwd: if non-null, state at the START of step k -> traj[k*traj_stride + env*16384]
+  float* traj;       // fwd: if non-null, state at the START of step k -> traj[k*traj_stride ...], [pair][32][512] float2
   const float* traj_in;  // bwd: the same array
   long long traj_stride;
   int batch, ksteps;
@@ -64,6 +64,8 @@ struct __align__(1024) AdSmem {
   float2 ay[kN], ey[kN];                     // column (y) tables: ay = -(p0/p1) dy ey
   float2 dyey[kN], dy2ey[kN], dy3ey[kN];     // bwd: dy^j ey
   float2 red[kThreads / 32][4];
+  float2 segc[4];             // bwd: (p0, 1/p1, p0/p1) of the current segment for the (a, b) pair
+  float2 gacc[4][kThreads];   // bwd: per-thread cotangent accumulators (cx, cy, p0, p1), kept out of the register file
   uint32_t tmem_base;
 };
 
@@ -198,12 +200,12 @@ __global__ void __launch_bounds__(kThreads, 1) ad128_fwd_kernel(const __grid_con
       cur_seg = seg;
     }
     if (p.traj != nullptr) {
-      // save the state at the start of the step (what the adjoint needs)
-      p1_scatter_nat(F.nb, x);
-      __syncthreads();
-      float* t = p.traj + (size_t)k * p.traj_stride;
-      ad_store_pair(S.W, t + oa, t + ob, C.b_valid);
-      __syncthreads();
+      // save the state at the start of the step (what the adjoint needs) straight from the registers:
+      // the trajectory is an internal buffer, so it is kept in the P1 register arrangement
+      // ([pair][n][thread] float2), written and read back with coalesced 8-byte accesses
+      float2* t = reinterpret_cast<float2*>(p.traj + (size_t)k * p.traj_stride) + (size_t)blockIdx.x * 32 * kThreads + threadIdx.x;
+#pragma unroll
+      for (int n = 0; n < 32; ++n) t[n * kThreads] = x[n];
     }
     const float dt = p.dt[k];
     park_all(C.park0, x);
@@ -302,9 +304,10 @@ __global__ void __launch_bounds__(kThreads, 1) ad128_bwd_kernel(const __grid_con
   const int n2c = F.m1.n2c;
 
   // gradient accumulators of the current control segment: (cx, cy, p0, p1) for the (a, b) pair
-  float2 g_cx = make_float2(0.f, 0.f), g_cy = g_cx, g_p0 = g_cx, g_p1 = g_cx;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) S.gacc[j][tid] = make_float2(0.f, 0.f);
   auto flush = [&](int seg) {
-    float2 g[4] = {g_cx, g_cy, g_p0, g_p1};
+    float2 g[4] = {S.gacc[0][tid], S.gacc[1][tid], S.gacc[2][tid], S.gacc[3][tid]};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
 #pragma unroll
@@ -328,12 +331,11 @@ __global__ void __launch_bounds__(kThreads, 1) ad128_bwd_kernel(const __grid_con
         *dst += s;
       }
     }
-    g_cx = g_cy = g_p0 = g_p1 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) S.gacc[j][tid] = make_float2(0.f, 0.f);
   };
 
   int cur_seg = -1;
-  float2 dxr, exr, p0, ip1, c0, vxr, vyc;
-  dxr = exr = p0 = ip1 = c0 = vxr = vyc = make_float2(0.f, 0.f);
   for (int k = p.ksteps - 1; k >= 0; --k) {
     const int seg = ad_seg(p, k);
     if (seg != cur_seg) {
@@ -341,20 +343,19 @@ __global__ void __launch_bounds__(kThreads, 1) ad128_bwd_kernel(const __grid_con
       __syncthreads();
       ad_tables(S, p, C.env_a, C.env_b, seg);
       __syncthreads();
-      const float* ca = p.ctrl + ((size_t)C.env_a * p.nseg + seg) * kAdCtrl;
-      const float* cb = p.ctrl + ((size_t)C.env_b * p.nseg + seg) * kAdCtrl;
-      dxr = S.dxv[r];
-      exr = S.ex[r];
-      p0 = make_float2(ca[2], cb[2]);
-      ip1 = make_float2(1.0f / ca[3], 1.0f / cb[3]);
-      c0 = f2mul(p0, ip1);
-      vyc = make_float2(-c0.x * exr.x, -c0.y * exr.y);  // vy = vyc * dy ey
-      vxr = f2mul(vyc, dxr);                              // vx = vxr * ey
+      if (tid == 0) {
+        const float* ca = p.ctrl + ((size_t)C.env_a * p.nseg + seg) * kAdCtrl;
+        const float* cb = p.ctrl + ((size_t)C.env_b * p.nseg + seg) * kAdCtrl;
+        const float2 p0 = make_float2(ca[2], cb[2]), ip1 = make_float2(1.0f / ca[3], 1.0f / cb[3]);
+        S.segc[0] = p0;
+        S.segc[1] = ip1;
+        S.segc[2] = f2mul(p0, ip1);
+      }
+      __syncthreads();
       cur_seg = seg;
     }
     const float dt = p.dt[k];
-    const float* ua = p.traj_in + (size_t)k * p.traj_stride + oa + r * kN + n2c;
-    const float* ub = p.traj_in + (size_t)k * p.traj_stride + ob + r * kN + n2c;
+    const float2* up = reinterpret_cast<const float2*>(p.traj_in + (size_t)k * p.traj_stride) + (size_t)blockIdx.x * 32 * kThreads + tid;
     // ---- lam_hat = F[lam1] -> park1 ----
     F.forward(x);
     park_all(C.park1, x);
@@ -370,27 +371,7 @@ __global__ void __launch_bounds__(kThreads, 1) ad128_bwd_kernel(const __grid_con
     });
     F.inverse(x);
     __syncthreads();
-    float2 S0 = make_float2(0.f, 0.f), S1 = S0, S2 = S0;
-    {
-      const float2 coef = f2scale(vxr, dt);
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        float2 v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int n = ch * 8 + i, c = 4 * n + n2c;
-          const float2 u = make_float2(__ldg(ua + 4 * n), __ldg(ub + 4 * n));
-          const float2 px = mul2(x[n], u);
-          const float2 ey = S.ey[c];
-          S0 = fma2(px, ey, S0);
-          S1 = fma2(px, S.dyey[c], S1);
-          S2 = fma2(px, S.dy2ey[c], S2);
-          v[i] = mul2(mul2(x[n], coef), ey);  // dt vx d/dx w
-        }
-        C.park0.store(ch, v);
-      }
-      C.park0.fence_store();
-    }
+    park_all(C.park0, x);  // d/dx w waits in TMEM until d/dy w is there, so u is read once per step
     // ---- d/dy w = F^-1[i ky m lam_hat] ----
     static_for<0, 4>([&](auto chc) {
       constexpr int ch = decltype(chc)::value;
@@ -405,24 +386,31 @@ __global__ void __launch_bounds__(kThreads, 1) ad128_bwd_kernel(const __grid_con
     });
     F.inverse(x);
     __syncthreads();
-    float2 T0 = make_float2(0.f, 0.f), T1 = T0, T2 = T0, T3 = T0;
+    float2 S0 = make_float2(0.f, 0.f), S1 = S0, S2 = S0;
+    float2 T0 = S0, T1 = S0, T2 = S0, T3 = S0;
     {
-      const float2 coef = f2scale(vyc, dt);
+      // vx = vxr * ey, vxr = -(p0/p1) dx ex ;  vy = vyc * dy ey, vyc = -(p0/p1) ex   (row constants
+      // re-read from shared memory where used: keeping them in registers across the transforms spilled)
+      const float2 coefy = f2scale(f2mul(S.segc[2], S.ex[r]), -dt);
+      const float2 coefx = f2mul(coefy, S.dxv[r]);
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         float2 v[8];
-        C.park0.load(ch, v);
+        C.park0.load(ch, v);  // d/dx w
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int n = ch * 8 + i, c = 4 * n + n2c;
-          const float2 u = make_float2(__ldg(ua + 4 * n), __ldg(ub + 4 * n));
-          const float2 py = mul2(x[n], u);
-          const float2 de = S.dyey[c];
-          T0 = fma2(py, S.ey[c], T0);
+          const float2 u = __ldg(up + n * kThreads);
+          const float2 px = mul2(v[i], u), py = mul2(x[n], u);
+          const float2 ey = S.ey[c], de = S.dyey[c], d2e = S.dy2ey[c];
+          S0 = fma2(px, ey, S0);
+          S1 = fma2(px, de, S1);
+          S2 = fma2(px, d2e, S2);
+          T0 = fma2(py, ey, T0);
           T1 = fma2(py, de, T1);
-          T2 = fma2(py, S.dy2ey[c], T2);
+          T2 = fma2(py, d2e, T2);
           T3 = fma2(py, S.dy3ey[c], T3);
-          v[i] = fma2(mul2(x[n], coef), de, v[i]);  // + dt vy d/dy w
+          v[i] = fma2(mul2(x[n], coefy), de, mul2(mul2(v[i], coefx), ey));  // dt (vx d/dx w + vy d/dy w)
         }
         C.park0.store(ch, v);
       }
@@ -451,6 +439,9 @@ __global__ void __launch_bounds__(kThreads, 1) ad128_bwd_kernel(const __grid_con
     __syncthreads();
     // ---- parameter cotangents of this step (per-thread partial sums over its 32 columns) ----
     {
+      const float2 dxr = S.dxv[r], exr = S.ex[r], ip1 = S.segc[1], c0 = S.segc[2];
+      const float2 vyc = make_float2(-c0.x * exr.x, -c0.y * exr.y), vxr = f2mul(vyc, dxr);
+      float2 g_cx = S.gacc[0][tid], g_cy = S.gacc[1][tid], g_p0 = S.gacc[2][tid], g_p1 = S.gacc[3][tid];
       const float2 dx2 = f2mul(dxr, dxr);
       const float2 ip1sq_h = f2scale(f2mul(ip1, ip1), 0.5f);
       const float2 pa = make_float2(fmaf(dx2.x, ip1sq_h.x, -ip1.x), fmaf(dx2.y, ip1sq_h.y, -ip1.y));  // -1/p1 + dx^2/(2 p1^2)
@@ -469,6 +460,10 @@ __global__ void __launch_bounds__(kThreads, 1) ad128_bwd_kernel(const __grid_con
       g_cx = f2fma(f2mul(f2mul(vyd, ip1), dxr), T1, g_cx);
       g_p1 = f2fma(f2mul(vyd, pa), T1, g_p1);
       g_p1 = f2fma(f2mul(vyd, ip1sq_h), T3, g_p1);
+      S.gacc[0][tid] = g_cx;
+      S.gacc[1][tid] = g_cy;
+      S.gacc[2][tid] = g_p0;
+      S.gacc[3][tid] = g_p1;
     }
   }
   if (cur_seg >= 0) flush(cur_seg);
