@@ -267,18 +267,26 @@ extern "C" pdeopt_status pdeopt_strang_lines_step_batched(const pdeopt_gpe_desc*
       LineGeom ctab = cols;
       ctab.outer = 0;
       const LfMidCTab mid{etab, ctab};
-      e = lf_run<LF_FWD, true>(ny, rows.n_lines, LfLoadC{src, rows}, LfMidNone{}, LfStoreC{W, rows}, st);
-      if (e != cudaSuccess) break;
+      const LfMidCTabScaled mid_scaled{etab, norm, ctab, ilog2(ny), dx2};
+      // 4 kernels per step (W holds the row-transformed state between steps):
+      //   [rows fwd, first step only]  cols fwd*e*inv  rows inv*potential*fwd  cols fwd*e*scale*inv  rows inv -> y1 [-> fwd]
+      if (k == 0) {
+        e = lf_run<LF_FWD, true>(ny, rows.n_lines, LfLoadC{src, rows}, LfMidNone{}, LfStoreC{W, rows}, st);
+        if (e != cudaSuccess) break;
+        g_launches.fetch_add(1);
+      }
       e = lf_run<LF_FWD_MUL_INV, false>(nx, cols.n_lines, LfLoadC{W, cols}, mid, LfStoreC{W, cols}, st);
       if (e != cudaSuccess) break;
-      e = lf_run<LF_INV, true>(ny, rows.n_lines, LfLoadC{W, rows}, LfMidNone{}, LfStorePotential{W, src, norm, c, dt, 0.f, rows}, st);
+      e = lf_run<LF_INV_MID_FWD, true>(ny, rows.n_lines, LfLoadC{W, rows}, LfMidPotentialIMF{src, norm, c, dt, 0.f}, LfStoreC{W, rows}, st);
       if (e != cudaSuccess) break;
-      e = lf_run<LF_FWD, true>(ny, rows.n_lines, LfLoadNormalised{W, norm, nx, ny, ilog2(nx), dx2, rows}, LfMidNone{}, LfStoreC{W, rows}, st);
+      e = lf_run<LF_FWD_MUL_INV, false>(nx, cols.n_lines, LfLoadC{W, cols}, mid_scaled, LfStoreC{W, cols}, st);
       if (e != cudaSuccess) break;
-      e = lf_run<LF_FWD_MUL_INV, false>(nx, cols.n_lines, LfLoadC{W, cols}, mid, LfStoreC{W, cols}, st);
-      if (e != cudaSuccess) break;
-      e = lf_run<LF_INV, true>(ny, rows.n_lines, LfLoadC{W, rows}, LfMidNone{}, LfStoreC{dst, rows}, st);
-      g_launches.fetch_add(6);
+      if (k + 1 < ksteps) {
+        e = lf_run<LF_INV_MID_FWD, true>(ny, rows.n_lines, LfLoadC{W, rows}, LfMidStoreState{dst}, LfStoreC{W, rows}, st);
+      } else {
+        e = lf_run<LF_INV, true>(ny, rows.n_lines, LfLoadC{W, rows}, LfMidNone{}, LfStoreC{dst, rows}, st);
+      }
+      g_launches.fetch_add(4);
     }
     src = dst;
   }

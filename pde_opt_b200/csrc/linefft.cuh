@@ -108,7 +108,7 @@ __device__ __forceinline__ LfOff lf_off(const LineGeom& g) {
   return o;
 }
 
-enum : int { LF_FWD = 0, LF_INV = 1, LF_FWD_MUL_INV = 2 };
+enum : int { LF_FWD = 0, LF_INV = 1, LF_FWD_MUL_INV = 2, LF_INV_MID_FWD = 3 };
 
 // Functor concepts (offsets are element offsets computed from the functor's own geometries):
 //   Loader: LineGeom gin() ;  float2 load(long long off, long long line, int idx)
@@ -338,6 +338,51 @@ __global__ void __launch_bounds__(LineTile<N, CONTIG>::kThreads) linefft_kernel(
         }
         lf_stage<N, CT, R1, N, true, false, true, true>(c, ld, st);
       }
+    } else if constexpr (MODE == LF_INV_MID_FWD) {
+      // contiguous lines: inverse transform, a pointwise operator in natural order (with its own
+      // global reads, e.g. psi0 of the potential step), forward transform again, one pass over memory.
+      // Mid concept here: float2 pre(long long off) ; float2 apply(float2 v, long long off, long long line,
+      // int idx, float2 pre) ; void flush(long long l0)
+      static_assert(MODE != LF_INV_MID_FWD || CONTIG, "LF_INV_MID_FWD is for contiguous lines");
+      copy_in();
+      if constexpr (NS >= 3) {
+        lf_stage<N, CT, R3, S3, true, false, false, false>(c, ld, st);
+        __syncthreads();
+      }
+      if constexpr (NS >= 2) {
+        lf_stage<N, CT, R2, S2, true, false, false, false>(c, ld, st);
+        __syncthreads();
+      }
+      lf_stage<N, CT, R1, N, true, false, false, false>(c, ld, st);
+      __syncthreads();
+      for (int w0 = threadIdx.x; w0 < N * T; w0 += 4 * NT) {
+        float2 pre[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int w = w0 + q * NT, idx = w % N, line = w / N;
+          pre[q] = (w < N * T && l0 + line < n_lines) ? mid.pre(lb_out[line] + io_out[idx]) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int w = w0 + q * NT, idx = w % N, line = w / N;
+          if (w < N * T && l0 + line < n_lines) {
+            const int si = lf_sidx<N, CT>(idx, line);
+            Sm[si] = mid.apply(Sm[si], lb_out[line] + io_out[idx], l0 + line, idx, pre[q]);
+          }
+        }
+      }
+      __syncthreads();
+      lf_stage<N, CT, R1, N, false, false, false, false>(c, ld, st);
+      if constexpr (NS >= 2) {
+        __syncthreads();
+        lf_stage<N, CT, R2, S2, false, false, false, false>(c, ld, st);
+      }
+      if constexpr (NS >= 3) {
+        __syncthreads();
+        lf_stage<N, CT, R3, S3, false, false, false, false>(c, ld, st);
+      }
+      copy_out();
+      mid.flush(l0);
     } else {
       if constexpr (NS == 1) {
         lf_stage_fmi<N, CT, R1, true, true, LU>(c, ld, mid, st);

@@ -91,6 +91,55 @@ struct LfStorePotential {
   }
 };
 
+// Fused K3+K4 (rows): inverse, times exp(b(psi0) dt_c) with the norm accumulated, forward again.  The
+// L2 renormalisation (solvers.py:111) is a scalar per environment and commutes with the transforms,
+// so it is applied by the following column pass (LfMidCTabScaled) instead of a pass of its own.
+struct LfMidPotentialIMF {
+  const float2* psi0;
+  float* norm;  // [batch]
+  GpeLinesConst c;
+  float dt;
+  float acc;
+  __device__ __forceinline__ LineGeom gaux() const { return LineGeom{1, 1, 0, 0, 1, 0, 0}; }
+  __device__ __forceinline__ float2 pre(long long o) const { return psi0[o]; }
+  __device__ __forceinline__ float2 apply(float2 v, long long, long long line, int idx, float2 p0) {
+    const int l32 = (int)line, env = l32 >> c.log2nx, r = l32 & (c.nx - 1);
+    const float2 w = cmul(v, gpe_potential_factor(c, env, r, idx, p0, dt));
+    acc = fmaf(w.x, w.x, fmaf(w.y, w.y, acc));
+    return w;
+  }
+  __device__ __forceinline__ void flush(long long l0) {
+    const float t = lf_block_sum(acc);
+    if (threadIdx.x == 0) atomicAdd(norm + (l0 >> c.log2nx), t);
+    acc = 0.f;
+  }
+};
+// Fused K6+K1 (rows): inverse -> y1 (the state the next step's b(psi0) needs, and the output) -> forward
+struct LfMidStoreState {
+  float2* y1;
+  __device__ __forceinline__ LineGeom gaux() const { return LineGeom{1, 1, 0, 0, 1, 0, 0}; }
+  __device__ __forceinline__ float2 pre(long long) const { return make_float2(0.f, 0.f); }
+  __device__ __forceinline__ float2 apply(float2 v, long long o, long long, int, float2) const {
+    y1[o] = v;
+    return v;
+  }
+  __device__ __forceinline__ void flush(long long) {}
+};
+// column pass multiplier exp(A dt_c / 2) / N^2 times the pending renormalisation 1/sqrt(norm dx^2)
+struct LfMidCTabScaled {
+  const float2* tab;
+  const float* norm;
+  LineGeom g;  // column-pass geometry with outer = 0 (table shared by the batch)
+  int log2ny;
+  float dx2;
+  __device__ __forceinline__ LineGeom gaux() const { return g; }
+  __device__ __forceinline__ float2 apply(float2 v, long long off_aux, long long line, int) const {
+    const float s = rsqrtf(norm[(int)line >> log2ny] * dx2);
+    const float2 t = tab[off_aux];
+    return cmul(v, make_float2(t.x * s, t.y * s));
+  }
+};
+
 // K4 loader: W / sqrt(norm dx^2)
 struct LfLoadNormalised {
   const float2* p;
