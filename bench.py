@@ -109,19 +109,30 @@ def cpu_arm(envs_per_core, nsteps, cores=None):
 
 
 def run_reference(args):
+    """The reference's CPU arithmetic (NumPy restatement; jax/diffrax cannot be installed here) on all
+    host cores: a persistent pool of one worker per core, each bench step = cores x 48 environments
+    x 16 numeric steps (about one second), so process start-up is outside the timed region."""
+    import multiprocessing as mp
+
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    envs_per_core = 8  # one bench "step" = cores*8 envs x 16 numeric steps (~0.2 s of CPU work per core)
-    for _ in range(args.warmup):
-        cpu_arm(envs_per_core, K_FUSED, cores)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_arm(envs_per_core, K_FUSED, cores)
-    wall = time.perf_counter() - t0
+    envs_per_core = 48
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        def one_step(i):
+            jobs = [(list(range((i * cores + c) * envs_per_core, (i * cores + c + 1) * envs_per_core)), K_FUSED) for c in range(cores)]
+            pool.map(_cpu_worker, jobs)
+
+        for i in range(max(args.warmup, 1)):
+            one_step(i)
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            one_step(1000 + i)
+        wall = time.perf_counter() - t0
     value = args.steps * cores * envs_per_core * K_FUSED / wall
-    sample = f"{cores * envs_per_core} envs x {K_FUSED} numeric steps per bench step, {args.steps} steps"
+    sample = f"{cores * envs_per_core} envs x {K_FUSED} numeric steps per bench step, {args.steps} steps, persistent pool of {cores} workers"
     line = {
         "impl": "reference",
         "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
