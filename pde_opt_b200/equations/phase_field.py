@@ -28,6 +28,41 @@ def _symbols(domain):
     return two_pi_i_kx, two_pi_i_ky, k2
 
 
+def _on(device, a, cache, key):
+    import torch
+
+    k = (key, str(device))
+    if k not in cache:
+        cache[k] = torch.as_tensor(a, device=device)
+    return cache[k]
+
+
+def spectral_rhs_ch(eq, state, qs, k2):
+    """CahnHilliard{2,3}DPeriodic.rhs_fourier (cahn_hilliard.py:82-87, :165-175) for grids without a
+    fused kernel: the same expression on the line-FFT engine (linefft.fftn / ifftn) with the
+    pointwise closures evaluated by torch.  `state` has a leading batch axis."""
+    from ..linefft import fftn, ifftn
+
+    dims = tuple(range(1, state.dim()))
+    sh = fftn(state, dims)
+    tmp = fftn(eq.mu(state).contiguous(), dims) - eq.kappa * k2 * sh
+    Du = eq.D(state)
+    acc = None
+    for q in qs:
+        term = q * fftn((Du * ifftn(q * tmp, dims)).contiguous(), dims)
+        acc = term if acc is None else acc + term
+    return ifftn(acc.contiguous(), dims).real.contiguous()
+
+
+def spectral_rhs_ac(eq, state, k2):
+    """AllenCahn2DPeriodic.rhs_fourier (allen_cahn.py:74-79) on the line-FFT engine."""
+    from ..linefft import fftn, ifftn
+
+    dims = tuple(range(1, state.dim()))
+    mu = ifftn((fftn(eq.mu(state).contiguous(), dims) - eq.kappa * k2 * fftn(state, dims)).contiguous(), dims)
+    return (-eq.R(state) * mu.real).contiguous()
+
+
 class _PhaseField2D(BaseEquation):
     _kind = None
 
@@ -76,6 +111,15 @@ class _PhaseField2D(BaseEquation):
         single = state.dim() == 2
         y = state.unsqueeze(0) if single else state
         y = y.contiguous()
+        if self.derivs == "fourier" and not self.fused:
+            # no fused kernel for this grid / closure: the reference expression on the line-FFT engine
+            c = self.__dict__.setdefault("_dev_cache", {})
+            k2 = _on(y.device, self.two_pi_i_k_2, c, "k2")
+            if self._kind == "ac2d":
+                f = spectral_rhs_ac(self, y, k2)
+            else:
+                f = spectral_rhs_ch(self, y, [_on(y.device, self.two_pi_i_kx, c, "qx"), _on(y.device, self.two_pi_i_ky, c, "qy")], k2)
+            return f[0] if single else f
         out = torch.empty_like(y)
         plan = self.plan()
         st = _lib.load().pdeopt_rhs_batched(
@@ -181,5 +225,15 @@ class CahnHilliard3DPeriodic(BaseEquation):
     def rhs(self, state, t=0.0):
         single = state.dim() == 3
         y = (state.unsqueeze(0) if single else state).contiguous()
-        f = self.plan().rhs(y)
+        if self.derivs == "fourier":
+            # cahn_hilliard.py:165-175 on the line-FFT engine (7 complex 3-D transforms)
+            c = self.__dict__.setdefault("_dev_cache", {})
+            if "q" not in c:
+                kx, ky, kz = self.domain.fft_mesh()
+                c["q"] = [(2j * np.pi * k).astype(np.complex64) for k in (kx, ky, kz)]
+                c["k2n"] = c["q"][0] ** 2 + c["q"][1] ** 2 + c["q"][2] ** 2
+            qs = [_on(y.device, q, c, f"q{i}") for i, q in enumerate(c["q"])]
+            f = spectral_rhs_ch(self, y, qs, _on(y.device, c["k2n"], c, "k2"))
+        else:
+            f = self.plan().rhs(y)
         return f[0] if single else f

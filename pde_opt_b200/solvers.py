@@ -87,29 +87,32 @@ class SemiImplicitFourierSpectral:
             self._sym_dev[key] = torch.from_numpy(np.ascontiguousarray(s)).to(device)
         return self._sym_dev[key]
 
-    def _rollout3d(self, terms, dts, y0, out=None):
+    def _rollout3d(self, terms, dts, y0, out=None, times=None):
         eq = getattr(terms, "equation", None)
-        if eq is None or getattr(eq, "_kind", None) != "ch3d" or not eq.fused:
-            raise NotImplementedError("3-D semi-implicit stepping needs ODETerm(CahnHilliard3DPeriodic) with enumerated mu / D")
         single = y0.dim() == 3
         y = (y0.unsqueeze(0) if single else y0).contiguous()
-        y1 = eq.plan().step(y, dts, self.symbol_pos_on(y.device), out=out)
-        return y1[0] if single else y1
+        if eq is not None and getattr(eq, "_kind", None) == "ch3d" and eq.fused:
+            y1 = eq.plan().step(y, dts, self.symbol_pos_on(y.device), out=out)
+            return y1[0] if single else y1
+        # unfused 3-D path (derivs="fourier", or any vector field): terms.vf evaluated by the caller's
+        # code, then y1 = y0 + dt Re ifft(fft(f0) / (1 + A dt symbol)) on the line-FFT engine (solvers.py:59-63)
+        from .linefft import fftn, ifftn
 
-    def order(self, terms):
-        return 1
-
-    def init(self, terms, t0, t1, y0, args):
-        return None
-
-    def func(self, terms, t0, y0, args):
-        return terms.vf(t0, y0, args)
-
-    def symbol_on(self, device):
-        key = str(device)
+        key = ("nat", str(y.device))
         if key not in self._sym_dev:
-            self._sym_dev[key] = torch.from_numpy(self._quad).to(device)
-        return self._sym_dev[key]
+            s_ = np.asarray(self.fourier_symbol)
+            self._sym_dev[key] = torch.from_numpy((np.float32(self.A) * s_.real.astype(np.float32)).astype(np.float32)).to(y.device)
+        sym = self._sym_dev[key]
+        t = 0.0 if times is None else float(times[0])
+        for k, dt in enumerate(dts):
+            f0 = terms.vf(t if times is None else float(times[k]), y[0] if single else y, None)
+            f0 = (f0.unsqueeze(0) if single else f0).contiguous()
+            g = ifftn((fftn(f0, (1, 2, 3)) / (1.0 + float(dt) * sym)).contiguous(), (1, 2, 3)).real
+            y = y + float(dt) * g
+        if out is not None:
+            out.copy_(y)
+            y = out
+        return y[0] if single else y
 
     def _rollout_ad(self, eq, times, y0, out=None):
         """Advection-diffusion (recovered equation): the fused forward kernel (differentiable)."""
@@ -172,7 +175,7 @@ class SemiImplicitFourierSpectral:
         times = np.asarray(times, dtype=np.float32)
         dts = (times[1:] - times[:-1]).astype(np.float32)
         if self._is3d:
-            return self._rollout3d(terms, dts, y0, out=out)
+            return self._rollout3d(terms, dts, y0, out=out, times=times)
         if type(getattr(terms, "equation", None)).__name__ == "AdvectionDiffusion2D":
             return self._rollout_ad(terms.equation, times, y0, out=out)
         single = y0.dim() == 2

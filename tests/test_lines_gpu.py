@@ -221,3 +221,46 @@ def test_r2c_and_c2r_lines(n):
     y1 = torch.empty_like(y0)
     _lib.check(lib.pdeopt_fft_lines_c2r_update(ctypes.c_void_p(half.data_ptr()), n, L, ctypes.c_void_p(y0.data_ptr()), ctypes.c_void_p(y1.data_ptr()), 0.5 / n, st))
     assert rel_l2(y1.cpu().numpy(), y0.cpu().numpy() + 0.5 * x) <= 2e-6
+
+
+def test_rhs_fourier_on_the_line_engine_3d_and_small_2d():
+    """derivs='fourier' on grids without a fused kernel (3-D, 64x64 2-D): the reference expression
+    (cahn_hilliard.py:82-87, :165-175; allen_cahn.py:74-79) on linefft.fftn / ifftn, and the unfused
+    semi-implicit step on top of it, against the oracle."""
+    from pde_opt_b200 import Domain
+    from pde_opt_b200.equations import AllenCahn2DPeriodic, CahnHilliard2DPeriodic, CahnHilliard3DPeriodic
+    from pde_opt_b200.functions import DegenerateMobility, LogRegular, OnePlusSquare
+    from pde_opt_b200.solvers import ODETerm, SemiImplicitFourierSpectral
+
+    # 3-D Cahn-Hilliard
+    pts = (16, 32, 8)
+    box = tuple((0.0, n * 0.01) for n in pts)
+    eq = CahnHilliard3DPeriodic(Domain(pts, box, "d"), 0.002, LogRegular(3.0), DegenerateMobility(), derivs="fourier")
+    oeq = O.CahnHilliardPeriodic(O.Domain(pts, box), 0.002, lambda c: O.mu_log(c, 3.0), lambda c: (1 - c) * c, "fourier", np.float32)
+    o64 = O.CahnHilliardPeriodic(O.Domain(pts, box), 0.002, lambda c: O.mu_log(c, 3.0), lambda c: (1 - c) * c, "fourier", np.float64)
+    u = np.clip(0.5 + 0.05 * np.random.default_rng(0).normal(size=(2,) + pts), 0.05, 0.95).astype(np.float32)
+    f = eq.rhs(torch.from_numpy(u).cuda()).cpu().numpy()
+    for b in range(2):
+        assert rel_l2(f[b], o64.rhs(u[b].astype(np.float64))) <= 5e-5
+    solver = SemiImplicitFourierSpectral(0.5, eq.fourier_symbol, eq.fft, eq.ifft)
+    times = np.arange(4, dtype=np.float32) * np.float32(1e-6)
+    got = solver.rollout(ODETerm(eq), times, torch.from_numpy(u).cuda()).cpu().numpy()
+    for b in range(2):
+        y = u[b]
+        for a, bb in zip(times[:-1], times[1:]):
+            y = O.sifs_step(oeq.rhs, y, a, bb, 0.5, oeq.fourier_symbol)
+        assert rel_l2(got[b], y) <= 1e-5
+    # 2-D 64x64 (no fused fourier kernel): RHS only
+    box2 = ((0.0, 0.64), (0.0, 0.64))
+    u2 = np.clip(0.5 + 0.05 * np.random.default_rng(1).normal(size=(2, 64, 64)), 0.05, 0.95).astype(np.float32)
+    for kind in ("ch", "ac"):
+        if kind == "ch":
+            e2 = CahnHilliard2DPeriodic(Domain((64, 64), box2, "d"), 0.002, LogRegular(3.0), DegenerateMobility(), derivs="fourier")
+            o2 = O.CahnHilliardPeriodic(O.Domain((64, 64), box2), 0.002, lambda c: O.mu_log(c, 3.0), lambda c: (1 - c) * c, "fourier", np.float64)
+        else:
+            e2 = AllenCahn2DPeriodic(Domain((64, 64), box2, "d"), 0.002, LogRegular(3.0), OnePlusSquare(), derivs="fourier")
+            o2 = O.AllenCahn2DPeriodic(O.Domain((64, 64), box2), 0.002, lambda c: O.mu_log(c, 3.0), lambda c: 1 + c**2, "fourier", np.float64)
+        assert not e2.fused
+        f2 = e2.rhs(torch.from_numpy(u2).cuda()).cpu().numpy()
+        for b in range(2):
+            assert rel_l2(f2[b], o2.rhs(u2[b].astype(np.float64))) <= 5e-5
