@@ -71,8 +71,6 @@ __global__ void __launch_bounds__(kThreads, 1) strang128_kernel(const __grid_con
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
 #endif
-  if (has_A)
-    for (int i = tid; i < kTabLen; i += kThreads) S.atab[i] = reinterpret_cast<const float2*>(p.a_term)[i];
   if (tid < 128) {
     float s, c;
     sincospif(-2.0f * float(tid) / 128.0f, &s, &c);
@@ -126,9 +124,18 @@ __global__ void __launch_bounds__(kThreads, 1) strang128_kernel(const __grid_con
   const float vrow = 0.5f * p.trap * (1.0f + p.e) * xr * xr;
   const float gxr = has_light ? S.gx[r] : 0.f;
 
-  auto half_kinetic = [&](float dt) {
-    // exp(A_term * 0.5 * dt_c) / N^2 in the spectral (P3) arrangement
+  // exp(A_term * 0.5 * dt_c) / N^2 is tabulated in shared memory per distinct dt (the step lengths of
+  // the float32 time grid differ by ulps, so the table is rebuilt only when dt changes): the half
+  // kinetic step is then one LDS.64 + one complex multiply per element instead of exp + sincos.
+  float dt_tab = __int_as_float(0x7fc00000);
+  auto build_etab = [&](float dt) {
     const float hr = 0.5f * dt * p.ts_re, hi = 0.5f * dt * p.ts_im;
+    __syncthreads();  // earlier readers of the table are done
+    for (int i = tid; i < kTabLen; i += kThreads)
+      S.atab[i] = cexp_times(reinterpret_cast<const float2*>(p.a_term)[i], hr, hi, 1.0f / float(kN * kN));
+    __syncthreads();
+  };
+  auto half_kinetic = [&]() {
     static_for<0, 2>([&](auto bc) {
       constexpr int b = decltype(bc)::value;
       const int kc = F.p3_kc(b);
@@ -137,14 +144,17 @@ __global__ void __launch_bounds__(kThreads, 1) strang128_kernel(const __grid_con
         constexpr int pp = decltype(pc)::value;
         const int kr = F.p3_kr(pp);
         const int fr = kr <= 64 ? kr : 128 - kr;
-        const float2 ea = cexp_times(S.atab[fr * kTabDim + fc], hr, hi, 1.0f / float(kN * kN));
-        x[b * 16 + pp] = cmul(x[b * 16 + pp], ea);
+        x[b * 16 + pp] = cmul(x[b * 16 + pp], S.atab[fr * kTabDim + fc]);
       });
     });
   };
 
   for (int k = 0; k < p.ksteps; ++k) {
     const float dt = p.dt[k];
+    if (has_A && dt != dt_tab) {
+      build_etab(dt);
+      dt_tab = dt;
+    }
     // park psi0 (needed for b(psi0) after the first half step)
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
@@ -156,7 +166,7 @@ __global__ void __launch_bounds__(kThreads, 1) strang128_kernel(const __grid_con
     park.fence_store();
     if (has_A) {
       F.forward(x);
-      half_kinetic(dt);
+      half_kinetic();
       F.inverse(x);
     }
     // tmp *= exp(b(psi0) dt_c);  b dt_c = V dt (ts_im - i ts_re)
@@ -195,7 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1) strang128_kernel(const __grid_con
     for (int n = 0; n < 32; ++n) x[n] = make_float2(x[n].x * scale, x[n].y * scale);
     if (has_A) {
       F.forward(x);
-      half_kinetic(dt);
+      half_kinetic();
       F.inverse(x);
     }
   }

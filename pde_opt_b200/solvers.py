@@ -114,6 +114,21 @@ class SemiImplicitFourierSpectral:
             y = out
         return y[0] if single else y
 
+    def order(self, terms):
+        return 1
+
+    def init(self, terms, t0, t1, y0, args):
+        return None
+
+    def func(self, terms, t0, y0, args):
+        return terms.vf(t0, y0, args)
+
+    def symbol_on(self, device):
+        key = str(device)
+        if key not in self._sym_dev:
+            self._sym_dev[key] = torch.from_numpy(self._quad).to(device)
+        return self._sym_dev[key]
+
     def _rollout_ad(self, eq, times, y0, out=None):
         """Advection-diffusion (recovered equation): the fused forward kernel (differentiable)."""
         from .adjoint import ad_rollout

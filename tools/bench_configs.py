@@ -63,6 +63,31 @@ def c3(args):
                               "kernel_traffic_GBps": passes * N * N * 8 * B * K / t / 1e9, "note": "line-FFT path, 4 kernels per step, state L2-resident (64 MB)"}))
 
 
+def c3b(args):
+    """GPE 128x128 (the reference's own test size, tests/test_solvers.py:107-205) on the fused single-CTA kernel."""
+    from pde_opt_b200 import Domain
+    from pde_opt_b200.equations import GPE2DTSControl
+    from pde_opt_b200.solvers import ODETerm, StrangSplitting
+
+    N, B, K = 128, 2048, 16
+    L_ = 29.4
+    dom = Domain((N, N), ((-L_ / 2, L_ / 2),) * 2, "dimensionless")
+    eq = GPE2DTSControl(dom, 3371.7, 0.0, None, 1.0)
+    rng = np.random.default_rng(0)
+    psi = rng.normal(size=(B, N, N, 2)).astype(np.float32)
+    psi /= np.sqrt((psi**2).sum(axis=(1, 2, 3), keepdims=True) * eq.dx**2)
+    y = torch.from_numpy(psi).cuda()
+    times = np.arange(K + 1, dtype=np.float32) * np.float32(2 * np.pi * 1e-4)
+    for kinetic in (True, False):
+        a = (0.5j * eq.two_pi_i_k_2).astype(np.complex64) if kinetic else eq.A_term
+        solver = StrangSplitting(a, eq.dx, eq.fft, eq.ifft, -1j)
+        out = torch.empty_like(y)
+        t = timed(lambda: solver.rollout(ODETerm(eq), times, y, out=out))
+        flop = (4 * 5 * 14 + 40 if kinetic else 40) * N * N
+        print(json.dumps({"config": "GPE 128x128 c64 Strang (fused single-CTA kernel)", "kinetic": kinetic, "envs": B, "steps": K,
+                          "env_steps_per_s": B * K / t, "tflops_algorithmic": flop * B * K / t / 1e12}))
+
+
 def c4(args):
     from pde_opt_b200 import Domain
     from pde_opt_b200.adjoint import ad_rollout
@@ -202,6 +227,6 @@ if __name__ == "__main__":
     ap.add_argument("--envs4", type=int, default=512)
     ap.add_argument("--check", action="store_true")
     a = ap.parse_args()
-    todo = [a.only] if a.only else ["c3", "c4", "c5"]
+    todo = [a.only] if a.only else ["c3", "c3b", "c4", "c5"]
     for name in todo:
-        {"c3": c3, "c4": c4, "c5": c5, "c5slab": c5slab}[name](a)
+        {"c3": c3, "c3b": c3b, "c4": c4, "c5": c5, "c5slab": c5slab}[name](a)
