@@ -26,9 +26,12 @@
 
 namespace pdeopt {
 
-// ---- radix plan: N = R1 * R2 * R3 with R1 = min(N, 8) etc. -----------------------------------
-constexpr int lf_r1(int n) { return n >= 8 ? 8 : n; }
-constexpr int lf_r2(int n) { return lf_r1(n / lf_r1(n)); }
+// ---- radix plan: N = R1 * R2 (* R3) -------------------------------------------------------------
+// Two register stages wherever possible (radix up to 32 per thread): every stage costs a shared-memory
+// round trip, a barrier and a set of address computations, and the kernels are issue / L1-bound, so
+// 256 = 16 x 16 and 512 = 16 x 32 beat three radix-8 stages.
+constexpr int lf_r1(int n) { return n >= 128 ? 16 : (n == 16 ? 16 : (n >= 8 ? 8 : n)); }
+constexpr int lf_r2(int n) { return (n / lf_r1(n)) > 32 ? 32 : (n / lf_r1(n)); }
 constexpr int lf_r3(int n) { return n / lf_r1(n) / lf_r2(n); }
 
 // storage position -> frequency index after the forward transform
@@ -47,9 +50,10 @@ __host__ __device__ inline int line_pos_to_freq(int n, int p) {
 //  * T >= 16 with the odd pitch LP = T + 1: a half-warp is 16 lines at one position (16 consecutive
 //    slots) or 16 consecutive positions of one line (slots 17 apart): conflict free both ways.
 //  * T = 8 (512-point strided lines, halves the tile: 6 CTAs per SM instead of 3): no padding,
-//    position index XORed with its bit 3, so that the two positions of a half-warp — neighbours, or
-//    8 apart in the span-8 stage — always land in different halves of the 16 slots.  Not usable
-//    when lanes run along positions, hence CT kernels keep T = 16.
+//    bit 0 of the position XORed with the bit that separates neighbouring last-stage blocks, so that
+//    the two positions of a half-warp — neighbours, or one block apart in the last stage — always
+//    land in different halves of the 16 slots.  Not usable when lanes run along positions, hence CT
+//    kernels keep T = 16.
 template <int N, bool CT>
 struct LineTile {
   static constexpr int T = (N >= 512 && !CT) ? 8 : ((N >= 256) ? 16 : 32);  // lines per tile
@@ -66,11 +70,15 @@ struct LineTile {
 template <int N, bool CT>
 __device__ __forceinline__ int lf_sidx(int pos, int line) {
   if constexpr (LineTile<N, CT>::kXor8) {
-    return ((pos ^ ((pos >> 3) & 1)) << 3) + line;
+    // the two positions of a half-warp are neighbours (span > radix stages) or one last-stage block
+    // apart: flipping bit 0 with the bit that distinguishes neighbouring blocks separates both cases
+    constexpr int LASTR = lf_r3(N) > 1 ? lf_r3(N) : (lf_r2(N) > 1 ? lf_r2(N) : lf_r1(N));
+    return ((pos ^ ((pos >> ilog2(LASTR)) & 1)) << 3) + line;
   } else {
     constexpr int LP = LineTile<N, CT>::LP;
     constexpr int SH = ilog2(N / lf_r1(N));
-    return pos * LP + (line ^ ((pos >> SH) & 7));
+    constexpr int MASK = (lf_r1(N) < LineTile<N, CT>::T ? lf_r1(N) : LineTile<N, CT>::T) - 1;
+    return pos * LP + (line ^ ((pos >> SH) & MASK));
   }
 }
 
