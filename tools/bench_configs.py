@@ -35,6 +35,28 @@ def peak_hbm():
         return 6538.3
 
 
+def c1(args):
+    """BASELINE config 1: Allen-Cahn 64x64, single env, 1000 semi-implicit steps (latency-bound: one CTA)."""
+    from pde_opt_b200 import Domain
+    from pde_opt_b200.equations import AllenCahn2DPeriodic
+    from pde_opt_b200.functions import ConstantMobility, DoubleWell
+    from pde_opt_b200.solvers import ODETerm, SemiImplicitFourierSpectral
+
+    n = 64
+    dom = Domain((n, n), ((0.0, 0.01 * n),) * 2, "dimensionless")
+    eq = AllenCahn2DPeriodic(dom, 0.002, DoubleWell(), ConstantMobility(1.0))
+    solver = SemiImplicitFourierSpectral(1.0, eq.fourier_symbol, eq.fft, eq.ifft)
+    y = torch.from_numpy((0.01 * np.random.default_rng(0).normal(size=(n, n))).astype(np.float32)).cuda()
+    times = (np.arange(1001, dtype=np.float64) * 5e-6).astype(np.float32)
+    t = timed(lambda: solver.rollout(ODETerm(eq), times, y), 2, 5)
+    for B in (1, 296):
+        yb = y[None].repeat(B, 1, 1).contiguous()
+        tb = timed(lambda: solver.rollout(ODETerm(eq), times, yb), 2, 5)
+        print(json.dumps({"config": "C1 Allen-Cahn 64x64, 1000 steps (generic kernel)", "envs": B, "ms_per_1000_steps": tb * 1e3,
+                          "env_steps_per_s": B * 1000 / tb, "note": "single env = one CTA: latency-bound"}))
+    del t
+
+
 def c3(args):
     from pde_opt_b200 import Domain
     from pde_opt_b200.equations import GPE2DTSControl
@@ -227,6 +249,6 @@ if __name__ == "__main__":
     ap.add_argument("--envs4", type=int, default=512)
     ap.add_argument("--check", action="store_true")
     a = ap.parse_args()
-    todo = [a.only] if a.only else ["c3", "c3b", "c4", "c5"]
+    todo = [a.only] if a.only else ["c1", "c3", "c3b", "c4", "c5"]
     for name in todo:
-        {"c3": c3, "c3b": c3b, "c4": c4, "c5": c5, "c5slab": c5slab}[name](a)
+        {"c1": c1, "c3": c3, "c3b": c3b, "c4": c4, "c5": c5, "c5slab": c5slab}[name](a)
