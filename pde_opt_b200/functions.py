@@ -153,6 +153,13 @@ class GaussianVelocity:
     def control_row(self):
         return (float(self.centre[0]), float(self.centre[1]), float(self.p0), float(self.p1))
 
+    def tensor_leaves(self):
+        """The tensor-valued members (the analogue of the inexact-array leaves eqx.partition extracts
+        from an equation parameter, pde_model.py:400-402): what PDEModel.train / optimize update."""
+        import torch
+
+        return [v for v in (self.centre[0], self.centre[1], self.p0, self.p1) if torch.is_tensor(v)]
+
     def control_block(self, batch, nseg, device):
         """[batch, nseg, 4] float32 (cx, cy, p0, p1), differentiable w.r.t. tensor-valued members."""
         import torch

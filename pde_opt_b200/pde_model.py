@@ -1,8 +1,10 @@
 """PDEModel — mirror of pde_opt/pde_model.py for the stepping path: `solve` (:68-136) and the
 differentiable-rollout objectives `residual_single` / `regularization` / `residuals` / `mse`
 (:138-323).  Gradients come from the hand-written adjoint kernel (pde_opt_b200/adjoint.py) through
-torch.autograd, the role jax.grad + diffrax adjoints play in the reference; the optimistix drivers
-`train` / `optimize` (:325-551) are out of scope."""
+torch.autograd, the role jax.grad + diffrax adjoints play in the reference.  `train(method="mse")`
+and `optimize` (:325-551) are host loops over those gradients (optimistix BFGS in the reference,
+torch.optim.LBFGS here: same quasi-Newton family, not the same iterates); the Levenberg-Marquardt
+`least_squares` method needs forward-mode JVPs and is not provided."""
 from typing import Any, Dict
 
 import numpy as np
@@ -139,3 +141,68 @@ class PDEModel:
         `.backward()` runs the adjoint kernel."""
         res, reg = self.residuals(parameters, y0s__values, solver_parameters, ts, weights, lambda_reg, adjoint, dt0)
         return (res**2).mean() + reg
+
+    # ---- optimisation drivers (host loops over the adjoint gradients) --------------------------------
+    @staticmethod
+    def _leaves(opt_parameters):
+        leaves = []
+        for v in opt_parameters.values():
+            if torch.is_tensor(v):
+                leaves.append(v)
+            elif hasattr(v, "tensor_leaves"):
+                leaves.extend(v.tensor_leaves())
+        leaves = [t for t in leaves if t.is_floating_point()]
+        if not leaves:
+            raise ValueError("opt_parameters holds no floating-point tensors to optimise")
+        for t in leaves:
+            t.requires_grad_(True)
+        return leaves
+
+    def _minimise(self, loss_fn, leaves, max_steps, verbose=False):
+        opt = torch.optim.LBFGS(leaves, lr=1.0, max_iter=int(max_steps), tolerance_grad=1e-10, tolerance_change=1e-14,
+                                history_size=20, line_search_fn="strong_wolfe")
+        history = []
+
+        def closure():
+            opt.zero_grad()
+            loss = loss_fn()
+            loss.backward()
+            history.append(float(loss.detach()))
+            if verbose:
+                print(f"loss {history[-1]:.6e}")
+            return loss
+
+        opt.step(closure)
+        self.last_loss_history = history
+        return history
+
+    def train(self, data, inds, opt_parameters, other_parameters, solver_parameters, weights, lambda_reg, method="mse",
+              max_steps=100, dt0=0.000001, verbose=False):
+        """Fit `opt_parameters` to observed trajectories (pde_model.py:325-460), method "mse": minimise
+        PDEModel.mse with a quasi-Newton loop over the adjoint gradients.  `data = {"ys": [...], "ts":
+        [...]}`, `inds` = per trajectory [initial index, later indices...].  Returns the optimised
+        parameters merged with `other_parameters` (the tensors are updated in place)."""
+        if method != "mse":
+            raise NotImplementedError("only method='mse' (reverse-mode gradients through the adjoint kernel) is provided")
+        dev = "cuda"
+        y0s = torch.stack([torch.as_tensor(data["ys"][ind[0]], dtype=torch.float32) for ind in inds]).to(dev)
+        values = torch.stack([torch.stack([torch.as_tensor(data["ys"][i], dtype=torch.float32) for i in ind[1:]]) for ind in inds]).to(dev)
+        ts = np.asarray([data["ts"][i] - data["ts"][inds[0][0]] for i in inds[0]], dtype=np.float32)
+        leaves = self._leaves(opt_parameters)
+        self._minimise(lambda: self.mse({**opt_parameters, **other_parameters}, (y0s, values), solver_parameters, ts, weights,
+                                        lambda_reg, dt0=dt0), leaves, max_steps, verbose)
+        return {**opt_parameters, **other_parameters}
+
+    def optimize(self, objective_function, y0, ts, opt_parameters, other_parameters, solver_parameters, weights, lambda_reg,
+                 max_steps=100, dt0=0.000001, verbose=False):
+        """Minimise objective_function(solution) + regularisation over `opt_parameters`
+        (pde_model.py:462-551); `solution` has shape (len(ts), *y0.shape)."""
+        leaves = self._leaves(opt_parameters)
+
+        def loss_fn():
+            allp = {**opt_parameters, **other_parameters}
+            sol = self.solve(allp, y0, ts, solver_parameters, dt0=dt0)
+            return objective_function(sol) + self.regularization(allp, weights, lambda_reg)
+
+        self._minimise(loss_fn, leaves, max_steps, verbose)
+        return {**opt_parameters, **other_parameters}
