@@ -227,6 +227,18 @@ pdeopt_status pdeopt_fft_lines_imex(const void* in_dev, void* out_dev, int32_t n
                                     const float* sym_dev, const pdeopt_line_geom* gsym, float dt, float scale,
                                     void* stream);
 
+/* Transform fused with the slab transpose (the all-to-all of the slab-decomposed 3-D FFT): forward
+ * transform of strided lines (sym_dev == NULL) or forward * scale/(1 + dt*sym) * inverse
+ * (sym_dev != NULL), whose last stage stores element `pos` of every line straight into the buffer of
+ * peer pos / gout->chunk (P2P stores over NVLink into peer-mapped memory, e.g. torch symmetric
+ * memory), at offset src_off + line_base + (pos % chunk) * gout->lo.  peer_ptrs_host: n_peers device
+ * pointers (this rank's own buffer included); gout->chunk * n_peers == n, gout->hi == 0.  The caller
+ * orders the consumers with a cross-rank barrier. */
+pdeopt_status pdeopt_fft_lines_to_peers(const void* in_dev, int32_t n, const pdeopt_line_geom* gin,
+                                        void* const* peer_ptrs_host, int32_t n_peers, const pdeopt_line_geom* gout,
+                                        int64_t src_off, const float* sym_dev, const pdeopt_line_geom* gsym, float dt,
+                                        float scale, void* stream);
+
 /* Inverse transform of the last axis fused with the update y1 = y0 + dt * Re(.) (solvers.py:63). */
 pdeopt_status pdeopt_fft_lines_inv_update(const void* spec_dev, int32_t n, const pdeopt_line_geom* gin,
                                           const float* y0_dev, float* y1_dev, const pdeopt_line_geom* gout, float dt,

@@ -119,6 +119,7 @@ EXPORTS = [
     "pdeopt_fft_lines",
     "pdeopt_fft_lines_imex",
     "pdeopt_fft_lines_inv_update",
+    "pdeopt_fft_lines_to_peers",
     "pdeopt_fft_lines_r2c",
     "pdeopt_fft_lines_c2r_update",
     "pdeopt_ch3d_rhs",
@@ -177,6 +178,8 @@ def load():
     lib.pdeopt_fft_lines_imex.restype = ctypes.c_int
     lib.pdeopt_fft_lines_inv_update.argtypes = [vp, i32, gp, vp, vp, gp, f32, vp]
     lib.pdeopt_fft_lines_inv_update.restype = ctypes.c_int
+    lib.pdeopt_fft_lines_to_peers.argtypes = [vp, i32, gp, ctypes.POINTER(vp), i32, gp, i64, vp, gp, f32, f32, vp]
+    lib.pdeopt_fft_lines_to_peers.restype = ctypes.c_int
     lib.pdeopt_fft_lines_r2c.argtypes = [vp, vp, i32, i64, vp]
     lib.pdeopt_fft_lines_r2c.restype = ctypes.c_int
     lib.pdeopt_fft_lines_c2r_update.argtypes = [vp, i32, i64, vp, vp, f32, vp]

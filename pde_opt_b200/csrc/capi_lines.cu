@@ -77,6 +77,36 @@ extern "C" pdeopt_status pdeopt_fft_lines_imex(const void* in_dev, void* out_dev
   return PDEOPT_OK;
 }
 
+extern "C" pdeopt_status pdeopt_fft_lines_to_peers(const void* in_dev, int32_t n, const pdeopt_line_geom* gin,
+                                                   void* const* peer_ptrs_host, int32_t n_peers,
+                                                   const pdeopt_line_geom* gout, int64_t src_off, const float* sym_dev,
+                                                   const pdeopt_line_geom* gsym, float dt, float scale, void* stream) {
+  if (!in_dev || !peer_ptrs_host) return fail(PDEOPT_ERR_INVALID, "null argument");
+  if (!lf_size_ok(n)) return fail(PDEOPT_ERR_UNSUPPORTED, "fft_lines: n must be a power of two in [8, 512]");
+  if (n_peers < 1 || n_peers > 8) return fail(PDEOPT_ERR_INVALID, "1..8 peers");
+  if (!geom_ok(gin, n) || !geom_ok(gout, n) || gin->n_lines != gout->n_lines) return fail(PDEOPT_ERR_INVALID, "bad line geometry");
+  if (gout->chunk * n_peers != n || gout->hi != 0) return fail(PDEOPT_ERR_INVALID, "peer scatter: chunk * n_peers must equal n and hi must be 0");
+  if (sym_dev && !geom_ok(gsym, n)) return fail(PDEOPT_ERR_INVALID, "bad symbol geometry");
+  const LineGeom gi = to_geom(gin), go = to_geom(gout);
+  if (gi.lo == 1 || go.lo == 1) return fail(PDEOPT_ERR_UNSUPPORTED, "peer scatter is for strided lines");
+  LfStorePeers sto;
+  for (int i = 0; i < 8; ++i) sto.peers[i] = (float2*)(i < n_peers ? peer_ptrs_host[i] : nullptr);
+  sto.g = go;
+  sto.shift = ilog2(gout->chunk);
+  sto.src_off = src_off;
+  LfLoadC ld{(const float2*)in_dev, gi};
+  cudaError_t e;
+  if (sym_dev) {
+    LfMidImex mid{sym_dev, to_geom(gsym), dt, scale};
+    e = lf_run<LF_FWD_MUL_INV, false>(n, gi.n_lines, ld, mid, sto, (cudaStream_t)stream);
+  } else {
+    e = lf_run<LF_FWD, false>(n, gi.n_lines, ld, LfMidNone{}, sto, (cudaStream_t)stream);
+  }
+  if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("fft_lines_to_peers: ") + cudaGetErrorString(e));
+  g_launches.fetch_add(1);
+  return PDEOPT_OK;
+}
+
 extern "C" pdeopt_status pdeopt_fft_lines_inv_update(const void* spec_dev, int32_t n, const pdeopt_line_geom* gin,
                                                      const float* y0_dev, float* y1_dev, const pdeopt_line_geom* gout,
                                                      float dt, void* stream) {

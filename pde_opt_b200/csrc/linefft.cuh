@@ -586,6 +586,21 @@ struct LfStoreCScaled {
   }
   __device__ __forceinline__ void flush(long long) {}
 };
+// Fused transpose of the slab decomposition: the last stage of a transform stores straight into the
+// PEER GPUs' buffers over NVLink (P2P stores into symmetric memory), the destination rank being the
+// chunk index of the position, instead of writing a local send buffer for an NCCL all-to-all.
+struct LfStorePeers {
+  float2* peers[8];
+  LineGeom g;         // geometry inside one peer's buffer (hi must be 0: the chunk selects the peer)
+  int shift;          // log2(chunk)
+  long long src_off;  // where this rank's block starts inside every peer's buffer
+  __device__ __forceinline__ LineGeom gout() const { return g; }
+  __device__ __forceinline__ float2 pre(long long) const { return make_float2(0.f, 0.f); }
+  __device__ __forceinline__ void store(long long off, long long, int pos, float2 v, float2) const {
+    peers[pos >> shift][src_off + off] = v;
+  }
+  __device__ __forceinline__ void flush(long long) {}
+};
 struct LfMidNone {
   __device__ __forceinline__ LineGeom gaux() const { return LineGeom{1, 1, 0, 0, 1, 0, 0}; }
   __device__ __forceinline__ float2 apply(float2 v, long long, long long, int) const { return v; }

@@ -81,6 +81,17 @@ class _DeviceBackend:
                                                ctypes.byref(gin), ctypes.byref(gout), int(inverse), int(in_real), float(scale),
                                                self._stream(src)))
 
+    def fft_lines_to_peers(self, src, n, gin, peer_ptrs, gout, src_off, sym=None, gsym=None, dt=0.0, scale=1.0):
+        import ctypes
+
+        from . import _lib
+
+        arr = (ctypes.c_void_p * len(peer_ptrs))(*[ctypes.c_void_p(int(p)) for p in peer_ptrs])
+        _lib.check(_lib.load().pdeopt_fft_lines_to_peers(
+            ctypes.c_void_p(src.data_ptr()), n, ctypes.byref(gin), arr, len(peer_ptrs), ctypes.byref(gout), int(src_off),
+            ctypes.c_void_p(sym.data_ptr()) if sym is not None else None, ctypes.byref(gsym) if gsym is not None else None,
+            float(dt), float(scale), self._stream(src)))
+
     def fft_lines_imex(self, buf, n, g, sym, gsym, dt, scale):
         import ctypes
 
@@ -114,11 +125,15 @@ class SlabCahnHilliard3D:
       5. x pass: forward FFT, multiply by 1/(N (1 + A dt sigma)), inverse FFT in one kernel,
       6. all-to-all #2 back (no pack needed: x-ranges are contiguous),
       7. inverse y pass reading the packed layout, half-spectrum-to-real z pass fused with y1 = y0 + dt g.
+    With transport="peer" (GPUs of one NVSwitch domain) the two all-to-alls are not separate
+    collectives: the y pass and the x pass store their last stage straight into the peers' buffers
+    (torch symmetric memory, P2P over NVLink; pdeopt_fft_lines_to_peers), so the transpose rides on the
+    transform kernels and only a cross-rank barrier separates producer and consumer.
     The spectrum stays in the line engine's position order throughout; the symbol table is permuted
     once at construction.  Collectives: torch.distributed (NCCL on GPUs; gloo in the CPU tests, where
     `backend` is an emulation of the four device operations)."""
 
-    def __init__(self, equation, A, group=None, backend=None, device=None, symbol_pos_local=None):
+    def __init__(self, equation, A, group=None, backend=None, device=None, symbol_pos_local=None, transport="nccl"):
         from .linefft import geom, to_position_order
 
         self.group = group
@@ -156,6 +171,21 @@ class SlabCahnHilliard3D:
         self.g_y_packed = geom(nxl * Hz, Hz, C * Hz, 1, Ny, Hz, chunk=C, hi=nxl * C * Hz)
         self.g_x = geom(C * Hz, C * Hz, 0, 1, Nx, C * Hz)
         self._bufs = None
+        self.transport = transport if self.world > 1 else "nccl"
+        if self.transport == "peer":
+            import torch.distributed._symmetric_memory as symm_mem
+
+            n = nxl * Ny * Hz  # complex elements per rank in either packed layout
+            grp = group if group is not None else dist.group.WORLD
+            self._sym_recv1 = symm_mem.empty(2 * n, dtype=torch.float32, device=device)  # x-line layout [Nx][C][Hz]
+            self._sym_recv2 = symm_mem.empty(2 * n, dtype=torch.float32, device=device)  # packed y layout [P][nxl][C][Hz]
+            self._h1 = symm_mem.rendezvous(self._sym_recv1, grp)
+            self._h2 = symm_mem.rendezvous(self._sym_recv2, grp)
+            self._peers1 = list(self._h1.buffer_ptrs)
+            self._peers2 = list(self._h2.buffer_ptrs)
+            # destination geometries inside one peer's buffer (hi = 0: the chunk index selects the peer)
+            self.g_y_to_peers = geom(nxl * Hz, Hz, C * Hz, 1, Ny, Hz, chunk=C, hi=0)
+            self.g_x_to_peers = geom(C * Hz, C * Hz, 0, 1, Nx, C * Hz, chunk=nxl, hi=0)
 
     def _buffers(self, like):
         if self._bufs is None:
@@ -197,6 +227,18 @@ class SlabCahnHilliard3D:
         lo, hi = self.exchange_halos(u)
         f = be.rhs(u, lo, hi)
         be.fft_r2c(f, b["W"], self.Nz, self.nxl * self.Ny)
+        if self.transport == "peer":
+            blk = self.rank * self.nxl * self.C * self.Hz
+            r1 = torch.view_as_complex(self._sym_recv1.view(-1, 2))
+            r2 = torch.view_as_complex(self._sym_recv2.view(-1, 2))
+            # y pass -> peers' x-line buffers; barrier; x pass (fwd * m * inv) -> peers' packed y buffers; barrier
+            be.fft_lines_to_peers(b["W"], self.Ny, self.g_y, self._peers1, self.g_y_to_peers, blk)
+            self._h1.barrier(channel=0)
+            be.fft_lines_to_peers(r1, self.Nx, self.g_x, self._peers2, self.g_x_to_peers, blk, self.sym, self.g_x, dt, self.scale)
+            self._h2.barrier(channel=1)
+            be.fft_lines(r2, b["W"], self.Ny, self.g_y_packed, self.g_y, True, False, 1.0)
+            be.fft_c2r_update(b["W"], self.Nz, self.nxl * self.Ny, u, y1, dt)
+            return y1
         be.fft_lines(b["W"], b["send"], self.Ny, self.g_y, self.g_y_packed, False, False, 1.0)
         self._all_to_all(b["recv"], b["send"])
         be.fft_lines_imex(b["recv"], self.Nx, self.g_x, self.sym, self.g_x, dt, self.scale)

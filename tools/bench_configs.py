@@ -193,7 +193,7 @@ def c5slab(args):
     k2 = (kx[:, None, None] + ky[None, :, None]) + kz[None, None, :]
     sym = (0.5 * 0.002 * k2 * k2).contiguous()
     del k2
-    slab = SlabCahnHilliard3D(eq, 0.5, device="cuda", symbol_pos_local=sym)
+    slab = SlabCahnHilliard3D(eq, 0.5, device=torch.device("cuda", torch.cuda.current_device()), symbol_pos_local=sym, transport=args.transport)
     full = np.clip(0.5 + 0.01 * np.random.default_rng(0).normal(size=pts), 0.01, 0.99).astype(np.float32)
     u = torch.from_numpy(full[rank * nxl : (rank + 1) * nxl].copy()).cuda()
     out = torch.empty_like(u)
@@ -233,7 +233,7 @@ def c5slab(args):
                       "rel_l2_increment": float((((allo - u0) - (ref - u0)).norm() / (ref - u0).norm()).item())}
     if rank == 0:
         tt = float(t.item())
-        print(json.dumps({"config": f"C5 Cahn-Hilliard 3D {n}^3 slab-decomposed", "n_gpus": world, "ms_per_step": tt * 1e3,
+        print(json.dumps({"config": f"C5 Cahn-Hilliard 3D {n}^3 slab-decomposed", "transport": slab.transport, "n_gpus": world, "ms_per_step": tt * 1e3,
                           "grid_point_steps_per_s": n**3 / tt, "all_to_all_MB_per_rank_per_step": 2 * nxl * n * n * 8 * (world - 1) / world / 1e6,
                           "checksum": float(chk.item()), "parity_vs_single_gpu": parity}))
     if world > 1:
@@ -248,6 +248,7 @@ if __name__ == "__main__":
     ap.add_argument("--envs3", type=int, default=128)
     ap.add_argument("--envs4", type=int, default=512)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--transport", default="nccl", choices=["nccl", "peer"])
     a = ap.parse_args()
     todo = [a.only] if a.only else ["c1", "c3", "c3b", "c4", "c5"]
     for name in todo:
