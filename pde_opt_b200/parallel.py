@@ -133,7 +133,7 @@ class SlabCahnHilliard3D:
     once at construction.  Collectives: torch.distributed (NCCL on GPUs; gloo in the CPU tests, where
     `backend` is an emulation of the four device operations)."""
 
-    def __init__(self, equation, A, group=None, backend=None, device=None, symbol_pos_local=None, transport="nccl"):
+    def __init__(self, equation, A, group=None, backend=None, device=None, symbol_pos_local=None, transport="auto"):
         from .linefft import geom, to_position_order
 
         self.group = group
@@ -171,6 +171,11 @@ class SlabCahnHilliard3D:
         self.g_y_packed = geom(nxl * Hz, Hz, C * Hz, 1, Ny, Hz, chunk=C, hi=nxl * C * Hz)
         self.g_x = geom(C * Hz, C * Hz, 0, 1, Nx, C * Hz)
         self._bufs = None
+        if transport not in ("auto", "peer", "nccl"):
+            raise ValueError("transport must be 'auto', 'peer' or 'nccl'")
+        on_gpu = isinstance(self.backend, _DeviceBackend) and device is not None and torch.device(device).type == "cuda"
+        if transport == "auto":  # peer stores on the GPUs of one box, collectives otherwise (CPU emulation, one rank)
+            transport = "peer" if (on_gpu and self.world > 1) else "nccl"
         self.transport = transport if self.world > 1 else "nccl"
         if self.transport == "peer":
             import torch.distributed._symmetric_memory as symm_mem

@@ -248,7 +248,7 @@ if __name__ == "__main__":
     ap.add_argument("--envs3", type=int, default=128)
     ap.add_argument("--envs4", type=int, default=512)
     ap.add_argument("--check", action="store_true")
-    ap.add_argument("--transport", default="nccl", choices=["nccl", "peer"])
+    ap.add_argument("--transport", default="auto", choices=["auto", "nccl", "peer"])
     a = ap.parse_args()
     todo = [a.only] if a.only else ["c1", "c3", "c3b", "c4", "c5"]
     for name in todo:
