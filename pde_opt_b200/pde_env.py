@@ -133,6 +133,14 @@ class PDEVecEnv:
     def __init__(self, equation, solver, num_envs, end_time, step_dt, numeric_dt, reset_func,
                  action_to_control: Optional[Callable] = None, obs_range=(0.0, 1.0), reward="var",
                  device="cuda", auto_reset=True):
+        if getattr(equation, "_kind", None) not in ("ch2d", "ac2d") or not getattr(equation, "fused", False) \
+                or getattr(equation, "derivs", "fd") != "fd":
+            # the fused observation / reward epilogue exists in the finite-difference phase-field kernels
+            # only; failing here is better than returning stale observation buffers
+            raise NotImplementedError(
+                "PDEVecEnv needs a Cahn-Hilliard / Allen-Cahn 2-D equation with derivs='fd' and enumerated closures; "
+                "use PDEEnv (one environment) for the other equation types"
+            )
         self.eq, self.solver, self.B = equation, solver, int(num_envs)
         self.end_time, self.step_dt, self.numeric_dt = end_time, step_dt, numeric_dt
         self.reset_func = reset_func
