@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kGenThreads, 1) ad_generic_fwd_kernel(const __
     __syncthreads();
     fft_fwd();
     for (int i = tid; i < npts; i += kGenThreads) {
-      const int r = i / ny, c = i % ny;
+      const int r = i >> gp.logny, c = i & (ny - 1);
       const int kx = brev_rt(r, gp.lognx), ky = brev_rt(c, gp.logny);
       const int fx = kx <= nx / 2 ? kx : nx - kx, fy = ky <= ny / 2 ? ky : ny - ky;
       const float l = -tabL[fx * tly + fy];
@@ -107,25 +107,25 @@ __global__ void __launch_bounds__(kGenThreads, 1) ad_generic_fwd_kernel(const __
     __syncthreads();
     // ---- ACC += -i kx F[vx u] ----
     for (int i = tid; i < npts; i += kGenThreads) {
-      const int r = i / ny, c = i % ny;
+      const int r = i >> gp.logny, c = i & (ny - 1);
       Z[i] = f2mul(f2mul(U[i], ax[r]), ey[c]);
     }
     __syncthreads();
     fft_fwd();
     for (int i = tid; i < npts; i += kGenThreads) {
-      const float kk = kxs[brev_rt(i / ny, gp.lognx)];
+      const float kk = kxs[brev_rt(i >> gp.logny, gp.lognx)];
       ACC[i] = make_float2(fmaf(Z[i].y, kk, ACC[i].x), fmaf(-Z[i].x, kk, ACC[i].y));
     }
     __syncthreads();
     // ---- ACC += -i ky F[vy u];  filter ----
     for (int i = tid; i < npts; i += kGenThreads) {
-      const int r = i / ny, c = i % ny;
+      const int r = i >> gp.logny, c = i & (ny - 1);
       Z[i] = f2mul(f2mul(U[i], ex[r]), ay[c]);
     }
     __syncthreads();
     fft_fwd();
     for (int i = tid; i < npts; i += kGenThreads) {
-      const int r = i / ny, c = i % ny;
+      const int r = i >> gp.logny, c = i & (ny - 1);
       const int kx = brev_rt(r, gp.lognx), ky = brev_rt(c, gp.logny);
       const int fx = kx <= nx / 2 ? kx : nx - kx, fy = ky <= ny / 2 ? ky : ny - ky;
       const float kk = kys[ky];

@@ -30,12 +30,14 @@ __device__ __forceinline__ int brev_rt(int v, int bits) { return (int)(__brev((u
 template <bool INV>
 __device__ __forceinline__ void r2_stage(float2* Z, const float2* tw, int twstep_shift, int half, int loglen, int stride,
                                          int other, int ostride, int npts) {
-  // butterflies: for block base b (multiple of 2*half), j in [0, half): (b + j, b + j + half)
+  // butterflies: for block base b (multiple of 2*half), j in [0, half): (b + j, b + j + half).
+  // `other` (the size of the other axis) and `half` are powers of two: shifts and masks, no divisions.
   const int len = 1 << loglen;
   const int nb = npts / 2;
+  const int oshift = 31 - __clz(other), omask = other - 1;
   for (int i = threadIdx.x; i < nb; i += kGenThreads) {
-    const int o = i % other;          // position along the other axis
-    const int k = i / other;          // butterfly index along this axis, 0 .. len/2-1
+    const int o = i & omask;          // position along the other axis
+    const int k = i >> oshift;        // butterfly index along this axis, 0 .. len/2-1
     const int j = k & (half - 1);
     const int base = ((k - j) << 1) + j;
     const int ia = base * stride + o * ostride, ib = ia + half * stride;
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(kGenThreads, 1) sifs_generic_kernel(const __gr
       __syncthreads();
     } else {
       for (int i = tid; i < npts; i += kGenThreads) {
-        const int r = i / ny, c = i % ny;
+        const int r = i >> gp.logny, c = i & (ny - 1);
         const int rp = (r + 1) & (nx - 1), rm = (r + nx - 1) & (nx - 1), cp = (c + 1) & (ny - 1), cm = (c + ny - 1) & (ny - 1);
         const float2 u0 = U[i], up = U[rp * ny + c], um = U[rm * ny + c], ur = U[r * ny + cp], ul = U[r * ny + cm];
         float2 lap;
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(kGenThreads, 1) sifs_generic_kernel(const __gr
       float2 f[kGenMaxPts / kGenThreads];
       int n = 0;
       for (int i = tid; i < npts; i += kGenThreads, ++n) {
-        const int r = i / ny, c = i % ny;
+        const int r = i >> gp.logny, c = i & (ny - 1);
         const float2 u0 = U[i], m0 = Z[i];
         const float2 D0 = make_float2(mob<MOB_RUNTIME>(u0.x, p.pw), mob<MOB_RUNTIME>(u0.y, p.pw));
         if (EQ == EQ_AC) {
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(kGenThreads, 1) sifs_generic_kernel(const __gr
     const float dt = p.dt[k];
     const float inv_n = 1.0f / float(npts);
     for (int i = tid; i < npts; i += kGenThreads) {
-      const int r = i / ny, c = i % ny;
+      const int r = i >> gp.logny, c = i & (ny - 1);
       const int kx = brev_rt(r, gp.lognx), ky = brev_rt(c, gp.logny);
       const int fx = kx <= nx / 2 ? kx : nx - kx, fy = ky <= ny / 2 ? ky : ny - ky;
       const float m = __fdividef(inv_n, fmaf(dt, p.symbol[fx * (ny / 2 + 1) + fy], 1.0f));
