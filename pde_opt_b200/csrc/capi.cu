@@ -6,6 +6,7 @@
 #include "capi_common.h"
 #include "sifs128.cuh"
 #include "sifs_generic.cuh"
+#include "sifs_small.cuh"
 #include "fourier128.cuh"
 
 using namespace pdeopt;
@@ -212,6 +213,30 @@ static pdeopt_status sifs_launch(pdeopt_plan* plan, int mode, const float* f0_de
     gp.ny = d.ny;
     gp.lognx = ilog2(d.nx);
     gp.logny = ilog2(d.ny);
+    if (d.nx == d.ny && (d.nx == 64 || d.nx == 32)) {
+      // tuned small-grid kernel (two register stages per axis, few barriers per step)
+      cudaError_t se = cudaSuccess;
+#define PDEOPT_SMALL_LAUNCH(NN, EE)                                                                                   \
+  {                                                                                                                   \
+    static bool sattr = false;                                                                                        \
+    if (!sattr) {                                                                                                     \
+      se = cudaFuncSetAttribute(sifs_small_kernel<NN, EE>, cudaFuncAttributeMaxDynamicSharedMemorySize,               \
+                                (int)sizeof(SmallSmem<NN>));                                                          \
+      sattr = se == cudaSuccess;                                                                                      \
+    }                                                                                                                 \
+    if (se == cudaSuccess) sifs_small_kernel<NN, EE><<<grid, kSmallThreads, sizeof(SmallSmem<NN>), st>>>(gp);         \
+  }
+      if (d.nx == 64) {
+        if (d.kind == PDEOPT_AC2D) PDEOPT_SMALL_LAUNCH(64, EQ_AC) else PDEOPT_SMALL_LAUNCH(64, EQ_CH)
+      } else {
+        if (d.kind == PDEOPT_AC2D) PDEOPT_SMALL_LAUNCH(32, EQ_AC) else PDEOPT_SMALL_LAUNCH(32, EQ_CH)
+      }
+#undef PDEOPT_SMALL_LAUNCH
+      if (se == cudaSuccess) se = cudaGetLastError();
+      if (se != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(se));
+      g_launches.fetch_add(1);
+      return PDEOPT_OK;
+    }
     const size_t smem = gen_smem_bytes(d.nx, d.ny);
     cudaError_t ge;
     if (d.kind == PDEOPT_AC2D) {

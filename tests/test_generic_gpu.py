@@ -44,7 +44,7 @@ def test_config1_allen_cahn_64_single_env_1000_steps():
     assert rel_l2(yN, y) <= 1e-3
 
 
-@pytest.mark.parametrize("shape", [(64, 64), (64, 128), (32, 16), (256, 1)])
+@pytest.mark.parametrize("shape", [(64, 64), (32, 32), (64, 128), (32, 16), (256, 1)])
 def test_generic_cahn_hilliard_shapes(shape):
     from pde_opt_b200.fused import SifsPlan, fold_symbol
 

@@ -52,7 +52,7 @@ def c1(args):
     for B in (1, 296):
         yb = y[None].repeat(B, 1, 1).contiguous()
         tb = timed(lambda: solver.rollout(ODETerm(eq), times, yb), 2, 5)
-        print(json.dumps({"config": "C1 Allen-Cahn 64x64, 1000 steps (generic kernel)", "envs": B, "ms_per_1000_steps": tb * 1e3,
+        print(json.dumps({"config": "C1 Allen-Cahn 64x64, 1000 steps (small-grid kernel)", "envs": B, "ms_per_1000_steps": tb * 1e3,
                           "env_steps_per_s": B * 1000 / tb, "note": "single env = one CTA: latency-bound"}))
     del t
 
