@@ -2,6 +2,7 @@
 #include "capi_common.h"
 #include "ad128.cuh"
 #include "ad_generic.cuh"
+#include "ad_small.cuh"
 using namespace pdeopt;
 
 // ---- advection-diffusion rollout and its adjoint ------------------------------------------------
@@ -71,6 +72,28 @@ extern "C" pdeopt_status pdeopt_ad_rollout_fwd(const pdeopt_ad_desc* desc, const
     gp.ny = desc->ny;
     gp.lognx = ilog2(desc->nx);
     gp.logny = ilog2(desc->ny);
+    if (desc->nx == desc->ny && (desc->nx == 64 || desc->nx == 32)) {
+      cudaError_t se;
+      if (desc->nx == 64) {
+        static bool a64 = false;
+        if (!a64) {
+          CUDA_TRY(cudaFuncSetAttribute(ad_small_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AdSmallSmem<64>)));
+          a64 = true;
+        }
+        ad_small_fwd_kernel<64><<<(batch + 1) / 2, kSmallThreads, sizeof(AdSmallSmem<64>), (cudaStream_t)stream>>>(gp);
+      } else {
+        static bool a32 = false;
+        if (!a32) {
+          CUDA_TRY(cudaFuncSetAttribute(ad_small_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AdSmallSmem<32>)));
+          a32 = true;
+        }
+        ad_small_fwd_kernel<32><<<(batch + 1) / 2, kSmallThreads, sizeof(AdSmallSmem<32>), (cudaStream_t)stream>>>(gp);
+      }
+      se = cudaGetLastError();
+      if (se != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(se));
+      g_launches.fetch_add(1);
+      return PDEOPT_OK;
+    }
     static bool gattr = false;
     if (!gattr) {
       CUDA_TRY(cudaFuncSetAttribute(ad_generic_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
