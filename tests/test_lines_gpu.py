@@ -264,3 +264,28 @@ def test_rhs_fourier_on_the_line_engine_3d_and_small_2d():
         f2 = e2.rhs(torch.from_numpy(u2).cuda()).cpu().numpy()
         for b in range(2):
             assert rel_l2(f2[b], o2.rhs(u2[b].astype(np.float64))) <= 5e-5
+
+
+def test_pde_model_solve_3d_saveat():
+    """PDEModel.solve on CahnHilliard3DPeriodic (docs/notebooks/optimization_3D.ipynb: 32^3, log potential,
+    D = 0.15): SaveAt(ts) semantics against the oracle's constant-step integrator."""
+    from pde_opt_b200 import Domain
+    from pde_opt_b200.equations import CahnHilliard3DPeriodic
+    from pde_opt_b200.functions import ConstantMobility, LogRegular
+    from pde_opt_b200.pde_model import PDEModel
+    from pde_opt_b200.solvers import SemiImplicitFourierSpectral
+
+    pts = (32, 32, 32)
+    box = tuple((0.0, n * 0.01) for n in pts)
+    model = PDEModel(CahnHilliard3DPeriodic, Domain(pts, box, "d"), SemiImplicitFourierSpectral)
+    u = _u0(pts, 1, 9)[0]
+    ts = np.asarray([0.0, 4e-6, 1.05e-5], dtype=np.float32)
+    ys = model.solve({"kappa": 0.002, "mu": LogRegular(3.0), "D": ConstantMobility(0.15)}, torch.from_numpy(u).cuda(), ts,
+                     {"A": 0.5}, dt0=1e-6)
+    assert tuple(ys.shape) == (3,) + pts
+    oeq = O.CahnHilliardPeriodic(O.Domain(pts, box), 0.002, lambda c: O.mu_log(c, 3.0), lambda c: 0.15 * np.ones_like(c), "fd", np.float32)
+    want = O.integrate(lambda y, a, b: O.sifs_step(oeq.rhs, y, a, b, 0.5, oeq.fourier_symbol), u, ts[0], ts[-1], 1e-6, save_ts=ts)
+    got = ys.cpu().numpy()
+    for i in range(3):
+        assert rel_l2(got[i], want[i]) <= 1e-5
+    assert rel_l2(got[2] - u, want[2] - u) <= 2e-3
