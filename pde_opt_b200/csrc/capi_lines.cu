@@ -244,7 +244,7 @@ extern "C" pdeopt_status pdeopt_ch3d_step(const pdeopt_ch3d_desc* d, const float
 
 extern "C" int64_t pdeopt_strang_lines_work_floats(int32_t nx, int32_t ny, int32_t batch) {
   if (nx <= 0 || ny <= 0 || batch <= 0) return 0;
-  return 2 * (int64_t)nx * ny * batch + 2 * (int64_t)nx * ny + ((batch + 63) / 64) * 64;
+  return 2 * (int64_t)nx * ny * batch + 2 * (int64_t)nx * ny + 2 * (((int64_t)batch + 63) / 64) * 64;
 }
 
 extern "C" pdeopt_status pdeopt_strang_lines_step_batched(const pdeopt_gpe_desc* desc, const float* y0_dev, float* y1_dev,
@@ -263,6 +263,7 @@ extern "C" pdeopt_status pdeopt_strang_lines_step_batched(const pdeopt_gpe_desc*
   float2* W = (float2*)work_dev;
   float2* etab = W + total;
   float* norm = (float*)(etab + npts);
+  const int64_t nstride = (((int64_t)batch + 63) / 64) * 64;
   GpeLinesConst c;
   c.nx = nx; c.ny = ny; c.log2nx = ilog2(nx);
   c.lo_x = (float)desc->lo_x; c.lo_y = (float)desc->lo_y; c.hx = (float)desc->hx; c.hy = (float)desc->hy;
@@ -278,15 +279,29 @@ extern "C" pdeopt_status pdeopt_strang_lines_step_batched(const pdeopt_gpe_desc*
   cudaError_t e = cudaSuccess;
   for (int k = 0; k < ksteps && e == cudaSuccess; ++k) {
     const float dt = dt_host[k];
+    if (a_term_full_dev == nullptr) {
+      // one kernel per step; norms ping-pong so that step k can read the norm of step k-1 while
+      // accumulating its own; the last norm is applied by the scale kernel after the loop
+      float* nk = norm + (size_t)(k & 1) * nstride;
+      const float* nprev = k > 0 ? norm + (size_t)((k - 1) & 1) * nstride : nullptr;
+      e = cudaMemsetAsync(nk, 0, sizeof(float) * batch, st);
+      if (e != cudaSuccess) break;
+      const int bpe = (int)((npts + 16383) / 16384);
+      // ping-pong between W and dst so that a launch never reads what it writes
+      const float2* kin = k == 0 ? src : ((k & 1) ? W : dst);
+      float2* kout = (k & 1) ? dst : W;
+      strang_lines_potential_kernel<<<batch * bpe, 256, 0, st>>>(kin, kout, nprev, nk, c, dt, dx2, bpe);
+      g_launches.fetch_add(1);
+      if (k + 1 == ksteps) {
+        strang_lines_scale_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(kout, dst, nk, (int)npts, dx2, total);
+        g_launches.fetch_add(1);
+      }
+      e = cudaGetLastError();
+      continue;
+    }
     e = cudaMemsetAsync(norm, 0, sizeof(float) * batch, st);
     if (e != cudaSuccess) break;
-    if (a_term_full_dev == nullptr) {
-      const int bpe = (int)((npts + 16383) / 16384);
-      strang_lines_potential_kernel<<<batch * bpe, 256, 0, st>>>(src, W, norm, c, dt, bpe);
-      strang_lines_scale_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(W, dst, norm, (int)npts, dx2, total);
-      e = cudaGetLastError();
-      g_launches.fetch_add(2);
-    } else {
+    {
       if (!have_tab || dt != last_dt) {
         strang_lines_etab_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, st>>>((const float2*)a_term_full_dev, etab, nx, ny,
                                                                                0.5f * dt * ts_re, 0.5f * dt * ts_im);

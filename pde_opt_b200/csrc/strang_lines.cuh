@@ -169,18 +169,24 @@ __global__ void strang_lines_etab_kernel(const float2* __restrict__ a_term, floa
   etab[i] = make_float2(m * c, m * s);
 }
 
-// A_term == 0: y = psi0 * exp(b(psi0) dt_c), norm accumulation; one block handles a slice of one env
-__global__ void __launch_bounds__(256) strang_lines_potential_kernel(const float2* __restrict__ psi0, float2* __restrict__ out,
+// A_term == 0 (the equation as shipped, gross_pitaevskii.py:62): the step is pointwise except for the
+// renormalisation, y = psi0 * exp(b(psi0) dt_c) / ||.||.  One kernel per step: the division by the
+// norm of step k-1 is deferred to the load of step k (psi0 = w_{k-1} / ||w_{k-1}||, `prev_norm`), so
+// each step reads and writes the state once; a final scale kernel applies the last norm.
+__global__ void __launch_bounds__(256) strang_lines_potential_kernel(const float2* __restrict__ in, float2* __restrict__ out,
+                                                                     const float* __restrict__ prev_norm,
                                                                      float* __restrict__ norm, GpeLinesConst c, float dt,
-                                                                     int blocks_per_env) {
+                                                                     float dx2, int blocks_per_env) {
   const int env = blockIdx.x / blocks_per_env, blk = blockIdx.x % blocks_per_env;
   const int npts = c.nx * c.ny;
   const int per = (npts + blocks_per_env - 1) / blocks_per_env;
   const int beg = blk * per, end = min(npts, beg + per);
+  const float s = prev_norm ? rsqrtf(prev_norm[env] * dx2) : 1.0f;
   float acc = 0.f;
   for (int i = beg + threadIdx.x; i < end; i += blockDim.x) {
     const size_t o = (size_t)env * npts + i;
-    const float2 p0 = psi0[o];
+    float2 p0 = in[o];
+    p0 = make_float2(p0.x * s, p0.y * s);
     const float2 w = cmul(p0, gpe_potential_factor(c, env, i / c.ny, i % c.ny, p0, dt));
     out[o] = w;
     acc = fmaf(w.x, w.x, fmaf(w.y, w.y, acc));
