@@ -166,6 +166,8 @@ __device__ __forceinline__ void rhs_phase(float2* __restrict__ W, const SifsPara
     for (int j = 0; j < 4; ++j) gyv[j] = gy[4 * lane + j];
   }
   const float2 ihx2 = splat2(p.inv_hx2), ihy2 = splat2(p.inv_hy2), mkappa = splat2(-p.kappa), m2 = splat2(-2.0f);
+  const bool square = p.inv_hx2 == p.inv_hy2;  // uniform
+  const float2 mkih2 = splat2(-p.kappa * p.inv_hx2);
 
   // mu and mobility of one row from its three-row neighbourhood.
   auto mu_row = [&](int rho, const float2 (&um)[4], const float2 (&u0)[4], const float2 (&up)[4], float2 (&mu)[4],
@@ -177,14 +179,21 @@ __device__ __forceinline__ void rhs_phase(float2* __restrict__ W, const SifsPara
     for (int j = 0; j < 4; ++j) {
       const float2 left = (j == 0) ? uL : u0[j - 1];
       const float2 right = (j == 3) ? uR : u0[j + 1];
-      // derivatives.py:8-12: (u[i+1] - 2u + u[i-1])/hx^2 + (u[j+1] - 2u + u[j-1])/hy^2
-      const float2 dxx = add2(fma2(u0[j], m2, up[j]), um[j]);
-      const float2 dyy = add2(fma2(u0[j], m2, right), left);
-      const float2 lap = fma2(dyy, ihy2, mul2(dxx, ihx2));
       float2 mh;
       mu_mob_pair<MU, MOB>(u0[j], p.pw, ec.w_off, mh, D[j]);
       if (ec.has_bump) mh = fma2(gxr, gyv[j], mh);
-      mu[j] = fma2(lap, mkappa, mh);
+      if (square) {
+        // hx == hy: -kappa lap(u) = (-kappa/h^2) ((u[i+1] + u[i-1]) + (u[j+1] + u[j-1]) - 4u): 5 packed
+        // operations instead of 7 (same value as derivatives.py:8-12 up to the summation order)
+        const float2 s4 = add2(add2(up[j], um[j]), add2(right, left));
+        mu[j] = fma2(fma2(u0[j], splat2(-4.0f), s4), mkih2, mh);
+      } else {
+        // derivatives.py:8-12: (u[i+1] - 2u + u[i-1])/hx^2 + (u[j+1] - 2u + u[j-1])/hy^2
+        const float2 dxx = add2(fma2(u0[j], m2, up[j]), um[j]);
+        const float2 dyy = add2(fma2(u0[j], m2, right), left);
+        const float2 lap = fma2(dyy, ihy2, mul2(dxx, ihx2));
+        mu[j] = fma2(lap, mkappa, mh);
+      }
     }
   };
 
