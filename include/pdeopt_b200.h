@@ -135,6 +135,20 @@ pdeopt_status pdeopt_rhs_batched(pdeopt_plan* plan, const float* y_dev, float* f
 pdeopt_status pdeopt_sifs_filter_batched(pdeopt_plan* plan, const float* y0_dev, const float* f0_dev, float* y1_dev,
                                          int32_t batch, float dt, const float* symbol_dev, void* stream);
 
+/* Discrete adjoint of ONE semi-implicit step of the finite-difference Cahn-Hilliard / Allen-Cahn
+ * equation of `plan` (no control forcing): what reverse-mode differentiation through diffeqsolve
+ * yields for PDEModel.mse (pde_model.py:274-323) when the optimised leaves are the closure
+ * coefficients (docs/notebooks/optimization_3D.ipynb fits Legendre coefficients of mu and D).
+ *   u_dev     : [batch][nx][ny] state at the START of the step
+ *   lam1_dev  : cotangent of the state after the step;  lam0_dev: cotangent before it (may alias)
+ *   work_dev  : pdeopt_phasefield_adjoint_work_floats(plan, batch) floats of scratch
+ *   gmu_dev, gmob_dev : [batch][PDEOPT_MAX_COEF] cotangents of mu_coef / mob_coef, ACCUMULATED (+=)
+ * The plan's coefficients are the point of linearisation: re-create the plan when they change. */
+int64_t pdeopt_phasefield_adjoint_work_floats(const pdeopt_plan* plan, int32_t batch);
+pdeopt_status pdeopt_phasefield_adjoint_step(pdeopt_plan* plan, const float* u_dev, const float* lam1_dev, float* lam0_dev,
+                                             int32_t batch, float dt, const float* symbol_dev, float* work_dev,
+                                             float* gmu_dev, float* gmob_dev, void* stream);
+
 /* GPE2DTSControl (gross_pitaevskii.py:18-81) geometry and constants. */
 typedef struct {
   int32_t nx, ny;

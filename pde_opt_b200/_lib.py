@@ -111,6 +111,8 @@ EXPORTS = [
     "pdeopt_sifs_step_batched_host",
     "pdeopt_rhs_batched",
     "pdeopt_sifs_filter_batched",
+    "pdeopt_phasefield_adjoint_work_floats",
+    "pdeopt_phasefield_adjoint_step",
     "pdeopt_strang_step_batched",
     "pdeopt_ad_tables_len",
     "pdeopt_ad_rollout_fwd",
@@ -160,6 +162,10 @@ def load():
     lib.pdeopt_rhs_batched.restype = ctypes.c_int
     lib.pdeopt_sifs_filter_batched.argtypes = [vp, vp, vp, vp, i32, f32, vp, vp]
     lib.pdeopt_sifs_filter_batched.restype = ctypes.c_int
+    lib.pdeopt_phasefield_adjoint_work_floats.argtypes = [vp, i32]
+    lib.pdeopt_phasefield_adjoint_work_floats.restype = ctypes.c_int64
+    lib.pdeopt_phasefield_adjoint_step.argtypes = [vp, vp, vp, vp, i32, f32, vp, vp, vp, vp, vp]
+    lib.pdeopt_phasefield_adjoint_step.restype = ctypes.c_int
     lib.pdeopt_strang_step_batched.argtypes = [ctypes.POINTER(GpeDesc), vp, vp, i32, i32, vp, vp, f32, f32, vp, vp]
     lib.pdeopt_strang_step_batched.restype = ctypes.c_int
     i64 = ctypes.c_int64

@@ -1,0 +1,72 @@
+"""Differentiable rollout of the finite-difference Cahn-Hilliard / Allen-Cahn equations: the fused
+forward kernels (one launch per step, the state before every step kept in HBM) and the adjoint step
+(pdeopt_phasefield_adjoint_step) behind a torch.autograd.Function — the custom_vjp of the north star
+for the reference's main training use case, fitting the coefficients of mu and D
+(docs/notebooks/optimization_3D.ipynb; pde_model.py:226-460).
+
+Gradients flow to the initial state and to the closure coefficients (`mu` / `D` closures built from
+1-D torch tensors, shared by the batch)."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _vp(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p()
+
+
+class _PhaseFieldRollout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y0, mu_coef, mob_coef, eq, dts, sym):
+        plan = eq.plan()  # built from the current coefficient values
+        y = y0.contiguous()
+        K = len(dts)
+        need_grad = y0.requires_grad or (mu_coef is not None and mu_coef.requires_grad) or (mob_coef is not None and mob_coef.requires_grad)
+        if not need_grad:
+            return plan.step(y, dts, sym)
+        traj = torch.empty((K + 1,) + tuple(y.shape), dtype=torch.float32, device=y.device)
+        traj[0].copy_(y)
+        for k in range(K):
+            plan.step(traj[k], dts[k : k + 1], sym, out=traj[k + 1])
+        ctx.plan, ctx.dts, ctx.sym = plan, dts, sym
+        ctx.has_mu, ctx.has_mob = mu_coef is not None, mob_coef is not None
+        ctx.n_mu = int(mu_coef.numel()) if mu_coef is not None else 0
+        ctx.n_mob = int(mob_coef.numel()) if mob_coef is not None else 0
+        ctx.save_for_backward(traj)
+        return traj[K].clone()
+
+    @staticmethod
+    def backward(ctx, gy):
+        (traj,) = ctx.saved_tensors
+        plan, dts, sym = ctx.plan, ctx.dts, ctx.sym
+        lib = _lib.load()
+        lam = gy.contiguous().clone()
+        B = lam.shape[0]
+        gmu = torch.zeros((B, _lib.MAX_COEF), dtype=torch.float32, device=lam.device)
+        gmob = torch.zeros_like(gmu)
+        work = torch.empty(int(lib.pdeopt_phasefield_adjoint_work_floats(plan._h, B)), dtype=torch.float32, device=lam.device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(lam.device).cuda_stream)
+        for k in range(len(dts) - 1, -1, -1):
+            _lib.check(lib.pdeopt_phasefield_adjoint_step(plan._h, _vp(traj[k]), _vp(lam), _vp(lam), B, float(dts[k]), _vp(sym),
+                                                          _vp(work), _vp(gmu), _vp(gmob), stream))
+        g_mu = gmu.sum(0)[: ctx.n_mu] if ctx.has_mu else None
+        g_mob = gmob.sum(0)[: ctx.n_mob] if ctx.has_mob else None
+        return lam, g_mu, g_mob, None, None, None
+
+
+def phasefield_rollout(eq, solver, y0, times):
+    """Differentiable rollout of CahnHilliard2DPeriodic / AllenCahn2DPeriodic (derivs='fd', enumerated
+    closures, no control forcing) over the step boundaries `times`.  y0: [B, nx, ny] float32 CUDA.
+    Differentiable w.r.t. y0 and the tensor coefficients of eq.mu and of the mobility closure."""
+    if not getattr(eq, "fused", False) or eq.derivs != "fd" or eq.control is not None:
+        raise NotImplementedError("the adjoint needs derivs='fd', enumerated closures and no control forcing")
+    times = np.asarray(times, dtype=np.float32)
+    dts = np.ascontiguousarray((times[1:] - times[:-1]).astype(np.float32))
+    mu_c, mob_c = eq._mu_c, eq._mob_c
+    mu_t = mu_c.coef if mu_c.tensor_leaves() else None
+    mob_t = mob_c.coef if mob_c.tensor_leaves() else None
+    sym = solver.symbol_on(y0.device)
+    return _PhaseFieldRollout.apply(y0, mu_t, mob_t, eq, dts, sym)

@@ -7,6 +7,7 @@
 #include "sifs128.cuh"
 #include "sifs_generic.cuh"
 #include "sifs_small.cuh"
+#include "ch_adjoint.cuh"
 #include "fourier128.cuh"
 
 using namespace pdeopt;
@@ -310,6 +311,51 @@ extern "C" pdeopt_status pdeopt_sifs_filter_batched(pdeopt_plan* plan, const flo
                                                     void* stream) {
   return sifs_launch(plan, MODE_GIVEN_F, f0_dev, y0_dev, y1_dev, batch, 1, &dt, symbol_dev, nullptr, nullptr, 0.f, 1.f,
                      nullptr, stream);
+}
+
+static_assert(PDEOPT_ADJ_NCOEF == PDEOPT_MAX_COEF, "coefficient count mismatch");
+
+extern "C" int64_t pdeopt_phasefield_adjoint_work_floats(const pdeopt_plan* plan, int32_t batch) {
+  if (!plan || batch <= 0) return 0;
+  return 6 * (int64_t)batch * plan->d.nx * plan->d.ny;
+}
+
+extern "C" pdeopt_status pdeopt_phasefield_adjoint_step(pdeopt_plan* plan, const float* u_dev, const float* lam1_dev,
+                                                        float* lam0_dev, int32_t batch, float dt, const float* symbol_dev,
+                                                        float* work_dev, float* gmu_dev, float* gmob_dev, void* stream) {
+  if (!plan || !u_dev || !lam1_dev || !lam0_dev || !symbol_dev || !work_dev || !gmu_dev || !gmob_dev)
+    return fail(PDEOPT_ERR_INVALID, "null argument");
+  if (batch <= 0 || batch > 65535) return fail(PDEOPT_ERR_INVALID, "batch must be in [1, 65535]");
+  const pdeopt_plan_desc& d = plan->d;
+  if (d.derivs != PDEOPT_DERIVS_FD) return fail(PDEOPT_ERR_UNSUPPORTED, "adjoint: derivs='fd' only");
+  const int64_t npts = (int64_t)d.nx * d.ny, n = npts * batch;
+  float* zeros = work_dev;
+  float* w = work_dev + n;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemsetAsync(zeros, 0, sizeof(float) * n, st));
+  // w = dt G lam1 through the fused filter kernel (y1 = 0 + dt Re ifft(fft(lam1) / (1 + dt A sigma)))
+  pdeopt_status s = sifs_launch(plan, MODE_GIVEN_F, lam1_dev, zeros, w, batch, 1, &dt, symbol_dev, nullptr, nullptr, 0.f, 1.f,
+                                nullptr, stream);
+  if (s != PDEOPT_OK) return s;
+  ChAdjParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.nx = d.nx; p.ny = d.ny; p.batch = batch; p.eq = d.kind == PDEOPT_AC2D ? 1 : 0;
+  p.u = u_dev; p.w = w; p.lam1 = lam1_dev; p.lam0 = lam0_dev;
+  p.mu = work_dev + 2 * n; p.dd = work_dev + 3 * n; p.mub = work_dev + 4 * n; p.db = work_dev + 5 * n;
+  p.gmu = gmu_dev; p.gmob = gmob_dev;
+  p.inv_hx = (float)(1.0 / d.hx); p.inv_hy = (float)(1.0 / d.hy);
+  p.inv_hx2 = (float)(1.0 / (d.hx * d.hx)); p.inv_hy2 = (float)(1.0 / (d.hy * d.hy));
+  p.kappa = (float)d.kappa;
+  p.pw.mu_family = d.mu_family; p.pw.mu_ncoef = d.mu_ncoef; p.pw.mob_family = d.mob_family; p.pw.mob_ncoef = d.mob_ncoef;
+  for (int i = 0; i < PDEOPT_MAX_COEF; ++i) { p.pw.mu_coef[i] = (float)d.mu_coef[i]; p.pw.mob_coef[i] = (float)d.mob_coef[i]; }
+  dim3 grid((unsigned)((npts + 255) / 256), batch);
+  ch_adj_mu_kernel<<<grid, 256, 0, st>>>(p);
+  ch_adj_bar_kernel<<<grid, 256, 0, st>>>(p);
+  ch_adj_out_kernel<<<grid, 256, 0, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("adjoint step: ") + cudaGetErrorString(e));
+  g_launches.fetch_add(3);
+  return PDEOPT_OK;
 }
 
 extern "C" pdeopt_status pdeopt_sifs_step_batched_host(pdeopt_plan* plan, const float* y0_host, float* y1_host,

@@ -17,13 +17,33 @@ def _lib(x):
     return torch
 
 
+def _is_tensor(x):
+    return type(x).__module__.startswith("torch") and hasattr(x, "requires_grad")
+
+
+def _coef(params):
+    """Coefficients of a closure: a tuple of floats, or — kept as is — a 1-D torch tensor (the leaves
+    PDEModel.train / mse differentiate with respect to, through the adjoint kernels)."""
+    if _is_tensor(params):
+        return params.reshape(-1)
+    return tuple(float(p) for p in np.asarray(params, dtype=np.float64).ravel())
+
+
 class Closure:
     kind = None  # "mu" | "mob"
     family = None
     coef = ()
 
+    def values(self):
+        """Current coefficient values as floats (what the kernels are launched with)."""
+        c = self.coef
+        return tuple(float(v) for v in (c.detach().cpu().tolist() if _is_tensor(c) else c))
+
     def descriptor(self):
-        return (self.family, tuple(float(c) for c in self.coef))
+        return (self.family, self.values())
+
+    def tensor_leaves(self):
+        return [self.coef] if _is_tensor(self.coef) else []
 
 
 class DoubleWell(Closure):
@@ -39,11 +59,11 @@ class LogRegular(Closure):
     kind, family = "mu", "log"
 
     def __init__(self, omega=3.0):
-        self.coef = (float(omega),)
+        self.coef = _coef(omega) if _is_tensor(omega) else (float(omega),)
 
     def __call__(self, c):
         m = _lib(c)
-        return m.log(c / (1.0 - c)) + self.coef[0] * (1.0 - 2.0 * c)
+        return m.log(c / (1.0 - c)) + self.values()[0] * (1.0 - 2.0 * c)
 
 
 def _legendre(params, x):
@@ -65,14 +85,14 @@ class ChemicalPotentialLegendrePolynomials(Closure):
     kind = "mu"
 
     def __init__(self, params, prior_fn=None):
-        self.coef = tuple(float(p) for p in np.asarray(params).ravel())
+        self.coef = _coef(params)
         if prior_fn not in (None, "log"):
             raise ValueError("fused path supports prior_fn=None or 'log'")
         self.prior_fn = prior_fn
         self.family = "legendre_logprior" if prior_fn == "log" else "legendre"
 
     def __call__(self, c):
-        r = _legendre(self.coef, 2.0 * c - 1.0)
+        r = _legendre(self.values(), 2.0 * c - 1.0)
         if self.prior_fn == "log":
             r = r + _lib(c).log(c / (1.0 - c))
         return r
@@ -83,10 +103,10 @@ class ConstantMobility(Closure):
     kind, family = "mob", "const"
 
     def __init__(self, value=1.0):
-        self.coef = (float(value),)
+        self.coef = _coef(value) if _is_tensor(value) else (float(value),)
 
     def __call__(self, c):
-        return c * 0 + self.coef[0]
+        return c * 0 + self.values()[0]
 
 
 class DegenerateMobility(Closure):
@@ -110,10 +130,10 @@ class DiffusionLegendrePolynomials(Closure):
     kind, family = "mob", "legendre_exp"
 
     def __init__(self, params):
-        self.coef = tuple(float(p) for p in np.asarray(params).ravel())
+        self.coef = _coef(params)
 
     def __call__(self, c):
-        return _lib(c).exp(_legendre(self.coef, 2.0 * c - 1.0))
+        return _lib(c).exp(_legendre(self.values(), 2.0 * c - 1.0))
 
 
 class GaussianLight:

@@ -1,0 +1,76 @@
+"""Adjoint of the finite-difference Cahn-Hilliard / Allen-Cahn steps: gradients w.r.t. the initial
+state and the closure coefficients vs torch.autograd on the float64 oracle twin (tolerance 1e-4,
+the north star's bar for adjoint gradients)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ch_torch_oracle as TO
+
+pytestmark = pytest.mark.gpu
+
+H, KAPPA = 0.01, 0.002
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+def _setup(n, kind, family):
+    from pde_opt_b200 import Domain
+    from pde_opt_b200.equations import AllenCahn2DPeriodic, CahnHilliard2DPeriodic
+    from pde_opt_b200.functions import (ChemicalPotentialLegendrePolynomials, ConstantMobility, DegenerateMobility,
+                                        DiffusionLegendrePolynomials, LogRegular, OnePlusSquare)
+
+    box = ((0.0, n * H), (0.0, n * H))
+    dom = Domain((n, n), box, "dimensionless")
+    if family == "legendre":
+        mu_t = torch.tensor([0.1, 2.5, -0.3, 0.8], device="cuda", requires_grad=True)
+        mob_t = torch.tensor([-1.0, 0.3, -0.2], device="cuda", requires_grad=True)
+        mu, mob = ChemicalPotentialLegendrePolynomials(mu_t, "log"), DiffusionLegendrePolynomials(mob_t)
+        mu_ref = lambda p: (lambda c: TO.mu_legendre(p, c, True))
+        mob_ref = lambda p: (lambda c: TO.D_legendre(p, c))
+    else:
+        mu_t = torch.tensor([3.0], device="cuda", requires_grad=True)
+        mob_t = torch.tensor([0.7], device="cuda", requires_grad=True)
+        mu, mob = LogRegular(mu_t), ConstantMobility(mob_t)
+        mu_ref = lambda p: (lambda c: torch.log(c / (1 - c)) + p[0] * (1 - 2 * c))
+        mob_ref = lambda p: (lambda c: p[0] * torch.ones_like(c))
+    cls = CahnHilliard2DPeriodic if kind == "ch" else AllenCahn2DPeriodic
+    eq = cls(dom, KAPPA, mu, mob)
+    return eq, box, mu_t, mob_t, mu_ref, mob_ref
+
+
+@pytest.mark.parametrize("n,kind,family", [(128, "ch", "legendre"), (64, "ch", "legendre"), (128, "ch", "log_const"),
+                                           (128, "ac", "legendre"), (32, "ac", "log_const")])
+def test_phasefield_adjoint_matches_autograd(n, kind, family):
+    from pde_opt_b200.adjoint_ch import phasefield_rollout
+    from pde_opt_b200.solvers import SemiImplicitFourierSpectral
+
+    eq, box, mu_t, mob_t, mu_ref, mob_ref = _setup(n, kind, family)
+    A = 0.5 if kind == "ch" else 1.0
+    dt = 1e-6 if kind == "ch" else 5e-6
+    solver = SemiImplicitFourierSpectral(A, eq.fourier_symbol, eq.fft, eq.ifft)
+    B, K = 3, 12
+    rng = np.random.default_rng(n)
+    y0 = np.clip(0.5 + 0.05 * rng.normal(size=(B, n, n)), 0.1, 0.9).astype(np.float32)
+    wgt = rng.normal(size=(B, n, n)).astype(np.float32)
+    times = (np.arange(K + 1, dtype=np.float64) * dt).astype(np.float32)
+    yg = torch.from_numpy(y0).cuda().requires_grad_(True)
+    yT = phasefield_rollout(eq, solver, yg, times)
+    loss = (yT * torch.from_numpy(wgt).cuda()).sum() + 0.5 * (yT**2).mean()
+    loss.backward()
+
+    yr = torch.from_numpy(y0.astype(np.float64)).requires_grad_(True)
+    pm = torch.tensor(mu_t.detach().cpu().numpy().astype(np.float64), requires_grad=True)
+    pd = torch.tensor(mob_t.detach().cpu().numpy().astype(np.float64), requires_grad=True)
+    dts = (times[1:] - times[:-1]).astype(np.float64)
+    yTr = TO.rollout(yr, dts, (n, n), box, KAPPA, A, mu_ref(pm), mob_ref(pd), kind)
+    lr = (yTr * torch.from_numpy(wgt.astype(np.float64))).sum() + 0.5 * (yTr**2).mean()
+    lr.backward()
+
+    assert abs(loss.item() - lr.item()) <= 1e-5 * abs(lr.item())
+    assert _rel(yg.grad.cpu().numpy(), yr.grad.numpy()) <= 1e-4
+    assert _rel(mu_t.grad.cpu().numpy(), pm.grad.numpy()) <= 1e-4
+    assert _rel(mob_t.grad.cpu().numpy(), pd.grad.numpy()) <= 1e-4
