@@ -35,6 +35,8 @@ class PDEModel:
         solver = self.solver_type(**prepare_solver_params(self.solver_type, solver_parameters, equation))  # :112-117
         if type(equation).__name__ == "AdvectionDiffusion2D":
             return self._solve_differentiable(equation, solver, y0, ts, dt0, max_steps, adjoint)
+        if self._wants_phasefield_grad(equation, y0):
+            return self._solve_differentiable(equation, solver, y0, ts, dt0, max_steps, adjoint)
         terms = ODETerm(equation)
         ts = np.asarray([float(t) for t in ts], dtype=np.float32)
         times = constant_step_times(ts[0], ts[-1], dt0, np.float32, max_steps)
@@ -66,11 +68,26 @@ class PDEModel:
         del truncated
         return out
 
-    # ---- differentiable rollouts (advection-diffusion + hand-written adjoint) -----------------------
+    # ---- differentiable rollouts (hand-written adjoints) ----------------------------------------------
+    @staticmethod
+    def _wants_phasefield_grad(equation, y0):
+        """Cahn-Hilliard / Allen-Cahn 2-D with tensor-valued closure coefficients (or an initial state
+        that requires grad): route through the adjoint-capable rollout."""
+        if getattr(equation, "_kind", None) not in ("ch2d", "ac2d") or getattr(equation, "derivs", "") != "fd":
+            return False
+        if not getattr(equation, "fused", False) or getattr(equation, "control", None) is not None:
+            return False
+        leaves = equation._mu_c.tensor_leaves() + equation._mob_c.tensor_leaves()
+        return any(t.requires_grad for t in leaves) or (torch.is_tensor(y0) and y0.requires_grad)
+
     def _solve_differentiable(self, equation, solver, y0, ts, dt0, max_steps, adjoint):
-        """solve() for AdvectionDiffusion2D: same save-time semantics, every segment an autograd node
-        whose backward is the adjoint kernel.  `adjoint` may carry `checkpoint_every` (int)."""
+        """solve() on the differentiable paths (advection-diffusion; phase-field equations with tensor
+        coefficients): same save-time semantics, every segment an autograd node whose backward is an
+        adjoint kernel.  `adjoint` may carry `checkpoint_every` (int, advection-diffusion only)."""
         from .adjoint import ad_rollout
+        from .adjoint_ch import phasefield_rollout
+
+        is_ad = type(equation).__name__ == "AdvectionDiffusion2D"
 
         ts = np.asarray([float(t) for t in ts], dtype=np.float32)
         times = constant_step_times(ts[0], ts[-1], dt0, np.float32, max_steps)
@@ -79,10 +96,18 @@ class PDEModel:
         single = y.dim() == 2
         if single:
             y = y.unsqueeze(0)
-        ctrl = equation.control_block(y.shape[0], y.device, self._nseg(equation))
-        hold = max(1, -(-(len(times) - 1) // ctrl.shape[1]))
-        ck = getattr(adjoint, "checkpoint_every", None)
-        A = float(solver.A)
+        if is_ad:
+            ctrl = equation.control_block(y.shape[0], y.device, self._nseg(equation))
+            hold = max(1, -(-(len(times) - 1) // ctrl.shape[1]))
+            ck = getattr(adjoint, "checkpoint_every", None)
+            A = float(solver.A)
+
+            def roll(y_, seg_times, step0):
+                return ad_rollout(equation, y_, ctrl, seg_times, hold=hold, A=A, checkpoint_every=ck, step0=step0)
+        else:
+            def roll(y_, seg_times, step0):
+                return phasefield_rollout(equation, solver, y_, seg_times)
+
         out, i_cur = [], 0
         for s_ in ts:
             j = int(np.searchsorted(times, s_, side="left"))
@@ -91,14 +116,14 @@ class PDEModel:
                 continue
             if j == 0 or times[j] == s_:
                 if j > i_cur:
-                    y = ad_rollout(equation, y, ctrl, times[i_cur : j + 1], hold=hold, A=A, checkpoint_every=ck, step0=i_cur)
+                    y = roll(y, times[i_cur : j + 1], i_cur)
                     i_cur = j
                 out.append(y)
                 continue
             if j - 1 > i_cur:
-                y = ad_rollout(equation, y, ctrl, times[i_cur:j], hold=hold, A=A, checkpoint_every=ck, step0=i_cur)
+                y = roll(y, times[i_cur:j], i_cur)
                 i_cur = j - 1
-            y_b = ad_rollout(equation, y, ctrl, times[j - 1 : j + 1], hold=hold, A=A, checkpoint_every=ck, step0=j - 1)
+            y_b = roll(y, times[j - 1 : j + 1], j - 1)
             w = float(np.float32((s_ - times[j - 1]) / (times[j] - times[j - 1])))
             out.append(y + (y_b - y) * w)  # LocalLinearInterpolation
             y, i_cur = y_b, j

@@ -199,3 +199,29 @@ def test_torch_gradient_oracle_matches_numpy_oracle_and_finite_differences():
         cm[idx] -= eps
         fd = (f(cp) - f(cm)) / (2 * eps)
         assert abs(fd - float(ct.grad[idx])) <= 1e-5 * max(abs(fd), 1e-12) + 1e-14
+
+
+def test_torch_phasefield_gradient_oracle_matches_numpy_oracle():
+    """oracle/ch_torch_oracle.py (the float64 gradient oracle of the phase-field adjoint tests)
+    reproduces the NumPy oracle's Cahn-Hilliard and Allen-Cahn rollouts, Legendre closures included."""
+    import torch
+
+    from oracle import ch_torch_oracle as TO
+
+    n, h = 32, 0.01
+    box = ((0.0, n * h), (0.0, n * h))
+    u = np.clip(0.5 + 0.05 * np.random.default_rng(0).normal(size=(n, n)), 0.1, 0.9)
+    pm, pd = [0.1, 2.5, -0.3, 0.8], [-1.0, 0.3, -0.2]
+    dom = O.Domain((n, n), box)
+    for kind, A in (("ch", 0.5), ("ac", 1.0)):
+        if kind == "ch":
+            eq = O.CahnHilliardPeriodic(dom, 0.002, lambda c: O.mu_legendre(pm, c, O.prior_log), lambda c: O.D_legendre(pd, c), "fd", np.float64)
+        else:
+            eq = O.AllenCahn2DPeriodic(dom, 0.002, lambda c: O.mu_legendre(pm, c, O.prior_log), lambda c: O.D_legendre(pd, c), "fd", np.float64)
+        y = u
+        for _ in range(4):
+            y = O.sifs_step(eq.rhs, y, 0.0, 1e-6, A, eq.fourier_symbol)
+        tm, td = torch.tensor(pm, dtype=torch.float64), torch.tensor(pd, dtype=torch.float64)
+        yt = TO.rollout(torch.from_numpy(u)[None], [1e-6] * 4, (n, n), box, 0.002, A, lambda c: TO.mu_legendre(tm, c, True),
+                        lambda c: TO.D_legendre(td, c), kind)
+        assert np.abs(yt[0].numpy() - y).max() <= 1e-13
