@@ -294,6 +294,14 @@ pdeopt_status pdeopt_ch3d_step(const pdeopt_ch3d_desc* desc, const float* y0_dev
                                int32_t ksteps, const float* dt_host, const float* symbol_pos_dev, float* work_dev,
                                void* stream);
 
+/* Discrete adjoint of one step of pdeopt_ch3d_step (see pdeopt_phasefield_adjoint_step for the 2-D form
+ * and the meaning of the arguments): docs/notebooks/optimization_3D.ipynb fits the Legendre
+ * coefficients of mu and D of CahnHilliard3DPeriodic by differentiating such rollouts. */
+int64_t pdeopt_ch3d_adjoint_work_floats(const pdeopt_ch3d_desc* desc, int32_t batch);
+pdeopt_status pdeopt_ch3d_adjoint_step(const pdeopt_ch3d_desc* desc, const float* u_dev, const float* lam1_dev,
+                                       float* lam0_dev, int32_t batch, float dt, const float* symbol_pos_dev,
+                                       float* work_dev, float* gmu_dev, float* gmob_dev, void* stream);
+
 /* ---- StrangSplitting.step on grids that do not fit one SM (256x256 complex64; any nx, ny powers of
  * two in [32, 512]): multi-kernel path on the line-FFT engine, state resident in L2.
  *   a_term_full_dev : [nx][ny][2] complex A_term in natural (fftfreq) order, or NULL when it is

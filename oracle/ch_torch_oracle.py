@@ -32,15 +32,19 @@ def D_legendre(params, c):  # legendre.py:37-53
     return torch.exp(legendre(params, 2.0 * c - 1.0))
 
 
-def _lap(u, h):  # derivatives.py:8-12
-    return (torch.roll(u, -1, -2) - 2 * u + torch.roll(u, 1, -2)) / h[0] ** 2 + (torch.roll(u, -1, -1) - 2 * u + torch.roll(u, 1, -1)) / h[1] ** 2
+def _axes(h):
+    return list(zip(range(-len(h), 0), h))
 
 
-def rhs_ch(u, h, kappa, mu_fn, D_fn):  # cahn_hilliard.py:89-109
+def _lap(u, h):  # derivatives.py:8-21 (2-D and 3-D)
+    return sum((torch.roll(u, -1, ax) - 2 * u + torch.roll(u, 1, ax)) / hh**2 for ax, hh in _axes(h))
+
+
+def rhs_ch(u, h, kappa, mu_fn, D_fn):  # cahn_hilliard.py:89-109, :177-200
     mu = mu_fn(u) - kappa * _lap(u, h)
     D = D_fn(u)
     out = 0
-    for ax, hh in ((-2, h[0]), (-1, h[1])):
+    for ax, hh in _axes(h):
         F = 0.5 * (D + torch.roll(D, -1, ax)) * ((torch.roll(mu, -1, ax) - mu) / hh)
         out = out + (F - torch.roll(F, 1, ax)) / hh
     return out
@@ -51,7 +55,8 @@ def rhs_ac(u, h, kappa, mu_fn, R_fn):  # allen_cahn.py:81-84
 
 
 def rollout(y0, dts, points, box, kappa, A, mu_fn, D_fn, kind="ch"):
-    """y0 [B, nx, ny]; returns the state after len(dts) semi-implicit steps (differentiable)."""
+    """y0 [B, nx, ny] or [B, nx, ny, nz]; returns the state after len(dts) semi-implicit steps
+    (differentiable)."""
     dtype = y0.dtype
     h = [(hi - lo) / n for (lo, hi), n in zip(box, points)]
     ks = torch.meshgrid(*[torch.fft.fftfreq(n, hh, dtype=dtype) for n, hh in zip(points, h)], indexing="ij")
@@ -61,6 +66,7 @@ def rollout(y0, dts, points, box, kappa, A, mu_fn, D_fn, kind="ch"):
     for dt in dts:
         dt = float(dt)
         f0 = rhs_ch(y, h, kappa, mu_fn, D_fn) if kind == "ch" else rhs_ac(y, h, kappa, mu_fn, D_fn)
-        g = torch.fft.ifftn(torch.fft.fftn(f0, dim=(-2, -1)) / (1.0 + A * dt * sigma), dim=(-2, -1)).real
+        dims = tuple(range(-len(points), 0))
+        g = torch.fft.ifftn(torch.fft.fftn(f0, dim=dims) / (1.0 + A * dt * sigma), dim=dims).real
         y = y + dt * g
     return y

@@ -127,6 +127,8 @@ EXPORTS = [
     "pdeopt_ch3d_rhs",
     "pdeopt_ch3d_work_floats",
     "pdeopt_ch3d_step",
+    "pdeopt_ch3d_adjoint_work_floats",
+    "pdeopt_ch3d_adjoint_step",
     "pdeopt_strang_lines_work_floats",
     "pdeopt_strang_lines_step_batched",
     "pdeopt_measure_fp32_peak",
@@ -197,6 +199,10 @@ def load():
     lib.pdeopt_ch3d_work_floats.restype = ctypes.c_int64
     lib.pdeopt_ch3d_step.argtypes = [c3, vp, vp, i32, i32, vp, vp, vp, vp]
     lib.pdeopt_ch3d_step.restype = ctypes.c_int
+    lib.pdeopt_ch3d_adjoint_work_floats.argtypes = [c3, i32]
+    lib.pdeopt_ch3d_adjoint_work_floats.restype = ctypes.c_int64
+    lib.pdeopt_ch3d_adjoint_step.argtypes = [c3, vp, vp, vp, i32, f32, vp, vp, vp, vp, vp]
+    lib.pdeopt_ch3d_adjoint_step.restype = ctypes.c_int
     lib.pdeopt_strang_lines_work_floats.argtypes = [i32, i32, i32]
     lib.pdeopt_strang_lines_work_floats.restype = ctypes.c_int64
     lib.pdeopt_strang_lines_step_batched.argtypes = [ctypes.POINTER(GpeDesc), vp, vp, i32, i32, vp, vp, f32, f32, vp, vp, vp]

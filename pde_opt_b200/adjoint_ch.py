@@ -22,6 +22,7 @@ class _PhaseFieldRollout(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y0, mu_coef, mob_coef, eq, dts, sym):
         plan = eq.plan()  # built from the current coefficient values
+        ctx.is3d = getattr(eq, "_kind", None) == "ch3d"
         y = y0.contiguous()
         K = len(dts)
         need_grad = y0.requires_grad or (mu_coef is not None and mu_coef.requires_grad) or (mob_coef is not None and mob_coef.requires_grad)
@@ -47,26 +48,31 @@ class _PhaseFieldRollout(torch.autograd.Function):
         B = lam.shape[0]
         gmu = torch.zeros((B, _lib.MAX_COEF), dtype=torch.float32, device=lam.device)
         gmob = torch.zeros_like(gmu)
-        work = torch.empty(int(lib.pdeopt_phasefield_adjoint_work_floats(plan._h, B)), dtype=torch.float32, device=lam.device)
         stream = ctypes.c_void_p(torch.cuda.current_stream(lam.device).cuda_stream)
-        for k in range(len(dts) - 1, -1, -1):
-            _lib.check(lib.pdeopt_phasefield_adjoint_step(plan._h, _vp(traj[k]), _vp(lam), _vp(lam), B, float(dts[k]), _vp(sym),
-                                                          _vp(work), _vp(gmu), _vp(gmob), stream))
+        if ctx.is3d:
+            for k in range(len(dts) - 1, -1, -1):
+                plan.adjoint_step(traj[k], lam, dts[k], sym, gmu, gmob)
+        else:
+            work = torch.empty(int(lib.pdeopt_phasefield_adjoint_work_floats(plan._h, B)), dtype=torch.float32, device=lam.device)
+            for k in range(len(dts) - 1, -1, -1):
+                _lib.check(lib.pdeopt_phasefield_adjoint_step(plan._h, _vp(traj[k]), _vp(lam), _vp(lam), B, float(dts[k]), _vp(sym),
+                                                              _vp(work), _vp(gmu), _vp(gmob), stream))
         g_mu = gmu.sum(0)[: ctx.n_mu] if ctx.has_mu else None
         g_mob = gmob.sum(0)[: ctx.n_mob] if ctx.has_mob else None
         return lam, g_mu, g_mob, None, None, None
 
 
 def phasefield_rollout(eq, solver, y0, times):
-    """Differentiable rollout of CahnHilliard2DPeriodic / AllenCahn2DPeriodic (derivs='fd', enumerated
-    closures, no control forcing) over the step boundaries `times`.  y0: [B, nx, ny] float32 CUDA.
+    """Differentiable rollout of CahnHilliard2DPeriodic / AllenCahn2DPeriodic / CahnHilliard3DPeriodic
+    (derivs='fd', enumerated closures, no control forcing) over the step boundaries `times`.
+    y0: [B, nx, ny] or [B, nx, ny, nz] float32 CUDA.
     Differentiable w.r.t. y0 and the tensor coefficients of eq.mu and of the mobility closure."""
-    if not getattr(eq, "fused", False) or eq.derivs != "fd" or eq.control is not None:
+    if not getattr(eq, "fused", False) or eq.derivs != "fd" or getattr(eq, "control", None) is not None:
         raise NotImplementedError("the adjoint needs derivs='fd', enumerated closures and no control forcing")
     times = np.asarray(times, dtype=np.float32)
     dts = np.ascontiguousarray((times[1:] - times[:-1]).astype(np.float32))
     mu_c, mob_c = eq._mu_c, eq._mob_c
     mu_t = mu_c.coef if mu_c.tensor_leaves() else None
     mob_t = mob_c.coef if mob_c.tensor_leaves() else None
-    sym = solver.symbol_on(y0.device)
+    sym = solver.symbol_pos_on(y0.device) if getattr(eq, "_kind", None) == "ch3d" else solver.symbol_on(y0.device)
     return _PhaseFieldRollout.apply(y0, mu_t, mob_t, eq, dts, sym)

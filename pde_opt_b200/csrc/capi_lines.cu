@@ -3,6 +3,7 @@
 #include "linefft.cuh"
 #include "ch3d.cuh"
 #include "strang_lines.cuh"
+#include "ch_adjoint.cuh"
 using namespace pdeopt;
 
 // ---- line-FFT engine, 3-D Cahn-Hilliard, Strang on large grids ---------------------------------
@@ -239,6 +240,59 @@ extern "C" pdeopt_status pdeopt_ch3d_step(const pdeopt_ch3d_desc* d, const float
     if ((s = pdeopt_fft_lines_c2r_update(W, (int32_t)nz, (int64_t)batch * nx * ny, src, y1_dev, dt_host[k], stream)) != PDEOPT_OK) return s;
     src = y1_dev;
   }
+  return PDEOPT_OK;
+}
+
+extern "C" int64_t pdeopt_ch3d_adjoint_work_floats(const pdeopt_ch3d_desc* d, int32_t batch) {
+  if (!d || batch <= 0) return 0;
+  const int64_t vol = (int64_t)d->nx * d->ny * d->nz;
+  return (int64_t)batch * (6 * vol + 2 * (int64_t)d->nx * d->ny * (d->nz / 2 + 1));
+}
+
+extern "C" pdeopt_status pdeopt_ch3d_adjoint_step(const pdeopt_ch3d_desc* d, const float* u_dev, const float* lam1_dev,
+                                                  float* lam0_dev, int32_t batch, float dt, const float* symbol_pos_dev,
+                                                  float* work_dev, float* gmu_dev, float* gmob_dev, void* stream) {
+  pdeopt_status s = ch3d_check(d, batch);
+  if (s != PDEOPT_OK) return s;
+  if (!u_dev || !lam1_dev || !lam0_dev || !symbol_pos_dev || !work_dev || !gmu_dev || !gmob_dev)
+    return fail(PDEOPT_ERR_INVALID, "null argument");
+  if (!lf_size_ok(d->nx) || !lf_size_ok(d->ny) || !lf_size_ok(d->nz))
+    return fail(PDEOPT_ERR_UNSUPPORTED, "ch3d adjoint: nx, ny, nz must be powers of two in [8, 512]");
+  const int64_t nx = d->nx, ny = d->ny, nz = d->nz, vol = nx * ny * nz, n = vol * batch;
+  const int64_t hp = nz / 2 + 1, hpl = ny * hp, hvol = nx * hpl;
+  float* zeros = work_dev;
+  float* w = work_dev + n;
+  float* W = work_dev + 6 * n;  // complex half spectrum
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemsetAsync(zeros, 0, sizeof(float) * n, st));
+  // w = dt G lam1: the forward step's spectral filter applied to lam1 with a zero state
+  pdeopt_line_geom gy{(int64_t)batch * nx * hp, hp, hpl, 1, (int32_t)ny, 0, 0, hp};
+  pdeopt_line_geom gx{(int64_t)batch * hpl, hpl, hvol, 1, (int32_t)nx, 0, 0, hpl};
+  pdeopt_line_geom gsym = gx;
+  gsym.outer = 0;
+  if ((s = pdeopt_fft_lines_r2c(lam1_dev, W, (int32_t)nz, (int64_t)batch * nx * ny, stream)) != PDEOPT_OK) return s;
+  if ((s = pdeopt_fft_lines(W, W, (int32_t)ny, &gy, &gy, 0, 0, 1.0f, stream)) != PDEOPT_OK) return s;
+  if ((s = pdeopt_fft_lines_imex(W, W, (int32_t)nx, &gx, symbol_pos_dev, &gsym, dt, 1.0f / (float)vol, stream)) != PDEOPT_OK) return s;
+  if ((s = pdeopt_fft_lines(W, W, (int32_t)ny, &gy, &gy, 1, 0, 1.0f, stream)) != PDEOPT_OK) return s;
+  if ((s = pdeopt_fft_lines_c2r_update(W, (int32_t)nz, (int64_t)batch * nx * ny, zeros, w, dt, stream)) != PDEOPT_OK) return s;
+  Ch3AdjParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.nx = d->nx; p.ny = d->ny; p.nz = d->nz; p.batch = batch;
+  p.u = u_dev; p.w = w; p.lam1 = lam1_dev; p.lam0 = lam0_dev;
+  p.mu = work_dev + 2 * n; p.dd = work_dev + 3 * n; p.mub = work_dev + 4 * n; p.db = work_dev + 5 * n;
+  p.gmu = gmu_dev; p.gmob = gmob_dev;
+  p.inv_hx = (float)(1.0 / d->hx); p.inv_hy = (float)(1.0 / d->hy); p.inv_hz = (float)(1.0 / d->hz);
+  p.inv_hx2 = (float)(1.0 / (d->hx * d->hx)); p.inv_hy2 = (float)(1.0 / (d->hy * d->hy)); p.inv_hz2 = (float)(1.0 / (d->hz * d->hz));
+  p.kappa = (float)d->kappa;
+  p.pw.mu_family = d->mu_family; p.pw.mu_ncoef = d->mu_ncoef; p.pw.mob_family = d->mob_family; p.pw.mob_ncoef = d->mob_ncoef;
+  for (int i = 0; i < PDEOPT_MAX_COEF; ++i) { p.pw.mu_coef[i] = (float)d->mu_coef[i]; p.pw.mob_coef[i] = (float)d->mob_coef[i]; }
+  dim3 grid((unsigned)((vol + 255) / 256), batch);
+  ch3_adj_mu_kernel<<<grid, 256, 0, st>>>(p);
+  ch3_adj_bar_kernel<<<grid, 256, 0, st>>>(p);
+  ch3_adj_out_kernel<<<grid, 256, 0, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("ch3d adjoint step: ") + cudaGetErrorString(e));
+  g_launches.fetch_add(3);
   return PDEOPT_OK;
 }
 

@@ -79,7 +79,7 @@ __device__ __forceinline__ float mob_prime(float c, float Dval, const PointwiseP
 }
 
 // pass 1: mu and D of the saved state
-__global__ void __launch_bounds__(256) ch_adj_mu_kernel(const __grid_constant__ ChAdjParams p) {
+static __global__ void __launch_bounds__(256) ch_adj_mu_kernel(const __grid_constant__ ChAdjParams p) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int npts = p.nx * p.ny;
   if (i >= npts) return;
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(256) ch_adj_mu_kernel(const __grid_constant__ 
 }
 
 // pass 2: mu_bar and D_bar
-__global__ void __launch_bounds__(256) ch_adj_bar_kernel(const __grid_constant__ ChAdjParams p) {
+static __global__ void __launch_bounds__(256) ch_adj_bar_kernel(const __grid_constant__ ChAdjParams p) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int npts = p.nx * p.ny;
   if (i >= npts) return;
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) ch_adj_bar_kernel(const __grid_constant__
 }
 
 // pass 3: lam0 and the coefficient cotangents (block reduction + one atomic per block and coefficient)
-__global__ void __launch_bounds__(256) ch_adj_out_kernel(const __grid_constant__ ChAdjParams p) {
+static __global__ void __launch_bounds__(256) ch_adj_out_kernel(const __grid_constant__ ChAdjParams p) {
   __shared__ float red[8][33];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int npts = p.nx * p.ny;
@@ -187,6 +187,140 @@ __global__ void __launch_bounds__(256) ch_adj_out_kernel(const __grid_constant__
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
     if (lane == 0) red[warp][n] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * PDEOPT_ADJ_NCOEF) {
+    float t = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) t += red[wv][threadIdx.x];
+    if (t != 0.f) {
+      if (threadIdx.x < PDEOPT_ADJ_NCOEF) atomicAdd(p.gmu + (size_t)b * PDEOPT_ADJ_NCOEF + threadIdx.x, t);
+      else atomicAdd(p.gmob + (size_t)b * PDEOPT_ADJ_NCOEF + threadIdx.x - PDEOPT_ADJ_NCOEF, t);
+    }
+  }
+}
+
+}  // namespace pdeopt
+
+// ---- 3-D forms (CahnHilliard3DPeriodic, cahn_hilliard.py:177-200): same three passes --------------
+namespace pdeopt {
+
+struct Ch3AdjParams {
+  int nx, ny, nz, batch;
+  const float *u, *w, *lam1;
+  float *lam0, *mu, *dd, *mub, *db, *gmu, *gmob;
+  float inv_hx, inv_hy, inv_hz, inv_hx2, inv_hy2, inv_hz2, kappa;
+  PointwiseParams pw;
+};
+
+struct Ch3Idx {
+  int i, ixp, ixm, iyp, iym, izp, izm;
+  __device__ __forceinline__ Ch3Idx(const Ch3AdjParams& p, int idx) {
+    const int pl = p.ny * p.nz;
+    const int x = idx / pl, rem = idx - x * pl, y = rem / p.nz, z = rem - y * p.nz;
+    i = idx;
+    ixp = ((x + 1 == p.nx) ? 0 : x + 1) * pl + rem;
+    ixm = ((x == 0) ? p.nx - 1 : x - 1) * pl + rem;
+    iyp = x * pl + ((y + 1 == p.ny) ? 0 : y + 1) * p.nz + z;
+    iym = x * pl + ((y == 0) ? p.ny - 1 : y - 1) * p.nz + z;
+    izp = x * pl + y * p.nz + ((z + 1 == p.nz) ? 0 : z + 1);
+    izm = x * pl + y * p.nz + ((z == 0) ? p.nz - 1 : z - 1);
+  }
+};
+
+static __global__ void __launch_bounds__(256) ch3_adj_mu_kernel(const __grid_constant__ Ch3AdjParams p) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int npts = p.nx * p.ny * p.nz;
+  if (idx >= npts) return;
+  const size_t o = (size_t)blockIdx.y * npts;
+  const float* u = p.u + o;
+  const Ch3Idx n(p, idx);
+  const float u0 = u[idx];
+  const float lap = ((u[n.ixp] - 2.0f * u0) + u[n.ixm]) * p.inv_hx2 + ((u[n.iyp] - 2.0f * u0) + u[n.iym]) * p.inv_hy2 +
+                    ((u[n.izp] - 2.0f * u0) + u[n.izm]) * p.inv_hz2;
+  p.mu[o + idx] = mu_h<MU_RUNTIME>(u0, p.pw, 0.0f) - p.kappa * lap;
+  p.dd[o + idx] = mob<MOB_RUNTIME>(u0, p.pw);
+}
+
+static __global__ void __launch_bounds__(256) ch3_adj_bar_kernel(const __grid_constant__ Ch3AdjParams p) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int npts = p.nx * p.ny * p.nz;
+  if (idx >= npts) return;
+  const size_t o = (size_t)blockIdx.y * npts;
+  const float *mu = p.mu + o, *D = p.dd + o, *w = p.w + o;
+  const Ch3Idx n(p, idx);
+  const float w0 = w[idx], m0 = mu[idx], D0 = D[idx];
+  float mub = 0.f, db = 0.f;
+  auto dir = [&](int ip, int im, float inv_h) {
+    const float gwp = (w[ip] - w0) * inv_h, gwm = (w0 - w[im]) * inv_h;
+    const float gmp = (mu[ip] - m0) * inv_h, gmm = (m0 - mu[im]) * inv_h;
+    mub += (0.5f * (D0 + D[ip]) * gwp - 0.5f * (D[im] + D0) * gwm) * inv_h;
+    db += gwp * gmp + gwm * gmm;
+  };
+  dir(n.ixp, n.ixm, p.inv_hx);
+  dir(n.iyp, n.iym, p.inv_hy);
+  dir(n.izp, n.izm, p.inv_hz);
+  p.mub[o + idx] = mub;
+  p.db[o + idx] = -0.5f * db;
+}
+
+static __global__ void __launch_bounds__(256) ch3_adj_out_kernel(const __grid_constant__ Ch3AdjParams p) {
+  __shared__ float red[8][33];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int npts = p.nx * p.ny * p.nz;
+  const int b = blockIdx.y;
+  const size_t o = (size_t)b * npts;
+  float gm[PDEOPT_ADJ_NCOEF], gd[PDEOPT_ADJ_NCOEF];
+#pragma unroll
+  for (int n = 0; n < PDEOPT_ADJ_NCOEF; ++n) gm[n] = gd[n] = 0.f;
+  if (idx < npts) {
+    const Ch3Idx n(p, idx);
+    const float* mb = p.mub + o;
+    const float u0 = p.u[o + idx], mb0 = mb[idx], db0 = p.db[o + idx], D0 = p.dd[o + idx];
+    const float lap = ((mb[n.ixp] - 2.0f * mb0) + mb[n.ixm]) * p.inv_hx2 + ((mb[n.iyp] - 2.0f * mb0) + mb[n.iym]) * p.inv_hy2 +
+                      ((mb[n.izp] - 2.0f * mb0) + mb[n.izm]) * p.inv_hz2;
+    p.lam0[o + idx] = p.lam1[o + idx] + (mu_h_prime(u0, p.pw) * mb0 - p.kappa * lap) + mob_prime(u0, D0, p.pw) * db0;
+    const float x = 2.0f * u0 - 1.0f;
+    if (p.pw.mu_family == MU_LOG) {
+      gm[0] = (1.0f - 2.0f * u0) * mb0;
+    } else if (p.pw.mu_family == MU_LEGENDRE || p.pw.mu_family == MU_LEGENDRE_LOGPRIOR) {
+      float pp = 1.0f, pc = x;
+      gm[0] = mb0;
+      if (p.pw.mu_ncoef > 1) gm[1] = x * mb0;
+#pragma unroll
+      for (int k = 2; k < PDEOPT_ADJ_NCOEF; ++k) {
+        if (k < p.pw.mu_ncoef) {
+          const float pn = (float(2 * k - 1) * x * pc - float(k - 1) * pp) / float(k);
+          gm[k] = pn * mb0;
+          pp = pc;
+          pc = pn;
+        }
+      }
+    }
+    if (p.pw.mob_family == MOB_CONST) {
+      gd[0] = db0;
+    } else if (p.pw.mob_family == MOB_LEGENDRE_EXP) {
+      float pp = 1.0f, pc = x;
+      gd[0] = D0 * db0;
+      if (p.pw.mob_ncoef > 1) gd[1] = D0 * x * db0;
+#pragma unroll
+      for (int k = 2; k < PDEOPT_ADJ_NCOEF; ++k) {
+        if (k < p.pw.mob_ncoef) {
+          const float pn = (float(2 * k - 1) * x * pc - float(k - 1) * pp) / float(k);
+          gd[k] = D0 * pn * db0;
+          pp = pc;
+          pc = pn;
+        }
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 2 * PDEOPT_ADJ_NCOEF; ++k) {
+    float v = k < PDEOPT_ADJ_NCOEF ? gm[k] : gd[k - PDEOPT_ADJ_NCOEF];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    if (lane == 0) red[warp][k] = v;
   }
   __syncthreads();
   if (threadIdx.x < 2 * PDEOPT_ADJ_NCOEF) {

@@ -175,3 +175,16 @@ class Ch3dPlan:
         stream = ctypes.c_void_p(torch.cuda.current_stream(y0.device).cuda_stream)
         _lib.check(lib.pdeopt_ch3d_step(ctypes.byref(self.desc), _ptr(y0), _ptr(y1), y0.shape[0], len(dts), _ptr(dts), _ptr(symbol_pos), _ptr(work), stream))
         return y1
+
+    def adjoint_step(self, u, lam, dt, symbol_pos, gmu, gmob):
+        """In place on `lam`: cotangent after one step from state u -> cotangent before it
+        (pdeopt_ch3d_adjoint_step); gmu / gmob [B, 16] accumulate the coefficient cotangents."""
+        lib = _lib.load()
+        B = u.shape[0]
+        key = ("adj", B, str(u.device))
+        if key not in self._work:
+            n = int(lib.pdeopt_ch3d_adjoint_work_floats(ctypes.byref(self.desc), B))
+            self._work[key] = torch.empty(n, dtype=torch.float32, device=u.device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(u.device).cuda_stream)
+        _lib.check(lib.pdeopt_ch3d_adjoint_step(ctypes.byref(self.desc), _ptr(u), _ptr(lam), _ptr(lam), B, float(dt), _ptr(symbol_pos),
+                                                _ptr(self._work[key]), _ptr(gmu), _ptr(gmob), stream))

@@ -73,7 +73,7 @@ class PDEModel:
     def _wants_phasefield_grad(equation, y0):
         """Cahn-Hilliard / Allen-Cahn 2-D with tensor-valued closure coefficients (or an initial state
         that requires grad): route through the adjoint-capable rollout."""
-        if getattr(equation, "_kind", None) not in ("ch2d", "ac2d") or getattr(equation, "derivs", "") != "fd":
+        if getattr(equation, "_kind", None) not in ("ch2d", "ac2d", "ch3d") or getattr(equation, "derivs", "") != "fd":
             return False
         if not getattr(equation, "fused", False) or getattr(equation, "control", None) is not None:
             return False
@@ -93,7 +93,7 @@ class PDEModel:
         times = constant_step_times(ts[0], ts[-1], dt0, np.float32, max_steps)
         y = y0 if torch.is_tensor(y0) else torch.as_tensor(np.asarray(y0, dtype=np.float32))
         y = y.to(device="cuda", dtype=torch.float32) if not y.is_cuda else y.to(torch.float32)
-        single = y.dim() == 2
+        single = y.dim() == len(self.domain.points)
         if single:
             y = y.unsqueeze(0)
         if is_ad:
