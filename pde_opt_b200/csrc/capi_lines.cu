@@ -4,6 +4,7 @@
 #include "ch3d.cuh"
 #include "strang_lines.cuh"
 #include "ch_adjoint.cuh"
+#include "strang_cluster.cuh"
 using namespace pdeopt;
 
 // ---- line-FFT engine, 3-D Cahn-Hilliard, Strang on large grids ---------------------------------
@@ -313,6 +314,45 @@ extern "C" pdeopt_status pdeopt_strang_lines_step_batched(const pdeopt_gpe_desc*
   if (ksteps <= 0) return fail(PDEOPT_ERR_INVALID, "ksteps must be positive");
   if (!(desc->hx > 0) || !(desc->hy > 0)) return fail(PDEOPT_ERR_INVALID, "grid spacing must be positive");
   cudaStream_t st = (cudaStream_t)stream;
+  if (a_term_full_dev == nullptr && nx == kClN && ny == kClN) {
+    // the equation as shipped on 256x256: cluster-of-4 kernel, state in registers for all K steps
+    static bool cattr = false;
+    if (!cattr) {
+      cudaError_t ce = cudaFuncSetAttribute(strang_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
+      (void)ce;
+      cattr = true;
+    }
+    const float* src = y0_dev;
+    for (int done = 0; done < ksteps;) {
+      const int kk = ksteps - done < kMaxK ? ksteps - done : kMaxK;
+      StrangClusterParams cp;
+      std::memset(&cp, 0, sizeof(cp));
+      cp.y0 = src; cp.y1 = y1_dev; cp.batch = batch; cp.ksteps = kk;
+      cp.ts_re = ts_re; cp.ts_im = ts_im; cp.dx = (float)desc->hx;
+      cp.k_int = (float)desc->k; cp.e = (float)desc->e; cp.trap = (float)desc->trap_factor;
+      cp.lo_x = (float)desc->lo_x; cp.lo_y = (float)desc->lo_y; cp.hx = (float)desc->hx; cp.hy = (float)desc->hy;
+      cp.ctrl = ctrl_dev;
+      for (int k = 0; k < kk; ++k) cp.dt[k] = dt_host[done + k];
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(batch * kClCtas));
+      cfg.blockDim = dim3(kClThreads);
+      cfg.dynamicSmemBytes = 0;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = kClCtas;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cudaError_t le = cudaLaunchKernelEx(&cfg, strang_cluster_kernel, cp);
+      if (le != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("strang cluster launch: ") + cudaGetErrorString(le));
+      g_launches.fetch_add(1);
+      src = y1_dev;
+      done += kk;
+    }
+    return PDEOPT_OK;
+  }
   const int64_t npts = (int64_t)nx * ny, total = npts * batch;
   float2* W = (float2*)work_dev;
   float2* etab = W + total;
