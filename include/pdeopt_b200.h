@@ -142,12 +142,12 @@ pdeopt_status pdeopt_sifs_filter_batched(pdeopt_plan* plan, const float* y0_dev,
  *   u_dev     : [batch][nx][ny] state at the START of the step
  *   lam1_dev  : cotangent of the state after the step;  lam0_dev: cotangent before it (may alias)
  *   work_dev  : pdeopt_phasefield_adjoint_work_floats(plan, batch) floats of scratch
- *   gmu_dev, gmob_dev : [batch][PDEOPT_MAX_COEF] cotangents of mu_coef / mob_coef, ACCUMULATED (+=)
+ *   gmu_dev, gmob_dev : [batch][PDEOPT_MAX_COEF] float64 cotangents of mu_coef / mob_coef, ACCUMULATED (+=)
  * The plan's coefficients are the point of linearisation: re-create the plan when they change. */
 int64_t pdeopt_phasefield_adjoint_work_floats(const pdeopt_plan* plan, int32_t batch);
 pdeopt_status pdeopt_phasefield_adjoint_step(pdeopt_plan* plan, const float* u_dev, const float* lam1_dev, float* lam0_dev,
                                              int32_t batch, float dt, const float* symbol_dev, float* work_dev,
-                                             float* gmu_dev, float* gmob_dev, void* stream);
+                                             double* gmu_dev, double* gmob_dev, void* stream);
 
 /* GPE2DTSControl (gross_pitaevskii.py:18-81) geometry and constants. */
 typedef struct {
@@ -300,7 +300,7 @@ pdeopt_status pdeopt_ch3d_step(const pdeopt_ch3d_desc* desc, const float* y0_dev
 int64_t pdeopt_ch3d_adjoint_work_floats(const pdeopt_ch3d_desc* desc, int32_t batch);
 pdeopt_status pdeopt_ch3d_adjoint_step(const pdeopt_ch3d_desc* desc, const float* u_dev, const float* lam1_dev,
                                        float* lam0_dev, int32_t batch, float dt, const float* symbol_pos_dev,
-                                       float* work_dev, float* gmu_dev, float* gmob_dev, void* stream);
+                                       float* work_dev, double* gmu_dev, double* gmob_dev, void* stream);
 
 /* ---- StrangSplitting.step on grids that do not fit one SM (256x256 complex64; any nx, ny powers of
  * two in [32, 512]): multi-kernel path on the line-FFT engine, state resident in L2.

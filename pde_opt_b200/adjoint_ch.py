@@ -46,7 +46,7 @@ class _PhaseFieldRollout(torch.autograd.Function):
         lib = _lib.load()
         lam = gy.contiguous().clone()
         B = lam.shape[0]
-        gmu = torch.zeros((B, _lib.MAX_COEF), dtype=torch.float32, device=lam.device)
+        gmu = torch.zeros((B, _lib.MAX_COEF), dtype=torch.float64, device=lam.device)
         gmob = torch.zeros_like(gmu)
         stream = ctypes.c_void_p(torch.cuda.current_stream(lam.device).cuda_stream)
         if ctx.is3d:
@@ -57,8 +57,8 @@ class _PhaseFieldRollout(torch.autograd.Function):
             for k in range(len(dts) - 1, -1, -1):
                 _lib.check(lib.pdeopt_phasefield_adjoint_step(plan._h, _vp(traj[k]), _vp(lam), _vp(lam), B, float(dts[k]), _vp(sym),
                                                               _vp(work), _vp(gmu), _vp(gmob), stream))
-        g_mu = gmu.sum(0)[: ctx.n_mu] if ctx.has_mu else None
-        g_mob = gmob.sum(0)[: ctx.n_mob] if ctx.has_mob else None
+        g_mu = gmu.sum(0)[: ctx.n_mu].to(torch.float32) if ctx.has_mu else None
+        g_mob = gmob.sum(0)[: ctx.n_mob].to(torch.float32) if ctx.has_mob else None
         return lam, g_mu, g_mob, None, None, None
 
 

@@ -322,7 +322,7 @@ extern "C" int64_t pdeopt_phasefield_adjoint_work_floats(const pdeopt_plan* plan
 
 extern "C" pdeopt_status pdeopt_phasefield_adjoint_step(pdeopt_plan* plan, const float* u_dev, const float* lam1_dev,
                                                         float* lam0_dev, int32_t batch, float dt, const float* symbol_dev,
-                                                        float* work_dev, float* gmu_dev, float* gmob_dev, void* stream) {
+                                                        float* work_dev, double* gmu_dev, double* gmob_dev, void* stream) {
   if (!plan || !u_dev || !lam1_dev || !lam0_dev || !symbol_dev || !work_dev || !gmu_dev || !gmob_dev)
     return fail(PDEOPT_ERR_INVALID, "null argument");
   if (batch <= 0 || batch > 65535) return fail(PDEOPT_ERR_INVALID, "batch must be in [1, 65535]");

@@ -252,7 +252,7 @@ extern "C" int64_t pdeopt_ch3d_adjoint_work_floats(const pdeopt_ch3d_desc* d, in
 
 extern "C" pdeopt_status pdeopt_ch3d_adjoint_step(const pdeopt_ch3d_desc* d, const float* u_dev, const float* lam1_dev,
                                                   float* lam0_dev, int32_t batch, float dt, const float* symbol_pos_dev,
-                                                  float* work_dev, float* gmu_dev, float* gmob_dev, void* stream) {
+                                                  float* work_dev, double* gmu_dev, double* gmob_dev, void* stream) {
   pdeopt_status s = ch3d_check(d, batch);
   if (s != PDEOPT_OK) return s;
   if (!u_dev || !lam1_dev || !lam0_dev || !symbol_pos_dev || !work_dev || !gmu_dev || !gmob_dev)

@@ -36,8 +36,8 @@ struct ChAdjParams {
   float* dd;          // [B][nx][ny] scratch: D(u)
   float* mub;         // [B][nx][ny] scratch: mu_bar
   float* db;          // [B][nx][ny] scratch: D_bar
-  float* gmu;         // [B][16] accumulated cotangents of mu_coef
-  float* gmob;        // [B][16] accumulated cotangents of mob_coef
+  double* gmu;        // [B][16] accumulated cotangents of mu_coef (float64: thousands of steps of signed terms)
+  double* gmob;       // [B][16] accumulated cotangents of mob_coef
   float inv_hx, inv_hy, inv_hx2, inv_hy2, kappa;
   PointwiseParams pw;
 };
@@ -194,8 +194,8 @@ static __global__ void __launch_bounds__(256) ch_adj_out_kernel(const __grid_con
 #pragma unroll
     for (int wv = 0; wv < 8; ++wv) t += red[wv][threadIdx.x];
     if (t != 0.f) {
-      if (threadIdx.x < PDEOPT_ADJ_NCOEF) atomicAdd(p.gmu + (size_t)b * PDEOPT_ADJ_NCOEF + threadIdx.x, t);
-      else atomicAdd(p.gmob + (size_t)b * PDEOPT_ADJ_NCOEF + threadIdx.x - PDEOPT_ADJ_NCOEF, t);
+      if (threadIdx.x < PDEOPT_ADJ_NCOEF) atomicAdd(p.gmu + (size_t)b * PDEOPT_ADJ_NCOEF + threadIdx.x, (double)t);
+      else atomicAdd(p.gmob + (size_t)b * PDEOPT_ADJ_NCOEF + threadIdx.x - PDEOPT_ADJ_NCOEF, (double)t);
     }
   }
 }
@@ -208,7 +208,8 @@ namespace pdeopt {
 struct Ch3AdjParams {
   int nx, ny, nz, batch;
   const float *u, *w, *lam1;
-  float *lam0, *mu, *dd, *mub, *db, *gmu, *gmob;
+  float *lam0, *mu, *dd, *mub, *db;
+  double *gmu, *gmob;
   float inv_hx, inv_hy, inv_hz, inv_hx2, inv_hy2, inv_hz2, kappa;
   PointwiseParams pw;
 };
@@ -328,8 +329,8 @@ static __global__ void __launch_bounds__(256) ch3_adj_out_kernel(const __grid_co
 #pragma unroll
     for (int wv = 0; wv < 8; ++wv) t += red[wv][threadIdx.x];
     if (t != 0.f) {
-      if (threadIdx.x < PDEOPT_ADJ_NCOEF) atomicAdd(p.gmu + (size_t)b * PDEOPT_ADJ_NCOEF + threadIdx.x, t);
-      else atomicAdd(p.gmob + (size_t)b * PDEOPT_ADJ_NCOEF + threadIdx.x - PDEOPT_ADJ_NCOEF, t);
+      if (threadIdx.x < PDEOPT_ADJ_NCOEF) atomicAdd(p.gmu + (size_t)b * PDEOPT_ADJ_NCOEF + threadIdx.x, (double)t);
+      else atomicAdd(p.gmob + (size_t)b * PDEOPT_ADJ_NCOEF + threadIdx.x - PDEOPT_ADJ_NCOEF, (double)t);
     }
   }
 }
