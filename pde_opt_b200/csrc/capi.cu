@@ -94,17 +94,14 @@ extern "C" int64_t pdeopt_table_len(const pdeopt_plan* plan) {
   return (int64_t)(plan->d.nx / 2 + 1) * (plan->d.ny / 2 + 1);
 }
 
-template <int EQ, int MU, int MOB>
-static cudaError_t launch(const SifsParams& p, int grid, cudaStream_t st) {
-  auto kern = sifs128_kernel<EQ, MU, MOB>;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SifsSmem));
-    if (e != cudaSuccess) return e;
-    attr = true;
-  }
-  kern<<<grid, kThreads, sizeof(SifsSmem), st>>>(p);
-  return cudaGetLastError();
+// The five instantiations of the fused 128x128 kernel are compiled in their own translation units
+// (sifs128_inst_*.cu) so that the build parallelises; variant ids below.
+enum : int { SIFS_V_AC_RT = 0, SIFS_V_CH_LOG_DEG = 1, SIFS_V_CH_LOG_CONST = 2, SIFS_V_CH_DW_CONST = 3, SIFS_V_CH_RT = 4 };
+cudaError_t pdeopt_sifs128_launch_a(int variant, const pdeopt::SifsParams& p, int grid, cudaStream_t st);
+cudaError_t pdeopt_sifs128_launch_b(int variant, const pdeopt::SifsParams& p, int grid, cudaStream_t st);
+static cudaError_t launch_variant(int variant, const SifsParams& p, int grid, cudaStream_t st) {
+  return (variant == SIFS_V_CH_LOG_DEG || variant == SIFS_V_CH_LOG_CONST) ? pdeopt_sifs128_launch_a(variant, p, grid, st)
+                                                                            : pdeopt_sifs128_launch_b(variant, p, grid, st);
 }
 
 static pdeopt_status sifs_launch(pdeopt_plan* plan, int mode, const float* f0_dev, const float* y0_dev, float* y1_dev,
@@ -277,15 +274,15 @@ static pdeopt_status sifs_launch(pdeopt_plan* plan, int mode, const float* f0_de
 #endif
   cudaError_t e;
   if (d.kind == PDEOPT_AC2D) {
-    e = launch<EQ_AC, MU_RUNTIME, MOB_RUNTIME>(p, grid, st);
+    e = launch_variant(SIFS_V_AC_RT, p, grid, st);
   } else if (d.mu_family == PDEOPT_MU_LOG && d.mob_family == PDEOPT_MOB_DEGENERATE) {
-    e = launch<EQ_CH, MU_LOG, MOB_DEGENERATE>(p, grid, st);
+    e = launch_variant(SIFS_V_CH_LOG_DEG, p, grid, st);
   } else if (d.mu_family == PDEOPT_MU_LOG && d.mob_family == PDEOPT_MOB_CONST) {
-    e = launch<EQ_CH, MU_LOG, MOB_CONST>(p, grid, st);
+    e = launch_variant(SIFS_V_CH_LOG_CONST, p, grid, st);
   } else if (d.mu_family == PDEOPT_MU_DOUBLE_WELL && d.mob_family == PDEOPT_MOB_CONST) {
-    e = launch<EQ_CH, MU_DOUBLE_WELL, MOB_CONST>(p, grid, st);
+    e = launch_variant(SIFS_V_CH_DW_CONST, p, grid, st);
   } else {
-    e = launch<EQ_CH, MU_RUNTIME, MOB_RUNTIME>(p, grid, st);
+    e = launch_variant(SIFS_V_CH_RT, p, grid, st);
   }
   if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
   g_launches.fetch_add(1);

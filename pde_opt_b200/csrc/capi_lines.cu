@@ -1,38 +1,14 @@
 // C ABI: line-FFT engine, 3-D Cahn-Hilliard, Strang on large grids (see include/pdeopt_b200.h).
 #include "capi_common.h"
-#include "linefft.cuh"
+#include "capi_lines_common.h"
 #include "ch3d.cuh"
-#include "strang_lines.cuh"
 #include "ch_adjoint.cuh"
-#include "strang_cluster.cuh"
 using namespace pdeopt;
 
 // ---- line-FFT engine, 3-D Cahn-Hilliard, Strang on large grids ---------------------------------
-static LineGeom to_geom(const pdeopt_line_geom* g) {
-  LineGeom r;
-  r.n_lines = g->n_lines;
-  r.n_inner = g->n_inner;
-  r.outer = g->outer;
-  r.inner = g->inner;
-  r.chunk = g->chunk;
-  r.hi = g->hi;
-  r.lo = g->lo;
-  return r;
-}
-static bool geom_ok(const pdeopt_line_geom* g, int n) {
-  return g && g->n_lines > 0 && g->n_inner > 0 && g->chunk > 0 && g->chunk <= n && (g->chunk & (g->chunk - 1)) == 0;
-}
-static bool lf_size_ok(int n) { return n >= 8 && n <= 512 && (n & (n - 1)) == 0; }
-
 extern "C" int32_t pdeopt_fft_pos_to_freq(int32_t n, int32_t pos) {
   if (!lf_size_ok(n) || pos < 0 || pos >= n) return -1;
   return line_pos_to_freq(n, pos);
-}
-
-template <int MODE, bool CONTIG, class L, class M, class S>
-static cudaError_t lf_run(int n, long long n_lines, L ld, M mid, S st, cudaStream_t stream) {
-  PDEOPT_LF_DISPATCH(n, return (lf_launch<LFN, MODE, CONTIG>(n_lines, ld, mid, st, stream)));
-  return cudaSuccess;
 }
 
 extern "C" pdeopt_status pdeopt_fft_lines(const void* in_dev, void* out_dev, int32_t n, const pdeopt_line_geom* gin,
@@ -294,142 +270,6 @@ extern "C" pdeopt_status pdeopt_ch3d_adjoint_step(const pdeopt_ch3d_desc* d, con
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("ch3d adjoint step: ") + cudaGetErrorString(e));
   g_launches.fetch_add(3);
-  return PDEOPT_OK;
-}
-
-extern "C" int64_t pdeopt_strang_lines_work_floats(int32_t nx, int32_t ny, int32_t batch) {
-  if (nx <= 0 || ny <= 0 || batch <= 0) return 0;
-  return 2 * (int64_t)nx * ny * batch + 2 * (int64_t)nx * ny + 2 * (((int64_t)batch + 63) / 64) * 64;
-}
-
-extern "C" pdeopt_status pdeopt_strang_lines_step_batched(const pdeopt_gpe_desc* desc, const float* y0_dev, float* y1_dev,
-                                                          int32_t batch, int32_t ksteps, const float* dt_host,
-                                                          const float* a_term_full_dev, float ts_re, float ts_im,
-                                                          const float* ctrl_dev, float* work_dev, void* stream) {
-  if (!desc || !y0_dev || !y1_dev || !dt_host || !work_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
-  const int nx = desc->nx, ny = desc->ny;
-  if (!lf_size_ok(nx) || !lf_size_ok(ny) || nx < 32 || ny < 32)
-    return fail(PDEOPT_ERR_UNSUPPORTED, "strang_lines: nx, ny must be powers of two in [32, 512]");
-  if (batch <= 0) return fail(PDEOPT_ERR_INVALID, "batch must be positive");
-  if (ksteps <= 0) return fail(PDEOPT_ERR_INVALID, "ksteps must be positive");
-  if (!(desc->hx > 0) || !(desc->hy > 0)) return fail(PDEOPT_ERR_INVALID, "grid spacing must be positive");
-  cudaStream_t st = (cudaStream_t)stream;
-  if (a_term_full_dev == nullptr && nx == kClN && ny == kClN) {
-    // the equation as shipped on 256x256: cluster-of-4 kernel, state in registers for all K steps
-    static bool cattr = false;
-    if (!cattr) {
-      cudaError_t ce = cudaFuncSetAttribute(strang_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
-      (void)ce;
-      cattr = true;
-    }
-    const float* src = y0_dev;
-    for (int done = 0; done < ksteps;) {
-      const int kk = ksteps - done < kMaxK ? ksteps - done : kMaxK;
-      StrangClusterParams cp;
-      std::memset(&cp, 0, sizeof(cp));
-      cp.y0 = src; cp.y1 = y1_dev; cp.batch = batch; cp.ksteps = kk;
-      cp.ts_re = ts_re; cp.ts_im = ts_im; cp.dx = (float)desc->hx;
-      cp.k_int = (float)desc->k; cp.e = (float)desc->e; cp.trap = (float)desc->trap_factor;
-      cp.lo_x = (float)desc->lo_x; cp.lo_y = (float)desc->lo_y; cp.hx = (float)desc->hx; cp.hy = (float)desc->hy;
-      cp.ctrl = ctrl_dev;
-      for (int k = 0; k < kk; ++k) cp.dt[k] = dt_host[done + k];
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3((unsigned)(batch * kClCtas));
-      cfg.blockDim = dim3(kClThreads);
-      cfg.dynamicSmemBytes = 0;
-      cfg.stream = st;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = kClCtas;
-      attr[0].val.clusterDim.y = 1;
-      attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      cudaError_t le = cudaLaunchKernelEx(&cfg, strang_cluster_kernel, cp);
-      if (le != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("strang cluster launch: ") + cudaGetErrorString(le));
-      g_launches.fetch_add(1);
-      src = y1_dev;
-      done += kk;
-    }
-    return PDEOPT_OK;
-  }
-  const int64_t npts = (int64_t)nx * ny, total = npts * batch;
-  float2* W = (float2*)work_dev;
-  float2* etab = W + total;
-  float* norm = (float*)(etab + npts);
-  const int64_t nstride = (((int64_t)batch + 63) / 64) * 64;
-  GpeLinesConst c;
-  c.nx = nx; c.ny = ny; c.log2nx = ilog2(nx);
-  c.lo_x = (float)desc->lo_x; c.lo_y = (float)desc->lo_y; c.hx = (float)desc->hx; c.hy = (float)desc->hy;
-  c.trap = (float)desc->trap_factor; c.e = (float)desc->e; c.k_int = (float)desc->k;
-  c.ts_re = ts_re; c.ts_im = ts_im; c.ctrl = ctrl_dev;
-  const float dx2 = (float)desc->hx * (float)desc->hx;
-  const LineGeom rows{(long long)batch * nx, 1, ny, 0, ny, 0, 1};
-  const LineGeom cols{(long long)batch * ny, ny, npts, 1, nx, 0, ny};
-  const float2* src = (const float2*)y0_dev;
-  float2* dst = (float2*)y1_dev;
-  float last_dt = 0.f;
-  bool have_tab = false;
-  cudaError_t e = cudaSuccess;
-  for (int k = 0; k < ksteps && e == cudaSuccess; ++k) {
-    const float dt = dt_host[k];
-    if (a_term_full_dev == nullptr) {
-      // one kernel per step; norms ping-pong so that step k can read the norm of step k-1 while
-      // accumulating its own; the last norm is applied by the scale kernel after the loop
-      float* nk = norm + (size_t)(k & 1) * nstride;
-      const float* nprev = k > 0 ? norm + (size_t)((k - 1) & 1) * nstride : nullptr;
-      e = cudaMemsetAsync(nk, 0, sizeof(float) * batch, st);
-      if (e != cudaSuccess) break;
-      const int bpe = (int)((npts + 16383) / 16384);
-      // ping-pong between W and dst so that a launch never reads what it writes
-      const float2* kin = k == 0 ? src : ((k & 1) ? W : dst);
-      float2* kout = (k & 1) ? dst : W;
-      strang_lines_potential_kernel<<<batch * bpe, 256, 0, st>>>(kin, kout, nprev, nk, c, dt, dx2, bpe);
-      g_launches.fetch_add(1);
-      if (k + 1 == ksteps) {
-        strang_lines_scale_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(kout, dst, nk, (int)npts, dx2, total);
-        g_launches.fetch_add(1);
-      }
-      e = cudaGetLastError();
-      continue;
-    }
-    e = cudaMemsetAsync(norm, 0, sizeof(float) * batch, st);
-    if (e != cudaSuccess) break;
-    {
-      if (!have_tab || dt != last_dt) {
-        strang_lines_etab_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, st>>>((const float2*)a_term_full_dev, etab, nx, ny,
-                                                                               0.5f * dt * ts_re, 0.5f * dt * ts_im);
-        have_tab = true;
-        last_dt = dt;
-        g_launches.fetch_add(1);
-      }
-      LineGeom ctab = cols;
-      ctab.outer = 0;
-      const LfMidCTab mid{etab, ctab};
-      const LfMidCTabScaled mid_scaled{etab, norm, ctab, ilog2(ny), dx2};
-      // 4 kernels per step (W holds the row-transformed state between steps):
-      //   [rows fwd, first step only]  cols fwd*e*inv  rows inv*potential*fwd  cols fwd*e*scale*inv  rows inv -> y1 [-> fwd]
-      if (k == 0) {
-        e = lf_run<LF_FWD, true>(ny, rows.n_lines, LfLoadC{src, rows}, LfMidNone{}, LfStoreC{W, rows}, st);
-        if (e != cudaSuccess) break;
-        g_launches.fetch_add(1);
-      }
-      e = lf_run<LF_FWD_MUL_INV, false>(nx, cols.n_lines, LfLoadC{W, cols}, mid, LfStoreC{W, cols}, st);
-      if (e != cudaSuccess) break;
-      e = lf_run<LF_INV_MID_FWD, true>(ny, rows.n_lines, LfLoadC{W, rows}, LfMidPotentialIMF{src, norm, c, dt, 0.f}, LfStoreC{W, rows}, st);
-      if (e != cudaSuccess) break;
-      e = lf_run<LF_FWD_MUL_INV, false>(nx, cols.n_lines, LfLoadC{W, cols}, mid_scaled, LfStoreC{W, cols}, st);
-      if (e != cudaSuccess) break;
-      if (k + 1 < ksteps) {
-        e = lf_run<LF_INV_MID_FWD, true>(ny, rows.n_lines, LfLoadC{W, rows}, LfMidStoreState{dst}, LfStoreC{W, rows}, st);
-      } else {
-        e = lf_run<LF_INV, true>(ny, rows.n_lines, LfLoadC{W, rows}, LfMidNone{}, LfStoreC{dst, rows}, st);
-      }
-      g_launches.fetch_add(4);
-    }
-    src = dst;
-  }
-  if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("strang_lines: ") + cudaGetErrorString(e));
   return PDEOPT_OK;
 }
 
