@@ -183,11 +183,20 @@ __global__ void __launch_bounds__(kThreads, 1) strang128_kernel(const __grid_con
         float V = vrow + 0.5f * p.trap * (1.0f - p.e) * yc * yc + p.k_int * (v[i].x * v[i].x + v[i].y * v[i].y);
         if (has_light) V = fmaf(gxr, S.gy[c], V);
         const float a = V * dt;
-        const float m = __expf(a * p.ts_im);
-        const float ph = -a * p.ts_re;
-        float s, cth;
-        __sincosf(ph - 6.283185307179586f * rintf(ph * 0.15915494309189535f), &s, &cth);
-        x[n] = cmul(x[n], make_float2(m * cth, m * s));
+        if (p.ts_re == 0.f) {  // imaginary time: real factor (uniform branch)
+          const float m = __expf(a * p.ts_im);
+          x[n] = make_float2(x[n].x * m, x[n].y * m);
+        } else {
+          const float ph = -a * p.ts_re;
+          float s, cth;
+          __sincosf(ph - 6.283185307179586f * rintf(ph * 0.15915494309189535f), &s, &cth);
+          if (p.ts_im != 0.f) {
+            const float m = __expf(a * p.ts_im);
+            s *= m;
+            cth *= m;
+          }
+          x[n] = cmul(x[n], make_float2(cth, s));
+        }
         part = fmaf(x[n].x, x[n].x, fmaf(x[n].y, x[n].y, part));
       }
     }

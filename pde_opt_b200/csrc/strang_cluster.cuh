@@ -84,6 +84,7 @@ static __global__ void __launch_bounds__(kClThreads, 1) strang_cluster_kernel(co
   const float gyv = has_light ? gy[col] : gyc;
   const uint32_t part_saddr = (uint32_t)__cvta_generic_to_shared(&part[0][0]);
 
+  const bool pure_imag = p.ts_re == 0.f, pure_real = p.ts_im == 0.f;  // uniform
   for (int k = 0; k < p.ksteps; ++k) {
     const float dt = p.dt[k];
     float acc = 0.f;
@@ -94,11 +95,22 @@ static __global__ void __launch_bounds__(kClThreads, 1) strang_cluster_kernel(co
       float V = fmaf(0.5f * p.trap * (1.0f + p.e) * xr, xr, vcol) + p.k_int * (x[j].x * x[j].x + x[j].y * x[j].y);
       if (has_light) V = fmaf(gx[rl], gyv, V);
       const float a = V * dt;
-      const float m = __expf(a * p.ts_im);
-      const float ph = -a * p.ts_re;
-      float s, c;
-      __sincosf(ph - 6.283185307179586f * rintf(ph * 0.15915494309189535f), &s, &c);
-      x[j] = cmul(x[j], make_float2(m * c, m * s));
+      // exp(b dt_c) = exp(a ts_im) (cos(-a ts_re) + i sin(-a ts_re)); pure imaginary / pure real time
+      // (the two cases the reference uses) need one or two MUFU operations instead of three
+      if (pure_imag) {
+        const float m = __expf(a * p.ts_im);
+        x[j] = make_float2(x[j].x * m, x[j].y * m);
+      } else {
+        const float ph = -a * p.ts_re;
+        float s, c;
+        __sincosf(ph - 6.283185307179586f * rintf(ph * 0.15915494309189535f), &s, &c);
+        if (!pure_real) {
+          const float m = __expf(a * p.ts_im);
+          s *= m;
+          c *= m;
+        }
+        x[j] = cmul(x[j], make_float2(c, s));
+      }
       acc = fmaf(x[j].x, x[j].x, fmaf(x[j].y, x[j].y, acc));
     }
     // CTA sum, then one float to each CTA of the cluster (own slot included)

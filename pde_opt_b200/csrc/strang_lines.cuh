@@ -40,10 +40,12 @@ __device__ __forceinline__ float2 gpe_potential_factor(const GpeLinesConst& c, i
     }
   }
   const float a = V * dt;
-  const float m = __expf(a * c.ts_im);
+  if (c.ts_re == 0.f) return make_float2(__expf(a * c.ts_im), 0.f);  // imaginary time: real factor
   const float ph = -a * c.ts_re;
   float s, cth;
   __sincosf(ph - 6.283185307179586f * rintf(ph * 0.15915494309189535f), &s, &cth);
+  if (c.ts_im == 0.f) return make_float2(cth, s);                     // real time: pure phase
+  const float m = __expf(a * c.ts_im);
   return make_float2(m * cth, m * s);
 }
 
