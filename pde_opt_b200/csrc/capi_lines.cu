@@ -171,7 +171,18 @@ extern "C" pdeopt_status pdeopt_ch3d_rhs(const pdeopt_ch3d_desc* d, const float*
   if (xl > 0 && d->ny % kC3TY == 0 && d->nz % kC3TZ == 0 && (int64_t)batch * (d->nx / xl) <= 65535) {
     // fused 2.5-D marching kernel: one read of u, one write of f
     dim3 grid(d->nz / kC3TZ, d->ny / kC3TY, batch * (d->nx / xl));
-    ch3d_rhs_fused_kernel<<<grid, kC3Threads, 0, st>>>(p, xl);
+    auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    if (aligned16(u_dev) && aligned16(f_dev) && aligned16(halo_lo_dev) && aligned16(halo_hi_dev)) {
+      // register-marching version (128-bit accesses), specialised for the closure families with packed forms
+      const int mf = d->mu_family, bf = d->mob_family;
+      if (mf == MU_LOG && bf == MOB_CONST) ch3d_rhs_march_kernel<MU_LOG, MOB_CONST><<<grid, kC3Threads, 0, st>>>(p, xl);
+      else if (mf == MU_LOG && bf == MOB_DEGENERATE) ch3d_rhs_march_kernel<MU_LOG, MOB_DEGENERATE><<<grid, kC3Threads, 0, st>>>(p, xl);
+      else if (mf == MU_DOUBLE_WELL && bf == MOB_CONST) ch3d_rhs_march_kernel<MU_DOUBLE_WELL, MOB_CONST><<<grid, kC3Threads, 0, st>>>(p, xl);
+      else if (bf == MOB_CONST) ch3d_rhs_march_kernel<MU_RUNTIME, MOB_CONST><<<grid, kC3Threads, 0, st>>>(p, xl);
+      else ch3d_rhs_march_kernel<MU_RUNTIME, MOB_RUNTIME><<<grid, kC3Threads, 0, st>>>(p, xl);
+    } else {
+      ch3d_rhs_fused_kernel<<<grid, kC3Threads, 0, st>>>(p, xl);
+    }
     g_launches.fetch_add(1);
   } else {
     ch3d_mu_kernel<<<g1, block, 0, st>>>(p);

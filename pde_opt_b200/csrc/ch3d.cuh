@@ -209,6 +209,229 @@ __global__ void __launch_bounds__(kC3Threads) ch3d_rhs_fused_kernel(const __grid
   }
 }
 
+// ---- register-marching single-pass RHS ----------------------------------------------------------
+// Same tile (16 x 64 points of a (y, z) plane per 256-thread CTA, marching along x) as the kernel
+// above, but every thread keeps the x-column of its four consecutive z points in registers and
+// shared memory only carries what NEIGHBOURS need: one plane of u (tile + halo 2) and one plane of
+// (mu, D) (tile + ring 1), both double buffered, so one barrier per plane.  128-bit shared and global
+// accesses, z-neighbours inside a warp by shuffle, packed f32x2 arithmetic; 160 threads additionally
+// march one ring point each.  The loop body is instantiated for both buffer parities so that every
+// shared-memory access is base register + immediate.
+//   f = cx (Gx - Gx_prev) + cy (Gy+ - Gy-) + cz (Gz+ - Gz-),  G = (D + D_nbr) (mu_nbr - mu), c = 1/(2h^2)
+// (cahn_hilliard.py:177-200 with the constant factors collected as in sifs128.cuh; a few ulp).
+constexpr int kM3P = 76;            // row pitch in floats: 4 halo columns | 64 | halo; 76 mod 32 = 12 keeps the
+                                    // column-ring accesses (one per row) at two per bank
+constexpr int kM3UR = kC3TY + 4;    // u rows (halo 2)
+constexpr int kM3MR = kC3TY + 2;    // mu / D rows (ring 1)
+constexpr int kM3US = kM3UR * kM3P, kM3MS = kM3MR * kM3P;  // buffer strides
+
+struct Ch3dMarchSmem {
+  float U[2][kM3UR][kM3P];   // [y_local + 2][z_local + 4]
+  float Mu[2][kM3MR][kM3P];  // [y_local + 1][z_local + 4]
+  float Dm[2][kM3MR][kM3P];
+};
+
+__device__ __forceinline__ float2 lo2(float4 v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(float4 v) { return make_float2(v.z, v.w); }
+__device__ __forceinline__ float4 ld4(const float* q) { return *reinterpret_cast<const float4*>(q); }
+
+#ifndef PDEOPT_M3_MINB
+#define PDEOPT_M3_MINB 3
+#endif
+
+template <int MU, int MOB>
+__global__ void __launch_bounds__(kC3Threads, PDEOPT_M3_MINB) ch3d_rhs_march_kernel(const __grid_constant__ Ch3dParams p, int xl) {
+  __shared__ __align__(16) Ch3dMarchSmem S;
+  constexpr bool DCONST = (MOB == MOB_CONST);
+  const int tid = threadIdx.x;
+  const int z0 = blockIdx.x * kC3TZ, y0 = blockIdx.y * kC3TY;
+  const int nchunk = p.nx / xl;
+  const int b = blockIdx.z / nchunk, x0 = (blockIdx.z % nchunk) * xl;
+  const int ty = tid >> 4, tq = tid & 15;
+  const int own_off = (y0 + ty) * p.nz + z0 + 4 * tq;
+  const size_t pl = (size_t)p.ny * p.nz;
+
+  // ring roles: threads 0..159 march one ring-1 point (mu, D needed there); threads 92..255 stage one
+  // ring-2 / corner point of u (only neighbours read it)
+  auto wrap_off = [&](int yl, int zl) {
+    int gy = y0 + yl, gz = z0 + zl;
+    gy = gy < 0 ? gy + p.ny : (gy >= p.ny ? gy - p.ny : gy);
+    gz = gz < 0 ? gz + p.nz : (gz >= p.nz ? gz - p.nz : gz);
+    return gy * p.nz + gz;
+  };
+  const bool r1 = tid < 160;
+  int r1y = 0, r1z = 0;
+  if (tid < 64) { r1y = -1; r1z = tid; }
+  else if (tid < 128) { r1y = kC3TY; r1z = tid - 64; }
+  else if (tid < 144) { r1y = tid - 128; r1z = -1; }
+  else if (tid < 160) { r1y = tid - 144; r1z = kC3TZ; }
+  const int r1_off = wrap_off(r1y, r1z);
+  const bool r2 = tid >= 92;
+  int r2y = 0, r2z = 0;
+  {
+    const int j = tid - 92;
+    if (j < 64) { r2y = -2; r2z = j; }
+    else if (j < 128) { r2y = kC3TY + 1; r2z = j - 64; }
+    else if (j < 144) { r2y = j - 128; r2z = -2; }
+    else if (j < 160) { r2y = j - 144; r2z = kC3TZ + 1; }
+    else { r2y = (j & 2) ? kC3TY : -1; r2z = (j & 1) ? kC3TZ : -1; }
+  }
+  const int r2_off = r2 ? wrap_off(r2y, r2z) : 0;
+  // per-thread shared-memory bases (buffer 0); the other buffer is a compile-time offset away
+  float* const Uown = &S.U[0][ty + 2][4 + 4 * tq];
+  float* const Ur1 = &S.U[0][r1y + 2][r1z + 4];
+  float* const Ur2 = &S.U[0][r2y + 2][r2z + 4];
+  float* const Mown = &S.Mu[0][ty + 1][4 + 4 * tq];
+  float* const Mr1 = &S.Mu[0][r1y + 1][r1z + 4];
+  constexpr int kMD = 2 * kM3MS;  // Mu -> Dm
+
+  const float2 ihx2 = splat2(p.inv_hx2), ihy2 = splat2(p.inv_hy2), ihz2 = splat2(p.inv_hz2), m2 = splat2(-2.0f);
+  const float2 mkappa = splat2(-p.kappa), zero2 = make_float2(0.f, 0.f);
+  const float dscale = DCONST ? 2.0f * p.pw.mob_coef[0] : 1.0f;  // (D + D) folded into the face coefficient
+  const float2 cx = splat2(0.5f * p.inv_hx * p.inv_hx * dscale), cy = splat2(0.5f * p.inv_hy * p.inv_hy * dscale),
+               cz = splat2(0.5f * p.inv_hz * p.inv_hz * dscale);
+
+  // mu = mu_h(u) - kappa lap(u) (derivatives.py:15-21, cahn_hilliard.py:179) and D(u) for a packed pair
+  auto mu_of = [&](float2 uc, float2 uxp, float2 uxm, float2 uyp, float2 uym, float2 uzp, float2 uzm, float2& mu, float2& D) {
+    const float2 dxx = add2(fma2(uc, m2, uxp), uxm);
+    const float2 dyy = add2(fma2(uc, m2, uyp), uym);
+    const float2 dzz = add2(fma2(uc, m2, uzp), uzm);
+    const float2 lap = fma2(dzz, ihz2, fma2(dyy, ihy2, mul2(dxx, ihx2)));
+    float2 mh;
+    mu_mob_pair<MU, MOB>(uc, p.pw, zero2, mh, D);
+    mu = fma2(lap, mkappa, mh);
+  };
+
+  // marching registers: planes c-1, c, c+1 and the prefetched c+2.  The plane pointer advances by one
+  // plane per fetch and is re-derived only where the periodic wrap / slab halo changes the array.
+  float4 um, u0, up, pf;
+  float rum = 0.f, ru0 = 0.f, rup = 0.f, rpf = 0.f, r2up = 0.f, r2pf = 0.f;
+  int xnext = x0 - 2;
+  const float* pnext = ch3d_plane(p, b, xnext);
+  auto fetch = [&](float4& v, float& rv, float& r2v) {
+    v = __ldg(reinterpret_cast<const float4*>(pnext + own_off));
+    if (r1) rv = __ldg(pnext + r1_off);
+    if (r2) r2v = __ldg(pnext + r2_off);
+    ++xnext;
+    pnext += pl;
+    if (xnext == 0 || xnext == p.nx) pnext = ch3d_plane(p, b, xnext);
+  };
+  {
+    float dummy = 0.f;
+    fetch(um, rum, dummy);      // x0 - 2
+    fetch(u0, ru0, r2up);       // x0 - 1
+    *reinterpret_cast<float4*>(Uown) = u0;
+    if (r1) *Ur1 = ru0;
+    if (r2) *Ur2 = r2up;
+    fetch(up, rup, r2up);       // x0
+    fetch(pf, rpf, r2pf);       // x0 + 1
+  }
+  __syncthreads();
+
+  float2 mu_p[2] = {zero2, zero2}, D_p[2] = {zero2, zero2}, gx_p[2] = {zero2, zero2}, dy_p[2] = {zero2, zero2},
+         dz_p[2] = {zero2, zero2};
+  float* fout = p.f + ((size_t)b * p.nx + x0) * pl + own_off;  // plane x0 is emitted at it = 1
+  const bool edgeL = tq == 0, edgeR = tq == 15;
+
+  // one plane: `PAR` is the parity of the (u, mu) buffers that hold plane c
+  auto plane = [&](auto par_c, int it) {
+    constexpr int PU = decltype(par_c)::value * kM3US, PUn = (1 - decltype(par_c)::value) * kM3US;
+    constexpr int PM = decltype(par_c)::value * kM3MS;
+    // ---- mu, D of plane c: own four points (packed pairs), then the ring point ----
+    float2 mu[2], D[2];
+    {
+      const float4 uyp = ld4(Uown + PU + kM3P), uym = ld4(Uown + PU - kM3P);
+      float uL = __shfl_up_sync(0xffffffffu, u0.w, 1), uR = __shfl_down_sync(0xffffffffu, u0.x, 1);
+      if (edgeL) uL = Uown[PU - 1];
+      if (edgeR) uR = Uown[PU + 4];
+      const float2 uc[2] = {lo2(u0), hi2(u0)};
+      const float2 uxp[2] = {lo2(up), hi2(up)}, uxm[2] = {lo2(um), hi2(um)};
+      const float2 uyp2[2] = {lo2(uyp), hi2(uyp)}, uym2[2] = {lo2(uym), hi2(uym)};
+      const float2 mid = make_float2(u0.y, u0.z);
+      const float2 uzm[2] = {make_float2(uL, u0.x), mid}, uzp[2] = {mid, make_float2(u0.w, uR)};
+#pragma unroll
+      for (int h = 0; h < 2; ++h) mu_of(uc[h], uxp[h], uxm[h], uyp2[h], uym2[h], uzp[h], uzm[h], mu[h], D[h]);
+      *reinterpret_cast<float4*>(Mown + PM) = make_float4(mu[0].x, mu[0].y, mu[1].x, mu[1].y);
+      if constexpr (!DCONST) *reinterpret_cast<float4*>(Mown + PM + kMD) = make_float4(D[0].x, D[0].y, D[1].x, D[1].y);
+    }
+    if (r1) {
+      // same packed expression as the owner of this point in the neighbouring tile: fluxes across tile
+      // edges are bit-identical on both sides
+      float2 rm, rD;
+      mu_of(splat2(ru0), splat2(rup), splat2(rum), splat2(Ur1[PU + kM3P]), splat2(Ur1[PU - kM3P]), splat2(Ur1[PU + 1]),
+            splat2(Ur1[PU - 1]), rm, rD);
+      Mr1[PM] = rm.x;
+      if constexpr (!DCONST) Mr1[PM + kMD] = rD.x;
+    }
+    // plane c+1 becomes visible to the neighbours for the next iteration
+    *reinterpret_cast<float4*>(Uown + PUn) = up;
+    if (r1) Ur1[PUn] = rup;
+    if (r2) Ur2[PUn] = r2up;
+    // z-neighbours of mu inside the warp (tile edges come from the ring after the barrier)
+    float mL = __shfl_up_sync(0xffffffffu, mu[1].y, 1), mR = __shfl_down_sync(0xffffffffu, mu[0].x, 1);
+    float dL = 0.f, dR = 0.f;
+    if constexpr (!DCONST) {
+      dL = __shfl_up_sync(0xffffffffu, D[1].y, 1);
+      dR = __shfl_down_sync(0xffffffffu, D[0].x, 1);
+    }
+    __syncthreads();
+
+    // ---- fluxes: x-face between c-1 and c, in-plane divergence of plane c; emit f of plane c-1 ----
+    {
+      const float4 myp = ld4(Mown + PM + kM3P), mym = ld4(Mown + PM - kM3P);
+      if (edgeL) mL = Mown[PM - 1];
+      if (edgeR) mR = Mown[PM + 4];
+      const float2 myp2[2] = {lo2(myp), hi2(myp)}, mym2[2] = {lo2(mym), hi2(mym)};
+      const float2 mmid = make_float2(mu[0].y, mu[1].x);
+      const float2 mzm[2] = {make_float2(mL, mu[0].x), mmid}, mzp[2] = {mmid, make_float2(mu[1].y, mR)};
+      float2 Dyp2[2], Dym2[2], Dzm[2], Dzp[2];
+      if constexpr (!DCONST) {
+        const float4 dyp = ld4(Mown + PM + kMD + kM3P), dym = ld4(Mown + PM + kMD - kM3P);
+        if (edgeL) dL = Mown[PM + kMD - 1];
+        if (edgeR) dR = Mown[PM + kMD + 4];
+        Dyp2[0] = lo2(dyp); Dyp2[1] = hi2(dyp); Dym2[0] = lo2(dym); Dym2[1] = hi2(dym);
+        const float2 dmid = make_float2(D[0].y, D[1].x);
+        Dzm[0] = make_float2(dL, D[0].x); Dzm[1] = dmid; Dzp[0] = dmid; Dzp[1] = make_float2(D[1].y, dR);
+      }
+      float2 o2[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float2 gx, dy, dz;
+        if constexpr (DCONST) {
+          gx = sub2(mu[h], mu_p[h]);
+          dy = sub2(sub2(myp2[h], mu[h]), sub2(mu[h], mym2[h]));
+          dz = sub2(sub2(mzp[h], mu[h]), sub2(mu[h], mzm[h]));
+        } else {
+          gx = mul2(add2(D_p[h], D[h]), sub2(mu[h], mu_p[h]));
+          dy = sub2(mul2(add2(D[h], Dyp2[h]), sub2(myp2[h], mu[h])), mul2(add2(Dym2[h], D[h]), sub2(mu[h], mym2[h])));
+          dz = sub2(mul2(add2(D[h], Dzp[h]), sub2(mzp[h], mu[h])), mul2(add2(Dzm[h], D[h]), sub2(mu[h], mzm[h])));
+        }
+        // f(c-1) = (cx (gx - gx_prev) + cy dy_prev) + cz dz_prev
+        o2[h] = fma2(dz_p[h], cz, fma2(dy_p[h], cy, mul2(sub2(gx, gx_p[h]), cx)));
+        gx_p[h] = gx;
+        dy_p[h] = dy;
+        dz_p[h] = dz;
+        mu_p[h] = mu[h];
+        if constexpr (!DCONST) D_p[h] = D[h];
+      }
+      if (it >= 1) {
+        *reinterpret_cast<float4*>(fout) = make_float4(o2[0].x, o2[0].y, o2[1].x, o2[1].y);
+        fout += pl;
+      }
+    }
+    // rotate the column registers and prefetch plane c+3
+    um = u0; u0 = up; up = pf;
+    rum = ru0; ru0 = rup; rup = rpf;
+    r2up = r2pf;
+    if (it + 1 < xl) fetch(pf, rpf, r2pf);
+  };
+  // it = -1 .. xl (an even number of planes: xl is a multiple of 8)
+  for (int it = -1; it <= xl; it += 2) {
+    plane(std::integral_constant<int, 0>{}, it);
+    plane(std::integral_constant<int, 1>{}, it + 1);
+  }
+}
+
 // ---- line-FFT functors of the 3-D semi-implicit step -------------------------------------------
 struct LfLoadReal {  // real array -> complex with zero imaginary part
   const float* p;

@@ -55,9 +55,16 @@ def _ch3d(points, h, mu_name="log"):
     from pde_opt_b200.equations import CahnHilliard3DPeriodic
     from pde_opt_b200.functions import ConstantMobility, DegenerateMobility, DoubleWell, LogRegular
 
-    box = tuple((0.0, n * h) for n in points)
+    hs = h if isinstance(h, tuple) else (h, h, h)
+    box = tuple((0.0, n * hh) for n, hh in zip(points, hs))
     dom, odom = Domain(points, box, "dimensionless"), O.Domain(points, box)
-    if mu_name == "log":  # docs/notebooks/optimization_3D.ipynb cell 8: log potential, D = 0.15
+    if mu_name == "logdeg":  # notebooks/optimize_nn_script.py:33-37 closures on a 3-D grid
+        eq = CahnHilliard3DPeriodic(dom, 0.002, LogRegular(3.0), DegenerateMobility())
+        oeq = O.CahnHilliardPeriodic(odom, 0.002, lambda c: O.mu_log(c, 3.0), lambda c: (1 - c) * c, "fd", np.float32)
+    elif mu_name == "dwconst":
+        eq = CahnHilliard3DPeriodic(dom, 0.002, DoubleWell(), ConstantMobility(0.7))
+        oeq = O.CahnHilliardPeriodic(odom, 0.002, O.mu_double_well, lambda c: 0.7 * np.ones_like(c), "fd", np.float32)
+    elif mu_name == "log":  # docs/notebooks/optimization_3D.ipynb cell 8: log potential, D = 0.15
         eq = CahnHilliard3DPeriodic(dom, 0.002, LogRegular(3.0), ConstantMobility(0.15))
         oeq = O.CahnHilliardPeriodic(odom, 0.002, lambda c: O.mu_log(c, 3.0), lambda c: 0.15 * np.ones_like(c), "fd", np.float32)
     else:
@@ -70,9 +77,13 @@ def _u0(points, B, seed=0):
     return np.stack([np.clip(0.5 + 0.01 * np.random.default_rng(seed + i).normal(size=points), 0.01, 0.99) for i in range(B)]).astype(np.float32)
 
 
-@pytest.mark.parametrize("points,mu_name", [((32, 32, 32), "log"), ((16, 32, 64), "dw")])
-def test_ch3d_rhs_matches_oracle(points, mu_name):
-    eq, oeq = _ch3d(points, 0.01, mu_name)
+@pytest.mark.parametrize("points,mu_name,h", [((32, 32, 32), "log", 0.01), ((16, 32, 64), "dw", 0.01),
+                                              # register-marching kernel (ny % 16 == 0, nz % 64 == 0): every closure
+                                              # specialisation, several tiles per axis, anisotropic spacing
+                                              ((16, 32, 128), "log", 0.01), ((8, 48, 64), "logdeg", (0.01, 0.012, 0.008)),
+                                              ((24, 16, 192), "dwconst", (0.02, 0.01, 0.015)), ((64, 64, 64), "dw", 0.01)])
+def test_ch3d_rhs_matches_oracle(points, mu_name, h):
+    eq, oeq = _ch3d(points, h, mu_name)
     u = _u0(points, 2)
     f = eq.rhs(torch.from_numpy(u).cuda()).cpu().numpy()
     o64 = O.CahnHilliardPeriodic(oeq.domain, 0.002, oeq.mu, oeq.D, "fd", np.float64)
