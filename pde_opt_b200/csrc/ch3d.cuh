@@ -212,10 +212,12 @@ __global__ void __launch_bounds__(kC3Threads) ch3d_rhs_fused_kernel(const __grid
 // ---- register-marching single-pass RHS ----------------------------------------------------------
 // Same tile (16 x 64 points of a (y, z) plane per 256-thread CTA, marching along x) as the kernel
 // above, but every thread keeps the x-column of its four consecutive z points in registers and
-// shared memory only carries what NEIGHBOURS need: one plane of u (tile + halo 2) and one plane of
-// (mu, D) (tile + ring 1), both double buffered, so one barrier per plane.  128-bit shared and global
-// accesses, z-neighbours inside a warp by shuffle, packed f32x2 arithmetic; 160 threads additionally
-// march one ring point each.  The loop body is instantiated for both buffer parities so that every
+// shared memory only carries what NEIGHBOURS need: planes of u (tile + halo 2) and of (mu, D)
+// (tile + ring 1).  u planes arrive by cp.async into a four-stage ring (planes c .. c+3: three planes
+// per CTA in flight, which is what it takes to cover HBM latency at three CTAs per SM); (mu, D) are
+// double buffered, so there is one barrier per plane.  128-bit shared and global accesses,
+// z-neighbours inside a warp by shuffle, packed f32x2 arithmetic; 20 lanes of every warp additionally
+// march one ring point each.  The loop body is instantiated per ring stage so that every
 // shared-memory access is base register + immediate.
 //   f = cx (Gx - Gx_prev) + cy (Gy+ - Gy-) + cz (Gz+ - Gz-),  G = (D + D_nbr) (mu_nbr - mu), c = 1/(2h^2)
 // (cahn_hilliard.py:177-200 with the constant factors collected as in sifs128.cuh; a few ulp).
@@ -223,24 +225,30 @@ constexpr int kM3P = 76;            // row pitch in floats: 4 halo columns | 64 
                                     // column-ring accesses (one per row) at two per bank
 constexpr int kM3UR = kC3TY + 4;    // u rows (halo 2)
 constexpr int kM3MR = kC3TY + 2;    // mu / D rows (ring 1)
+constexpr int kM3NS = 4;            // u stages
 constexpr int kM3US = kM3UR * kM3P, kM3MS = kM3MR * kM3P;  // buffer strides
 
 struct Ch3dMarchSmem {
-  float U[2][kM3UR][kM3P];   // [y_local + 2][z_local + 4]
-  float Mu[2][kM3MR][kM3P];  // [y_local + 1][z_local + 4]
+  float U[kM3NS][kM3UR][kM3P];  // [y_local + 2][z_local + 4]
+  float Mu[2][kM3MR][kM3P];     // [y_local + 1][z_local + 4]
   float Dm[2][kM3MR][kM3P];
 };
 
 __device__ __forceinline__ float2 lo2(float4 v) { return make_float2(v.x, v.y); }
 __device__ __forceinline__ float2 hi2(float4 v) { return make_float2(v.z, v.w); }
 __device__ __forceinline__ float4 ld4(const float* q) { return *reinterpret_cast<const float4*>(q); }
-
-#ifndef PDEOPT_M3_MINB
-#define PDEOPT_M3_MINB 3
-#endif
+__device__ __forceinline__ void cp_async16(float* smem, const float* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* smem, const float* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int MU, int MOB>
-__global__ void __launch_bounds__(kC3Threads, PDEOPT_M3_MINB) ch3d_rhs_march_kernel(const __grid_constant__ Ch3dParams p, int xl) {
+__global__ void __launch_bounds__(kC3Threads, 3) ch3d_rhs_march_kernel(const __grid_constant__ Ch3dParams p, int xl) {
   __shared__ __align__(16) Ch3dMarchSmem S;
   constexpr bool DCONST = (MOB == MOB_CONST);
   const int tid = threadIdx.x;
@@ -251,25 +259,29 @@ __global__ void __launch_bounds__(kC3Threads, PDEOPT_M3_MINB) ch3d_rhs_march_ker
   const int own_off = (y0 + ty) * p.nz + z0 + 4 * tq;
   const size_t pl = (size_t)p.ny * p.nz;
 
-  // ring roles: threads 0..159 march one ring-1 point (mu, D needed there); threads 92..255 stage one
-  // ring-2 / corner point of u (only neighbours read it)
+  // ring roles, spread evenly over the 8 warps so that no warp is late at the barrier: lanes 0..19 of
+  // every warp march one ring-1 point (mu, D needed there), lanes 0..20 stage one ring-2 / corner
+  // point of u (only neighbours read it)
   auto wrap_off = [&](int yl, int zl) {
     int gy = y0 + yl, gz = z0 + zl;
     gy = gy < 0 ? gy + p.ny : (gy >= p.ny ? gy - p.ny : gy);
     gz = gz < 0 ? gz + p.nz : (gz >= p.nz ? gz - p.nz : gz);
     return gy * p.nz + gz;
   };
-  const bool r1 = tid < 160;
+  const int lane = tid & 31, warp = tid >> 5;
+  const bool r1 = lane < 20;
+  const int ri = warp * 20 + lane;
   int r1y = 0, r1z = 0;
-  if (tid < 64) { r1y = -1; r1z = tid; }
-  else if (tid < 128) { r1y = kC3TY; r1z = tid - 64; }
-  else if (tid < 144) { r1y = tid - 128; r1z = -1; }
-  else if (tid < 160) { r1y = tid - 144; r1z = kC3TZ; }
+  if (ri < 64) { r1y = -1; r1z = ri; }
+  else if (ri < 128) { r1y = kC3TY; r1z = ri - 64; }
+  else if (ri < 144) { r1y = ri - 128; r1z = -1; }
+  else if (ri < 160) { r1y = ri - 144; r1z = kC3TZ; }
   const int r1_off = wrap_off(r1y, r1z);
-  const bool r2 = tid >= 92;
+  const int rj = warp * 21 + lane;
+  const bool r2 = lane < 21 && rj < 164;
   int r2y = 0, r2z = 0;
-  {
-    const int j = tid - 92;
+  if (r2) {
+    const int j = rj;
     if (j < 64) { r2y = -2; r2z = j; }
     else if (j < 128) { r2y = kC3TY + 1; r2z = j - 64; }
     else if (j < 144) { r2y = j - 128; r2z = -2; }
@@ -277,7 +289,7 @@ __global__ void __launch_bounds__(kC3Threads, PDEOPT_M3_MINB) ch3d_rhs_march_ker
     else { r2y = (j & 2) ? kC3TY : -1; r2z = (j & 1) ? kC3TZ : -1; }
   }
   const int r2_off = r2 ? wrap_off(r2y, r2z) : 0;
-  // per-thread shared-memory bases (buffer 0); the other buffer is a compile-time offset away
+  // per-thread shared-memory bases (stage / buffer 0); the others are compile-time offsets away
   float* const Uown = &S.U[0][ty + 2][4 + 4 * tq];
   float* const Ur1 = &S.U[0][r1y + 2][r1z + 4];
   float* const Ur2 = &S.U[0][r2y + 2][r2z + 4];
@@ -302,41 +314,51 @@ __global__ void __launch_bounds__(kC3Threads, PDEOPT_M3_MINB) ch3d_rhs_march_ker
     mu = fma2(lap, mkappa, mh);
   };
 
-  // marching registers: planes c-1, c, c+1 and the prefetched c+2.  The plane pointer advances by one
-  // plane per fetch and is re-derived only where the periodic wrap / slab halo changes the array.
-  float4 um, u0, up, pf;
-  float rum = 0.f, ru0 = 0.f, rup = 0.f, rpf = 0.f, r2up = 0.f, r2pf = 0.f;
+  // asynchronous plane copies: the plane pointer advances by one plane per issue and is re-derived
+  // only where the periodic wrap / slab halo changes the array.  One commit group per plane (empty
+  // past the last plane, so the wait counts stay uniform).
   int xnext = x0 - 2;
+  const int xlast = x0 + xl + 1;
   const float* pnext = ch3d_plane(p, b, xnext);
-  auto fetch = [&](float4& v, float& rv, float& r2v) {
-    v = __ldg(reinterpret_cast<const float4*>(pnext + own_off));
-    if (r1) rv = __ldg(pnext + r1_off);
-    if (r2) r2v = __ldg(pnext + r2_off);
-    ++xnext;
-    pnext += pl;
-    if (xnext == 0 || xnext == p.nx) pnext = ch3d_plane(p, b, xnext);
+  auto issue = [&](int stage_off) {
+    if (xnext <= xlast) {
+      cp_async16(Uown + stage_off, pnext + own_off);
+      if (r1) cp_async4(Ur1 + stage_off, pnext + r1_off);
+      if (r2) cp_async4(Ur2 + stage_off, pnext + r2_off);
+      ++xnext;
+      pnext += pl;
+      if (xnext == 0 || xnext == p.nx) pnext = ch3d_plane(p, b, xnext);
+    }
+    cp_async_commit();
   };
-  {
-    float dummy = 0.f;
-    fetch(um, rum, dummy);      // x0 - 2
-    fetch(u0, ru0, r2up);       // x0 - 1
-    *reinterpret_cast<float4*>(Uown) = u0;
-    if (r1) *Ur1 = ru0;
-    if (r2) *Ur2 = r2up;
-    fetch(up, rup, r2up);       // x0
-    fetch(pf, rpf, r2pf);       // x0 + 1
+  issue(0 * kM3US);  // x0 - 2
+  issue(1 * kM3US);  // x0 - 1
+  issue(2 * kM3US);  // x0
+  issue(3 * kM3US);  // x0 + 1
+  cp_async_wait<2>();
+  // column registers: planes c-1, c (c+1 is read from its stage when needed)
+  float4 um = ld4(Uown), u0 = ld4(Uown + kM3US), up;
+  float rum = 0.f, ru0 = 0.f, rup = 0.f;
+  if (r1) {
+    rum = Ur1[0];
+    ru0 = Ur1[kM3US];
   }
-  __syncthreads();
+  __syncthreads();     // plane x0 - 1 visible to everybody; stage 0 free again
+  issue(0 * kM3US);    // x0 + 2
 
   float2 mu_p[2] = {zero2, zero2}, D_p[2] = {zero2, zero2}, gx_p[2] = {zero2, zero2}, dy_p[2] = {zero2, zero2},
          dz_p[2] = {zero2, zero2};
   float* fout = p.f + ((size_t)b * p.nx + x0) * pl + own_off;  // plane x0 is emitted at it = 1
   const bool edgeL = tq == 0, edgeR = tq == 15;
 
-  // one plane: `PAR` is the parity of the (u, mu) buffers that hold plane c
-  auto plane = [&](auto par_c, int it) {
-    constexpr int PU = decltype(par_c)::value * kM3US, PUn = (1 - decltype(par_c)::value) * kM3US;
-    constexpr int PM = decltype(par_c)::value * kM3MS;
+  // one plane c held in stage ST (planes c+1 .. c+3 follow in the ring)
+  auto plane = [&](auto st_c, int it) {
+    constexpr int ST = decltype(st_c)::value;
+    constexpr int PU = ST * kM3US, PUn = ((ST + 1) % kM3NS) * kM3US;
+    constexpr int PM = (ST & 1) * kM3MS;
+    cp_async_wait<2>();  // this thread's part of plane c+1 has landed
+    up = ld4(Uown + PUn);
+    if (r1) rup = Ur1[PUn];
     // ---- mu, D of plane c: own four points (packed pairs), then the ring point ----
     float2 mu[2], D[2];
     {
@@ -363,10 +385,6 @@ __global__ void __launch_bounds__(kC3Threads, PDEOPT_M3_MINB) ch3d_rhs_march_ker
       Mr1[PM] = rm.x;
       if constexpr (!DCONST) Mr1[PM + kMD] = rD.x;
     }
-    // plane c+1 becomes visible to the neighbours for the next iteration
-    *reinterpret_cast<float4*>(Uown + PUn) = up;
-    if (r1) Ur1[PUn] = rup;
-    if (r2) Ur2[PUn] = r2up;
     // z-neighbours of mu inside the warp (tile edges come from the ring after the barrier)
     float mL = __shfl_up_sync(0xffffffffu, mu[1].y, 1), mR = __shfl_down_sync(0xffffffffu, mu[0].x, 1);
     float dL = 0.f, dR = 0.f;
@@ -374,7 +392,8 @@ __global__ void __launch_bounds__(kC3Threads, PDEOPT_M3_MINB) ch3d_rhs_march_ker
       dL = __shfl_up_sync(0xffffffffu, D[1].y, 1);
       dR = __shfl_down_sync(0xffffffffu, D[0].x, 1);
     }
-    __syncthreads();
+    __syncthreads();  // (mu, D) of plane c complete; plane c+1 landed for everybody; stage ST free
+    issue(PU);        // plane c+4
 
     // ---- fluxes: x-face between c-1 and c, in-plane divergence of plane c; emit f of plane c-1 ----
     {
@@ -419,17 +438,20 @@ __global__ void __launch_bounds__(kC3Threads, PDEOPT_M3_MINB) ch3d_rhs_march_ker
         fout += pl;
       }
     }
-    // rotate the column registers and prefetch plane c+3
-    um = u0; u0 = up; up = pf;
-    rum = ru0; ru0 = rup; rup = rpf;
-    r2up = r2pf;
-    if (it + 1 < xl) fetch(pf, rpf, r2pf);
+    um = u0; u0 = up;
+    rum = ru0; ru0 = rup;
   };
-  // it = -1 .. xl (an even number of planes: xl is a multiple of 8)
-  for (int it = -1; it <= xl; it += 2) {
-    plane(std::integral_constant<int, 0>{}, it);
-    plane(std::integral_constant<int, 1>{}, it + 1);
+  // it = -1 .. xl: xl + 2 planes, starting in stage 1 (xl is a multiple of 8, so 4k + 2 planes)
+  int it = -1;
+  for (; it + 3 <= xl; it += 4) {
+    plane(std::integral_constant<int, 1>{}, it);
+    plane(std::integral_constant<int, 2>{}, it + 1);
+    plane(std::integral_constant<int, 3>{}, it + 2);
+    plane(std::integral_constant<int, 0>{}, it + 3);
   }
+  plane(std::integral_constant<int, 1>{}, it);
+  plane(std::integral_constant<int, 2>{}, it + 1);
+  cp_async_wait<0>();
 }
 
 // ---- line-FFT functors of the 3-D semi-implicit step -------------------------------------------
