@@ -172,6 +172,17 @@ pdeopt_status pdeopt_strang_step_batched(const pdeopt_gpe_desc* desc, const floa
                                          const float* a_term_dev, float ts_re, float ts_im, const float* ctrl_dev,
                                          void* stream);
 
+/* Quantised-vortex detection on batched GPE states: integer phase circulation of every grid cell
+ * (pde_opt/rl_utils.py:19-84, detect_vortices; the reward helper of the GPE environments).
+ *   psi_dev     : [batch][n0][n1][2] float32 (re, im)
+ *   amp_thresh  : cells whose corner-averaged density is below it are suppressed (0 = off)
+ *   tol         : keep windings with |circulation| >= tol * 2 pi
+ *   winding_dev : [batch][n0][n1] int32 or NULL
+ *   counts_dev  : [batch][3] int32 = (num_vortices, total_topological_charge, abs_charge_count) */
+pdeopt_status pdeopt_gpe_detect_vortices(const float* psi_dev, int32_t batch, int32_t n0, int32_t n1,
+                                         float amp_thresh, float tol, int32_t* winding_dev, int32_t* counts_dev,
+                                         void* stream);
+
 /* Advection-diffusion (recovered equation; notebooks/run_advection_diffusion.ipynb
  * cells 0-2): du/dt = -div(v u) + D lap(u), spectral derivatives, v = p0 grad exp(-r^2/(2 p1))
  * about a controlled centre, stepped by SemiImplicitFourierSpectral.step (solvers.py:56-70). */

@@ -427,3 +427,43 @@ def initialize_Psi(N, width=100, vortexnumber=0):
         phi = vortexnumber * np.arctan2((i - N // 2), (j - N // 2))
         psi = psi * np.exp(1.0j * np.mod(phi, 2 * np.pi))
     return psi
+
+
+def detect_vortices(psi, amp_thresh=0.0, tol=0.5):
+    """pde_opt/rl_utils.py:19-84: integer phase circulation of every plaquette of a periodic grid."""
+    two_pi = 2.0 * np.pi
+
+    def wrap(x):  # rl_utils.py:15-17
+        return (x + np.pi) % two_pi - np.pi
+
+    theta = np.angle(psi)
+    dth_x = wrap(np.roll(theta, -1, axis=1) - theta)
+    dth_y = wrap(np.roll(theta, -1, axis=0) - theta)
+    circulation = dth_x + np.roll(dth_y, -1, axis=1) - np.roll(dth_x, -1, axis=0) - dth_y
+    n_float = circulation / two_pi
+    n_int = np.rint(n_float).astype(np.int32)
+    n_int = np.where(np.abs(n_float) >= tol, n_int, 0)
+    if amp_thresh > 0.0:
+        rho = np.abs(psi) ** 2
+        rho_cell = 0.25 * (rho + np.roll(rho, -1, axis=0) + np.roll(rho, -1, axis=1) + np.roll(rho, (-1, -1), axis=(0, 1)))
+        n_int = np.where(rho_cell >= amp_thresh, n_int, 0)
+    idx = np.argwhere(n_int != 0)
+    charges = n_int[n_int != 0]
+    return {
+        "winding": n_int,
+        "positions": idx.astype(np.float32) + 0.5,
+        "charges": charges,
+        "num_vortices": idx.shape[0],
+        "total_topological_charge": int(charges.sum()),
+        "abs_charge_count": int(np.abs(charges).sum()),
+    }
+
+
+def vortex_test_field(N, centres):
+    """product of (z - z_k)^(q_k) / |.| phase factors times a smooth envelope: known windings"""
+    i, j = np.meshgrid(np.arange(N) + 0.0, np.arange(N) + 0.0, indexing="ij")
+    psi = np.ones((N, N), complex)
+    for (ci, cj, q) in centres:
+        z = (j - cj) + 1j * (i - ci)
+        psi *= (z / np.abs(z)) ** q
+    return psi * np.exp(-((i - N / 2) ** 2 + (j - N / 2) ** 2) / (0.18 * N * N))

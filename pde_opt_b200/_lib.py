@@ -114,6 +114,7 @@ EXPORTS = [
     "pdeopt_phasefield_adjoint_work_floats",
     "pdeopt_phasefield_adjoint_step",
     "pdeopt_strang_step_batched",
+    "pdeopt_gpe_detect_vortices",
     "pdeopt_ad_tables_len",
     "pdeopt_ad_rollout_fwd",
     "pdeopt_ad_rollout_bwd",
@@ -170,6 +171,8 @@ def load():
     lib.pdeopt_phasefield_adjoint_step.restype = ctypes.c_int
     lib.pdeopt_strang_step_batched.argtypes = [ctypes.POINTER(GpeDesc), vp, vp, i32, i32, vp, vp, f32, f32, vp, vp]
     lib.pdeopt_strang_step_batched.restype = ctypes.c_int
+    lib.pdeopt_gpe_detect_vortices.argtypes = [vp, i32, i32, i32, f32, f32, vp, vp, vp]
+    lib.pdeopt_gpe_detect_vortices.restype = ctypes.c_int
     i64 = ctypes.c_int64
     lib.pdeopt_ad_tables_len.argtypes = [ctypes.POINTER(AdDesc)]
     lib.pdeopt_ad_tables_len.restype = ctypes.c_int64

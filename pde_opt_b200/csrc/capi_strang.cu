@@ -1,6 +1,7 @@
 // C ABI: fused 128x128 Strang split-step (see include/pdeopt_b200.h).
 #include "capi_common.h"
 #include "strang128.cuh"
+#include "vortex.cuh"
 using namespace pdeopt;
 
 extern "C" pdeopt_status pdeopt_strang_step_batched(const pdeopt_gpe_desc* desc, const float* y0_dev, float* y1_dev,
@@ -47,3 +48,24 @@ extern "C" pdeopt_status pdeopt_strang_step_batched(const pdeopt_gpe_desc* desc,
   return PDEOPT_OK;
 }
 
+
+extern "C" pdeopt_status pdeopt_gpe_detect_vortices(const float* psi_dev, int32_t batch, int32_t n0, int32_t n1,
+                                                    float amp_thresh, float tol, int32_t* winding_dev,
+                                                    int32_t* counts_dev, void* stream) {
+  if (!psi_dev || !counts_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
+  if (batch <= 0 || batch > 65535 || n0 < 2 || n1 < 2) return fail(PDEOPT_ERR_INVALID, "detect_vortices: bad sizes");
+  VortexParams p;
+  p.psi = reinterpret_cast<const float2*>(psi_dev);
+  p.winding = winding_dev;
+  p.counts = counts_dev;
+  p.n0 = n0; p.n1 = n1; p.batch = batch;
+  p.amp_thresh = amp_thresh; p.tol = tol;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemsetAsync(counts_dev, 0, sizeof(int32_t) * 3 * (size_t)batch, st));
+  dim3 grid((n1 + 31) / 32, (n0 + 7) / 8, batch);
+  vortex_kernel<<<grid, 256, 0, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("detect_vortices: ") + cudaGetErrorString(e));
+  g_launches.fetch_add(1);
+  return PDEOPT_OK;
+}

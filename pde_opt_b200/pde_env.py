@@ -127,7 +127,8 @@ class PDEVecEnv:
     The control is the C-ABI control block (include/pdeopt_b200.h): `action_to_control(actions,
     ctrl)` is a user callback that writes the [B, 8] float32 block (device tensor) from the
     actions; observation (uint8, Box(0,255,(1,*points))) and reward (variance by default, the
-    reference notebooks' `np.var`) come from the kernel epilogue.  Environments whose time
+    reference notebooks' `np.var`; "mean"; or ("probe", i, j) for the value at one grid point) come from
+    the kernel epilogue.  Environments whose time
     reaches `end_time` are reset automatically (pde_env.py:206-215 gives the criterion)."""
 
     def __init__(self, equation, solver, num_envs, end_time, step_dt, numeric_dt, reset_func,
@@ -183,7 +184,10 @@ class PDEVecEnv:
         )
         self.state, self._next = self._next, self.state
         self.time += self.step_dt
-        reward = self.stats[:, 1] if self.reward_kind == "var" else self.stats[:, 0]
+        if isinstance(self.reward_kind, tuple) and self.reward_kind[0] == "probe":
+            reward = self.state[:, self.reward_kind[1], self.reward_kind[2]]  # point probe of the new state
+        else:
+            reward = self.stats[:, 1] if self.reward_kind == "var" else self.stats[:, 0]
         terminated = self.time >= self.end_time
         if self.auto_reset and terminated.any():
             for b in np.nonzero(terminated)[0]:

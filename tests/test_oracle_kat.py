@@ -225,3 +225,22 @@ def test_torch_phasefield_gradient_oracle_matches_numpy_oracle():
         yt = TO.rollout(torch.from_numpy(u)[None], [1e-6] * 4, (n, n), box, 0.002, A, lambda c: TO.mu_legendre(tm, c, True),
                         lambda c: TO.D_legendre(td, c), kind)
         assert np.abs(yt[0].numpy() - y).max() <= 1e-13
+
+
+def test_detect_vortices_oracle_counts_known_windings():
+    """pde_opt/rl_utils.py:19-84 restated: four singly quantised vortices at cell centres inside the
+    grid; a periodic field has zero total circulation, so the remaining charge sits on the boundary
+    cells where the non-periodic test field jumps — the amplitude mask removes those."""
+    N = 64
+    centres = [(20.5, 20.5, 1), (40.5, 24.5, -1), (30.5, 44.5, 1), (44.5, 44.5, 1)]
+    psi = O.vortex_test_field(N, centres)
+    amp = 0.15  # corner-averaged density is ~0.4 at the four cores and < 0.07 on the boundary
+    r = O.detect_vortices(psi, amp_thresh=amp, tol=0.5)
+    w = r["winding"]
+    for (ci, cj, q) in centres:
+        assert w[int(ci), int(cj)] == q
+    assert r["num_vortices"] == 4 and r["total_topological_charge"] == 2 and r["abs_charge_count"] == 4
+    assert np.array_equal(np.sort(r["charges"]), np.array([-1, 1, 1, 1]))
+    assert r["positions"].shape == (4, 2) and np.allclose(r["positions"] % 1.0, 0.5)
+    # without the mask the periodic plaquette sum vanishes identically (Stokes on a torus)
+    assert O.detect_vortices(psi)["total_topological_charge"] == 0
