@@ -12,6 +12,7 @@
 //
 // The header is host-compilable (tests/test_regfft_host.py builds it with g++).
 #pragma once
+#include <cmath>
 #include <type_traits>
 
 #if defined(__CUDACC__)
@@ -143,6 +144,14 @@ PDEOPT_HD float2 mul_tw(float2 a) {
   }
 }
 
+// true when w_N^J is none of the cases mul_tw specialises (1, -1, +-i, 8th roots)
+template <int N, int J>
+constexpr bool tw_is_general() {
+  constexpr int Jm = ((J % N) + N) % N;
+  return !(Jm == 0 || Jm * 4 == N || Jm * 2 == N || Jm * 4 == 3 * N || Jm * 8 == N || Jm * 8 == 3 * N || Jm * 8 == 5 * N ||
+           Jm * 8 == 7 * N);
+}
+
 template <int I, int E, class F>
 PDEOPT_HD void static_for(F&& f) {
   if constexpr (I < E) {
@@ -178,9 +187,22 @@ struct Dit {
       Dit<N / 2, S, INV>::run(x + (N / 2) * S);
       static_for<0, N / 2>([&](auto jc) {
         constexpr int j = decltype(jc)::value;
-        float2 a = x[j * S], b = mul_tw<N, j, INV>(x[(j + N / 2) * S]);
-        x[j * S] = cadd(a, b);
-        x[(j + N / 2) * S] = csub(a, b);
+        if constexpr (tw_is_general<N, j>()) {
+          // a + w b by four FMAs, a - w b = 2a - (a + w b) by two more: six pipe slots per butterfly
+          // instead of eight (the FP32 pipe charges an add like an FMA)
+          constexpr float wr = Tw<N, j>::re;
+          constexpr float wi = INV ? -Tw<N, j>::im : Tw<N, j>::im;
+          const float2 a = x[j * S], b = x[(j + N / 2) * S];
+          float2 p;
+          p.x = fmaf(wr, b.x, fmaf(-wi, b.y, a.x));
+          p.y = fmaf(wr, b.y, fmaf(wi, b.x, a.y));
+          x[j * S] = p;
+          x[(j + N / 2) * S] = make_float2(fmaf(2.0f, a.x, -p.x), fmaf(2.0f, a.y, -p.y));
+        } else {
+          float2 a = x[j * S], b = mul_tw<N, j, INV>(x[(j + N / 2) * S]);
+          x[j * S] = cadd(a, b);
+          x[(j + N / 2) * S] = csub(a, b);
+        }
       });
     }
   }
