@@ -148,3 +148,46 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libpdeopt_b200.so")
     with pytest.raises(_lib.PdeOptError, match="no CPU fallback"):
         _lib.load()
+
+
+def test_compute_entry_points_reject_bad_arguments_before_touching_the_gpu():
+    """Error behaviour of the C ABI (include/pdeopt_b200.h: every function returns a status, never throws):
+    argument validation happens before any CUDA call, so it can be checked on a machine without a GPU.
+    Fake non-null pointers are never dereferenced on these paths."""
+    lib = _lib.load()
+    fake = ctypes.c_void_p(0x1000)
+    dts = (ctypes.c_float * 600)(*([1e-6] * 600))
+    d = _lib.PlanDesc()
+    d.kind, d.derivs, d.nx, d.ny, d.hx, d.hy, d.kappa = _lib.KIND_CH2D, _lib.DERIVS_FD, 128, 128, 0.01, 0.01, 0.002
+    h = ctypes.c_void_p()
+    assert lib.pdeopt_plan_create(ctypes.byref(d), ctypes.byref(h)) == _lib.OK
+    step = lib.pdeopt_sifs_step_batched
+    assert step(None, fake, fake, 1, 1, dts, fake, None, None, 0.0, 1.0, None, None) == _lib.ERR_INVALID
+    assert step(h, None, fake, 1, 1, dts, fake, None, None, 0.0, 1.0, None, None) == _lib.ERR_INVALID
+    assert step(h, fake, fake, 0, 1, dts, fake, None, None, 0.0, 1.0, None, None) == _lib.ERR_INVALID  # empty batch
+    assert step(h, fake, fake, 1, 0, dts, fake, None, None, 0.0, 1.0, None, None) == _lib.ERR_INVALID
+    assert step(h, fake, fake, 1, 513, dts, fake, None, None, 0.0, 1.0, None, None) == _lib.ERR_INVALID  # > PDEOPT_MAX_FUSED_STEPS
+    assert lib.pdeopt_last_error() != b""
+    assert lib.pdeopt_rhs_batched(h, None, fake, 1, None, None) == _lib.ERR_INVALID
+    lib.pdeopt_plan_destroy(h)
+
+    g = _lib.GpeDesc()
+    g.nx, g.ny, g.hx, g.hy = 64, 64, 0.1, 0.1
+    assert lib.pdeopt_strang_step_batched(ctypes.byref(g), fake, fake, 1, 1, dts, None, 0.0, -1.0, None, None) == _lib.ERR_UNSUPPORTED
+    g.nx, g.ny = 128, 128
+    assert lib.pdeopt_strang_step_batched(ctypes.byref(g), fake, fake, 0, 1, dts, None, 0.0, -1.0, None, None) == _lib.ERR_INVALID
+    assert lib.pdeopt_strang_step_batched(ctypes.byref(g), None, fake, 1, 1, dts, None, 0.0, -1.0, None, None) == _lib.ERR_INVALID
+
+    assert lib.pdeopt_fft_pos_to_freq(100, 0) == -1 and lib.pdeopt_fft_pos_to_freq(64, 64) == -1
+    geom = _lib.LineGeom()
+    assert lib.pdeopt_fft_lines(fake, fake, 100, ctypes.byref(geom), ctypes.byref(geom), 0, 0, 1.0, None) == _lib.ERR_UNSUPPORTED
+
+    c = _lib.Ch3dDesc()
+    c.nx, c.ny, c.nz, c.hx, c.hy, c.hz, c.kappa = 48, 32, 32, 0.01, 0.01, 0.01, 0.002
+    assert lib.pdeopt_ch3d_step(ctypes.byref(c), fake, fake, 1, 1, dts, fake, fake, None) == _lib.ERR_UNSUPPORTED  # 48 is not 2^k
+    c.nx = 32
+    assert lib.pdeopt_ch3d_step(ctypes.byref(c), fake, fake, 1, 0, dts, fake, fake, None) == _lib.ERR_INVALID
+    assert lib.pdeopt_ch3d_rhs(ctypes.byref(c), None, None, None, fake, fake, 1, None) == _lib.ERR_INVALID
+
+    assert lib.pdeopt_gpe_detect_vortices(None, 1, 64, 64, 0.0, 0.5, None, fake, None) == _lib.ERR_INVALID
+    assert lib.pdeopt_gpe_detect_vortices(fake, 0, 64, 64, 0.0, 0.5, None, fake, None) == _lib.ERR_INVALID
