@@ -175,13 +175,40 @@ class PDEVecEnv:
         self.obs[:, 0] = torch.round(q).to(torch.uint8)
         return self.obs
 
-    def step(self, actions):
+    def step(self, actions, obs_host=None, stats_host=None, chunks=4):
+        """One env step of all B environments.  With pinned host tensors `obs_host` [B, 1, nx, ny] uint8
+        and `stats_host` [B, 2] float32 the batch is stepped in `chunks` slices on separate streams, so
+        that the device->host copy of one slice's observation overlaps the next slice's kernel; the
+        call returns when everything has landed on the host."""
         if self.action_to_control is not None:
             self.action_to_control(actions, self.ctrl)
-        self.solver.rollout(
-            self._terms, self._times, self.state, ctrl=self.ctrl, obs=self.obs, obs_range=self.obs_range,
-            reward=self.stats, out=self._next,
-        )
+        if obs_host is None:
+            self.solver.rollout(
+                self._terms, self._times, self.state, ctrl=self.ctrl, obs=self.obs, obs_range=self.obs_range,
+                reward=self.stats, out=self._next,
+            )
+        else:
+            chunks = max(1, min(int(chunks), self.B // 2))
+            if not hasattr(self, "_streams") or len(self._streams) != chunks:
+                self._streams = [torch.cuda.Stream(device=self.device) for _ in range(chunks)]
+            main = torch.cuda.current_stream(self.device)
+            step = 2 * ((self.B + 2 * chunks - 1) // (2 * chunks))  # even slices: two environments share a CTA
+            for c, st in enumerate(self._streams):
+                lo, hi = c * step, min(self.B, (c + 1) * step)
+                if lo >= hi:
+                    break
+                st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    self.solver.rollout(
+                        self._terms, self._times, self.state[lo:hi], ctrl=self.ctrl[lo:hi], obs=self.obs[lo:hi],
+                        obs_range=self.obs_range, reward=self.stats[lo:hi], out=self._next[lo:hi],
+                    )
+                    obs_host[lo:hi].copy_(self.obs[lo:hi], non_blocking=True)
+                    if stats_host is not None:
+                        stats_host[lo:hi].copy_(self.stats[lo:hi], non_blocking=True)
+            for st in self._streams:
+                main.wait_stream(st)
+            main.synchronize()
         self.state, self._next = self._next, self.state
         self.time += self.step_dt
         if isinstance(self.reward_kind, tuple) and self.reward_kind[0] == "probe":

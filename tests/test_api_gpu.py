@@ -184,6 +184,16 @@ def test_vec_env_matches_single_envs():
         np.testing.assert_allclose(float(reward[b]), y.astype(np.float64).var(), rtol=1e-3)
         assert (obs[b, 0].cpu().numpy() == O.quantise_obs(env.state[b].cpu().numpy())[0]).mean() > 0.999
     assert not term.any() and not trunc.any()
+    # host delivery: slices on separate streams, observation / reward copies overlapped with the kernels;
+    # identical results, on the host when the call returns
+    env2 = PDEVecEnv(eq, solver, B, end_time=1.0, step_dt=1.6e-5, numeric_dt=1e-6, reset_func=lambda d, seed=None: ic(seed or 0),
+                     action_to_control=act)
+    env2.reset(seed=100)
+    obs_h = torch.empty((B, 1, N, N), dtype=torch.uint8).pin_memory()
+    st_h = torch.empty((B, 2), dtype=torch.float32).pin_memory()
+    env2.step(actions, obs_host=obs_h, stats_host=st_h, chunks=2)
+    assert torch.equal(env2.state, env.state)
+    assert torch.equal(obs_h, obs.cpu()) and torch.equal(st_h, env.stats.cpu())
 
 
 def test_pde_env_with_advection_diffusion_and_gpe():
