@@ -467,3 +467,49 @@ def vortex_test_field(N, centres):
         z = (j - cj) + 1j * (i - ci)
         psi *= (z / np.abs(z)) ** q
     return psi * np.exp(-((i - N / 2) ** 2 + (j - N / 2) ** 2) / (0.18 * N * N))
+
+
+def integrate_adaptive(step_err_fn, y0, t0, t1, dt0, rtol, atol, save_ts=None, order=1, pcoeff=0.0, icoeff=1.0, dcoeff=0.0,
+                       factormin=0.2, factormax=10.0, safety=0.9, max_steps=1_000_000):
+    """diffeqsolve with diffrax's PIDController (third-party, restated from its published algorithm;
+    call site pde_model.py:120-134 with `stepsize_controller=PIDController(rtol, atol)`).
+    ``step_err_fn(y, ta, tb) -> (y1, y_error)`` (solvers.py:56-70).  Returns (ys at save_ts or the final
+    state, accepted, rejected)."""
+    dtype = y0.dtype
+    tt = dtype.type
+    t, t1 = tt(t0), tt(t1)
+    save_ts = None if save_ts is None else np.asarray(save_ts, dtype=dtype)
+    out = None if save_ts is None else np.full((len(save_ts),) + y0.shape, np.inf, dtype=dtype)
+    si = 0
+    y = y0
+    if save_ts is not None:
+        while si < len(save_ts) and save_ts[si] <= t:
+            out[si] = y
+            si += 1
+    dt, prev, prev_prev = float(dt0), 1.0, 1.0
+    acc = rej = 0
+    for _ in range(max_steps):
+        if not t < t1:
+            break
+        tn = tt(t + tt(dt))
+        if tn > t1 - tt(1e-6) or tn >= t1:
+            tn = t1
+        y1, y_err = step_err_fn(y, t, tn)
+        scale = atol + np.maximum(np.abs(y), np.abs(y1)) * rtol
+        err = float(np.sqrt(np.mean((y_err / scale).astype(np.float64) ** 2)))
+        keep = err < 1.0
+        inv = 1.0 / err if (err > 0.0 and np.isfinite(err)) else (1.0 if err == 0.0 else 0.0)
+        b1, b2, b3 = (icoeff + pcoeff + dcoeff) / order, -(pcoeff + 2.0 * dcoeff) / order, dcoeff / order
+        f = safety * (1.0 if b1 == 0 else inv**b1) * (1.0 if b2 == 0 else prev**b2) * (1.0 if b3 == 0 else prev_prev**b3)
+        dt = float(tn - t) * min(max(f, 1.0 if keep else factormin), factormax)
+        if not keep:
+            rej += 1
+            continue
+        acc += 1
+        prev, prev_prev = inv, prev
+        if save_ts is not None:
+            while si < len(save_ts) and save_ts[si] <= tn:
+                out[si] = y + (y1 - y) * tt((save_ts[si] - t) / (tn - t))
+                si += 1
+        y, t = y1, tn
+    return (y[None] if save_ts is None else out), acc, rej

@@ -27,12 +27,14 @@ class PDEModel:
         """Integrate from ts[0] to ts[-1] with constant step dt0 and return the solution at `ts`
         (shape (len(ts), *y0.shape)), linearly interpolated inside the step that brackets each
         save time, as diffrax's SaveAt(ts=ts) does with LocalLinearInterpolation
-        (pde_model.py:120-136).  `adjoint` / `stepsize_controller` are accepted for signature
-        compatibility; only the constant-step forward solve is implemented here."""
-        if stepsize_controller is not None and type(stepsize_controller).__name__ != "ConstantStepSize":
-            raise NotImplementedError("only ConstantStepSize is implemented on the fused path")
+        (pde_model.py:120-136).  `stepsize_controller`: None / ConstantStepSize (the reference's default,
+        fused K-step launches) or `pde_opt_b200.stepsize.PIDController` (one launch per attempted step)."""
         equation = self.equation_type(domain=self.domain, **parameters)  # :110
         solver = self.solver_type(**prepare_solver_params(self.solver_type, solver_parameters, equation))  # :112-117
+        if stepsize_controller is not None and type(stepsize_controller).__name__ != "ConstantStepSize":
+            if not hasattr(stepsize_controller, "adapt"):
+                raise NotImplementedError("stepsize_controller must be ConstantStepSize or pde_opt_b200.stepsize.PIDController")
+            return self._solve_adaptive(equation, solver, y0, ts, dt0, max_steps, stepsize_controller)
         if type(equation).__name__ == "AdvectionDiffusion2D":
             return self._solve_differentiable(equation, solver, y0, ts, dt0, max_steps, adjoint)
         if self._wants_phasefield_grad(equation, y0):
@@ -66,6 +68,46 @@ class PDEModel:
             out[si] = torch.lerp(y, y_b, float(w))
             y, i_cur = y_b, j
         del truncated
+        return out
+
+    def _solve_adaptive(self, equation, solver, y0, ts, dt0, max_steps, controller):
+        """diffeqsolve with an adaptive controller: one solver.step per attempt (the GPU step plus the
+        `y_error` of solvers.py:61-65), the controller's accept / reject decision on the host, rejected
+        steps retried from the same state, `SaveAt(ts)` by linear interpolation inside accepted steps.
+        Attempts (accepted or not) count towards `max_steps`; slots not reached stay at inf
+        (throw=False, pde_model.py:131)."""
+        if not hasattr(solver, "with_error"):
+            raise ValueError(f"{type(solver).__name__} provides no error estimate (y_error is None): use ConstantStepSize")
+        solver.with_error = True
+        terms = ODETerm(equation)
+        ts = np.asarray([float(t) for t in ts], dtype=np.float32)
+        y = y0 if torch.is_tensor(y0) else torch.as_tensor(np.asarray(y0, dtype=np.float32))
+        y = y.to(device="cuda", dtype=torch.float32).contiguous() if not y.is_cuda else y.to(torch.float32).contiguous()
+        out = torch.full((len(ts),) + tuple(y.shape), float("inf"), dtype=torch.float32, device=y.device)
+        t, t1 = np.float32(ts[0]), np.float32(ts[-1])
+        si = 0
+        while si < len(ts) and ts[si] <= t:
+            out[si] = y
+            si += 1
+        dt, state, order = float(dt0), controller.init_state(), solver.order(terms)
+        self.last_stats = {"accepted": 0, "rejected": 0}
+        for _ in range(int(max_steps)):
+            if not t < t1:
+                break
+            tn = np.float32(t + np.float32(dt))
+            if tn > t1 - np.float32(1e-6) or tn >= t1:
+                tn = t1
+            y1, y_err, _, _, _ = solver.step(terms, t, tn, y)
+            err = controller.scaled_error(y, y1, y_err)
+            keep, dt, state = controller.adapt(float(tn - t), err, order, state)
+            if not keep:
+                self.last_stats["rejected"] += 1
+                continue
+            self.last_stats["accepted"] += 1
+            while si < len(ts) and ts[si] <= tn:
+                out[si] = torch.lerp(y, y1, float(np.float32((ts[si] - t) / (tn - t))))
+                si += 1
+            y, t = y1, tn
         return out
 
     # ---- differentiable rollouts (hand-written adjoints) ----------------------------------------------

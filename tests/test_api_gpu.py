@@ -261,3 +261,36 @@ def test_pde_env_with_advection_diffusion_and_gpe():
     for ta, tb in zip(genv._times[:-1], genv._times[1:]):
         yy = O.strang_step(ogeq.B_terms, yy, ta, tb, ogeq.A_term, ogeq.dx, -1j)
     assert np.linalg.norm(genv._state.cpu().numpy() - yy) / np.linalg.norm(yy) <= 2e-5
+
+
+def test_pde_model_solve_with_pid_controller_matches_oracle():
+    """PDEModel.solve(..., stepsize_controller=PIDController(rtol, atol)) (pde_model.py:120-134 with an
+    adaptive controller; y_error from solvers.py:61-65): same accepted / rejected step counts as the
+    oracle's restatement of the controller, states at the save times within the north-star tolerance,
+    and the adaptive solution agrees with the constant-step one to the requested accuracy."""
+    from pde_opt_b200.equations import AllenCahn2DPeriodic
+    from pde_opt_b200.pde_model import PDEModel
+    from pde_opt_b200.functions import ConstantMobility, DoubleWell
+    from pde_opt_b200.solvers import SemiImplicitFourierSpectral
+    from pde_opt_b200.stepsize import ConstantStepSize, PIDController
+
+    model = PDEModel(AllenCahn2DPeriodic, pdom(), SemiImplicitFourierSpectral)
+    params = dict(kappa=KAPPA, mu=DoubleWell(), R=ConstantMobility(1.0))
+    y0 = (0.1 * np.random.default_rng(9).normal(size=(N, N))).astype(np.float32)
+    ts = np.linspace(0.0, 2e-3, 5).astype(np.float32)
+    rtol, atol = 1e-3, 1e-6
+    got = model.solve(params, torch.from_numpy(y0).cuda(), ts, {"A": 1.0}, dt0=1e-6,
+                      stepsize_controller=PIDController(rtol, atol)).cpu().numpy()
+    stats = dict(model.last_stats)
+    oeq = O.AllenCahn2DPeriodic(odom(), KAPPA, O.mu_double_well, lambda c: np.ones_like(c), "fd", np.float32)
+    want, acc, rej = O.integrate_adaptive(
+        lambda y, a, b: O.sifs_step(oeq.rhs, y, a, b, 1.0, oeq.fourier_symbol, with_error=True), y0, ts[0], ts[-1], 1e-6,
+        rtol, atol, save_ts=ts)
+    assert np.isfinite(got).all() and got.shape == (5, N, N)
+    assert (stats["accepted"], stats["rejected"]) == (acc, rej)
+    assert acc < 400  # constant stepping would take 2000 steps of 1e-6
+    for i in range(len(ts)):
+        assert rel_l2(got[i], want[i]) <= 1e-4
+    fine = model.solve(params, torch.from_numpy(y0).cuda(), ts, {"A": 1.0}, dt0=1e-6,
+                       stepsize_controller=ConstantStepSize()).cpu().numpy()
+    assert rel_l2(got[-1], fine[-1]) <= 0.05

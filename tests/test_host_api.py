@@ -191,3 +191,39 @@ def test_compute_entry_points_reject_bad_arguments_before_touching_the_gpu():
 
     assert lib.pdeopt_gpe_detect_vortices(None, 1, 64, 64, 0.0, 0.5, None, fake, None) == _lib.ERR_INVALID
     assert lib.pdeopt_gpe_detect_vortices(fake, 0, 64, 64, 0.0, 0.5, None, fake, None) == _lib.ERR_INVALID
+
+
+def test_pid_controller_matches_oracle_restatement_on_a_scalar_ode():
+    """pde_opt_b200.stepsize.PIDController against oracle.integrate_adaptive on y' = -50 y with an
+    implicit/explicit Euler pair (the error estimate of solvers.py:61-65): same accept / reject
+    sequence, same step sizes (CPU tensors; the controller itself needs no GPU)."""
+    import torch
+
+    from pde_opt_b200.stepsize import PIDController
+
+    lam = 50.0
+
+    def step_err(y, a, b):
+        dt = np.float32(b - a)
+        y1 = (y / (1 + lam * dt)).astype(np.float32)       # implicit Euler
+        return y1, y1 - (y + dt * (-lam * y))                 # minus explicit Euler
+
+    for pid in ({}, {"pcoeff": 0.3, "icoeff": 0.4}, {"pcoeff": 0.1, "icoeff": 0.3, "dcoeff": 0.05}):
+        y0 = np.array([1.0, 0.5], np.float32)
+        _, acc, rej = O.integrate_adaptive(step_err, y0, 0.0, 0.2, 1e-4, 1e-3, 1e-6, **pid)
+        ctl = PIDController(1e-3, 1e-6, **pid)
+        t, t1, dt, state, y = np.float32(0), np.float32(0.2), 1e-4, ctl.init_state(), y0
+        a2 = r2 = 0
+        while t < t1:
+            tn = np.float32(t + np.float32(dt))
+            if tn > t1 - np.float32(1e-6):
+                tn = t1
+            y1, e = step_err(y, t, tn)
+            err = ctl.scaled_error(torch.from_numpy(y), torch.from_numpy(y1), torch.from_numpy(e))
+            keep, dt, state = ctl.adapt(float(tn - t), err, 1, state)
+            if keep:
+                y, t, a2 = y1, tn, a2 + 1
+            else:
+                r2 += 1
+        assert (a2, r2) == (acc, rej) and acc > 5
+        np.testing.assert_allclose(y, np.exp(-lam * 0.2) * y0, atol=2e-3)
