@@ -167,7 +167,17 @@ extern "C" pdeopt_status pdeopt_ch3d_rhs(const pdeopt_ch3d_desc* d, const float*
   const int bx = d->nz >= 256 ? 256 : (d->nz >= 128 ? 128 : (d->nz >= 64 ? 64 : 32));
   dim3 block(bx), g1((d->nz + bx - 1) / bx, d->ny, batch * (d->nx + 2)), g2((d->nz + bx - 1) / bx, d->ny, batch * d->nx);
   cudaStream_t st = (cudaStream_t)stream;
-  const int xl = d->nx % 64 == 0 ? 64 : (d->nx % 32 == 0 ? 32 : (d->nx % 16 == 0 ? 16 : (d->nx % 8 == 0 ? 8 : 0)));
+  // planes marched per CTA: the longest chunk that still fills the GPU (3 CTAs per SM); short chunks
+  // re-read 3 planes per chunk but a 64^3 or 128^3 domain would otherwise run on 4 or 32 CTAs
+  int xl = 0;
+  {
+    const int64_t tiles = (int64_t)(d->ny / kC3TY) * (d->nz / kC3TZ) * batch;
+    for (int c : {64, 32, 16, 8}) {
+      if (d->nx % c != 0) continue;
+      xl = c;
+      if (tiles * (d->nx / c) >= 3 * 148) break;
+    }
+  }
   if (xl > 0 && d->ny % kC3TY == 0 && d->nz % kC3TZ == 0 && (int64_t)batch * (d->nx / xl) <= 65535) {
     // fused 2.5-D marching kernel: one read of u, one write of f
     dim3 grid(d->nz / kC3TZ, d->ny / kC3TY, batch * (d->nx / xl));
