@@ -59,7 +59,7 @@ struct LineTile {
   static constexpr int T = (N >= 512 && !CT) ? 8 : ((N >= 256) ? 16 : 32);  // lines per tile
   static constexpr bool kXor8 = (T == 8);
   static constexpr int LP = kXor8 ? T : T + 1;
-  static constexpr int kThreads = 256;
+  static constexpr int kThreads = (N >= 512 && !CT) ? 128 : 256;  // 512 = 16 x 32: the radix-32 stage has 128 work items per tile
   static constexpr size_t smem_bytes = sizeof(float2) * (size_t)(N * LP + N) + sizeof(long long) * (size_t)(3 * T);
 };
 
