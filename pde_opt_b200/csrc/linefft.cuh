@@ -444,6 +444,7 @@ __global__ void __launch_bounds__(LineTile<N, true>::kThreads) linefft_real_kern
   constexpr int T = LineTile<N, CT>::T, LP = LineTile<N, CT>::LP, NT = LineTile<N, CT>::kThreads;
   constexpr int R1 = lf_r1(N), R2 = lf_r2(N), R3 = lf_r3(N);
   constexpr int S2 = N / R1, S3 = N / R1 / R2, HP = N / 2 + 1;
+  constexpr int LB = (N * T / NT >= 16) ? 16 : 4, LH = (N * T / NT >= 16) ? 8 : 4;  // global loads in flight per thread
   float2* Sm = reinterpret_cast<float2*>(lf_smem);
   float2* tw = Sm + N * LP;
   int* f2p = reinterpret_cast<int*>(tw + N);  // frequency -> storage position
@@ -460,16 +461,17 @@ __global__ void __launch_bounds__(LineTile<N, true>::kThreads) linefft_real_kern
     c.l0 = l0;
     __syncthreads();
     if constexpr (!INV) {
-      // loads issued in batches of 4 per thread before the dependent shared-memory stores
-      for (int w0 = threadIdx.x; w0 < N * T; w0 += 4 * NT) {
-        float2 v[4];
+      // loads issued in batches of LB per thread before the dependent shared-memory stores (with three
+      // CTAs per SM it takes 2 x 16 loads of 4 bytes per thread in flight to cover HBM latency)
+      for (int w0 = threadIdx.x; w0 < N * T; w0 += LB * NT) {
+        float2 v[LB];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < LB; ++q) {
           const int w = w0 + q * NT, idx = w % N, pl = w / N;
           v[q] = (w < N * T && l0 + pl < n_pairs) ? io.load_pair(l0 + pl, idx) : make_float2(0.f, 0.f);
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < LB; ++q) {
           const int w = w0 + q * NT, idx = w % N, pl = w / N;
           if (w < N * T) Sm[lf_sidx<N, CT>(idx, pl)] = v[q];
         }
@@ -495,16 +497,16 @@ __global__ void __launch_bounds__(LineTile<N, true>::kThreads) linefft_real_kern
         }
       }
     } else {
-      for (int w0 = threadIdx.x; w0 < HP * T; w0 += 4 * NT) {
-        float2 A[4], B[4];
+      for (int w0 = threadIdx.x; w0 < HP * T; w0 += LH * NT) {
+        float2 A[LH], B[LH];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < LH; ++q) {
           const int w = w0 + q * NT, h = w % HP, pl = w / HP;
           A[q] = B[q] = make_float2(0.f, 0.f);
           if (w < HP * T && l0 + pl < n_pairs) io.load_half(l0 + pl, h, A[q], B[q]);
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < LH; ++q) {
           const int w = w0 + q * NT, h = w % HP, pl = w / HP;
           if (w < HP * T) {
             // Z[h] = A + i B ;  Z[N-h] = conj(A) + i conj(B)
@@ -524,15 +526,15 @@ __global__ void __launch_bounds__(LineTile<N, true>::kThreads) linefft_real_kern
       }
       lf_stage<N, CT, R1, N, true, false, false, false>(c, nio, nio);
       __syncthreads();
-      for (int w0 = threadIdx.x; w0 < N * T; w0 += 4 * NT) {
-        float2 pre[4];
+      for (int w0 = threadIdx.x; w0 < N * T; w0 += LH * NT) {
+        float2 pre[LH];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < LH; ++q) {
           const int w = w0 + q * NT, idx = w % N, pl = w / N;
           pre[q] = (w < N * T && l0 + pl < n_pairs) ? io.pre_pair(l0 + pl, idx) : make_float2(0.f, 0.f);
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < LH; ++q) {
           const int w = w0 + q * NT, idx = w % N, pl = w / N;
           if (w < N * T && l0 + pl < n_pairs) io.store_pair(l0 + pl, idx, Sm[lf_sidx<N, CT>(idx, pl)], pre[q]);
         }
