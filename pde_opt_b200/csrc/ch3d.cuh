@@ -471,6 +471,12 @@ struct LfMidImex {
     const float m = __fdividef(scale, fmaf(dt, sym[off_aux], 1.0f));
     return make_float2(v.x * m, v.y * m);
   }
+  using Aux = float;
+  __device__ __forceinline__ float fetch(long long off_aux, long long) const { return __ldg(sym + off_aux); }
+  __device__ __forceinline__ float2 apply_aux(float2 v, float sg, long long, int) const {
+    const float m = __fdividef(scale, fmaf(dt, sg, 1.0f));
+    return make_float2(v.x * m, v.y * m);
+  }
 };
 // y1 = y0 + dt * Re(g)   (solvers.py:63)
 struct LfStoreUpdate {

@@ -120,7 +120,9 @@ enum : int { LF_FWD = 0, LF_INV = 1, LF_FWD_MUL_INV = 2, LF_INV_MID_FWD = 3 };
 
 // Functor concepts (offsets are element offsets computed from the functor's own geometries):
 //   Loader: LineGeom gin() ;  float2 load(long long off, long long line, int idx)
-//   Mid   : LineGeom gaux();  float2 apply(float2 v, long long off_aux, long long line, int pos)
+//   Mid   : LineGeom gaux();  float2 apply(float2 v, long long off_aux, long long line, int pos), split for the
+//           fused forward * multiplier * inverse stage into  Aux fetch(long long off_aux, long long line)  (the
+//           functor's own global reads) and  float2 apply_aux(float2 v, Aux a, long long line, int pos)
 //   Storer: LineGeom gout();  float2 pre(long long off)  (the storer's own global read for that element, if any) ;
 //           void store(long long off, long long line, int idx, float2 v, float2 pre) ; void flush(long long l0)
 // CONTIG: elements of a line are adjacent in memory (lo == 1): warps run along idx when they touch
@@ -201,6 +203,14 @@ __device__ __forceinline__ void lf_stage_fmi(const LfCtx& c, Loader& ld, Mid& mi
     const int u = LANE_U ? (w % NB) : (w / T), line = LANE_U ? (w / NB) : (w % T);
     const int base = u * R;
     const bool valid = c.l0 + line < c.n_lines;
+    // the multiplier's own global reads are issued first, so that their latency overlaps the loads and
+    // the forward butterflies instead of sitting between the two transforms
+    typename Mid::Aux aux[R];
+    static_for<0, R>([&](auto pc) {
+      constexpr int p = decltype(pc)::value;
+      constexpr int k = brev<LOG2R>(p);
+      aux[p] = valid ? mid.fetch(c.lb_aux[line] + c.io_aux[base + k], c.l0 + line) : typename Mid::Aux{};
+    });
     float2 x[R];
 #pragma unroll
     for (int m = 0; m < R; ++m) {
@@ -211,7 +221,7 @@ __device__ __forceinline__ void lf_stage_fmi(const LfCtx& c, Loader& ld, Mid& mi
     static_for<0, R>([&](auto pc) {
       constexpr int p = decltype(pc)::value;
       constexpr int k = brev<LOG2R>(p);
-      if (valid) x[p] = mid.apply(x[p], c.lb_aux[line] + c.io_aux[base + k], c.l0 + line, base + k);
+      if (valid) x[p] = mid.apply_aux(x[p], aux[p], c.l0 + line, base + k);
     });
     Dit<R, 1, true>::run(x);
 #pragma unroll
@@ -604,8 +614,11 @@ struct LfStorePeers {
   __device__ __forceinline__ void flush(long long) {}
 };
 struct LfMidNone {
+  struct Aux {};
   __device__ __forceinline__ LineGeom gaux() const { return LineGeom{1, 1, 0, 0, 1, 0, 0}; }
   __device__ __forceinline__ float2 apply(float2 v, long long, long long, int) const { return v; }
+  __device__ __forceinline__ Aux fetch(long long, long long) const { return Aux{}; }
+  __device__ __forceinline__ float2 apply_aux(float2 v, Aux, long long, int) const { return v; }
 };
 
 template <int N, int MODE, bool CONTIG, class Loader, class Mid, class Storer>

@@ -67,6 +67,9 @@ struct LfMidCTab {
   LineGeom g;  // the column-pass geometry with outer = 0: the table is shared by the batch
   __device__ __forceinline__ LineGeom gaux() const { return g; }
   __device__ __forceinline__ float2 apply(float2 v, long long off_aux, long long, int) const { return cmul(v, tab[off_aux]); }
+  using Aux = float2;
+  __device__ __forceinline__ float2 fetch(long long off_aux, long long) const { return __ldg(tab + off_aux); }
+  __device__ __forceinline__ float2 apply_aux(float2 v, float2 t, long long, int) const { return cmul(v, t); }
 };
 
 // K3 storer: rows inverse done -> multiply by the potential factor (b at psi0), accumulate the norm.
@@ -138,6 +141,12 @@ struct LfMidCTabScaled {
   __device__ __forceinline__ float2 apply(float2 v, long long off_aux, long long line, int) const {
     const float s = rsqrtf(norm[(int)line >> log2ny] * dx2);
     const float2 t = tab[off_aux];
+    return cmul(v, make_float2(t.x * s, t.y * s));
+  }
+  using Aux = float2;
+  __device__ __forceinline__ float2 fetch(long long off_aux, long long) const { return __ldg(tab + off_aux); }
+  __device__ __forceinline__ float2 apply_aux(float2 v, float2 t, long long line, int) const {
+    const float s = rsqrtf(norm[(int)line >> log2ny] * dx2);
     return cmul(v, make_float2(t.x * s, t.y * s));
   }
 };
