@@ -149,6 +149,16 @@ __device__ __forceinline__ void lf_stage(const LfCtx& c, Loader& ld, Storer& st)
     const int j = u % SUB, base = (u / SUB) * S + j;
     const bool valid = c.l0 + line < c.n_lines;
     float2 x[R];
+    // the storer's own global reads (e.g. y0 of the update) are issued before the transform so that their
+    // latency is hidden and they are not serialised behind the stores they feed
+    float2 pre[GDST ? R : 1];
+    if constexpr (GDST) {
+#pragma unroll
+      for (int m = 0; m < R; ++m) {
+        const int pos = base + m * SUB;
+        pre[m] = valid ? st.pre(c.lb_out[line] + c.io_out[pos]) : make_float2(0.f, 0.f);
+      }
+    }
     if constexpr (!INV) {
 #pragma unroll
       for (int m = 0; m < R; ++m) {
@@ -164,7 +174,7 @@ __device__ __forceinline__ void lf_stage(const LfCtx& c, Loader& ld, Storer& st)
         if constexpr (k != 0 && SUB > 1) v = cmul(v, c.tw[(j * k * (N / S)) & (N - 1)]);
         const int pos = base + k * SUB;
         if constexpr (GDST) {
-          if (valid) st.store(c.lb_out[line] + c.io_out[pos], c.l0 + line, pos, v, st.pre(c.lb_out[line] + c.io_out[pos]));
+          if (valid) st.store(c.lb_out[line] + c.io_out[pos], c.l0 + line, pos, v, pre[k]);
         } else {
           c.Sm[lf_sidx<N, CT>(pos, line)] = v;
         }
@@ -185,7 +195,7 @@ __device__ __forceinline__ void lf_stage(const LfCtx& c, Loader& ld, Storer& st)
       for (int m = 0; m < R; ++m) {
         const int pos = base + m * SUB;
         if constexpr (GDST) {
-          if (valid) st.store(c.lb_out[line] + c.io_out[pos], c.l0 + line, pos, x[m], st.pre(c.lb_out[line] + c.io_out[pos]));
+          if (valid) st.store(c.lb_out[line] + c.io_out[pos], c.l0 + line, pos, x[m], pre[m]);
         } else {
           c.Sm[lf_sidx<N, CT>(pos, line)] = x[m];
         }
@@ -442,7 +452,22 @@ struct LfNoIo {
 template <int N>
 struct LineTileReal {
   static constexpr int T = LineTile<N, true>::T;
-  static constexpr size_t smem_bytes = sizeof(float2) * (size_t)(N * (T + 1) + N) + sizeof(int) * (size_t)N;
+  static constexpr size_t smem_bytes = sizeof(float2) * (size_t)(N * (T + 1) + N) + sizeof(int) * (size_t)N + sizeof(long long) * (size_t)T;
+};
+
+// Adapters that let the generic stages talk to a real-line Io: the first forward stage loads pairs of real
+// lines straight from global memory, the last inverse stage stores them (offset = local pair * N + idx).
+template <class Io>
+struct LfRealLoad {
+  Io io;
+  __device__ __forceinline__ float2 load(long long, long long pair, int idx) const { return io.load_pair(pair, idx); }
+};
+template <int N, class Io>
+struct LfRealStore {
+  Io io;
+  long long l0;
+  __device__ __forceinline__ float2 pre(long long off) const { return io.pre_pair(l0 + (off / N), (int)(off % N)); }
+  __device__ __forceinline__ void store(long long, long long pair, int idx, float2 v, float2 p) const { io.store_pair(pair, idx, v, p); }
 };
 
 // Io (forward):  float2 load_pair(long long pair, int idx) ; void store_half(long long pair, int h, float2 A, float2 B)
@@ -454,40 +479,29 @@ __global__ void __launch_bounds__(LineTile<N, true>::kThreads) linefft_real_kern
   constexpr int T = LineTile<N, CT>::T, LP = LineTile<N, CT>::LP, NT = LineTile<N, CT>::kThreads;
   constexpr int R1 = lf_r1(N), R2 = lf_r2(N), R3 = lf_r3(N);
   constexpr int S2 = N / R1, S3 = N / R1 / R2, HP = N / 2 + 1;
-  constexpr int LB = (N * T / NT >= 16) ? 16 : 4, LH = (N * T / NT >= 16) ? 8 : 4;  // global loads in flight per thread
+  constexpr int LH = (N * T / NT >= 16) ? 8 : 4;  // half-spectrum loads in flight per thread
   float2* Sm = reinterpret_cast<float2*>(lf_smem);
   float2* tw = Sm + N * LP;
   int* f2p = reinterpret_cast<int*>(tw + N);  // frequency -> storage position
+  long long* lb = reinterpret_cast<long long*>(f2p + N);  // [T] local pair * N: offsets handed to the storer adapter
   for (int i = threadIdx.x; i < N; i += NT) {
     float s, c;
     sincospif(-2.0f * float(i) / float(N), &s, &c);
     tw[i] = make_float2(c, s);
     f2p[line_pos_to_freq(N, i)] = i;
   }
-  LfCtx c{Sm, tw, LfOff{}, LfOff{}, LfOff{}, nullptr, nullptr, nullptr, 0, n_pairs};
+  if (threadIdx.x < T) lb[threadIdx.x] = (long long)threadIdx.x * N;
+  const LfOff ident{31, 0x7fffffff, 0, 1};  // offset of position pos = pos
+  LfCtx c{Sm, tw, ident, ident, LfOff{}, lb, lb, nullptr, 0, n_pairs};
   LfNoIo nio;
   for (long long tile = blockIdx.x; tile * T < n_pairs; tile += gridDim.x) {
     const long long l0 = tile * T;
     c.l0 = l0;
     __syncthreads();
     if constexpr (!INV) {
-      // loads issued in batches of LB per thread before the dependent shared-memory stores (with three
-      // CTAs per SM it takes 2 x 16 loads of 4 bytes per thread in flight to cover HBM latency)
-      for (int w0 = threadIdx.x; w0 < N * T; w0 += LB * NT) {
-        float2 v[LB];
-#pragma unroll
-        for (int q = 0; q < LB; ++q) {
-          const int w = w0 + q * NT, idx = w % N, pl = w / N;
-          v[q] = (w < N * T && l0 + pl < n_pairs) ? io.load_pair(l0 + pl, idx) : make_float2(0.f, 0.f);
-        }
-#pragma unroll
-        for (int q = 0; q < LB; ++q) {
-          const int w = w0 + q * NT, idx = w % N, pl = w / N;
-          if (w < N * T) Sm[lf_sidx<N, CT>(idx, pl)] = v[q];
-        }
-      }
-      __syncthreads();
-      lf_stage<N, CT, R1, N, false, false, false, false>(c, nio, nio);
+      // first radix stage fused with the global loads of the real pairs (lanes along the positions)
+      LfRealLoad<Io> rl{io};
+      lf_stage<N, CT, R1, N, false, true, false, true>(c, rl, nio);
       __syncthreads();
       if constexpr (R2 > 1) {
         lf_stage<N, CT, R2, S2, false, false, false, false>(c, nio, nio);
@@ -534,21 +548,9 @@ __global__ void __launch_bounds__(LineTile<N, true>::kThreads) linefft_real_kern
         lf_stage<N, CT, R2, S2, true, false, false, false>(c, nio, nio);
         __syncthreads();
       }
-      lf_stage<N, CT, R1, N, true, false, false, false>(c, nio, nio);
-      __syncthreads();
-      for (int w0 = threadIdx.x; w0 < N * T; w0 += LH * NT) {
-        float2 pre[LH];
-#pragma unroll
-        for (int q = 0; q < LH; ++q) {
-          const int w = w0 + q * NT, idx = w % N, pl = w / N;
-          pre[q] = (w < N * T && l0 + pl < n_pairs) ? io.pre_pair(l0 + pl, idx) : make_float2(0.f, 0.f);
-        }
-#pragma unroll
-        for (int q = 0; q < LH; ++q) {
-          const int w = w0 + q * NT, idx = w % N, pl = w / N;
-          if (w < N * T && l0 + pl < n_pairs) io.store_pair(l0 + pl, idx, Sm[lf_sidx<N, CT>(idx, pl)], pre[q]);
-        }
-      }
+      // last radix stage fused with the global stores (and the storer's own reads) of the real pairs
+      LfRealStore<N, Io> rs{io, l0};
+      lf_stage<N, CT, R1, N, true, false, true, true>(c, nio, rs);
     }
   }
 }
