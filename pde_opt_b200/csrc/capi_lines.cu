@@ -167,29 +167,40 @@ extern "C" pdeopt_status pdeopt_ch3d_rhs(const pdeopt_ch3d_desc* d, const float*
   const int bx = d->nz >= 256 ? 256 : (d->nz >= 128 ? 128 : (d->nz >= 64 ? 64 : 32));
   dim3 block(bx), g1((d->nz + bx - 1) / bx, d->ny, batch * (d->nx + 2)), g2((d->nz + bx - 1) / bx, d->ny, batch * d->nx);
   cudaStream_t st = (cudaStream_t)stream;
+  // tile of the marching kernels: 16 x 64 (y, z), or 32 x 32 for small grids
+  const bool tile64 = d->ny % kC3TY == 0 && d->nz % kC3TZ == 0;
+  const bool tile32 = !tile64 && d->ny % 32 == 0 && d->nz % 32 == 0;
+  const int tyy = tile64 ? kC3TY : 32, tzz = tile64 ? kC3TZ : 32;
   // planes marched per CTA: the longest chunk that still fills the GPU (3 CTAs per SM); short chunks
   // re-read 3 planes per chunk but a 64^3 or 128^3 domain would otherwise run on 4 or 32 CTAs
   int xl = 0;
-  {
-    const int64_t tiles = (int64_t)(d->ny / kC3TY) * (d->nz / kC3TZ) * batch;
+  if (tile64 || tile32) {
+    const int64_t tiles = (int64_t)(d->ny / tyy) * (d->nz / tzz) * batch;
     for (int c : {64, 32, 16, 8}) {
       if (d->nx % c != 0) continue;
       xl = c;
       if (tiles * (d->nx / c) >= 3 * 148) break;
     }
   }
-  if (xl > 0 && d->ny % kC3TY == 0 && d->nz % kC3TZ == 0 && (int64_t)batch * (d->nx / xl) <= 65535) {
+  auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  const bool aligned = aligned16(u_dev) && aligned16(f_dev) && aligned16(halo_lo_dev) && aligned16(halo_hi_dev);
+  if (xl > 0 && (int64_t)batch * (d->nx / xl) <= 65535 && (aligned || tile64)) {
     // fused 2.5-D marching kernel: one read of u, one write of f
-    dim3 grid(d->nz / kC3TZ, d->ny / kC3TY, batch * (d->nx / xl));
-    auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-    if (aligned16(u_dev) && aligned16(f_dev) && aligned16(halo_lo_dev) && aligned16(halo_hi_dev)) {
+    dim3 grid(d->nz / tzz, d->ny / tyy, batch * (d->nx / xl));
+    if (aligned) {
       // register-marching version (128-bit accesses), specialised for the closure families with packed forms
       const int mf = d->mu_family, bf = d->mob_family;
-      if (mf == MU_LOG && bf == MOB_CONST) ch3d_rhs_march_kernel<MU_LOG, MOB_CONST><<<grid, kC3Threads, 0, st>>>(p, xl);
-      else if (mf == MU_LOG && bf == MOB_DEGENERATE) ch3d_rhs_march_kernel<MU_LOG, MOB_DEGENERATE><<<grid, kC3Threads, 0, st>>>(p, xl);
-      else if (mf == MU_DOUBLE_WELL && bf == MOB_CONST) ch3d_rhs_march_kernel<MU_DOUBLE_WELL, MOB_CONST><<<grid, kC3Threads, 0, st>>>(p, xl);
-      else if (bf == MOB_CONST) ch3d_rhs_march_kernel<MU_RUNTIME, MOB_CONST><<<grid, kC3Threads, 0, st>>>(p, xl);
-      else ch3d_rhs_march_kernel<MU_RUNTIME, MOB_RUNTIME><<<grid, kC3Threads, 0, st>>>(p, xl);
+#define PDEOPT_MARCH(MU_, MOB_)                                                                          \
+  do {                                                                                                   \
+    if (tile64) ch3d_rhs_march_kernel<MU_, MOB_, kC3TY, kC3TZ><<<grid, kC3Threads, 0, st>>>(p, xl);      \
+    else ch3d_rhs_march_kernel<MU_, MOB_, 32, 32><<<grid, kC3Threads, 0, st>>>(p, xl);                   \
+  } while (0)
+      if (mf == MU_LOG && bf == MOB_CONST) PDEOPT_MARCH(MU_LOG, MOB_CONST);
+      else if (mf == MU_LOG && bf == MOB_DEGENERATE) PDEOPT_MARCH(MU_LOG, MOB_DEGENERATE);
+      else if (mf == MU_DOUBLE_WELL && bf == MOB_CONST) PDEOPT_MARCH(MU_DOUBLE_WELL, MOB_CONST);
+      else if (bf == MOB_CONST) PDEOPT_MARCH(MU_RUNTIME, MOB_CONST);
+      else PDEOPT_MARCH(MU_RUNTIME, MOB_RUNTIME);
+#undef PDEOPT_MARCH
     } else {
       ch3d_rhs_fused_kernel<<<grid, kC3Threads, 0, st>>>(p, xl);
     }

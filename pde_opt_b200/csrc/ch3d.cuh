@@ -221,17 +221,18 @@ __global__ void __launch_bounds__(kC3Threads) ch3d_rhs_fused_kernel(const __grid
 // shared-memory access is base register + immediate.
 //   f = cx (Gx - Gx_prev) + cy (Gy+ - Gy-) + cz (Gz+ - Gz-),  G = (D + D_nbr) (mu_nbr - mu), c = 1/(2h^2)
 // (cahn_hilliard.py:177-200 with the constant factors collected as in sifs128.cuh; a few ulp).
-constexpr int kM3P = 76;            // row pitch in floats: 4 halo columns | 64 | halo; 76 mod 32 = 12 keeps the
-                                    // column-ring accesses (one per row) at two per bank
-constexpr int kM3UR = kC3TY + 4;    // u rows (halo 2)
-constexpr int kM3MR = kC3TY + 2;    // mu / D rows (ring 1)
-constexpr int kM3NS = 4;            // u stages
-constexpr int kM3US = kM3UR * kM3P, kM3MS = kM3MR * kM3P;  // buffer strides
-
+// Tile shapes: 16 x 64 (y, z) for nz % 64 == 0, 32 x 32 for the small grids (nz % 32 == 0, ny % 32 == 0).
+constexpr int kM3NS = 4;  // u stages
+template <int TY, int TZ>
 struct Ch3dMarchSmem {
-  float U[kM3NS][kM3UR][kM3P];  // [y_local + 2][z_local + 4]
-  float Mu[2][kM3MR][kM3P];     // [y_local + 1][z_local + 4]
-  float Dm[2][kM3MR][kM3P];
+  // row pitch in floats: 4 halo columns | TZ | halo; 76 mod 32 = 12 keeps the column-ring accesses (one per
+  // row) at two per bank
+  static constexpr int P = TZ == 64 ? 76 : TZ + 8;  // (the 32 x 32 tile would pass 48 KB of static shared memory with +12)
+  static constexpr int UR = TY + 4;  // u rows (halo 2)
+  static constexpr int MR = TY + 2;  // mu / D rows (ring 1)
+  float U[kM3NS][UR][P];  // [y_local + 2][z_local + 4]
+  float Mu[2][MR][P];     // [y_local + 1][z_local + 4]
+  float Dm[2][MR][P];
 };
 
 __device__ __forceinline__ float2 lo2(float4 v) { return make_float2(v.x, v.y); }
@@ -247,21 +248,27 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int MU, int MOB>
+template <int MU, int MOB, int TY, int TZ>
 __global__ void __launch_bounds__(kC3Threads, 3) ch3d_rhs_march_kernel(const __grid_constant__ Ch3dParams p, int xl) {
-  __shared__ __align__(16) Ch3dMarchSmem S;
+  using Smem = Ch3dMarchSmem<TY, TZ>;
+  __shared__ __align__(16) Smem S;
+  constexpr int kM3P = Smem::P, kM3US = Smem::UR * Smem::P, kM3MS = Smem::MR * Smem::P;
+  constexpr int LZ = TZ / 4;  // lanes per tile row (four consecutive z points per thread)
+  static_assert(TY * LZ == kC3Threads, "tile must give every thread four points");
+  constexpr int kR1 = 2 * TZ + 2 * TY, kR2 = kR1 + 4;  // ring-1 points; ring-2 points + corners
+  constexpr int kR1W = kR1 / 8, kR2W = (kR2 + 7) / 8;  // per warp
   constexpr bool DCONST = (MOB == MOB_CONST);
   const int tid = threadIdx.x;
-  const int z0 = blockIdx.x * kC3TZ, y0 = blockIdx.y * kC3TY;
+  const int z0 = blockIdx.x * TZ, y0 = blockIdx.y * TY;
   const int nchunk = p.nx / xl;
   const int b = blockIdx.z / nchunk, x0 = (blockIdx.z % nchunk) * xl;
-  const int ty = tid >> 4, tq = tid & 15;
+  const int ty = tid / LZ, tq = tid % LZ;
   const int own_off = (y0 + ty) * p.nz + z0 + 4 * tq;
   const size_t pl = (size_t)p.ny * p.nz;
 
-  // ring roles, spread evenly over the 8 warps so that no warp is late at the barrier: lanes 0..19 of
-  // every warp march one ring-1 point (mu, D needed there), lanes 0..20 stage one ring-2 / corner
-  // point of u (only neighbours read it)
+  // ring roles, spread evenly over the 8 warps so that no warp is late at the barrier: the first lanes of
+  // every warp (20 for the 16 x 64 tile) march one ring-1 point (mu, D needed there), the first 21 stage
+  // one ring-2 / corner point of u (only neighbours read it)
   auto wrap_off = [&](int yl, int zl) {
     int gy = y0 + yl, gz = z0 + zl;
     gy = gy < 0 ? gy + p.ny : (gy >= p.ny ? gy - p.ny : gy);
@@ -269,24 +276,24 @@ __global__ void __launch_bounds__(kC3Threads, 3) ch3d_rhs_march_kernel(const __g
     return gy * p.nz + gz;
   };
   const int lane = tid & 31, warp = tid >> 5;
-  const bool r1 = lane < 20;
-  const int ri = warp * 20 + lane;
+  const bool r1 = lane < kR1W;
+  const int ri = warp * kR1W + lane;
   int r1y = 0, r1z = 0;
-  if (ri < 64) { r1y = -1; r1z = ri; }
-  else if (ri < 128) { r1y = kC3TY; r1z = ri - 64; }
-  else if (ri < 144) { r1y = ri - 128; r1z = -1; }
-  else if (ri < 160) { r1y = ri - 144; r1z = kC3TZ; }
+  if (ri < TZ) { r1y = -1; r1z = ri; }
+  else if (ri < 2 * TZ) { r1y = TY; r1z = ri - TZ; }
+  else if (ri < 2 * TZ + TY) { r1y = ri - 2 * TZ; r1z = -1; }
+  else if (ri < kR1) { r1y = ri - 2 * TZ - TY; r1z = TZ; }
   const int r1_off = wrap_off(r1y, r1z);
-  const int rj = warp * 21 + lane;
-  const bool r2 = lane < 21 && rj < 164;
+  const int rj = warp * kR2W + lane;
+  const bool r2 = lane < kR2W && rj < kR2;
   int r2y = 0, r2z = 0;
   if (r2) {
     const int j = rj;
-    if (j < 64) { r2y = -2; r2z = j; }
-    else if (j < 128) { r2y = kC3TY + 1; r2z = j - 64; }
-    else if (j < 144) { r2y = j - 128; r2z = -2; }
-    else if (j < 160) { r2y = j - 144; r2z = kC3TZ + 1; }
-    else { r2y = (j & 2) ? kC3TY : -1; r2z = (j & 1) ? kC3TZ : -1; }
+    if (j < TZ) { r2y = -2; r2z = j; }
+    else if (j < 2 * TZ) { r2y = TY + 1; r2z = j - TZ; }
+    else if (j < 2 * TZ + TY) { r2y = j - 2 * TZ; r2z = -2; }
+    else if (j < kR1) { r2y = j - 2 * TZ - TY; r2z = TZ + 1; }
+    else { r2y = ((j - kR1) & 2) ? TY : -1; r2z = ((j - kR1) & 1) ? TZ : -1; }
   }
   const int r2_off = r2 ? wrap_off(r2y, r2z) : 0;
   // per-thread shared-memory bases (stage / buffer 0); the others are compile-time offsets away
@@ -349,7 +356,7 @@ __global__ void __launch_bounds__(kC3Threads, 3) ch3d_rhs_march_kernel(const __g
   float2 mu_p[2] = {zero2, zero2}, D_p[2] = {zero2, zero2}, gx_p[2] = {zero2, zero2}, dy_p[2] = {zero2, zero2},
          dz_p[2] = {zero2, zero2};
   float* fout = p.f + ((size_t)b * p.nx + x0) * pl + own_off;  // plane x0 is emitted at it = 1
-  const bool edgeL = tq == 0, edgeR = tq == 15;
+  const bool edgeL = tq == 0, edgeR = tq == LZ - 1;
 
   // one plane c held in stage ST (planes c+1 .. c+3 follow in the ring)
   auto plane = [&](auto st_c, int it) {

@@ -81,7 +81,9 @@ def _u0(points, B, seed=0):
                                               # register-marching kernel (ny % 16 == 0, nz % 64 == 0): every closure
                                               # specialisation, several tiles per axis, anisotropic spacing
                                               ((16, 32, 128), "log", 0.01), ((8, 48, 64), "logdeg", (0.01, 0.012, 0.008)),
-                                              ((24, 16, 192), "dwconst", (0.02, 0.01, 0.015)), ((64, 64, 64), "dw", 0.01)])
+                                              ((24, 16, 192), "dwconst", (0.02, 0.01, 0.015)), ((64, 64, 64), "dw", 0.01),
+                                              # 32 x 32 tile of the marching kernel (nz % 64 != 0)
+                                              ((16, 64, 32), "logdeg", (0.01, 0.012, 0.008)), ((8, 32, 96), "dw", 0.01)])
 def test_ch3d_rhs_matches_oracle(points, mu_name, h):
     eq, oeq = _ch3d(points, h, mu_name)
     u = _u0(points, 2)
