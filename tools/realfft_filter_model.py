@@ -63,3 +63,38 @@ assert t == 256 and (owner >= 0).all()
 assert (np.bincount(owner.ravel()) == 32).all()
 assert (owner == owner[(-kr) % N, (-km) % H]).all()
 print("256 threads x 32 registers, every (kr, km) / (-kr, -km) pair in one thread: ok")
+
+
+# ---- three register passes of the 128 x 64 complex transform (13 index bits, 256 threads x 32 values) ----
+#   A  radix-32 over the high 5 bits of m            thread (r, m0),            m = 2 n + m0
+#   B  twiddle w64^(m0 k1m); radix-2 over m0; radix-16 over the high 4 bits of r; twiddle w128^(n2r k1r)
+#                                                     thread (k1m, n2r),         r = 8 n1r + n2r
+#   C  radix-8 over n2r, four (k1r, km) slots per thread
+#                                                     thread (class of k1r, class of km), kr = k1r + 16 k2r, km = k1m + 32 k2m
+def forward_three_pass(z):
+    w128, w64 = np.exp(-2j * np.pi / 128), np.exp(-2j * np.pi / 64)
+    a = z.reshape(N, 32, 2)                       # [r, n, m0]
+    a = np.fft.fft(a, axis=1)                     # A -> [r, k1m, m0]
+    k1m = np.arange(32)[None, :, None]
+    m0 = np.arange(2)[None, None, :]
+    a = a * w64 ** (m0 * k1m)
+    a = np.fft.fft(a, axis=2)                     # B, radix 2 -> [r, k1m, k2m]
+    a = a.reshape(16, 8, 32, 2)                   # [n1r, n2r, k1m, k2m]
+    a = np.fft.fft(a, axis=0)                     # B, radix 16 -> [k1r, n2r, k1m, k2m]
+    k1r = np.arange(16)[:, None, None, None]
+    n2r = np.arange(8)[None, :, None, None]
+    a = a * w128 ** (n2r * k1r)
+    a = np.fft.fft(a, axis=1)                     # C -> [k1r, k2r, k1m, k2m]
+    Zt = np.empty((N, H), complex)
+    k1r, k2r, k1m, k2m = np.meshgrid(np.arange(16), np.arange(8), np.arange(32), np.arange(2), indexing="ij")
+    Zt[k1r + 16 * k2r, k1m + 32 * k2m] = a
+    return Zt
+
+
+Z3 = forward_three_pass(z)
+err3 = np.abs(Z3 - Z).max() / np.abs(Z).max()
+print("three-pass 128 x 64 transform vs fft2: max rel err", err3)
+assert err3 < 1e-13
+# per-thread work of the passes: A 32-point DFT (80 butterflies), B 16 radix-2 + 2 x 16-point DFTs + 1 + 15 x 2
+# inter-pass twiddles, C 4 x 8-point DFTs: 5 N log2 N = 5 * 8192 * 13 flops per real field (7 % below half of the
+# 128 x 128 complex transform that serves two fields today)
