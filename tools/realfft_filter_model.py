@@ -98,3 +98,45 @@ assert err3 < 1e-13
 # per-thread work of the passes: A 32-point DFT (80 butterflies), B 16 radix-2 + 2 x 16-point DFTs + 1 + 15 x 2
 # inter-pass twiddles, C 4 x 8-point DFTs: 5 N log2 N = 5 * 8192 * 13 flops per real field (7 % below half of the
 # 128 x 128 complex transform that serves two fields today)
+
+
+# ---- exchange layouts (64 KB buffer = 8192 8-byte slots) and their bank behaviour -------------------------
+# A 64-bit shared-memory access is served per half-warp: conflict free iff its 16 lanes hit 16 distinct slots
+# modulo 16.  Thread index bits: pass A  t = (r[6:3] | r[2:0] | m0) with the low 4 bits = (r[2:0], m0);
+# pass B  t = (k1m[4:1] | n2r | k1m[0]) with the low 4 bits = (n2r, k1m[0]);  pass C  t = (k1r class | km class)
+# with the low 4 bits = km class [3:0].
+def slot_ab(r, m0, k1m):          # written by A (fixed k1m per instruction), read by B (fixed (m0, n1r))
+    return k1m * 256 + 2 * r + (m0 ^ (k1m & 1))
+
+
+def slot_bc(k1r, k2m, n2r, k1m):  # written by B (fixed (k2m, k1r)), read by C (fixed (slot of the class pair, n2r))
+    return ((k1r * 2 + k2m) * 8 + n2r) * 32 + (k1m ^ (n2r << 1))  # XOR: B's half-warp runs over (n2r, k1m[0])
+
+
+def distinct16(slots):
+    return len({int(s) % 16 for s in slots}) == 16
+
+
+r_, m0_, k_ = np.meshgrid(np.arange(N), np.arange(2), np.arange(32), indexing="ij")
+assert len(np.unique(slot_ab(r_, m0_, k_))) == 8192
+a_, b_, c_, d_ = np.meshgrid(np.arange(16), np.arange(2), np.arange(8), np.arange(32), indexing="ij")
+assert len(np.unique(slot_bc(a_, b_, c_, d_))) == 8192
+for k1m in range(32):                       # A writes: lanes = (r[2:0], m0)
+    for rhi in range(16):
+        assert distinct16([slot_ab(8 * rhi + (l >> 1), l & 1, k1m) for l in range(16)])
+for m0 in range(2):                         # B reads: lanes = (n2r, k1m[0])
+    for n1r in range(16):
+        for khi in range(16):
+            assert distinct16([slot_ab(8 * n1r + (l >> 1), m0, 2 * khi + (l & 1)) for l in range(16)])
+for k1r in range(16):                       # B writes: same lanes as its reads, (n2r, k1m[0])
+    for k2m in range(2):
+        for khi in range(16):
+            assert distinct16([slot_bc(k1r, k2m, l >> 1, 2 * khi + (l & 1)) for l in range(16)])
+for k1r in range(16):                       # C reads: lanes = km class [3:0]; members km = c and km = 64 - c (c = 0: 32)
+    for n2r in range(8):
+        for chi in range(2):
+            first = [(16 * chi + l) for l in range(16)]
+            assert distinct16([slot_bc(k1r, 0, n2r, c) for c in first])
+            second = [((64 - c) if c else 32) for c in first]
+            assert distinct16([slot_bc(k1r, 1, n2r, km - 32) for km in second])
+print("exchange layouts A->B and B->C: bijective and bank-conflict free")
