@@ -23,8 +23,11 @@
  * device pointers on the current device, *_host are host pointers.  `stream` is a
  * cudaStream_t passed as void* (NULL = legacy default stream).  Every function returns a
  * pdeopt_status and never throws; pdeopt_last_error() describes the last failure on the
- * calling thread.  No hidden allocation after plan creation.  A plan may be used from one
- * thread at a time.  There is no CPU fallback: without a CUDA device every compute entry
+ * calling thread.  The device-pointer entry points of fd plans never allocate; the host-buffer entry
+ * point and derivs='fourier' plans grow plan-owned scratch on first use (and when the batch grows)
+ * and reuse it afterwards.  A plan may be used from one thread at a time.  All device pointers of
+ * one call, the stream and the plan's scratch belong to the CURRENT device: callers that use
+ * several GPUs make the right device current around each call (the Python wrappers do).  There is no CPU fallback: without a CUDA device every compute entry
  * point returns PDEOPT_ERR_CUDA.
  */
 #ifndef PDEOPT_B200_H
@@ -36,7 +39,7 @@
 extern "C" {
 #endif
 
-#define PDEOPT_ABI_VERSION 2
+#define PDEOPT_ABI_VERSION 3
 #define PDEOPT_MAX_COEF 16
 #define PDEOPT_MAX_FUSED_STEPS 512 /* per launch; callers loop for longer rollouts */
 #define PDEOPT_NCTRL 8            /* floats per environment in the control block */
@@ -123,6 +126,19 @@ pdeopt_status pdeopt_sifs_step_batched(pdeopt_plan* plan, const float* y0_dev, f
                                        int32_t ksteps, const float* dt_host, const float* symbol_dev,
                                        const float* ctrl_dev, uint8_t* obs_dev, float obs_lo, float obs_hi,
                                        float* reward_dev, void* stream);
+
+/* Per-environment failure flags.  The reference has diffrax's `throw` switch only (pde_model.py:131
+ * returns NaN states silently with throw=False; PDEEnv.step raises, pde_env.py:293-303); a batched
+ * stepper needs to know WHICH environment failed.  After every stepping call on `plan`
+ * (pdeopt_sifs_step_batched, pdeopt_sifs_filter_batched) flags_dev[b] = 1 if y1 of environment b
+ * holds a NaN or Inf, else 0 (written by the fused 128x128 kernel's epilogue; one extra streaming
+ * launch for the other kernels).  flags_dev: caller-owned [batch] int32 or NULL to detach. */
+pdeopt_status pdeopt_plan_set_nonfinite_flags(pdeopt_plan* plan, int32_t* flags_dev);
+
+/* The same test on any batched float32 state (Strang / GPE [batch][nx][ny][2], 3-D fields):
+ * flags_dev[b] = 1 if y_dev[b*n_per_env .. (b+1)*n_per_env) holds a NaN or Inf. */
+pdeopt_status pdeopt_nonfinite_flags(const float* y_dev, int32_t batch, int64_t n_per_env, int32_t* flags_dev,
+                                     void* stream);
 
 /* eq.rhs(state, t) for `batch` states (CahnHilliard2DPeriodic.rhs_fd, cahn_hilliard.py:89-109;
  * AllenCahn2DPeriodic.rhs_fd, allen_cahn.py:81-84): f_dev[b] = rhs(y_dev[b]).  May alias. */

@@ -110,6 +110,8 @@ EXPORTS = [
     "pdeopt_sifs_step_batched",
     "pdeopt_sifs_step_batched_host",
     "pdeopt_rhs_batched",
+    "pdeopt_plan_set_nonfinite_flags",
+    "pdeopt_nonfinite_flags",
     "pdeopt_sifs_filter_batched",
     "pdeopt_phasefield_adjoint_work_floats",
     "pdeopt_phasefield_adjoint_step",
@@ -210,11 +212,37 @@ def load():
     lib.pdeopt_strang_lines_work_floats.restype = ctypes.c_int64
     lib.pdeopt_strang_lines_step_batched.argtypes = [ctypes.POINTER(GpeDesc), vp, vp, i32, i32, vp, vp, f32, f32, vp, vp, vp]
     lib.pdeopt_strang_lines_step_batched.restype = ctypes.c_int
+    lib.pdeopt_plan_set_nonfinite_flags.argtypes = [vp, vp]
+    lib.pdeopt_plan_set_nonfinite_flags.restype = ctypes.c_int
+    lib.pdeopt_nonfinite_flags.argtypes = [vp, i32, i64, vp, vp]
+    lib.pdeopt_nonfinite_flags.restype = ctypes.c_int
     lib.pdeopt_measure_fp32_peak.argtypes = [ctypes.POINTER(ctypes.c_double), vp]
     lib.pdeopt_measure_fp32_peak.restype = ctypes.c_int
     lib.pdeopt_launch_count.restype = ctypes.c_int64
     _lib = lib
     return lib
+
+
+def device_of(*tensors):
+    """Context manager that makes the CUDA device of the first tensor argument current: the C ABI
+    works on the current device (kernel attributes, plan scratch, stream), so every call through
+    ctypes is wrapped in it."""
+    import contextlib
+
+    import torch
+
+    for t in tensors:
+        if t is not None and hasattr(t, "is_cuda") and t.is_cuda:
+            return torch.cuda.device(t.device)
+    return contextlib.nullcontext()
+
+
+def stream_ptr(t):
+    """cudaStream_t (as void*) of torch's current stream on the device of tensor `t`."""
+    import torch
+
+    dev = t.device if (t is not None and hasattr(t, "is_cuda") and t.is_cuda) else None
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
 def check(status):

@@ -1,10 +1,12 @@
 // C ABI of libpdeopt_b200 (see include/pdeopt_b200.h for the contract and the reference
 // code each entry point replaces).
 #include <cstdio>
+#include <cstdlib>
 #include <new>
 
 #include "capi_common.h"
 #include "sifs128.cuh"
+#include "sifs128r.cuh"
 #include "sifs_generic.cuh"
 #include "sifs_small.cuh"
 #include "ch_adjoint.cuh"
@@ -29,6 +31,7 @@ struct pdeopt_plan {
   float* park = nullptr;  // only used by PDEOPT_PARK_GLOBAL builds
   size_t park_bytes = 0;
   bool attr_set = false;
+  int32_t* flags = nullptr;  // caller-owned [batch] non-finite flags (pdeopt_plan_set_nonfinite_flags)
   // derivs='fourier': wavenumber tables and the per-CTA scratch line
   float* kxy = nullptr;
   float2* fscratch = nullptr;
@@ -99,15 +102,76 @@ extern "C" int64_t pdeopt_table_len(const pdeopt_plan* plan) {
 enum : int { SIFS_V_AC_RT = 0, SIFS_V_CH_LOG_DEG = 1, SIFS_V_CH_LOG_CONST = 2, SIFS_V_CH_DW_CONST = 3, SIFS_V_CH_RT = 4 };
 cudaError_t pdeopt_sifs128_launch_a(int variant, const pdeopt::SifsParams& p, int grid, cudaStream_t st);
 cudaError_t pdeopt_sifs128_launch_b(int variant, const pdeopt::SifsParams& p, int grid, cudaStream_t st);
-static cudaError_t launch_variant(int variant, const SifsParams& p, int grid, cudaStream_t st) {
-  return (variant == SIFS_V_CH_LOG_DEG || variant == SIFS_V_CH_LOG_CONST) ? pdeopt_sifs128_launch_a(variant, p, grid, st)
-                                                                            : pdeopt_sifs128_launch_b(variant, p, grid, st);
+cudaError_t pdeopt_sifs128r_launch_a(int variant, const pdeopt::SifsParams& p, cudaStream_t st);
+cudaError_t pdeopt_sifs128r_launch_b(int variant, const pdeopt::SifsParams& p, cudaStream_t st);
+// PDEOPT_SIFS128_PAIR=1 selects the round-1 kernel (two environments per 512-thread CTA) for A/B
+// measurements; the default is the one-field-per-CTA kernel (sifs128r.cuh).
+static bool use_pair_kernel() {
+  static const bool v = [] {
+    const char* e = std::getenv("PDEOPT_SIFS128_PAIR");
+    return e && e[0] == '1';
+  }();
+  return v;
 }
+static cudaError_t launch_variant(int variant, const SifsParams& p, int grid, cudaStream_t st) {
+  const bool a = variant == SIFS_V_CH_LOG_DEG || variant == SIFS_V_CH_LOG_CONST;
+  if (!use_pair_kernel()) return a ? pdeopt_sifs128r_launch_a(variant, p, st) : pdeopt_sifs128r_launch_b(variant, p, st);
+  return a ? pdeopt_sifs128_launch_a(variant, p, grid, st) : pdeopt_sifs128_launch_b(variant, p, grid, st);
+}
+
+// 1 where the environment's field holds a NaN / Inf (the per-environment failure flag; the
+// reference only has diffrax's `throw` switch, pde_model.py:131 / pde_env.py:293-303)
+__global__ void nonfinite_flags_kernel(const float* __restrict__ y, long long n_per_env, int32_t* __restrict__ flags) {
+  const float* ye = y + (size_t)blockIdx.x * n_per_env;
+  int bad = 0;
+  for (long long i = threadIdx.x; i < n_per_env; i += blockDim.x) bad |= !(fabsf(ye[i]) <= 3.0e38f);
+  bad = __syncthreads_or(bad);
+  if (threadIdx.x == 0) flags[blockIdx.x] = bad ? 1 : 0;
+}
+
+extern "C" pdeopt_status pdeopt_nonfinite_flags(const float* y_dev, int32_t batch, int64_t n_per_env, int32_t* flags_dev,
+                                                void* stream) {
+  PdeoptDeviceGuard device_guard_(y_dev);
+  if (!y_dev || !flags_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
+  if (batch <= 0 || n_per_env <= 0) return fail(PDEOPT_ERR_INVALID, "batch and n_per_env must be positive");
+  nonfinite_flags_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(y_dev, (long long)n_per_env, flags_dev);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+  g_launches.fetch_add(1);
+  return PDEOPT_OK;
+}
+
+extern "C" pdeopt_status pdeopt_plan_set_nonfinite_flags(pdeopt_plan* plan, int32_t* flags_dev) {
+  if (!plan) return fail(PDEOPT_ERR_INVALID, "null argument");
+  plan->flags = flags_dev;
+  return PDEOPT_OK;
+}
+
+// env_offset: index of the first environment of this launch within the caller's batch (the host-buffer
+// entry point launches chunks of one batch on concurrent streams: plan-owned per-environment scratch
+// and the flag array are addressed by the global environment index).
+static pdeopt_status sifs_launch_impl(pdeopt_plan* plan, int mode, const float* f0_dev, const float* y0_dev, float* y1_dev,
+                                 int32_t batch, int32_t ksteps, const float* dt_host, const float* symbol_dev,
+                                 const float* ctrl_dev, uint8_t* obs_dev, float obs_lo, float obs_hi,
+                                 float* reward_dev, void* stream, int32_t env_offset, int32_t total_batch);
 
 static pdeopt_status sifs_launch(pdeopt_plan* plan, int mode, const float* f0_dev, const float* y0_dev, float* y1_dev,
                                  int32_t batch, int32_t ksteps, const float* dt_host, const float* symbol_dev,
                                  const float* ctrl_dev, uint8_t* obs_dev, float obs_lo, float obs_hi,
-                                 float* reward_dev, void* stream) {
+                                 float* reward_dev, void* stream, int32_t env_offset = 0, int32_t total_batch = 0) {
+  pdeopt_status s = sifs_launch_impl(plan, mode, f0_dev, y0_dev, y1_dev, batch, ksteps, dt_host, symbol_dev, ctrl_dev,
+                                     obs_dev, obs_lo, obs_hi, reward_dev, stream, env_offset,
+                                     total_batch > 0 ? total_batch : batch);
+  if (s != PDEOPT_OK || !plan->flags || mode == MODE_RHS_ONLY) return s;
+  const bool fused128 = plan->d.nx == 128 && plan->d.ny == 128 && plan->d.derivs == PDEOPT_DERIVS_FD && !use_pair_kernel();
+  if (fused128) return s;  // written by the kernel's epilogue
+  return pdeopt_nonfinite_flags(y1_dev, batch, (int64_t)plan->d.nx * plan->d.ny, plan->flags + env_offset, stream);
+}
+
+static pdeopt_status sifs_launch_impl(pdeopt_plan* plan, int mode, const float* f0_dev, const float* y0_dev, float* y1_dev,
+                                 int32_t batch, int32_t ksteps, const float* dt_host, const float* symbol_dev,
+                                 const float* ctrl_dev, uint8_t* obs_dev, float obs_lo, float obs_hi,
+                                 float* reward_dev, void* stream, int32_t env_offset, int32_t total_batch) {
   if (!plan || !y0_dev || !y1_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
   if (mode != MODE_RHS_ONLY && (!dt_host || !symbol_dev)) return fail(PDEOPT_ERR_INVALID, "null argument");
   if (mode == MODE_GIVEN_F && (!f0_dev || ksteps != 1)) return fail(PDEOPT_ERR_INVALID, "given-f mode needs f0 and ksteps == 1");
@@ -130,6 +194,7 @@ static pdeopt_status sifs_launch(pdeopt_plan* plan, int mode, const float* f0_de
   p.reward = reward_dev;
   p.mode = mode;
   p.f0 = f0_dev;
+  p.nonfinite = (plan->flags && mode != MODE_RHS_ONLY) ? plan->flags + env_offset : nullptr;
   p.inv_hx = (float)(1.0 / d.hx);
   p.inv_hy = (float)(1.0 / d.hy);
   p.inv_hx2 = (float)(1.0 / (d.hx * d.hx));
@@ -165,7 +230,9 @@ static pdeopt_status sifs_launch(pdeopt_plan* plan, int mode, const float* f0_de
       CUDA_TRY(cudaMalloc((void**)&plan->kxy, sizeof(h)));
       CUDA_TRY(cudaMemcpy(plan->kxy, h, sizeof(h), cudaMemcpyHostToDevice));
     }
-    const size_t need = (size_t)batch * 32 * kThreads * sizeof(float2);
+    // one scratch line per environment of the caller's WHOLE batch: chunks of one batch that run on
+    // concurrent streams (pdeopt_sifs_step_batched_host) address disjoint lines
+    const size_t need = (size_t)total_batch * 32 * kThreads * sizeof(float2);
     if (plan->fscratch_bytes < need) {
       if (plan->fscratch) cudaFree(plan->fscratch);
       plan->fscratch = nullptr;
@@ -185,7 +252,7 @@ static pdeopt_status sifs_launch(pdeopt_plan* plan, int mode, const float* f0_de
     fp.kx = plan->kxy;
     fp.ky = plan->kxy + kN;
     fp.ctrl = ctrl_dev;
-    fp.scratch = plan->fscratch;
+    fp.scratch = plan->fscratch + (size_t)env_offset * 32 * kThreads;
     fp.kappa = p.kappa;
     fp.lo_x = p.lo_x;
     fp.lo_y = p.lo_y;
@@ -193,11 +260,9 @@ static pdeopt_status sifs_launch(pdeopt_plan* plan, int mode, const float* f0_de
     fp.hy = p.hy;
     fp.pw = p.pw;
     for (int k = 0; k < ksteps && mode != MODE_RHS_ONLY; ++k) fp.dt[k] = dt_host[k];
-    static bool fattr = false;
-    if (!fattr) {
+    static bool fattr[kPdeoptMaxDevices] = {};
+    if (pdeopt_first_use_on_device(fattr))
       CUDA_TRY(cudaFuncSetAttribute(fourier128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FourierSmem)));
-      fattr = true;
-    }
     fourier128_kernel<<<batch, kThreads, sizeof(FourierSmem), st>>>(fp);
     cudaError_t fe = cudaGetLastError();
     if (fe != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(fe));
@@ -216,12 +281,10 @@ static pdeopt_status sifs_launch(pdeopt_plan* plan, int mode, const float* f0_de
       cudaError_t se = cudaSuccess;
 #define PDEOPT_SMALL_LAUNCH(NN, EE)                                                                                   \
   {                                                                                                                   \
-    static bool sattr = false;                                                                                        \
-    if (!sattr) {                                                                                                     \
+    static bool sattr[kPdeoptMaxDevices] = {};                                                                        \
+    if (pdeopt_first_use_on_device(sattr))                                                                            \
       se = cudaFuncSetAttribute(sifs_small_kernel<NN, EE>, cudaFuncAttributeMaxDynamicSharedMemorySize,               \
                                 (int)sizeof(SmallSmem<NN>));                                                          \
-      sattr = se == cudaSuccess;                                                                                      \
-    }                                                                                                                 \
     if (se == cudaSuccess) sifs_small_kernel<NN, EE><<<grid, kSmallThreads, sizeof(SmallSmem<NN>), st>>>(gp);         \
   }
       if (d.nx == 64) {
@@ -238,19 +301,17 @@ static pdeopt_status sifs_launch(pdeopt_plan* plan, int mode, const float* f0_de
     const size_t smem = gen_smem_bytes(d.nx, d.ny);
     cudaError_t ge;
     if (d.kind == PDEOPT_AC2D) {
-      static bool attr = false;
-      if (!attr) {
+      static bool attr[kPdeoptMaxDevices] = {};
+      if (pdeopt_first_use_on_device(attr)) {
         ge = cudaFuncSetAttribute(sifs_generic_kernel<EQ_AC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (ge != cudaSuccess) return fail(PDEOPT_ERR_CUDA, cudaGetErrorString(ge));
-        attr = true;
       }
       sifs_generic_kernel<EQ_AC><<<grid, kGenThreads, smem, st>>>(gp);
     } else {
-      static bool attr = false;
-      if (!attr) {
+      static bool attr[kPdeoptMaxDevices] = {};
+      if (pdeopt_first_use_on_device(attr)) {
         ge = cudaFuncSetAttribute(sifs_generic_kernel<EQ_CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (ge != cudaSuccess) return fail(PDEOPT_ERR_CUDA, cudaGetErrorString(ge));
-        attr = true;
       }
       sifs_generic_kernel<EQ_CH><<<grid, kGenThreads, smem, st>>>(gp);
     }
@@ -293,12 +354,14 @@ extern "C" pdeopt_status pdeopt_sifs_step_batched(pdeopt_plan* plan, const float
                                                   int32_t ksteps, const float* dt_host, const float* symbol_dev,
                                                   const float* ctrl_dev, uint8_t* obs_dev, float obs_lo, float obs_hi,
                                                   float* reward_dev, void* stream) {
+  PdeoptDeviceGuard device_guard_(y0_dev);
   return sifs_launch(plan, MODE_FUSED, nullptr, y0_dev, y1_dev, batch, ksteps, dt_host, symbol_dev, ctrl_dev, obs_dev,
                      obs_lo, obs_hi, reward_dev, stream);
 }
 
 extern "C" pdeopt_status pdeopt_rhs_batched(pdeopt_plan* plan, const float* y_dev, float* f_dev, int32_t batch,
                                             const float* ctrl_dev, void* stream) {
+  PdeoptDeviceGuard device_guard_(y_dev);
   return sifs_launch(plan, MODE_RHS_ONLY, nullptr, y_dev, f_dev, batch, 1, nullptr, nullptr, ctrl_dev, nullptr, 0.f, 1.f,
                      nullptr, stream);
 }
@@ -306,6 +369,7 @@ extern "C" pdeopt_status pdeopt_rhs_batched(pdeopt_plan* plan, const float* y_de
 extern "C" pdeopt_status pdeopt_sifs_filter_batched(pdeopt_plan* plan, const float* y0_dev, const float* f0_dev,
                                                     float* y1_dev, int32_t batch, float dt, const float* symbol_dev,
                                                     void* stream) {
+  PdeoptDeviceGuard device_guard_(y0_dev);
   return sifs_launch(plan, MODE_GIVEN_F, f0_dev, y0_dev, y1_dev, batch, 1, &dt, symbol_dev, nullptr, nullptr, 0.f, 1.f,
                      nullptr, stream);
 }
@@ -320,6 +384,7 @@ extern "C" int64_t pdeopt_phasefield_adjoint_work_floats(const pdeopt_plan* plan
 extern "C" pdeopt_status pdeopt_phasefield_adjoint_step(pdeopt_plan* plan, const float* u_dev, const float* lam1_dev,
                                                         float* lam0_dev, int32_t batch, float dt, const float* symbol_dev,
                                                         float* work_dev, double* gmu_dev, double* gmob_dev, void* stream) {
+  PdeoptDeviceGuard device_guard_(u_dev);
   if (!plan || !u_dev || !lam1_dev || !lam0_dev || !symbol_dev || !work_dev || !gmu_dev || !gmob_dev)
     return fail(PDEOPT_ERR_INVALID, "null argument");
   if (batch <= 0 || batch > 65535) return fail(PDEOPT_ERR_INVALID, "batch must be in [1, 65535]");
@@ -406,10 +471,10 @@ extern "C" pdeopt_status pdeopt_sifs_step_batched_host(pdeopt_plan* plan, const 
     CUDA_TRY(cudaStreamWaitEvent(ps, plan->ev_start, 0));
     float* yc = y_dev + (size_t)b0 * npts;
     CUDA_TRY(cudaMemcpyAsync(yc, y0_host + (size_t)b0 * npts, (size_t)nb * npts * sizeof(float), cudaMemcpyHostToDevice, ps));
-    status = pdeopt_sifs_step_batched(plan, yc, yc, nb, ksteps, dt_host, tab_dev,
-                                      ctrl_host ? ctrl_dev + (size_t)b0 * PDEOPT_NCTRL : nullptr,
-                                      obs_host ? obs_dev + (size_t)b0 * npts : nullptr, obs_lo, obs_hi,
-                                      reward_host ? rew_dev + (size_t)b0 * 2 : nullptr, (void*)ps);
+    status = sifs_launch(plan, MODE_FUSED, nullptr, yc, yc, nb, ksteps, dt_host, tab_dev,
+                         ctrl_host ? ctrl_dev + (size_t)b0 * PDEOPT_NCTRL : nullptr,
+                         obs_host ? obs_dev + (size_t)b0 * npts : nullptr, obs_lo, obs_hi,
+                         reward_host ? rew_dev + (size_t)b0 * 2 : nullptr, (void*)ps, b0, batch);
     if (status != PDEOPT_OK) break;
     CUDA_TRY(cudaMemcpyAsync(y1_host + (size_t)b0 * npts, yc, (size_t)nb * npts * sizeof(float), cudaMemcpyDeviceToHost, ps));
     if (obs_host) CUDA_TRY(cudaMemcpyAsync(obs_host + (size_t)b0 * npts, obs_dev + (size_t)b0 * npts, (size_t)nb * npts, cudaMemcpyDeviceToHost, ps));

@@ -53,6 +53,7 @@ extern "C" pdeopt_status pdeopt_ad_rollout_fwd(const pdeopt_ad_desc* desc, const
                                                const float* tables_dev, const float* ctrl_dev, int32_t nseg,
                                                int32_t hold, int32_t step0, float* traj_dev, int64_t traj_stride,
                                                void* stream) {
+  PdeoptDeviceGuard device_guard_(y0_dev);
   if (!y0_dev || !y1_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
 #ifdef PDEOPT_PARK_GLOBAL
   return fail(PDEOPT_ERR_UNSUPPORTED, "advection-diffusion: PDEOPT_PARK_GLOBAL builds are not supported");
@@ -75,18 +76,14 @@ extern "C" pdeopt_status pdeopt_ad_rollout_fwd(const pdeopt_ad_desc* desc, const
     if (desc->nx == desc->ny && (desc->nx == 64 || desc->nx == 32)) {
       cudaError_t se;
       if (desc->nx == 64) {
-        static bool a64 = false;
-        if (!a64) {
+        static bool a64[kPdeoptMaxDevices] = {};
+        if (pdeopt_first_use_on_device(a64))
           CUDA_TRY(cudaFuncSetAttribute(ad_small_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AdSmallSmem<64>)));
-          a64 = true;
-        }
         ad_small_fwd_kernel<64><<<(batch + 1) / 2, kSmallThreads, sizeof(AdSmallSmem<64>), (cudaStream_t)stream>>>(gp);
       } else {
-        static bool a32 = false;
-        if (!a32) {
+        static bool a32[kPdeoptMaxDevices] = {};
+        if (pdeopt_first_use_on_device(a32))
           CUDA_TRY(cudaFuncSetAttribute(ad_small_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AdSmallSmem<32>)));
-          a32 = true;
-        }
         ad_small_fwd_kernel<32><<<(batch + 1) / 2, kSmallThreads, sizeof(AdSmallSmem<32>), (cudaStream_t)stream>>>(gp);
       }
       se = cudaGetLastError();
@@ -94,22 +91,18 @@ extern "C" pdeopt_status pdeopt_ad_rollout_fwd(const pdeopt_ad_desc* desc, const
       g_launches.fetch_add(1);
       return PDEOPT_OK;
     }
-    static bool gattr = false;
-    if (!gattr) {
+    static bool gattr[kPdeoptMaxDevices] = {};
+    if (pdeopt_first_use_on_device(gattr))
       CUDA_TRY(cudaFuncSetAttribute(ad_generic_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-      gattr = true;
-    }
     ad_generic_fwd_kernel<<<(batch + 1) / 2, kGenThreads, ad_gen_smem_bytes(desc->nx, desc->ny), (cudaStream_t)stream>>>(gp);
     cudaError_t ge = cudaGetLastError();
     if (ge != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(ge));
     g_launches.fetch_add(1);
     return PDEOPT_OK;
   }
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[kPdeoptMaxDevices] = {};
+  if (pdeopt_first_use_on_device(attr))
     CUDA_TRY(cudaFuncSetAttribute(ad128_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AdSmem)));
-    attr = true;
-  }
   ad128_fwd_kernel<<<(batch + 1) / 2, kThreads, sizeof(AdSmem), (cudaStream_t)stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
@@ -122,6 +115,7 @@ extern "C" pdeopt_status pdeopt_ad_rollout_bwd(const pdeopt_ad_desc* desc, const
                                                const float* dt_host, const float* tables_dev, const float* ctrl_dev,
                                                int32_t nseg, int32_t hold, int32_t step0, float* gctrl_dev,
                                                void* stream) {
+  PdeoptDeviceGuard device_guard_(lam1_dev);
   if (!traj_dev || !lam1_dev || !lam0_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
   if (desc && !(desc->nx == 128 && desc->ny == 128))
     return fail(PDEOPT_ERR_UNSUPPORTED, "advection-diffusion: the adjoint kernel is implemented for 128x128 grids");
@@ -136,11 +130,9 @@ extern "C" pdeopt_status pdeopt_ad_rollout_bwd(const pdeopt_ad_desc* desc, const
   p.traj_in = traj_dev;
   p.traj_stride = traj_stride;
   p.gctrl = gctrl_dev;
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[kPdeoptMaxDevices] = {};
+  if (pdeopt_first_use_on_device(attr))
     CUDA_TRY(cudaFuncSetAttribute(ad128_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AdSmem)));
-    attr = true;
-  }
   ad128_bwd_kernel<<<(batch + 1) / 2, kThreads, sizeof(AdSmem), (cudaStream_t)stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));

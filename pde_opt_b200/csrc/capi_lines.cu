@@ -14,6 +14,7 @@ extern "C" int32_t pdeopt_fft_pos_to_freq(int32_t n, int32_t pos) {
 extern "C" pdeopt_status pdeopt_fft_lines(const void* in_dev, void* out_dev, int32_t n, const pdeopt_line_geom* gin,
                                           const pdeopt_line_geom* gout, int32_t inverse, int32_t in_real, float scale,
                                           void* stream) {
+  PdeoptDeviceGuard device_guard_(in_dev);
   if (!in_dev || !out_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
   if (!lf_size_ok(n)) return fail(PDEOPT_ERR_UNSUPPORTED, "fft_lines: n must be a power of two in [8, 512]");
   if (!geom_ok(gin, n) || !geom_ok(gout, n) || gin->n_lines != gout->n_lines) return fail(PDEOPT_ERR_INVALID, "bad line geometry");
@@ -41,6 +42,7 @@ extern "C" pdeopt_status pdeopt_fft_lines(const void* in_dev, void* out_dev, int
 extern "C" pdeopt_status pdeopt_fft_lines_imex(const void* in_dev, void* out_dev, int32_t n, const pdeopt_line_geom* g,
                                                const float* sym_dev, const pdeopt_line_geom* gsym, float dt, float scale,
                                                void* stream) {
+  PdeoptDeviceGuard device_guard_(in_dev);
   if (!in_dev || !out_dev || !sym_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
   if (!lf_size_ok(n)) return fail(PDEOPT_ERR_UNSUPPORTED, "fft_lines: n must be a power of two in [8, 512]");
   if (!geom_ok(g, n) || !geom_ok(gsym, n)) return fail(PDEOPT_ERR_INVALID, "bad line geometry");
@@ -59,6 +61,7 @@ extern "C" pdeopt_status pdeopt_fft_lines_to_peers(const void* in_dev, int32_t n
                                                    void* const* peer_ptrs_host, int32_t n_peers,
                                                    const pdeopt_line_geom* gout, int64_t src_off, const float* sym_dev,
                                                    const pdeopt_line_geom* gsym, float dt, float scale, void* stream) {
+  PdeoptDeviceGuard device_guard_(in_dev);
   if (!in_dev || !peer_ptrs_host) return fail(PDEOPT_ERR_INVALID, "null argument");
   if (!lf_size_ok(n)) return fail(PDEOPT_ERR_UNSUPPORTED, "fft_lines: n must be a power of two in [8, 512]");
   if (n_peers < 1 || n_peers > 8) return fail(PDEOPT_ERR_INVALID, "1..8 peers");
@@ -88,6 +91,7 @@ extern "C" pdeopt_status pdeopt_fft_lines_to_peers(const void* in_dev, int32_t n
 extern "C" pdeopt_status pdeopt_fft_lines_inv_update(const void* spec_dev, int32_t n, const pdeopt_line_geom* gin,
                                                      const float* y0_dev, float* y1_dev, const pdeopt_line_geom* gout,
                                                      float dt, void* stream) {
+  PdeoptDeviceGuard device_guard_(spec_dev);
   if (!spec_dev || !y0_dev || !y1_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
   if (!lf_size_ok(n)) return fail(PDEOPT_ERR_UNSUPPORTED, "fft_lines: n must be a power of two in [8, 512]");
   if (!geom_ok(gin, n) || !geom_ok(gout, n) || gin->n_lines != gout->n_lines) return fail(PDEOPT_ERR_INVALID, "bad line geometry");
@@ -103,6 +107,7 @@ extern "C" pdeopt_status pdeopt_fft_lines_inv_update(const void* spec_dev, int32
 }
 
 extern "C" pdeopt_status pdeopt_fft_lines_r2c(const float* in_dev, void* out_dev, int32_t n, int64_t n_lines, void* stream) {
+  PdeoptDeviceGuard device_guard_(in_dev);
   if (!in_dev || !out_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
   if (!lf_size_ok(n)) return fail(PDEOPT_ERR_UNSUPPORTED, "fft_lines: n must be a power of two in [8, 512]");
   if (n_lines <= 0 || (n_lines & 1)) return fail(PDEOPT_ERR_INVALID, "r2c needs a positive even number of lines");
@@ -120,6 +125,7 @@ extern "C" pdeopt_status pdeopt_fft_lines_r2c(const float* in_dev, void* out_dev
 
 extern "C" pdeopt_status pdeopt_fft_lines_c2r_update(const void* half_dev, int32_t n, int64_t n_lines, const float* y0_dev,
                                                      float* y1_dev, float dt, void* stream) {
+  PdeoptDeviceGuard device_guard_(half_dev);
   if (!half_dev || !y0_dev || !y1_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
   if (!lf_size_ok(n)) return fail(PDEOPT_ERR_UNSUPPORTED, "fft_lines: n must be a power of two in [8, 512]");
   if (n_lines <= 0 || (n_lines & 1)) return fail(PDEOPT_ERR_INVALID, "c2r needs a positive even number of lines");
@@ -150,6 +156,7 @@ static pdeopt_status ch3d_check(const pdeopt_ch3d_desc* d, int32_t batch) {
 extern "C" pdeopt_status pdeopt_ch3d_rhs(const pdeopt_ch3d_desc* d, const float* u_dev, const float* halo_lo_dev,
                                          const float* halo_hi_dev, float* mu_work_dev, float* f_dev, int32_t batch,
                                          void* stream) {
+  PdeoptDeviceGuard device_guard_(u_dev);
   pdeopt_status s = ch3d_check(d, batch);
   if (s != PDEOPT_OK) return s;
   if (!u_dev || !mu_work_dev || !f_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
@@ -224,6 +231,7 @@ extern "C" int64_t pdeopt_ch3d_work_floats(const pdeopt_ch3d_desc* d, int32_t ba
 extern "C" pdeopt_status pdeopt_ch3d_step(const pdeopt_ch3d_desc* d, const float* y0_dev, float* y1_dev, int32_t batch,
                                           int32_t ksteps, const float* dt_host, const float* symbol_pos_dev,
                                           float* work_dev, void* stream) {
+  PdeoptDeviceGuard device_guard_(y0_dev);
   pdeopt_status s = ch3d_check(d, batch);
   if (s != PDEOPT_OK) return s;
   if (!y0_dev || !y1_dev || !dt_host || !symbol_pos_dev || !work_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
@@ -261,6 +269,7 @@ extern "C" int64_t pdeopt_ch3d_adjoint_work_floats(const pdeopt_ch3d_desc* d, in
 extern "C" pdeopt_status pdeopt_ch3d_adjoint_step(const pdeopt_ch3d_desc* d, const float* u_dev, const float* lam1_dev,
                                                   float* lam0_dev, int32_t batch, float dt, const float* symbol_pos_dev,
                                                   float* work_dev, double* gmu_dev, double* gmob_dev, void* stream) {
+  PdeoptDeviceGuard device_guard_(u_dev);
   pdeopt_status s = ch3d_check(d, batch);
   if (s != PDEOPT_OK) return s;
   if (!u_dev || !lam1_dev || !lam0_dev || !symbol_pos_dev || !work_dev || !gmu_dev || !gmob_dev)

@@ -8,6 +8,7 @@ extern "C" pdeopt_status pdeopt_strang_step_batched(const pdeopt_gpe_desc* desc,
                                                     int32_t batch, int32_t ksteps, const float* dt_host,
                                                     const float* a_term_dev, float ts_re, float ts_im,
                                                     const float* ctrl_dev, void* stream) {
+  PdeoptDeviceGuard device_guard_(y0_dev);
   if (!desc || !y0_dev || !y1_dev || !dt_host) return fail(PDEOPT_ERR_INVALID, "null argument");
   if (desc->nx != 128 || desc->ny != 128)
     return fail(PDEOPT_ERR_UNSUPPORTED, "strang: only 128x128 grids are implemented (256x256 needs the cluster kernel)");
@@ -36,11 +37,9 @@ extern "C" pdeopt_status pdeopt_strang_step_batched(const pdeopt_gpe_desc* desc,
 #ifdef PDEOPT_PARK_GLOBAL
   return fail(PDEOPT_ERR_UNSUPPORTED, "strang: PDEOPT_PARK_GLOBAL builds are not supported");
 #endif
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[kPdeoptMaxDevices] = {};
+  if (pdeopt_first_use_on_device(attr))
     CUDA_TRY(cudaFuncSetAttribute(strang128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StrangSmem)));
-    attr = true;
-  }
   strang128_kernel<<<batch, kThreads, sizeof(StrangSmem), (cudaStream_t)stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
@@ -52,6 +51,7 @@ extern "C" pdeopt_status pdeopt_strang_step_batched(const pdeopt_gpe_desc* desc,
 extern "C" pdeopt_status pdeopt_gpe_detect_vortices(const float* psi_dev, int32_t batch, int32_t n0, int32_t n1,
                                                     float amp_thresh, float tol, int32_t* winding_dev,
                                                     int32_t* counts_dev, void* stream) {
+  PdeoptDeviceGuard device_guard_(psi_dev);
   if (!psi_dev || !counts_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
   if (batch <= 0 || batch > 65535 || n0 < 2 || n1 < 2) return fail(PDEOPT_ERR_INVALID, "detect_vortices: bad sizes");
   VortexParams p;

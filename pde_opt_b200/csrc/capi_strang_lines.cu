@@ -12,6 +12,7 @@ extern "C" pdeopt_status pdeopt_strang_lines_step_batched(const pdeopt_gpe_desc*
                                                           int32_t batch, int32_t ksteps, const float* dt_host,
                                                           const float* a_term_full_dev, float ts_re, float ts_im,
                                                           const float* ctrl_dev, float* work_dev, void* stream) {
+  PdeoptDeviceGuard device_guard_(y0_dev);
   if (!desc || !y0_dev || !y1_dev || !dt_host || !work_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
   const int nx = desc->nx, ny = desc->ny;
   if (!lf_size_ok(nx) || !lf_size_ok(ny) || nx < 32 || ny < 32)
@@ -22,11 +23,10 @@ extern "C" pdeopt_status pdeopt_strang_lines_step_batched(const pdeopt_gpe_desc*
   cudaStream_t st = (cudaStream_t)stream;
   if (a_term_full_dev == nullptr && nx == kClN && ny == kClN) {
     // the equation as shipped on 256x256: cluster-of-4 kernel, state in registers for all K steps
-    static bool cattr = false;
-    if (!cattr) {
+    static bool cattr[kPdeoptMaxDevices] = {};
+    if (pdeopt_first_use_on_device(cattr)) {
       cudaError_t ce = cudaFuncSetAttribute(strang_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
       (void)ce;
-      cattr = true;
     }
     const float* src = y0_dev;
     for (int done = 0; done < ksteps;) {

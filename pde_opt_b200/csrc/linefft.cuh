@@ -559,11 +559,12 @@ template <int N, bool INV, class Io>
 cudaError_t lf_launch_real(long long n_pairs, Io io, cudaStream_t stream) {
   auto kern = linefft_real_kernel<N, INV, Io>;
   constexpr size_t smem = LineTileReal<N>::smem_bytes;
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64] = {};  // kernel attributes are per-device state
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && !attr[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr[dev] = true;
   }
   const long long tiles = (n_pairs + LineTile<N, true>::T - 1) / LineTile<N, true>::T;
   const int per_sm = (int)((227 * 1024) / (smem + 1024));
@@ -627,11 +628,12 @@ template <int N, int MODE, bool CONTIG, class Loader, class Mid, class Storer>
 cudaError_t lf_launch(long long n_lines, Loader ld, Mid mid, Storer st, cudaStream_t stream) {
   auto kern = linefft_kernel<N, MODE, CONTIG, Loader, Mid, Storer>;
   constexpr size_t smem = LineTile<N, CONTIG>::smem_bytes;
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64] = {};  // kernel attributes are per-device state
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && !attr[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr[dev] = true;
   }
   const long long tiles = (n_lines + LineTile<N, CONTIG>::T - 1) / LineTile<N, CONTIG>::T;
   const int per_sm = (int)((227 * 1024) / (smem + 1024));

@@ -42,7 +42,7 @@ constexpr uint32_t kWBytes = kRows * kH * 8;
 
 // ---- shared-memory access: [base register (+ XOR of low bits)] + compile-time immediate --------
 // Device: 32-bit shared-window byte addresses.  Host emulation: byte offsets into g_emul.
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 template <int OFF>
 __device__ __forceinline__ float2 ld2(uint32_t a) {
   float2 v;
@@ -125,7 +125,7 @@ struct RFft {
       warp0 = j == 0;
       const int k1r[2] = {j, j == 0 ? 8 : 16 - j};
       const int k1m[2] = {c, (32 - c) & 31};
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 #pragma unroll
 #endif
       for (int i = 0; i < 2; ++i)
@@ -191,7 +191,7 @@ PDEOPT_RF_FN void passB_fwd(const RFft& F, const float2* __restrict__ twb, const
   });
   {
     const float2 w = tw64[F.b_k1m];
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 #pragma unroll
 #endif
     for (int n = 0; n < 16; ++n) {
@@ -243,7 +243,7 @@ PDEOPT_RF_FN void passB_inv(const RFft& F, const float2* __restrict__ twb, const
   Dit<16, 1, true>::run(x + 16);
   {
     const float2 w = tw64[F.b_k1m];
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 #pragma unroll
 #endif
     for (int n = 0; n < 16; ++n) {

@@ -8,11 +8,14 @@ using namespace pdeopt;
 template <int EQ, int MU, int MOB>
 static cudaError_t launch(const SifsParams& p, int grid, cudaStream_t st) {
   auto kern = sifs128_kernel<EQ, MU, MOB>;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SifsSmem));
+  static bool attr[64] = {};  // per device
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && !attr[dev]) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SifsSmem));
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr[dev] = true;
   }
   kern<<<grid, kThreads, sizeof(SifsSmem), st>>>(p);
   return cudaGetLastError();

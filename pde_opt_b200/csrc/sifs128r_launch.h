@@ -1,0 +1,35 @@
+// Launch helper shared by the sifs128r_inst_*.cu translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "sifs128r.cuh"
+
+using namespace pdeopt;
+
+// Per-device launch state: kernel attributes are per-device (and per-context) state, so they are
+// set once for every device a kernel is launched on, not once per process.
+constexpr int kMaxDevices = 64;
+
+template <int EQ, int MU, int MOB>
+static cudaError_t launch_r(const SifsParams& p, cudaStream_t st) {
+  auto kern = rf::sifs128r_kernel<EQ, MU, MOB>;
+  static bool attr[kMaxDevices] = {};
+  static int sms[kMaxDevices] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+  if (!attr[dev]) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(rf::RSmem));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    attr[dev] = true;
+  }
+  const int slots = 2 * sms[dev];
+  const int grid = p.batch < slots ? p.batch : slots;
+  kern<<<grid, rf::kThreadsR, sizeof(rf::RSmem), st>>>(p);
+  return cudaGetLastError();
+}

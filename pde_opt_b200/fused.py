@@ -71,9 +71,11 @@ class SifsPlan:
         except Exception:
             pass
 
-    def step(self, y0, dts, symbol, ctrl=None, obs=None, obs_range=(0.0, 1.0), reward=None, out=None):
+    def step(self, y0, dts, symbol, ctrl=None, obs=None, obs_range=(0.0, 1.0), reward=None, out=None, nonfinite=None):
         """K = len(dts) fused steps on y0 [B, nx, ny] float32 CUDA (pdeopt_sifs_step_batched).
-        `symbol` is the folded A*symbol table on the device.  Returns y1 (out or new)."""
+        `symbol` is the folded A*symbol table on the device.  Returns y1 (out or new).
+        `nonfinite`: optional int32 [B] CUDA tensor that receives 1 for every environment whose
+        y1 holds a NaN / Inf (pdeopt_plan_set_nonfinite_flags)."""
         lib = _lib.load()
         assert y0.is_cuda and y0.dtype == torch.float32 and y0.is_contiguous()
         B = y0.shape[0]
@@ -82,34 +84,40 @@ class SifsPlan:
         dts = np.ascontiguousarray(np.asarray(dts, dtype=np.float32))
         K = len(dts)
         assert symbol.is_cuda and symbol.dtype == torch.float32 and symbol.numel() == self.table_len
-        stream = ctypes.c_void_p(torch.cuda.current_stream(y0.device).cuda_stream)
         done, src = 0, y0
-        while done < K:
-            k = min(_lib.MAX_FUSED_STEPS, K - done)
-            last = done + k == K
-            st = lib.pdeopt_sifs_step_batched(
-                self._h, _ptr(src), _ptr(y1), B, k, _ptr(dts[done:]), _ptr(symbol), _ptr(ctrl),
-                _ptr(obs) if last else None, float(obs_range[0]), float(obs_range[1]),
-                _ptr(reward) if last else None, stream,
-            )
-            _lib.check(st)
-            src = y1
-            done += k
+        with _lib.device_of(y0):
+            stream = _lib.stream_ptr(y0)
+            if nonfinite is not None:
+                assert nonfinite.is_cuda and nonfinite.dtype == torch.int32 and nonfinite.numel() >= B
+            _lib.check(lib.pdeopt_plan_set_nonfinite_flags(self._h, _ptr(nonfinite)))
+            while done < K:
+                k = min(_lib.MAX_FUSED_STEPS, K - done)
+                last = done + k == K
+                st = lib.pdeopt_sifs_step_batched(
+                    self._h, _ptr(src), _ptr(y1), B, k, _ptr(dts[done:]), _ptr(symbol), _ptr(ctrl),
+                    _ptr(obs) if last else None, float(obs_range[0]), float(obs_range[1]),
+                    _ptr(reward) if last else None, stream,
+                )
+                _lib.check(st)
+                src = y1
+                done += k
         return y1
 
     def filter(self, y0, f0, dt, symbol, out=None):
         """One step with an externally evaluated vector field (pdeopt_sifs_filter_batched)."""
         lib = _lib.load()
         y1 = out if out is not None else torch.empty_like(y0)
-        stream = ctypes.c_void_p(torch.cuda.current_stream(y0.device).cuda_stream)
-        _lib.check(lib.pdeopt_sifs_filter_batched(self._h, _ptr(y0), _ptr(f0), _ptr(y1), y0.shape[0], float(dt), _ptr(symbol), stream))
+        with _lib.device_of(y0):
+            _lib.check(lib.pdeopt_plan_set_nonfinite_flags(self._h, None))
+            _lib.check(lib.pdeopt_sifs_filter_batched(self._h, _ptr(y0), _ptr(f0), _ptr(y1), y0.shape[0], float(dt), _ptr(symbol),
+                                                      _lib.stream_ptr(y0)))
         return y1
 
     def rhs(self, y, ctrl=None, out=None):
         lib = _lib.load()
         f = out if out is not None else torch.empty_like(y)
-        stream = ctypes.c_void_p(torch.cuda.current_stream(y.device).cuda_stream)
-        _lib.check(lib.pdeopt_rhs_batched(self._h, _ptr(y), _ptr(f), y.shape[0], _ptr(ctrl), stream))
+        with _lib.device_of(y):
+            _lib.check(lib.pdeopt_rhs_batched(self._h, _ptr(y), _ptr(f), y.shape[0], _ptr(ctrl), _lib.stream_ptr(y)))
         return f
 
     def step_host(self, y0, dts, symbol, ctrl=None, obs=None, obs_range=(0.0, 1.0), reward=None, out=None):
@@ -119,6 +127,7 @@ class SifsPlan:
         dts = np.ascontiguousarray(np.asarray(dts, dtype=np.float32))
         assert len(dts) <= _lib.MAX_FUSED_STEPS
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(lib.pdeopt_plan_set_nonfinite_flags(self._h, None))
         st = lib.pdeopt_sifs_step_batched_host(
             self._h, _ptr(y0), _ptr(y1), y0.shape[0], len(dts), _ptr(dts), _ptr(symbol), _ptr(ctrl), _ptr(obs),
             float(obs_range[0]), float(obs_range[1]), _ptr(reward), stream,
@@ -158,8 +167,9 @@ class Ch3dPlan:
         assert u.is_cuda and u.dtype == torch.float32 and u.is_contiguous() and tuple(u.shape[1:]) == self.points
         f = out if out is not None else torch.empty_like(u)
         work = self._workbuf(u.shape[0], u.device)
-        stream = ctypes.c_void_p(torch.cuda.current_stream(u.device).cuda_stream)
-        _lib.check(lib.pdeopt_ch3d_rhs(ctypes.byref(self.desc), _ptr(u), _ptr(halo_lo), _ptr(halo_hi), _ptr(work), _ptr(f), u.shape[0], stream))
+        with _lib.device_of(u):
+            _lib.check(lib.pdeopt_ch3d_rhs(ctypes.byref(self.desc), _ptr(u), _ptr(halo_lo), _ptr(halo_hi), _ptr(work), _ptr(f), u.shape[0],
+                                           _lib.stream_ptr(u)))
         return f
 
     def step(self, y0, dts, symbol_pos, out=None):
@@ -172,8 +182,9 @@ class Ch3dPlan:
         y1 = out if out is not None else torch.empty_like(y0)
         dts = np.ascontiguousarray(np.asarray(dts, dtype=np.float32))
         work = self._workbuf(y0.shape[0], y0.device)
-        stream = ctypes.c_void_p(torch.cuda.current_stream(y0.device).cuda_stream)
-        _lib.check(lib.pdeopt_ch3d_step(ctypes.byref(self.desc), _ptr(y0), _ptr(y1), y0.shape[0], len(dts), _ptr(dts), _ptr(symbol_pos), _ptr(work), stream))
+        with _lib.device_of(y0):
+            _lib.check(lib.pdeopt_ch3d_step(ctypes.byref(self.desc), _ptr(y0), _ptr(y1), y0.shape[0], len(dts), _ptr(dts), _ptr(symbol_pos),
+                                            _ptr(work), _lib.stream_ptr(y0)))
         return y1
 
     def adjoint_step(self, u, lam, dt, symbol_pos, gmu, gmob):
@@ -185,6 +196,6 @@ class Ch3dPlan:
         if key not in self._work:
             n = int(lib.pdeopt_ch3d_adjoint_work_floats(ctypes.byref(self.desc), B))
             self._work[key] = torch.empty(n, dtype=torch.float32, device=u.device)
-        stream = ctypes.c_void_p(torch.cuda.current_stream(u.device).cuda_stream)
-        _lib.check(lib.pdeopt_ch3d_adjoint_step(ctypes.byref(self.desc), _ptr(u), _ptr(lam), _ptr(lam), B, float(dt), _ptr(symbol_pos),
-                                                _ptr(self._work[key]), _ptr(gmu), _ptr(gmob), stream))
+        with _lib.device_of(u):
+            _lib.check(lib.pdeopt_ch3d_adjoint_step(ctypes.byref(self.desc), _ptr(u), _ptr(lam), _ptr(lam), B, float(dt), _ptr(symbol_pos),
+                                                    _ptr(self._work[key]), _ptr(gmu), _ptr(gmob), _lib.stream_ptr(u)))

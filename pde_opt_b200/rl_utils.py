@@ -42,7 +42,7 @@ def vortex_counts(psi, amp_thresh=0.0, tol=0.5, winding=False):
     _lib.check(
         _lib.load().pdeopt_gpe_detect_vortices(
             y.data_ptr(), B, n0, n1, float(amp_thresh), float(tol), w.data_ptr() if winding else None,
-            counts.data_ptr(), torch.cuda.current_stream().cuda_stream,
+            counts.data_ptr(), torch.cuda.current_stream(y.device).cuda_stream,
         )
     )
     return (counts, w) if winding else counts
