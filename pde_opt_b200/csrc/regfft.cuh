@@ -208,4 +208,40 @@ struct Dit {
   }
 };
 
+// Decimation in time with EVERY non-trivial twiddle (the 8th roots included) in the fused form
+// p = a + w b (four FMAs), q = 2a - p (two FMAs): six FP32-pipe slots per butterfly instead of eight,
+// four for the trivial twiddles 1 and -+i.  Position p holds x[brev(p)] on entry; natural order out.
+// Used for the forward AND inverse passes of the one-field-per-CTA kernel (register indices are
+// compile-time, so the bit-reversed placement of the inputs costs nothing).
+template <int N, int S, bool INV>
+struct DitF {
+  static PDEOPT_HD void run(float2* x) {
+    if constexpr (N >= 2) {
+      DitF<N / 2, S, INV>::run(x);
+      DitF<N / 2, S, INV>::run(x + (N / 2) * S);
+      static_for<0, N / 2>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        if constexpr (j == 0) {
+          const float2 a = x[0], b = x[(N / 2) * S];
+          x[0] = cadd(a, b);
+          x[(N / 2) * S] = csub(a, b);
+        } else if constexpr (j * 4 == N) {
+          const float2 a = x[j * S], b = mul_tw<N, j, INV>(x[(j + N / 2) * S]);
+          x[j * S] = cadd(a, b);
+          x[(j + N / 2) * S] = csub(a, b);
+        } else {
+          constexpr float wr = Tw<N, j>::re;
+          constexpr float wi = INV ? -Tw<N, j>::im : Tw<N, j>::im;
+          const float2 a = x[j * S], b = x[(j + N / 2) * S];
+          float2 p;
+          p.x = fmaf(wr, b.x, fmaf(-wi, b.y, a.x));
+          p.y = fmaf(wr, b.y, fmaf(wi, b.x, a.y));
+          x[j * S] = p;
+          x[(j + N / 2) * S] = make_float2(fmaf(2.0f, a.x, -p.x), fmaf(2.0f, a.y, -p.y));
+        }
+      });
+    }
+  }
+};
+
 }  // namespace pdeopt

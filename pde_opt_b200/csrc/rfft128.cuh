@@ -138,13 +138,18 @@ struct RFft {
 };
 
 // ---- natural layout <-> pass-A registers: x[n] <-> z[r][2 n + m0] --------------------------------
+// All transforms are decimation in time (six-slot butterflies, regfft.cuh DitF), which consume their
+// input in bit-reversed register order: BREV = true places element n in register brev5(n) (free: the
+// register indices are compile-time).  scatter_nat / gather_nat<false> use the natural order.
+template <bool BREV = false>
 PDEOPT_RF_FN void gather_nat(const RFft& F, float2 (&x)[32]) {
   static_for<0, 8>([&](auto lc) {
     constexpr int lo = decltype(lc)::value;
     const uint32_t a = F.nb ^ (uint32_t)(lo << 4);
     static_for<0, 4>([&](auto hc) {
       constexpr int hi = decltype(hc)::value;
-      x[hi * 8 + lo] = ld2<hi * 128>(a);
+      constexpr int n = hi * 8 + lo;
+      x[BREV ? brev<5>(n) : n] = ld2<hi * 128>(a);
     });
   });
 }
@@ -160,12 +165,12 @@ PDEOPT_RF_FN void scatter_nat(const RFft& F, const float2 (&x)[32]) {
 }
 
 // ---- pass A ------------------------------------------------------------------------------------
-// forward: 32-point DFT over n (natural in), k1m = brev5(position) out, stored to the A -> B layout
+// forward: 32-point DFT over n (x[brev5(n)] in, from gather_nat<true>), k1m = position out
 PDEOPT_RF_FN void passA_fwd(const RFft& F, float2 (&x)[32]) {
-  Dif<32, 1, false>::run(x);
+  DitF<32, 1, false>::run(x);
   static_for<0, 32>([&](auto kc) {
     constexpr int k1m = decltype(kc)::value;
-    st2<k1m * 2048>(F.ea ^ (uint32_t)((k1m & 15) * 8), x[brev<5>(k1m)]);
+    st2<k1m * 2048>(F.ea ^ (uint32_t)((k1m & 15) * 8), x[k1m]);
   });
 }
 // inverse: loads the A -> B layout, returns 8192 * zg in the pass-A arrangement (natural n)
@@ -174,11 +179,12 @@ PDEOPT_RF_FN void passA_inv(const RFft& F, float2 (&x)[32]) {
     constexpr int k1m = decltype(kc)::value;
     x[brev<5>(k1m)] = ld2<k1m * 2048>(F.ea ^ (uint32_t)((k1m & 15) * 8));
   });
-  Dit<32, 1, true>::run(x);
+  DitF<32, 1, true>::run(x);
 }
 
 // ---- pass B ------------------------------------------------------------------------------------
-// twb: [8][16] float2, twb[n2r][p] = w128^(n2r * brev4(p)) (forward sign); tw64: [32] float2 = w64^k1m
+// twb: [16][8] float2, twb[k1r][n2r] = w128^(n2r k1r) (forward sign; the eight entries a warp reads
+// at once are contiguous: one wavefront); tw64: [32] float2 = w64^k1m
 PDEOPT_RF_FN void passB_fwd(const RFft& F, const float2* __restrict__ twb, const float2* __restrict__ tw64,
                             float2 (&x)[32]) {
   static_for<0, 2>([&](auto mc) {
@@ -186,37 +192,41 @@ PDEOPT_RF_FN void passB_fwd(const RFft& F, const float2* __restrict__ twb, const
     const uint32_t a = F.bb ^ (uint32_t)(m0 * 8);
     static_for<0, 16>([&](auto nc) {
       constexpr int n1r = decltype(nc)::value;
-      x[m0 * 16 + n1r] = ld2<n1r * 128>(a);
+      x[m0 * 16 + brev<4>(n1r)] = ld2<n1r * 128>(a);
     });
   });
   {
+    // radix 2 over m0 with the twiddle fused: p = a + w b, q = 2a - p
     const float2 w = tw64[F.b_k1m];
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
     for (int n = 0; n < 16; ++n) {
-      const float2 a = x[n], b = cmul(x[16 + n], w);
-      x[n] = cadd(a, b);
-      x[16 + n] = csub(a, b);
+      const float2 a = x[n], b = x[16 + n];
+      float2 p;
+      p.x = fmaf(w.x, b.x, fmaf(-w.y, b.y, a.x));
+      p.y = fmaf(w.x, b.y, fmaf(w.y, b.x, a.y));
+      x[n] = p;
+      x[16 + n] = make_float2(fmaf(2.0f, a.x, -p.x), fmaf(2.0f, a.y, -p.y));
     }
   }
-  Dif<16, 1, false>::run(x);
-  Dif<16, 1, false>::run(x + 16);
+  DitF<16, 1, false>::run(x);
+  DitF<16, 1, false>::run(x + 16);
   {
-    const float2* tw = twb + F.b_n2r * 16;
+    const float2* tw = twb + F.b_n2r;
     static_for<1, 16>([&](auto pc) {
-      constexpr int p = decltype(pc)::value;
-      const float2 w = tw[p];
-      x[p] = cmul(x[p], w);
-      x[16 + p] = cmul(x[16 + p], w);
+      constexpr int k1r = decltype(pc)::value;
+      const float2 w = tw[k1r * 8];
+      x[k1r] = cmul(x[k1r], w);
+      x[16 + k1r] = cmul(x[16 + k1r], w);
     });
   }
   static_for<0, 2>([&](auto kc) {
     constexpr int k2m = decltype(kc)::value;
     const uint32_t a = F.bb ^ (uint32_t)(k2m * 8);
     static_for<0, 16>([&](auto pc) {
-      constexpr int p = decltype(pc)::value;
-      st2<brev<4>(p) * 128>(a, x[k2m * 16 + p]);
+      constexpr int k1r = decltype(pc)::value;
+      st2<k1r * 128>(a, x[k2m * 16 + k1r]);
     });
   });
 }
@@ -231,16 +241,16 @@ PDEOPT_RF_FN void passB_inv(const RFft& F, const float2* __restrict__ twb, const
     });
   });
   {
-    const float2* tw = twb + F.b_n2r * 16;
+    const float2* tw = twb + F.b_n2r;
     static_for<1, 16>([&](auto pc) {
       constexpr int p = decltype(pc)::value;
-      const float2 w = tw[p];
+      const float2 w = tw[brev<4>(p) * 8];
       x[p] = cmulc(x[p], w);
       x[16 + p] = cmulc(x[16 + p], w);
     });
   }
-  Dit<16, 1, true>::run(x);
-  Dit<16, 1, true>::run(x + 16);
+  DitF<16, 1, true>::run(x);
+  DitF<16, 1, true>::run(x + 16);
   {
     const float2 w = tw64[F.b_k1m];
 #if defined(__CUDACC__)
@@ -349,7 +359,7 @@ PDEOPT_RF_FN void passC_filter(const RFft& F, float2 (&x)[32]) {
       filter_pair<1, brev<3>(k2r), 1, 7 - brev<3>(k2r)>(x, ld4<4096 + k2r * 8192>(F.tlo), F.lane0);
     });
   }
-  static_for<0, 4>([&](auto sc) { Dit<8, 1, true>::run(x + 8 * decltype(sc)::value); });
+  static_for<0, 4>([&](auto sc) { DitF<8, 1, true>::run(x + 8 * decltype(sc)::value); });
   passC_store(F, x);
 }
 

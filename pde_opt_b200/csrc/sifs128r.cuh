@@ -92,10 +92,15 @@ __device__ __forceinline__ void rhs_phase_r(uint32_t wbase, const SifsParams& p,
     gyv[0] = make_float2(g4.x, g4.y);
     gyv[1] = make_float2(g4.z, g4.w);
   }
-  const float2 ihx2 = splat2(p.inv_hx2), ihy2 = splat2(p.inv_hy2), mkappa = splat2(-p.kappa), m2 = splat2(-2.0f);
-  const bool square = p.inv_hx2 == p.inv_hy2;  // uniform
-  const float2 mkih2 = splat2(-p.kappa * p.inv_hx2);
+  // -kappa lap(u) = ax (u[i+1] + u[i-1]) + ay (u[j+1] + u[j-1]) + a0 u  with ax = -kappa/hx^2, ay = -kappa/hy^2,
+  // a0 = 2 kappa (1/hx^2 + 1/hy^2): one packed add and three packed FMAs per pair, no hx == hy special
+  // case (derivatives.py:8-12 up to the summation order; the same value to a few ulp of the largest term)
+  const float2 ax = splat2(-p.kappa * p.inv_hx2), ay = splat2(-p.kappa * p.inv_hy2);
+  const float2 a0 = splat2(2.0f * p.kappa * (p.inv_hx2 + p.inv_hy2));
   const float2 woff2 = splat2(w_off);
+  // log family: mu_h = ln2 lg2(c) - ln2 lg2(1 - c) + w - 2 w c as three chained FMAs
+  const float wlog = p.pw.mu_coef[0] + w_off;
+  const float2 wl2 = splat2(wlog), m2wl2 = splat2(-2.0f * wlog);
 
   // mu and mobility of one row from its three-row neighbourhood
   auto mu_row = [&](int rho, const float2 (&um)[2], const float2 (&u0)[2], const float2 (&up)[2], float2 (&mu)[2],
@@ -111,19 +116,18 @@ __device__ __forceinline__ void rhs_phase_r(uint32_t wbase, const SifsParams& p,
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       float2 mh;
-      mu_mob_pair<MU, MOB>(u0[j], p.pw, woff2, mh, D[j]);
-      if (has_bump) mh = fma2(gxr, gyv[j], mh);
-      if (square) {
-        // hx == hy: -kappa lap(u) = (-kappa/h^2) ((u[i+1] + u[i-1]) + (u[j+1] + u[j-1]) - 4u)
-        const float2 s4 = add2(add2(up[j], um[j]), s[j]);
-        mu[j] = fma2(fma2(u0[j], splat2(-4.0f), s4), mkih2, mh);
+      if constexpr (MU == MU_LOG && (MOB == MOB_DEGENERATE || MOB == MOB_CONST)) {
+        const float2 c = u0[j];
+        const float2 sm = sub2(splat2(1.0f), c);
+        mh = fma2(c, m2wl2, wl2);
+        mh = fma2(make_float2(lg2_fast(sm.x), lg2_fast(sm.y)), splat2(-0.69314718055994531f), mh);
+        mh = fma2(make_float2(lg2_fast(c.x), lg2_fast(c.y)), splat2(0.69314718055994531f), mh);
+        D[j] = (MOB == MOB_DEGENERATE) ? mul2(sm, c) : splat2(p.pw.mob_coef[0]);
       } else {
-        // derivatives.py:8-12: (u[i+1] - 2u + u[i-1])/hx^2 + (u[j+1] - 2u + u[j-1])/hy^2
-        const float2 dxx = add2(fma2(u0[j], m2, up[j]), um[j]);
-        const float2 dyy = fma2(u0[j], m2, s[j]);
-        const float2 lap = fma2(dyy, ihy2, mul2(dxx, ihx2));
-        mu[j] = fma2(lap, mkappa, mh);
+        mu_mob_pair<MU, MOB>(u0[j], p.pw, woff2, mh, D[j]);
       }
+      if (has_bump) mh = fma2(gxr, gyv[j], mh);
+      mu[j] = fma2(ax, add2(up[j], um[j]), fma2(ay, s[j], fma2(a0, u0[j], mh)));
     }
   };
 
@@ -262,9 +266,9 @@ __global__ void __launch_bounds__(kThreadsR, 2) sifs128r_kernel(const __grid_con
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid < 128) {
-    const int n2r = tid >> 4, pp = tid & 15;
+    const int k1r = tid >> 3, n2r = tid & 7;
     float s, c;
-    sincospif(-2.0f * float(n2r * brev<4>(pp)) / 128.0f, &s, &c);
+    sincospif(-2.0f * float(n2r * k1r) / 128.0f, &s, &c);
     S.twb[tid] = make_float2(c, s);
   } else if (tid < 160) {
     float s, c;
@@ -353,7 +357,7 @@ __global__ void __launch_bounds__(kThreadsR, 2) sifs128r_kernel(const __grid_con
         rhs_phase_r<EQ, MU, MOB>(wbase, p, w_off, has_bump, S.gx, S.gy);
       }
       __syncthreads();
-      gather_nat(F, x);
+      gather_nat<true>(F, x);
       __syncthreads();  // everybody has read f0 before the buffer is reused as exchange space
       passA_fwd(F, x);
       __syncthreads();

@@ -18,9 +18,9 @@ void rfft128_filter(const float* f, const float* tab, float dt, float* g, float*
   g_emul = smem.data();
   float2 twb[8 * 16], tw64[32], sc[32];
   for (int n2r = 0; n2r < 8; ++n2r)
-    for (int p = 0; p < 16; ++p) {
-      const double a = -2.0 * M_PI * double(n2r * brev<4>(p)) / 128.0;
-      twb[n2r * 16 + p] = make_float2((float)std::cos(a), (float)std::sin(a));
+    for (int k1r = 0; k1r < 16; ++k1r) {
+      const double a = -2.0 * M_PI * double(n2r * k1r) / 128.0;
+      twb[k1r * 8 + n2r] = make_float2((float)std::cos(a), (float)std::sin(a));
     }
   for (int k = 0; k < 32; ++k) {
     const double a = -2.0 * M_PI * double(k) / 64.0;
@@ -38,7 +38,7 @@ void rfft128_filter(const float* f, const float* tab, float dt, float* g, float*
   auto X = [&](int t) -> float2(&)[32] { return *reinterpret_cast<float2(*)[32]>(&xs[t * 32]); };
   std::vector<RFft> F;
   for (int t = 0; t < kThreadsR; ++t) F.emplace_back(0u, kWBytes, t);
-  for (int t = 0; t < kThreadsR; ++t) gather_nat(F[t], X(t));
+  for (int t = 0; t < kThreadsR; ++t) gather_nat<true>(F[t], X(t));
   for (int t = 0; t < kThreadsR; ++t) passA_fwd(F[t], X(t));
   for (int t = 0; t < kThreadsR; ++t) passB_fwd(F[t], twb, tw64, X(t));
   for (int t = 0; t < kThreadsR; ++t) passC_filter(F[t], X(t));

@@ -52,3 +52,20 @@ def test_dif_inverse_and_dit_forward(lib, n):
     lib.dit_fwd(n, buf.ctypes.data_as(ctypes.c_void_p))
     ref = np.fft.fft(x.astype(np.complex128))
     np.testing.assert_allclose(buf.view(np.complex64), ref, rtol=0, atol=2e-6 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("n", [4, 8, 16, 32])
+def test_ditf_forward_and_inverse(lib, n):
+    """DitF: every non-trivial twiddle in the six-slot FMA form (bit-reversed in, natural out)."""
+    rng = np.random.default_rng(200 + n)
+    x = (rng.normal(size=n) + 1j * rng.normal(size=n)).astype(np.complex64)
+    bits = n.bit_length() - 1
+    perm = np.array([brev(p, bits) for p in range(n)])
+    buf = np.ascontiguousarray(x[perm].view(np.float32).copy())
+    lib.ditf_fwd(n, buf.ctypes.data_as(ctypes.c_void_p))
+    ref = np.fft.fft(x.astype(np.complex128))
+    np.testing.assert_allclose(buf.view(np.complex64), ref, rtol=0, atol=3e-6 * np.abs(ref).max())
+    buf = np.ascontiguousarray(x[perm].view(np.float32).copy())
+    lib.ditf_inv(n, buf.ctypes.data_as(ctypes.c_void_p))
+    ref = np.fft.ifft(x.astype(np.complex128)) * n
+    np.testing.assert_allclose(buf.view(np.complex64), ref, rtol=0, atol=3e-6 * np.abs(ref).max())
