@@ -203,11 +203,9 @@ PDEOPT_RF_FN void passB_fwd(const RFft& F, const float2* __restrict__ twb, const
 #endif
     for (int n = 0; n < 16; ++n) {
       const float2 a = x[n], b = x[16 + n];
-      float2 p;
-      p.x = fmaf(w.x, b.x, fmaf(-w.y, b.y, a.x));
-      p.y = fmaf(w.x, b.y, fmaf(w.y, b.x, a.y));
+      const float2 p = cmac(a, b, w.x, w.y);
       x[n] = p;
-      x[16 + n] = make_float2(fmaf(2.0f, a.x, -p.x), fmaf(2.0f, a.y, -p.y));
+      x[16 + n] = twice_minus(a, p);
     }
   }
   DitF<16, 1, false>::run(x);
@@ -293,6 +291,10 @@ PDEOPT_RF_FN void passC_store(const RFft& F, const float2 (&x)[32]) {
 }
 
 PDEOPT_HD float selp(bool c, float a, float b) { return c ? a : b; }
+// a Z + i b conj(P) = (a Z.x + b P.y, a Z.y + b P.x): two packed instructions
+PDEOPT_HD float2 filt(float a, float2 Z, float b, float2 P) {
+  return fma2(make_float2(b, b), make_float2(P.y, P.x), mul2(make_float2(a, a), Z));
+}
 
 // Two mutually conjugate positions: slot row IA / position PA and slot row IB / position PB.  Elements
 //   X = x[(IA,0),PA] (km = c),  U = x[(IA,1),PA] (km = 64 - c),  V = x[(IB,0),PB],  Y = x[(IB,1),PB];
@@ -306,10 +308,10 @@ PDEOPT_RF_FN void filter_pair(float2 (&x)[32], const float4 t, bool lane0) {
   float2& Y = x[(2 * IB + 1) * 8 + PB];
   const float2 pX = make_float2(selp(lane0, V.x, Y.x), selp(lane0, V.y, Y.y));
   const float2 pV = make_float2(selp(lane0, X.x, U.x), selp(lane0, X.y, U.y));
-  const float2 nX = make_float2(fmaf(t.z, pX.y, t.x * X.x), fmaf(t.z, pX.x, t.x * X.y));
-  const float2 nV = make_float2(fmaf(t.z, pV.y, t.x * V.x), fmaf(t.z, pV.x, t.x * V.y));
-  const float2 nY = make_float2(fmaf(t.w, X.y, t.y * Y.x), fmaf(t.w, X.x, t.y * Y.y));
-  const float2 nU = make_float2(fmaf(t.w, V.y, t.y * U.x), fmaf(t.w, V.x, t.y * U.y));
+  const float2 nX = filt(t.x, X, t.z, pX);
+  const float2 nV = filt(t.x, V, t.z, pV);
+  const float2 nY = filt(t.y, Y, t.w, X);
+  const float2 nU = filt(t.y, U, t.w, V);
   X = nX;
   V = nV;
   Y = nY;
@@ -321,8 +323,8 @@ PDEOPT_RF_FN void filter_self(float2 (&x)[32], const float4 t, bool lane0) {
   float2& X = x[(2 * I + 0) * 8 + P];
   float2& U = x[(2 * I + 1) * 8 + P];
   const float2 pX = make_float2(selp(lane0, X.x, U.x), selp(lane0, X.y, U.y));
-  const float2 nX = make_float2(fmaf(t.z, pX.y, t.x * X.x), fmaf(t.z, pX.x, t.x * X.y));
-  const float2 nU = make_float2(fmaf(t.w, X.y, t.y * U.x), fmaf(t.w, X.x, t.y * U.y));
+  const float2 nX = filt(t.x, X, t.z, pX);
+  const float2 nU = filt(t.y, U, t.w, X);
   X = nX;
   U = nU;
 }

@@ -1,6 +1,7 @@
 // Launch helper shared by the sifs128r_inst_*.cu translation units.
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdlib>
 
 #include "sifs128r.cuh"
 
@@ -28,8 +29,14 @@ static cudaError_t launch_r(const SifsParams& p, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr[dev] = true;
   }
-  const int slots = 2 * sms[dev];
+  // PDEOPT_SIFS128R_ONE=1: one CTA per SM (experiment: how much do two co-resident CTAs overlap?)
+  static const bool one = [] { const char* e = std::getenv("PDEOPT_SIFS128R_ONE"); return e && e[0] == '1'; }();
+  const int slots = (one ? 1 : 2) * sms[dev];
   const int grid = p.batch < slots ? p.batch : slots;
-  kern<<<grid, rf::kThreadsR, sizeof(rf::RSmem), st>>>(p);
+  if (one) {
+    static bool a2 = false;
+    if (!a2) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024); a2 = true; }
+  }
+  kern<<<grid, rf::kThreadsR, one ? 120 * 1024 : sizeof(rf::RSmem), st>>>(p);
   return cudaGetLastError();
 }
