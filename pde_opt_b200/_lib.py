@@ -6,7 +6,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpdeopt_b200.so")
+# PDEOPT_LIB: alternative build of the same library (kernel experiments); never a CPU fallback
+LIB_PATH = os.environ.get("PDEOPT_LIB") or os.path.join(HERE, "libpdeopt_b200.so")
 
 MAX_COEF = 16
 MAX_FUSED_STEPS = 512

@@ -246,29 +246,37 @@ struct Dit {
 // compile-time, so the bit-reversed placement of the inputs costs nothing).
 template <int N, int S, bool INV>
 struct DitF {
-  static PDEOPT_HD void run(float2* x) {
+  // butterfly J of the LAST stage (combines the two half-size transforms): x[J], x[J + N/2]
+  template <int J>
+  static PDEOPT_HD void last(float2* x) {
+    if constexpr (J == 0) {
+      const float2 a = x[0], b = x[(N / 2) * S];
+      x[0] = cadd(a, b);
+      x[(N / 2) * S] = csub(a, b);
+    } else if constexpr (J * 4 == N) {
+      const float2 a = x[J * S], b = mul_tw<N, J, INV>(x[(J + N / 2) * S]);
+      x[J * S] = cadd(a, b);
+      x[(J + N / 2) * S] = csub(a, b);
+    } else {
+      constexpr float wr = Tw<N, J>::re;
+      constexpr float wi = INV ? -Tw<N, J>::im : Tw<N, J>::im;
+      const float2 a = x[J * S], b = x[(J + N / 2) * S];
+      const float2 p = cmac(a, b, wr, wi);
+      x[J * S] = p;
+      x[(J + N / 2) * S] = twice_minus(a, p);
+    }
+  }
+  // everything but the last stage
+  static PDEOPT_HD void halves(float2* x) {
     if constexpr (N >= 2) {
       DitF<N / 2, S, INV>::run(x);
       DitF<N / 2, S, INV>::run(x + (N / 2) * S);
-      static_for<0, N / 2>([&](auto jc) {
-        constexpr int j = decltype(jc)::value;
-        if constexpr (j == 0) {
-          const float2 a = x[0], b = x[(N / 2) * S];
-          x[0] = cadd(a, b);
-          x[(N / 2) * S] = csub(a, b);
-        } else if constexpr (j * 4 == N) {
-          const float2 a = x[j * S], b = mul_tw<N, j, INV>(x[(j + N / 2) * S]);
-          x[j * S] = cadd(a, b);
-          x[(j + N / 2) * S] = csub(a, b);
-        } else {
-          constexpr float wr = Tw<N, j>::re;
-          constexpr float wi = INV ? -Tw<N, j>::im : Tw<N, j>::im;
-          const float2 a = x[j * S], b = x[(j + N / 2) * S];
-          const float2 p = cmac(a, b, wr, wi);
-          x[j * S] = p;
-          x[(j + N / 2) * S] = twice_minus(a, p);
-        }
-      });
+    }
+  }
+  static PDEOPT_HD void run(float2* x) {
+    if constexpr (N >= 2) {
+      halves(x);
+      static_for<0, N / 2>([&](auto jc) { last<decltype(jc)::value>(x); });
     }
   }
 };

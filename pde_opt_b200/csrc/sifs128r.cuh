@@ -26,6 +26,13 @@
 #include "rfft128.cuh"
 #include "sifs128.cuh"  // SifsParams, EnvCtrl, modes, TMEM helpers, pointwise closures
 
+// Ablation hooks for timing experiments (tools/_exp builds only; results are wrong without barriers).
+#ifdef PDEOPT_EXP_NO_BARRIERS
+#define PDEOPT_EXP_SYNC() __syncwarp()
+#else
+#define PDEOPT_EXP_SYNC() __syncthreads()
+#endif
+
 namespace pdeopt {
 namespace rf {
 
@@ -38,6 +45,7 @@ struct __align__(1024) RSmem {
   float gx[kRows], gy[kCols];
   float2 red[kThreadsR / 32];
   uint32_t tmem_base;
+  int next_env;
 };
 
 struct ParkR {
@@ -108,11 +116,13 @@ __device__ __forceinline__ void rhs_phase_r(uint32_t wbase, const SifsParams& p,
     const float uL = shf(u0[1].y, lm1), uR = shf(u0[0].x, lp1);
     float2 gxr = make_float2(0.f, 0.f);
     if (has_bump) gxr = splat2(gx[rho & (kRows - 1)]);
-    float2 s[2];  // left + right column neighbours
-    s[0].x = uL + u0[0].y;
-    s[0].y = u0[0].x + u0[1].x;
-    s[1].x = u0[0].y + u0[1].y;
-    s[1].y = u0[1].x + uR;
+    // left + right column neighbours: the operands straddle the aligned pairs, so the three shifted
+    // pairs (uL, c0), (c1, c2), (c3, uR) are assembled with register moves (ALU pipe, issued in the
+    // shadow of the packed instructions) and the sums stay packed
+    const float2 q = make_float2(u0[0].y, u0[1].x);
+    float2 s[2];
+    s[0] = add2(make_float2(uL, u0[0].x), q);
+    s[1] = add2(q, make_float2(u0[1].y, uR));
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       float2 mh;
@@ -177,22 +187,13 @@ __device__ __forceinline__ void rhs_phase_r(uint32_t wbase, const SifsParams& p,
     float2 dy[2];
     if (it >= 0 && it <= 15) {
       const float muR = shf(mu[0].x, lp1), DR = shf(D[0].x, lp1);
-      float2 ds[2], dm[2], g[2];
-      ds[0].x = D[0].x + D[0].y;
-      ds[0].y = D[0].y + D[1].x;
-      ds[1].x = D[1].x + D[1].y;
-      ds[1].y = D[1].y + DR;
-      dm[0].x = mu[0].y - mu[0].x;
-      dm[0].y = mu[1].x - mu[0].y;
-      dm[1].x = mu[1].y - mu[1].x;
-      dm[1].y = muR - mu[1].y;
-      g[0] = mul2(ds[0], dm[0]);
-      g[1] = mul2(ds[1], dm[1]);
+      float2 g[2];
+      const float2 qD = make_float2(D[0].y, D[1].x), qm = make_float2(mu[0].y, mu[1].x);
+      g[0] = mul2(add2(D[0], qD), sub2(qm, mu[0]));
+      g[1] = mul2(add2(D[1], make_float2(D[1].y, DR)), sub2(make_float2(mu[1].y, muR), mu[1]));
       const float gL = shf(g[1].y, lm1);
-      dy[0].x = g[0].x - gL;
-      dy[0].y = g[0].y - g[0].x;
-      dy[1].x = g[1].x - g[0].y;
-      dy[1].y = g[1].y - g[1].x;
+      dy[0] = sub2(g[0], make_float2(gL, g[0].x));
+      dy[1] = sub2(g[1], make_float2(g[0].y, g[1].x));
     }
     if (it >= 0) {
       float2 gxn[2];
@@ -289,7 +290,16 @@ __global__ void __launch_bounds__(kThreadsR, 2) sifs128r_kernel(const __grid_con
   const RFft F(wbase, (uint32_t)__cvta_generic_to_shared(S.T), tid);
   float dt_tab = __int_as_float(0x7fc00000);  // NaN: no table yet
 
-  for (int env = blockIdx.x; env < p.batch; env += gridDim.x) {
+#ifdef PDEOPT_SKEW_CYCLES
+  if (blockIdx.x >= gridDim.x / 2) {  // experiment: start half of the CTAs out of phase
+    const long long t0 = clock64();
+    while (clock64() - t0 < PDEOPT_SKEW_CYCLES) {}
+  }
+#endif
+  // Environments are handed out dynamically (one atomic per environment): the two CTAs of an SM do not
+  // progress at the same rate (the warp scheduler favours one of them), so a static split would leave
+  // the favoured CTA idle at the end of the launch while the other one finishes alone.
+  for (int env = blockIdx.x; env < p.batch;) {
     // ---- per-environment control (pde_env.py:274-286; our definition) ----
     float w_off = 0.f;
     bool has_bump = false;
@@ -354,19 +364,21 @@ __global__ void __launch_bounds__(kThreadsR, 2) sifs128r_kernel(const __grid_con
           store_srow(wbase, warp * 16 + i, lane, v);
         }
       } else {
+#ifndef PDEOPT_EXP_NO_RHS
         rhs_phase_r<EQ, MU, MOB>(wbase, p, w_off, has_bump, S.gx, S.gy);
+#endif
       }
-      __syncthreads();
+      PDEOPT_EXP_SYNC();
       gather_nat<true>(F, x);
-      __syncthreads();  // everybody has read f0 before the buffer is reused as exchange space
+      PDEOPT_EXP_SYNC();  // everybody has read f0 before the buffer is reused as exchange space
       passA_fwd(F, x);
-      __syncthreads();
+      PDEOPT_EXP_SYNC();
       passB_fwd(F, S.twb, S.tw64, x);
-      __syncthreads();
+      PDEOPT_EXP_SYNC();
       passC_filter(F, x);
-      __syncthreads();
+      PDEOPT_EXP_SYNC();
       passB_inv(F, S.twb, S.tw64, x);
-      __syncthreads();
+      PDEOPT_EXP_SYNC();
       passA_inv(F, x);
       // y1 = y0 + dt * g   (solvers.py:63); y0 comes back from the parking space
 #pragma unroll
@@ -381,9 +393,9 @@ __global__ void __launch_bounds__(kThreadsR, 2) sifs128r_kernel(const __grid_con
         park.store(ch, v);
       }
       tmem_wait_st();
-      __syncthreads();  // all exchange-layout reads are done before the natural layout is rewritten
+      PDEOPT_EXP_SYNC();  // all exchange-layout reads are done before the natural layout is rewritten
       scatter_nat(F, x);
-      __syncthreads();
+      PDEOPT_EXP_SYNC();
     }
 
     // ---- epilogue: y1 to global (coalesced), optional uint8 observation, (mean, var), non-finite flag ----
@@ -431,7 +443,9 @@ __global__ void __launch_bounds__(kThreadsR, 2) sifs128r_kernel(const __grid_con
         if (p.nonfinite != nullptr && tid == 0) p.nonfinite[env] = (fabsf(tot.x) <= 3.0e38f) ? 0 : 1;
       }
     }
+    if (tid == 0) S.next_env = (int)gridDim.x + atomicAdd(p.work_counter, 1);
     __syncthreads();  // the field buffer and the control tables are reused by the next environment
+    env = S.next_env;
   }
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(S.tmem_base));
