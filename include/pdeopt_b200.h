@@ -340,6 +340,17 @@ pdeopt_status pdeopt_strang_lines_step_batched(const pdeopt_gpe_desc* desc, cons
                                                const float* a_term_full_dev, float ts_re, float ts_im,
                                                const float* ctrl_dev, float* work_dev, void* stream);
 
+/* The same step with a caller-evaluated `lights(t, x, y)` field (gross_pitaevskii.py:61,72) added to the
+ * potential: the path for light callables outside the enumerated Gaussian family (time-dependent
+ * lights: one call per step with the field of that step's t0, which is where the reference evaluates
+ * b, solvers.py:109).  light_dev: [nx][ny] float32 per environment, light_env_stride floats apart
+ * (0 = one field shared by the batch), or NULL. */
+pdeopt_status pdeopt_strang_lines_step_batched_light(const pdeopt_gpe_desc* desc, const float* y0_dev, float* y1_dev,
+                                                     int32_t batch, int32_t ksteps, const float* dt_host,
+                                                     const float* a_term_full_dev, float ts_re, float ts_im,
+                                                     const float* ctrl_dev, const float* light_dev,
+                                                     int64_t light_env_stride, float* work_dev, void* stream);
+
 /* Same with HOST buffers: copies y0/ctrl/symbol in, runs, copies y1/obs/reward out, and
  * synchronises the stream before returning.  Scratch device memory is owned by the plan
  * (grown on first use, reused afterwards). */

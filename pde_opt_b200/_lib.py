@@ -135,6 +135,7 @@ EXPORTS = [
     "pdeopt_ch3d_adjoint_step",
     "pdeopt_strang_lines_work_floats",
     "pdeopt_strang_lines_step_batched",
+    "pdeopt_strang_lines_step_batched_light",
     "pdeopt_measure_fp32_peak",
     "pdeopt_launch_count",
 ]
@@ -217,6 +218,8 @@ def load():
     lib.pdeopt_plan_set_nonfinite_flags.restype = ctypes.c_int
     lib.pdeopt_nonfinite_flags.argtypes = [vp, i32, i64, vp, vp]
     lib.pdeopt_nonfinite_flags.restype = ctypes.c_int
+    lib.pdeopt_strang_lines_step_batched_light.argtypes = [ctypes.POINTER(GpeDesc), vp, vp, i32, i32, vp, vp, f32, f32, vp, vp, i64, vp, vp]
+    lib.pdeopt_strang_lines_step_batched_light.restype = ctypes.c_int
     lib.pdeopt_measure_fp32_peak.argtypes = [ctypes.POINTER(ctypes.c_double), vp]
     lib.pdeopt_measure_fp32_peak.restype = ctypes.c_int
     lib.pdeopt_launch_count.restype = ctypes.c_int64

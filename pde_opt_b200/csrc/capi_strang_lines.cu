@@ -12,8 +12,20 @@ extern "C" pdeopt_status pdeopt_strang_lines_step_batched(const pdeopt_gpe_desc*
                                                           int32_t batch, int32_t ksteps, const float* dt_host,
                                                           const float* a_term_full_dev, float ts_re, float ts_im,
                                                           const float* ctrl_dev, float* work_dev, void* stream) {
+  return pdeopt_strang_lines_step_batched_light(desc, y0_dev, y1_dev, batch, ksteps, dt_host, a_term_full_dev, ts_re, ts_im,
+                                                ctrl_dev, nullptr, 0, work_dev, stream);
+}
+
+extern "C" pdeopt_status pdeopt_strang_lines_step_batched_light(const pdeopt_gpe_desc* desc, const float* y0_dev,
+                                                                float* y1_dev, int32_t batch, int32_t ksteps,
+                                                                const float* dt_host, const float* a_term_full_dev,
+                                                                float ts_re, float ts_im, const float* ctrl_dev,
+                                                                const float* light_dev, int64_t light_env_stride,
+                                                                float* work_dev, void* stream) {
   PdeoptDeviceGuard device_guard_(y0_dev);
   if (!desc || !y0_dev || !y1_dev || !dt_host || !work_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
+  if (light_dev && light_env_stride != 0 && light_env_stride < (int64_t)desc->nx * desc->ny)
+    return fail(PDEOPT_ERR_INVALID, "light_env_stride must be 0 (shared field) or >= nx*ny");
   const int nx = desc->nx, ny = desc->ny;
   if (!lf_size_ok(nx) || !lf_size_ok(ny) || nx < 32 || ny < 32)
     return fail(PDEOPT_ERR_UNSUPPORTED, "strang_lines: nx, ny must be powers of two in [32, 512]");
@@ -21,7 +33,7 @@ extern "C" pdeopt_status pdeopt_strang_lines_step_batched(const pdeopt_gpe_desc*
   if (ksteps <= 0) return fail(PDEOPT_ERR_INVALID, "ksteps must be positive");
   if (!(desc->hx > 0) || !(desc->hy > 0)) return fail(PDEOPT_ERR_INVALID, "grid spacing must be positive");
   cudaStream_t st = (cudaStream_t)stream;
-  if (a_term_full_dev == nullptr && nx == kClN && ny == kClN) {
+  if (a_term_full_dev == nullptr && light_dev == nullptr && nx == kClN && ny == kClN) {
     // the equation as shipped on 256x256: cluster-of-4 kernel, state in registers for all K steps
     static bool cattr[kPdeoptMaxDevices] = {};
     if (pdeopt_first_use_on_device(cattr)) {
@@ -69,6 +81,7 @@ extern "C" pdeopt_status pdeopt_strang_lines_step_batched(const pdeopt_gpe_desc*
   c.lo_x = (float)desc->lo_x; c.lo_y = (float)desc->lo_y; c.hx = (float)desc->hx; c.hy = (float)desc->hy;
   c.trap = (float)desc->trap_factor; c.e = (float)desc->e; c.k_int = (float)desc->k;
   c.ts_re = ts_re; c.ts_im = ts_im; c.ctrl = ctrl_dev;
+  c.light = light_dev; c.light_env_stride = light_env_stride;
   const float dx2 = (float)desc->hx * (float)desc->hx;
   const LineGeom rows{(long long)batch * nx, 1, ny, 0, ny, 0, 1};
   const LineGeom cols{(long long)batch * ny, ny, npts, 1, nx, 0, ny};

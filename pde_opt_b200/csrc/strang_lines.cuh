@@ -26,6 +26,10 @@ struct GpeLinesConst {
   float trap, e, k_int;
   float ts_re, ts_im;
   const float* ctrl;  // [batch][8] or null: [1] amp [2] x0 [3] y0 [4] width of a Gaussian light spot
+  // caller-evaluated additive potential `lights(t, x, y)` (gross_pitaevskii.py:61,72) for callables
+  // outside the enumerated family: [nx][ny] floats per environment (stride 0 = shared), or null
+  const float* light;
+  long long light_env_stride;
 };
 
 // exp(b(psi0) dt_c) for one point: b = -i V, V = trap/2((1+e)x^2 + (1-e)y^2) + lights + k|psi0|^2
@@ -39,6 +43,7 @@ __device__ __forceinline__ float2 gpe_potential_factor(const GpeLinesConst& c, i
       V += cc[1] * expf(-(dx * dx + dy * dy) * 0.5f / (cc[4] * cc[4]));
     }
   }
+  if (c.light != nullptr) V += __ldg(c.light + (size_t)env * c.light_env_stride + (size_t)r * c.ny + col);
   const float a = V * dt;
   if (c.ts_re == 0.f) return make_float2(__expf(a * c.ts_im), 0.f);  // imaginary time: real factor
   const float ph = -a * c.ts_re;

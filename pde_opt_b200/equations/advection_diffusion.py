@@ -15,7 +15,7 @@ import numpy as np
 from ..domains import Domain
 from ..functions import GaussianVelocity
 from .base_eq import BaseEquation
-from .phase_field import _fft_marker, _symbols
+from .phase_field import _symbols, spatial_fft, spatial_ifft
 
 
 @dataclasses.dataclass
@@ -29,7 +29,7 @@ class AdvectionDiffusion2D(BaseEquation):
 
     def __post_init__(self):
         self.two_pi_i_kx, self.two_pi_i_ky, self.two_pi_i_k_2 = _symbols(self.domain)
-        self.fft, self.ifft = _fft_marker, _fft_marker
+        self.fft, self.ifft = spatial_fft(2), spatial_ifft(2)
         self.fourier_symbol = (-np.complex64(self.D) * self.two_pi_i_k_2).astype(np.complex64)
         self._tables = {}
 

@@ -13,7 +13,7 @@ import numpy as np
 from ..domains import Domain
 from ..functions import GaussianLight
 from .base_eq import TimeSplittingEquation
-from .phase_field import _fft_marker
+from .phase_field import spatial_fft, spatial_ifft
 
 hbar = 1.05e-34  # J*s
 mass_Na23 = 3.8175406e-26  # kg
@@ -38,29 +38,56 @@ class GPE2DTSControl(TimeSplittingEquation):
         self.two_pi_i_kx = (2j * np.pi * kx).astype(np.complex64)
         self.two_pi_i_ky = (2j * np.pi * ky).astype(np.complex64)
         self.two_pi_i_k_2 = self.two_pi_i_kx**2 + self.two_pi_i_ky**2
-        self.fft, self.ifft = _fft_marker, _fft_marker
+        self.fft, self.ifft = spatial_fft(2), spatial_ifft(2)
         self.xmesh, self.ymesh = self.domain.mesh()
         self.A_term = (np.complex64(0.5j) * self.two_pi_i_k_2 * np.complex64(0.0)).astype(np.complex64)  # :62
         self._light = self._recognize_lights(self.lights)
 
+    _PROBE_TIMES = (0.0, 1.0e-3, 0.37, 1.9, 41.0)
+
     def _recognize_lights(self, lights):
-        """`lights(t, x, y)` is a user callable in the reference (:61).  The fused kernel supports
-        no light (a callable returning zeros) and a Gaussian spot (functions.GaussianLight)."""
+        """`lights(t, x, y)` is a user callable in the reference (:61).  The fused kernels evaluate no
+        light and a Gaussian spot (functions.GaussianLight) themselves.  A callable is only treated as
+        "no light" when it returns zeros at SEVERAL times (a light that ramps up from 0 at t = 0 must not
+        be dropped); anything else returns None and takes the caller-evaluated-field path
+        (`light_field`, pdeopt_strang_lines_step_batched_light)."""
         if lights is None:
             return GaussianLight(0.0, 0.0, 0.0, 1.0)
         if isinstance(lights, GaussianLight):
             return lights
         try:
-            v = np.asarray(lights(0.0, self.xmesh, self.ymesh), dtype=np.float64)
-            if np.all(np.broadcast_to(v, self.xmesh.shape) == 0.0):
-                return GaussianLight(0.0, 0.0, 0.0, 1.0)
+            for t in self._PROBE_TIMES:
+                v = np.asarray(lights(t, self.xmesh, self.ymesh), dtype=np.float64)
+                if not np.all(np.broadcast_to(v, self.xmesh.shape) == 0.0):
+                    return None
+            return GaussianLight(0.0, 0.0, 0.0, 1.0)
         except Exception:
-            pass
-        return None
+            return None
 
     @property
     def fused(self):
+        """True when `lights` is evaluated inside the kernels (none / GaussianLight)."""
         return self._light is not None
+
+    def light_field(self, t, device):
+        """lights(t, x, y) evaluated by the caller's code on the cell-centred mesh (:61,72) as a float32
+        [nx, ny] CUDA tensor: the input of the unfused Strang path."""
+        import torch
+
+        c = self.__dict__.setdefault("_mesh_dev", {})
+        key = str(device)
+        if key not in c:
+            c[key] = (torch.as_tensor(self.xmesh, dtype=torch.float32, device=device),
+                      torch.as_tensor(self.ymesh, dtype=torch.float32, device=device))
+        x, y = c[key]
+        try:
+            v = self.lights(t, x, y)
+            if not torch.is_tensor(v):
+                v = torch.as_tensor(np.asarray(v, dtype=np.float32))
+        except Exception:
+            v = torch.as_tensor(np.asarray(self.lights(t, self.xmesh, self.ymesh), dtype=np.float32))
+        v = v.to(device=device, dtype=torch.float32)
+        return torch.broadcast_to(v, x.shape).contiguous()
 
     def control_block(self, batch, device):
         import torch
@@ -90,7 +117,8 @@ class GPE2DTSControl(TimeSplittingEquation):
         x = torch.as_tensor(self.xmesh, dtype=torch.float32, device=state.device)
         y = torch.as_tensor(self.ymesh, dtype=torch.float32, device=state.device)
         V = 0.5 * self.trap_factor * ((1 + self.e) * x**2 + (1 - self.e) * y**2)
-        V = V + self._light(0.0, x, y) + self.k * (state[..., 0] ** 2 + state[..., 1] ** 2)
+        light = self._light(t, x, y) if self._light is not None else self.light_field(t, state.device)
+        V = V + light + self.k * (state[..., 0] ** 2 + state[..., 1] ** 2)
         return torch.stack([torch.zeros_like(V), -V], dim=-1)
 
     def rhs(self, state, t):  # :77-81

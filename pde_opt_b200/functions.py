@@ -194,32 +194,60 @@ class GaussianVelocity:
         return torch.stack(cols, dim=-1).contiguous()
 
 
-_PROBE = np.array([0.07, 0.19, 0.33, 0.5, 0.61, 0.78, 0.93])
+_PROBE_IN = np.array([0.003, 0.07, 0.19, 0.33, 0.5, 0.61, 0.78, 0.93, 0.997])
+_PROBE_OUT = np.array([-1.2, -0.6, -0.05, 1.04, 1.6, 2.3])  # the reference's own CH test runs states in [-1, 1]
 
 
-def recognize(fn, kind):
-    """Map a user callable onto an enumerated family by probing it on a few points, so that
-    `lambda c: c**3 - c` style arguments (the reference's own idiom) keep working.  Returns a
-    Closure or None (None -> caller must use the unfused path)."""
-    if isinstance(fn, Closure):
-        return fn
+def _eval(fn, x):
     try:
-        y = np.asarray(fn(_PROBE.copy()), dtype=np.float64)
+        with np.errstate(all="ignore"):
+            y = np.asarray(fn(x.copy()), dtype=np.float64)
     except Exception:
         try:
             import torch
 
-            y = fn(torch.from_numpy(_PROBE.copy())).numpy().astype(np.float64)
+            y = fn(torch.from_numpy(x.copy())).numpy().astype(np.float64)
         except Exception:
             return None
-    if y.shape != _PROBE.shape:
+    if y.shape != x.shape:
         try:
-            y = np.broadcast_to(y, _PROBE.shape)
+            y = np.broadcast_to(y, x.shape)
         except ValueError:
             return None
-    x = _PROBE
+    return y
+
+
+def recognize(fn, kind):
+    """Map a user callable onto an enumerated family, so that `lambda c: c**3 - c` style arguments (the
+    reference's own idiom) keep working.  The callable is probed inside (0, 1) AND outside it (a family
+    is only accepted when every probe agrees: `np.clip((1-c)*c, 0, None)` or a piecewise potential must
+    not be replaced by a look-alike), except that the logarithmic families are only defined inside
+    (0, 1).  Returns a Closure or None (None -> the caller uses the unfused `terms.vf` path).  Passing a
+    Closure object is the explicit form; auto-recognition emits a one-time warning naming the family."""
+    if isinstance(fn, Closure):
+        return fn
+    c = _recognize(fn, kind)
+    if c is not None:
+        import warnings
+
+        warnings.warn(
+            f"pde_opt_b200: callable {getattr(fn, '__name__', fn)!r} recognised as the fused family "
+            f"{type(c).__name__}{c.values()!r}; pass a pde_opt_b200.functions closure to be explicit",
+            stacklevel=3,
+        )
+    return c
+
+
+def _recognize(fn, kind):
+    y = _eval(fn, _PROBE_IN)
+    if y is None:
+        return None
+    x = _PROBE_IN
+    yo, xo = _eval(fn, _PROBE_OUT), _PROBE_OUT
     if kind == "mu":
         if np.allclose(y, x**3 - x, rtol=1e-9, atol=1e-12):
+            if yo is None or not np.allclose(yo, xo**3 - xo, rtol=1e-9, atol=1e-12):
+                return None
             return DoubleWell()
         resid = y - np.log(x / (1 - x))
         basis = 1 - 2 * x
@@ -228,10 +256,12 @@ def recognize(fn, kind):
         if np.allclose(w, w[0], rtol=1e-8, atol=1e-10) and np.allclose(resid[~nz], 0, atol=1e-10):
             return LogRegular(float(w[0]))
         return None
-    if np.allclose(y, y[0], rtol=1e-12, atol=0):
+    if yo is None:
+        return None
+    if np.allclose(y, y[0], rtol=1e-12, atol=0) and np.allclose(yo, y[0], rtol=1e-12, atol=0):
         return ConstantMobility(float(y[0]))
-    if np.allclose(y, (1 - x) * x, rtol=1e-9):
+    if np.allclose(y, (1 - x) * x, rtol=1e-9) and np.allclose(yo, (1 - xo) * xo, rtol=1e-9):
         return DegenerateMobility()
-    if np.allclose(y, 1 + x**2, rtol=1e-9):
+    if np.allclose(y, 1 + x**2, rtol=1e-9) and np.allclose(yo, 1 + xo**2, rtol=1e-9):
         return OnePlusSquare()
     return None

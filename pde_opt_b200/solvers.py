@@ -271,10 +271,10 @@ class StrangSplitting:
         from . import _lib
 
         eq = getattr(terms, "equation", None)
-        if eq is None or not getattr(eq, "fused", False):
-            raise NotImplementedError(
-                "StrangSplitting needs ODETerm(equation) with an enumerated `lights` (none or GaussianLight)"
-            )
+        if eq is None or not hasattr(eq, "gpe_desc"):
+            raise NotImplementedError("StrangSplitting needs ODETerm(GPE2DTSControl equation)")
+        if not getattr(eq, "fused", False):
+            return self._rollout_callback_lights(eq, times, y0, out)
         times = np.asarray(times, dtype=np.float32)
         dts = np.ascontiguousarray((times[1:] - times[:-1]).astype(np.float32))
         single = y0.dim() == 3
@@ -318,6 +318,52 @@ class StrangSplitting:
             _lib.check(st)
             src = y1
             done += k
+        return y1[0] if single else y1
+
+    def _rollout_callback_lights(self, eq, times, y0, out=None):
+        """Unfused path for a `lights(t, x, y)` callable outside the enumerated family (any time
+        dependence): per numeric step the caller's callable is evaluated at the step's t0 — where the
+        reference evaluates b = terms.vf(t0, y0), solvers.py:109 — and the field is handed to the Strang
+        kernels of the line-FFT engine as an additive potential (pdeopt_strang_lines_step_batched_light)."""
+        import ctypes
+
+        from . import _lib
+
+        times = np.asarray(times, dtype=np.float32)
+        dts = np.ascontiguousarray((times[1:] - times[:-1]).astype(np.float32))
+        single = y0.dim() == 3
+        y = (y0.unsqueeze(0) if single else y0).contiguous()
+        assert y.is_cuda and y.dtype == torch.float32 and y.shape[-1] == 2
+        y1 = out if out is not None else torch.empty_like(y)
+        nx, ny = int(y.shape[1]), int(y.shape[2])
+        lib = _lib.load()
+        key = ("cb", nx, ny, y.shape[0], str(y.device))
+        if key not in self._work:
+            n = int(lib.pdeopt_strang_lines_work_floats(nx, ny, y.shape[0]))
+            self._work[key] = torch.empty(n, dtype=torch.float32, device=y.device)
+        a = np.asarray(self.A_term)
+        af = None
+        if np.any(a):
+            if ("full", str(y.device)) not in self._a_dev:
+                q = a.astype(np.complex64)
+                full = np.ascontiguousarray(np.stack([q.real, q.imag], -1).astype(np.float32))
+                self._a_dev[("full", str(y.device))] = torch.from_numpy(full).to(y.device)
+            af = self._a_dev[("full", str(y.device))]
+        ts = complex(self.time_scale)
+        desc = eq.gpe_desc()
+        src = y
+        with _lib.device_of(y):
+            stream = _lib.stream_ptr(y)
+            for k in range(len(dts)):
+                light = eq.light_field(float(times[k]), y.device)
+                st = lib.pdeopt_strang_lines_step_batched_light(
+                    ctypes.byref(desc), ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(y1.data_ptr()), y.shape[0], 1,
+                    dts[k:].ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(af.data_ptr()) if af is not None else None,
+                    float(ts.real), float(ts.imag), None, ctypes.c_void_p(light.data_ptr()), 0,
+                    ctypes.c_void_p(self._work[key].data_ptr()), stream,
+                )
+                _lib.check(st)
+                src = y1
         return y1[0] if single else y1
 
     def step(self, terms, t0, t1, y0, args=None, solver_state=None, made_jump=False):
