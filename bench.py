@@ -40,9 +40,21 @@ CPU_SAMPLE_ENVS_PER_CORE = 768  # ~10 s of CPU work per core for the cpu_baselin
 OMEGA = 3.0
 FLOP_PER_POINT = 70 + 35 + 1 + 2  # BASELINE.md section 3, log potential: 108 flop / grid point / numeric step
 BYTES_PER_ENV_LAUNCH = 2 * 4 * N * N  # one read + one write of the state per launch (K fused steps)
-# dram__bytes_read.sum + dram__bytes_write.sum of one sifs128_kernel launch of this exact config
-# (ncu --set full, profiles/ncu_raw_r1_bench_4096x16.txt): 269.1 MB + 283.6 MB
-NCU_DRAM_BYTES_PER_LAUNCH = 552.7e6
+KERNEL_NAME = "sifs128r_kernel"
+# roofline.traffic = dram__bytes_read.sum + dram__bytes_write.sum of one launch of the headline kernel at this exact
+# config, read from the committed summary of the `ncu --set full` capture (written by tools/ncu_summary.py --json);
+# null when the summary is missing or belongs to another kernel
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_bench_traffic.json")
+
+
+def ncu_traffic():
+    try:
+        t = json.load(open(TRAFFIC_FILE))
+        if KERNEL_NAME not in t.get("kernel", "") or t.get("grid_envs") != ENVS_PER_GPU or t.get("fused_steps") != K_FUSED:
+            return None, None
+        return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"]), os.path.relpath(TRAFFIC_FILE, ROOT) + " <- " + t.get("source", "?")
+    except Exception:
+        return None, None
 
 
 def make_ic(env_index):
@@ -158,6 +170,8 @@ def workload_config(n_gpus):
         "envs_per_gpu": ENVS_PER_GPU, "global_envs": ENVS_PER_GPU * n_gpus, "fused_steps": K_FUSED, "grid": [N, N],
         "parallelism": f"env-sharded x{n_gpus}, no collective in step, all_gather of rewards",
         "l2_policy": "state per GPU is 256 MiB in + 256 MiB out (> 126 MB L2); ping-pong buffers",
+        "initial_conditions": "clip(0.5 + 0.01 N(0,1), 0, 1) drawn on the device with torch.Generator(seed = 1234 + rank) "
+                              "(timing only; the parity tests use numpy default_rng(env_index), SURVEY 8d)",
     }
 
 
@@ -373,6 +387,15 @@ def run_ours(args):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_achieved = BYTES_PER_ENV_LAUNCH * B / (ms_per_step * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic()
+
+    # ---- secondary configs (every rank takes part under torchrun; bounded) ----
+    secondary = None
+    if not args.no_secondary:
+        torch.cuda.empty_cache()
+        from pde_opt_b200 import secondary_bench
+
+        secondary = secondary_bench.run_all(float(peak_tf.value), world)
 
     if rank == 0:
         cpu_value, cores, cpu_wall = (None, None, None)
@@ -396,8 +419,8 @@ def run_ours(args):
             "roofline": {
                 "bound": "fp32", "achieved": achieved_tf, "peak": float(peak_tf.value), "unit": "TFLOP/s",
                 "frac": achieved_tf / float(peak_tf.value) if peak_tf.value else None,
-                "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                "kernel": "pdeopt::sifs128_kernel<CH, MU_LOG, MOB_DEGENERATE>",
+                "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": "pdeopt::rf::sifs128r_kernel<CH, MU_LOG, MOB_DEGENERATE> (one environment per 256-thread CTA, two CTAs per SM)",
                 "how": f"{FLOP_PER_POINT} algorithmic flop/grid-point/step (BASELINE.md s3) x 16384 points x {B} envs x {K_FUSED} steps per launch / "
                        "CUDA-event launch time; peak = FFMA-chain peak measured live on this GPU (pdeopt_measure_fp32_peak); "
                        "MEASURED_PEAKS.json has no FP32 entry",
@@ -406,6 +429,8 @@ def run_ours(args):
             },
             "finite": finite,
         }
+        if secondary is not None:
+            line["secondary"] = secondary
         if cpu_value is not None:
             line["cpu_baseline"] = {"value": cpu_value, "unit": "env-steps/s", "cores": cores, "kind": "port",
                                     "sample": f"{cores * CPU_SAMPLE_ENVS_PER_CORE} envs x {K_FUSED} numeric steps, NumPy restatement of the reference (oracle/), {cpu_wall:.1f} s"}
@@ -421,6 +446,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the bounded C3/C4/C5 measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

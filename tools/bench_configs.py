@@ -28,6 +28,17 @@ def timed(fn, warmup=2, iters=5):
     return e0.elapsed_time(e1) / iters * 1e-3
 
 
+def fp32_peak():
+    """FFMA-chain peak measured live on this GPU (TFLOP/s): the denominator of the FP32-bound rooflines."""
+    import ctypes
+
+    from pde_opt_b200 import _lib
+
+    v = ctypes.c_double(0.0)
+    _lib.check(_lib.load().pdeopt_measure_fp32_peak(ctypes.byref(v), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return float(v.value)
+
+
 def peak_hbm():
     try:
         return json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]

@@ -1,10 +1,17 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep: key raw metrics + SASS-level aggregation by barrier-delimited phase.
-usage: tools/ncu_summary.py <report.ncu-rep> [nsm=148] [ksteps=16]"""
-import collections, csv, io, re, subprocess, sys
-rep = sys.argv[1]
-nsm = int(sys.argv[2]) if len(sys.argv) > 2 else 148
-ksteps = int(sys.argv[3]) if len(sys.argv) > 3 else 16
+usage: tools/ncu_summary.py <report.ncu-rep> [nsm=148] [ksteps=16] [--json out.json --envs B]
+--json writes the DRAM traffic of the captured launch (what bench.py reports as roofline.traffic)."""
+import collections, csv, io, json, re, subprocess, sys
+argv = [a for a in sys.argv[1:]]
+json_out = envs = None
+if "--json" in argv:
+    i = argv.index("--json"); json_out = argv[i + 1]; del argv[i:i + 2]
+if "--envs" in argv:
+    i = argv.index("--envs"); envs = int(argv[i + 1]); del argv[i:i + 2]
+rep = argv[0]
+nsm = int(argv[1]) if len(argv) > 1 else 148
+ksteps = int(argv[2]) if len(argv) > 2 else 16
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, vals = rows[0], rows[1], rows[2]
@@ -18,6 +25,14 @@ want = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg", "smsp__inst_executed
         "launch__grid_size", "launch__block_size", "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum",
         "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fmalite_cycles_active.avg.pct_of_peak_sustained_active"]
 print("kernel:", vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?")
+if json_out:
+    def _bytes(name):
+        i = hdr.index(name); v = float(vals[i].replace(",", "")); u = units[i].lower()
+        return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]
+    json.dump({"kernel": vals[hdr.index("Kernel Name")], "dram_bytes_read": _bytes("dram__bytes_read.sum"),
+               "dram_bytes_write": _bytes("dram__bytes_write.sum"), "grid_envs": envs, "fused_steps": ksteps,
+               "gpu_time_ms": float(vals[hdr.index("gpu__time_duration.sum")].replace(",", "")) * {"ms": 1, "us": 1e-3, "s": 1e3, "ns": 1e-6}.get(units[hdr.index("gpu__time_duration.sum")], 1),
+               "source": rep.split("/")[-1] + " (ncu --set full --clock-control none)"}, open(json_out, "w"), indent=1)
 for k in want:
     if k in hdr:
         i = hdr.index(k); print(f"{k:72s} {vals[i]:>16s} {units[i]}")
