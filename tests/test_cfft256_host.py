@@ -1,0 +1,73 @@
+"""The cluster-distributed 256x256 complex FFT (pde_opt_b200/csrc/cfft256.cuh) executed on the host: four
+emulated CTAs x 512 threads, remote stores as writes into the peers' buffers, against numpy.fft."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+N = 256
+
+
+@pytest.fixture(scope="module")
+def lib(tmp_path_factory):
+    out = tmp_path_factory.mktemp("cfft256") / "cfft256_host.so"
+    src = os.path.join(HERE, "host", "cfft256_host.cpp")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-x", "c++", src, "-o", str(out)])
+    return ctypes.CDLL(str(out))
+
+
+def test_forward_multiply_inverse(lib):
+    rng = np.random.default_rng(0)
+    z = (rng.normal(size=(N, N)) + 1j * rng.normal(size=(N, N))).astype(np.complex64)
+    k = np.fft.fftfreq(N, 0.1)
+    a_term = 0.5j * (-(2 * np.pi) ** 2) * (k[:, None] ** 2 + k[None, :] ** 2)
+    mult = np.exp(a_term * 0.5 * (1e-3 - 2e-4j)).astype(np.complex64)
+    inp = np.ascontiguousarray(z.view(np.float32).reshape(N, N, 2))
+    m = np.ascontiguousarray(mult.view(np.float32).reshape(N, N, 2))
+    out = np.empty_like(inp)
+    spec = np.empty_like(inp)
+    P = ctypes.c_void_p
+    lib.cfft256_roundtrip(inp.ctypes.data_as(P), m.ctypes.data_as(P), out.ctypes.data_as(P), spec.ctypes.data_as(P))
+    Z = np.fft.fft2(z.astype(np.complex128))
+    got_spec = spec.reshape(N, N * 2).view(np.complex64)
+    assert np.abs(got_spec - Z).max() / np.abs(Z).max() < 3e-6
+    ref = np.fft.ifft2(Z * mult.astype(np.complex128))
+    got = out.reshape(N, N * 2).view(np.complex64) / (N * N)
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 5e-6
+
+
+def test_identity(lib):
+    rng = np.random.default_rng(1)
+    z = (rng.normal(size=(N, N)) + 1j * rng.normal(size=(N, N))).astype(np.complex64)
+    inp = np.ascontiguousarray(z.view(np.float32).reshape(N, N, 2))
+    out = np.empty_like(inp)
+    lib.cfft256_roundtrip(inp.ctypes.data_as(ctypes.c_void_p), None, out.ctypes.data_as(ctypes.c_void_p), None)
+    got = out.reshape(N, N * 2).view(np.complex64) / (N * N)
+    assert np.abs(got - z).max() < 5e-6 * np.abs(z).max()
+
+
+def test_layout_is_bank_conflict_free():
+    """Every access pattern of the passes hits 16 distinct 8-byte banks per half-warp (remote transposed stores are
+    checked at the destination)."""
+    g = lambda line: ((line & 1) << 3) | (line & 6)
+    slot = lambda line, pos: line * 256 + (pos ^ g(line))
+    e1 = lambda line, k1, j: line * 256 + 32 * j + (k1 ^ j ^ ((line & 1) << 3))
+    ok = lambda s: len({int(v) % 16 for v in s}) == 16
+    for l0 in range(0, 64, 2):
+        half = [(l0 + (t >> 3), t & 7) for t in range(16)]
+        for n1 in range(32):
+            assert ok([slot(l, 8 * n1 + j) for l, j in half])                       # spatial load / store
+            assert ok([e1(l, n1, j) for l, j in half])                              # E1, thread j stores k1 = n1
+        for a in range(4):
+            for jj in range(8):
+                assert ok([e1(l, j + 8 * a, jj) for l, j in half])                  # E1, reads / inverse writes
+            for k0 in range(8):
+                assert ok([slot(l, j + 8 * a + 32 * k0) for l, j in half])          # frequency load
+                for q in range(4):
+                    assert ok([slot(j + 8 * a + 32 * (k0 & 1), 64 * q + l) for l, j in half])   # transposed store from freq
+        for n1 in range(32):
+            for q in range(4):
+                assert ok([slot(8 * (n1 & 7) + j, 64 * q + l) for l, j in half])    # transposed store from spatial
