@@ -2,6 +2,9 @@
 #include "capi_lines_common.h"
 #include "strang_lines.cuh"
 #include "strang_cluster.cuh"
+#include "strang_cluster_kin.cuh"
+
+#include <cstdlib>
 
 extern "C" int64_t pdeopt_strang_lines_work_floats(int32_t nx, int32_t ny, int32_t batch) {
   if (nx <= 0 || ny <= 0 || batch <= 0) return 0;
@@ -65,6 +68,65 @@ extern "C" pdeopt_status pdeopt_strang_lines_step_batched_light(const pdeopt_gpe
       cfg.numAttrs = 1;
       cudaError_t le = cudaLaunchKernelEx(&cfg, strang_cluster_kernel, cp);
       if (le != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("strang cluster launch: ") + cudaGetErrorString(le));
+      g_launches.fetch_add(1);
+      src = y1_dev;
+      done += kk;
+    }
+    return PDEOPT_OK;
+  }
+  static const bool force_lines = [] { const char* e = std::getenv("PDEOPT_STRANG_LINES"); return e && e[0] == '1'; }();
+  if (a_term_full_dev != nullptr && light_dev == nullptr && nx == cf::kN && ny == cf::kN && !force_lines) {
+    // kinetic term on 256x256: cluster-of-4 kernel, the wavefunction stays inside the cluster for all K steps
+    // (DSMEM transposes); one 512 KB kinetic table per distinct dt, built in the caller's scratch
+    static bool kattr[kPdeoptMaxDevices] = {};
+    if (pdeopt_first_use_on_device(kattr)) {
+      CUDA_TRY(cudaFuncSetAttribute(cf::strang_cluster_kin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(cf::KinSmem) + 2048));
+    }
+    const int64_t np = (int64_t)cf::kN * cf::kN;
+    const int max_tabs = batch < cf::kMaxTabs ? (batch < 1 ? 1 : batch) : cf::kMaxTabs;  // tables live in the W area
+    float2* tabs = (float2*)work_dev;
+    const float* src = y0_dev;
+    int done = 0;
+    while (done < ksteps) {
+      cf::KinParams kp;
+      std::memset(&kp, 0, sizeof(kp));
+      float dts[cf::kMaxTabs];
+      int ntab = 0, kk = 0;
+      for (; done + kk < ksteps && kk < kMaxK; ++kk) {
+        const float dt = dt_host[done + kk];
+        int t = 0;
+        while (t < ntab && dts[t] != dt) ++t;
+        if (t == ntab) {
+          if (ntab == max_tabs) break;
+          dts[ntab++] = dt;
+        }
+        kp.dt[kk] = dt;
+        kp.tab[kk] = (unsigned char)t;
+      }
+      for (int t = 0; t < ntab; ++t) {
+        cf::strang_cluster_etab_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>((const float2*)a_term_full_dev, tabs + (size_t)t * np,
+                                                                                   0.5f * dts[t] * ts_re, 0.5f * dts[t] * ts_im);
+        g_launches.fetch_add(1);
+      }
+      kp.y0 = src; kp.y1 = y1_dev; kp.batch = batch; kp.ksteps = kk;
+      kp.ts_re = ts_re; kp.ts_im = ts_im; kp.dx = (float)desc->hx;
+      kp.k_int = (float)desc->k; kp.e = (float)desc->e; kp.trap = (float)desc->trap_factor;
+      kp.lo_x = (float)desc->lo_x; kp.lo_y = (float)desc->lo_y; kp.hx = (float)desc->hx; kp.hy = (float)desc->hy;
+      kp.ctrl = ctrl_dev; kp.etab = tabs;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(batch * cf::kCtas));
+      cfg.blockDim = dim3(cf::kThreadsC);
+      cfg.dynamicSmemBytes = sizeof(cf::KinSmem) + 2048;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = cf::kCtas;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cudaError_t le = cudaLaunchKernelEx(&cfg, cf::strang_cluster_kin_kernel, kp);
+      if (le != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("strang kinetic cluster launch: ") + cudaGetErrorString(le));
       g_launches.fetch_add(1);
       src = y1_dev;
       done += kk;

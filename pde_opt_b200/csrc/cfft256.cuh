@@ -8,16 +8,18 @@
 // stores into the peers' shared memory (distributed shared memory, st.shared::cluster): the last
 // stage of a pass writes every value straight to the CTA and slot where the next pass will read it.
 //
-// One line = 8 threads (consecutive lanes of one warp) x 32 points:
+// One line = 8 threads x 32 points; the LANES of a warp are 32 different lines (thread t: line
+// l = (t & 31) + 32 ((t >> 5) & 1), j = t >> 6), so that a transposed store of a warp is 32 consecutive
+// positions of ONE destination line: 256 contiguous bytes per st.shared::cluster instruction (scattered
+// 8-byte remote stores run at a few bytes per clock):
 //   spatial arrangement   thread (l, j) holds n = 8 n1 + j,            n1 = 0..31  -> x[n1]
 //   S1   32-point DFT over n1 (in thread), twiddle w256^(j k1)
 //   E1   exchange among the 8 threads of the line through the line's own 2 KB of shared memory
-//        (same warp: __syncwarp, no CTA barrier)
+//        (they sit in different warps: CTA barriers around it)
 //   S2   four 8-point DFTs over j                                        -> k = k1 + 32 k0
 //   frequency arrangement thread (l, j') holds k = j' + 8 a + 32 k0,    a = 0..3, k0 = 0..7 -> x[8 a + k0]
-// The inverse mirrors it.  Shared-memory layout of a slab: 8-byte slot(line, pos) = 256 line + (pos ^ g(line)),
-// g(line) = ((line & 1) << 3) | (line & 6): every access pattern below (remote transposed stores included,
-// whose bank conflicts are paid at the DESTINATION) hits 16 distinct banks per half-warp.
+// The inverse mirrors it.  Shared-memory layout of a slab: 8-byte slot(line, pos) = 256 line + (pos ^ (line & 15)):
+// every access pattern below hits 16 distinct banks per half-warp (16 consecutive lines).
 // tests/test_cfft256_host.py runs this header on the host (4 emulated CTAs x 512 threads) against numpy.
 #pragma once
 #include <stdint.h>
@@ -33,159 +35,186 @@ constexpr int kLines = kN / kCtas;  // lines per CTA
 constexpr int kThreadsC = 512;      // 8 threads per line
 constexpr uint32_t kSlabBytes = kLines * kN * 8;  // 128 KB
 
-PDEOPT_HD int g_of(int line) { return ((line & 1) << 3) | (line & 6); }
+PDEOPT_HD int g_of(int line) { return line & 15; }
 PDEOPT_HD uint32_t slot_bytes(int line, int pos) { return (uint32_t)((line * kN + (pos ^ g_of(line))) * 8); }
-// exchange E1 inside a line's region: value (k1, j) at 32 j + (k1 ^ j ^ ((line & 1) << 3))
-PDEOPT_HD uint32_t e1_bytes(int line, int k1, int j) { return (uint32_t)((line * kN + 32 * j + (k1 ^ j ^ ((line & 1) << 3))) * 8); }
+// exchange E1 inside a line's region: value (k1, j) at 32 j + (k1 ^ (line & 15))
+PDEOPT_HD uint32_t e1_bytes(int line, int k1, int j) { return (uint32_t)((line * kN + 32 * j + (k1 ^ (line & 15))) * 8); }
+PDEOPT_HD int thread_line(int t) { return (t & 31) + 32 * ((t >> 5) & 1); }
+PDEOPT_HD int thread_j(int t) { return t >> 6; }
 
 // ---- memory access: device = shared-window addresses (+ mapa for peers); host = emulated slabs ----
+// All accesses are [register + compile-time immediate]; the slab is 2048-byte aligned so that the swizzle
+// XORs (bits 3..10) commute with the base address.
 #if defined(__CUDACC__)
-__device__ __forceinline__ float2 lds(uint32_t a) {
-  float2 v;
-  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ void sts(uint32_t a, float2 v) {
-  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
-}
+#define PDEOPT_CF_FN __device__ __forceinline__
+__device__ __forceinline__ void line_sync() { __syncthreads(); }
+struct Ctx {
+  uint32_t base;         // this CTA's slab (shared-window byte address, 2048-byte aligned)
+  uint32_t peer[kCtas];  // the same address mapped into every CTA of the cluster (own rank: the local address)
+  int self;              // this CTA's rank in the cluster
+  template <int OFF>
+  __device__ __forceinline__ float2 ld(uint32_t a) const {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(a), "n"(OFF));
+    return v;
+  }
+  template <int OFF>
+  __device__ __forceinline__ void st(uint32_t a, float2 v) const {
+    asm volatile("st.shared.v2.f32 [%0+%1], {%2, %3};" ::"r"(a), "n"(OFF), "f"(v.x), "f"(v.y) : "memory");
+  }
+  // `a` is already an address inside the peer's window (LineMap::Tp); the quarter of the transposed data
+  // that stays in this CTA takes the ordinary shared-memory path (Tp[self] is a local address)
+  template <int OFF>
+  __device__ __forceinline__ void st_to(int rank, uint32_t a, float2 v) const {
+    if (rank == self) {
+      asm volatile("st.shared.v2.f32 [%0+%1], {%2, %3};" ::"r"(a), "n"(OFF), "f"(v.x), "f"(v.y) : "memory");
+    } else {
+      asm volatile("st.shared::cluster.v2.f32 [%0+%1], {%2, %3};" ::"r"(a), "n"(OFF), "f"(v.x), "f"(v.y) : "memory");
+    }
+  }
+  __device__ __forceinline__ uint32_t local(uint32_t off) const { return base + off; }
+  __device__ __forceinline__ uint32_t remote(int rank, uint32_t off) const { return peer[rank] + off; }
+};
 __device__ __forceinline__ uint32_t peer_addr(uint32_t local, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void sts_peer(uint32_t mapped, float2 v) {
-  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(mapped), "f"(v.x), "f"(v.y) : "memory");
-}
-__device__ __forceinline__ void line_sync() { __syncwarp(); }
-#define PDEOPT_CF_FN __device__ __forceinline__
-struct Ctx {
-  uint32_t base;           // this CTA's slab (shared-window byte address)
-  uint32_t peer[kCtas];    // the same address mapped into every CTA of the cluster (own rank included)
-  __device__ __forceinline__ float2 ld(uint32_t off) const { return lds(base + off); }
-  __device__ __forceinline__ void st(uint32_t off, float2 v) const { sts(base + off, v); }
-  __device__ __forceinline__ void st_to(int rank, uint32_t off, float2 v) const { sts_peer(peer[rank] + off, v); }
-};
 #else
 #define PDEOPT_CF_FN inline
 inline void line_sync() {}
 struct Ctx {
   unsigned char* slabs[kCtas];  // emulated shared memory of the four CTAs
   int rank;
-  float2 ld(uint32_t off) const { return *reinterpret_cast<const float2*>(slabs[rank] + off); }
-  void st(uint32_t off, float2 v) const { *reinterpret_cast<float2*>(slabs[rank] + off) = v; }
-  void st_to(int r, uint32_t off, float2 v) const { *reinterpret_cast<float2*>(slabs[r] + off) = v; }
+  template <int OFF>
+  float2 ld(uint32_t a) const { return *reinterpret_cast<const float2*>(slabs[rank] + a + OFF); }
+  template <int OFF>
+  void st(uint32_t a, float2 v) const { *reinterpret_cast<float2*>(slabs[rank] + a + OFF) = v; }
+  template <int OFF>
+  void st_to(int r, uint32_t a, float2 v) const { *reinterpret_cast<float2*>(slabs[r] + a + OFF) = v; }
+  uint32_t local(uint32_t off) const { return off; }
+  uint32_t remote(int, uint32_t off) const { return off; }
 };
 #endif
 
+// Per-thread address bases: every slab address of a thread is one of these, XOR a one-bit constant, plus a
+// compile-time immediate (the swizzle occupies address bits 3..6, the immediates bits >= 7):
+//   slot(l, 8 i + j) / slot(l, j + 8 a + 32 k0) with i = a + 4 k0   = (B ^ 64 (i & 1)) + 128 (i >> 1)
+//   e1(l, k1, j)   [own j]                                          = (E ^ 8 (k1 & 15)) + 128 (k1 >> 4)
+//   e1(l, j + 8 a, jj) [thread jj's value]                          = (B ^ 64 (a & 1)) + 128 (a >> 1) + 256 jj
+//   slot(j + 8 m, gl) in CTA r                                      = (Tp[r] ^ 64 (m & 1)) + 16384 m
+// with B = slab + 2048 l + 8 (j ^ (l & 15)), E = slab + 2048 l + 256 j + 8 (l & 15), Tp[r] = peer r's slab + 2048 j + 8 (gl ^ j).
+struct LineMap {
+  uint32_t B, E, Tp[kCtas];
+  PDEOPT_CF_FN LineMap(const Ctx& c, int l, int j, int gl) {
+    B = c.local((uint32_t)(2048 * l + 8 * (j ^ (l & 15))));
+    E = c.local((uint32_t)(2048 * l + 256 * j + 8 * (l & 15)));
+    for (int r = 0; r < kCtas; ++r) Tp[r] = c.remote(r, (uint32_t)(2048 * j + 8 * (gl ^ j)));
+  }
+};
+
 // ---- loads of a line from the slab ------------------------------------------------------------------
 // spatial arrangement, placed bit-reversed for the decimation-in-time S1: x[brev5(n1)] = line[8 n1 + j]
-PDEOPT_CF_FN void load_spatial(const Ctx& c, int l, int j, float2 (&x)[32]) {
+PDEOPT_CF_FN void load_spatial(const Ctx& c, const LineMap& m, float2 (&x)[32]) {
   static_for<0, 32>([&](auto nc) {
     constexpr int n1 = decltype(nc)::value;
-    x[brev<5>(n1)] = c.ld(slot_bytes(l, 8 * n1 + j));
+    x[brev<5>(n1)] = c.template ld<128 * (n1 >> 1)>(m.B ^ (uint32_t)(64 * (n1 & 1)));
   });
 }
 // frequency arrangement in natural register order: x[8 a + k0] = line[j + 8 a + 32 k0]
-PDEOPT_CF_FN void load_freq(const Ctx& c, int l, int j, float2 (&x)[32]) {
+PDEOPT_CF_FN void load_freq(const Ctx& c, const LineMap& m, float2 (&x)[32]) {
   static_for<0, 32>([&](auto ic) {
     constexpr int i = decltype(ic)::value;
-    x[i] = c.ld(slot_bytes(l, j + 8 * (i >> 3) + 32 * (i & 7)));
+    constexpr int idx = (i >> 3) + 4 * (i & 7);
+    x[i] = c.template ld<128 * (idx >> 1)>(m.B ^ (uint32_t)(64 * (idx & 1)));
+  });
+}
+// plain store of the spatial arrangement (natural n1 order) into the own slab
+PDEOPT_CF_FN void store_spatial(const Ctx& c, const LineMap& m, const float2 (&x)[32]) {
+  static_for<0, 32>([&](auto nc) {
+    constexpr int n1 = decltype(nc)::value;
+    c.template st<128 * (n1 >> 1)>(m.B ^ (uint32_t)(64 * (n1 & 1)), x[n1]);
   });
 }
 
 // ---- forward transform of a line: x[brev5(n1)] spatial in -> x[8 a + k0] frequency out ---------------
-// tw: [8][32] float2, tw[j][k1] = w256^(j k1) (forward sign).  Two parts with the line's exchange in
-// between (the host emulation runs each part for all threads of a line before the next one).
-PDEOPT_CF_FN void line_fwd_a(const Ctx& c, const float2* __restrict__ tw, int l, int j, float2 (&x)[32]) {
+// tw: [8][32] float2, tw[j][k1] = w256^(j k1) (forward sign), `t` = tw + 32 j.  Two parts with the line's
+// exchange in between (the host emulation runs each part for all threads of a line before the next one).
+PDEOPT_CF_FN void line_fwd_a(const Ctx& c, const float2* __restrict__ t, const LineMap& m, float2 (&x)[32]) {
   DitF<32, 1, false>::run(x);  // x[k1]
-  const float2* t = tw + j * 32;
-  static_for<1, 32>([&](auto kc) {
-    constexpr int k1 = decltype(kc)::value;
-    x[k1] = cmul(x[k1], t[k1]);
-  });
   line_sync();  // every thread of the line has read its inputs from the line's region
+  // twiddle and store element by element (keeps at most a few twiddles live in registers)
   static_for<0, 32>([&](auto kc) {
     constexpr int k1 = decltype(kc)::value;
-    c.st(e1_bytes(l, k1, j), x[k1]);
+    float2 v = x[k1];
+    if constexpr (k1 > 0) v = cmul(v, t[k1]);
+    c.template st<128 * (k1 >> 4)>(m.E ^ (uint32_t)(8 * (k1 & 15)), v);
   });
 }
-PDEOPT_CF_FN void line_fwd_b(const Ctx& c, int l, int j, float2 (&x)[32]) {
+PDEOPT_CF_FN void line_fwd_b(const Ctx& c, const LineMap& m, float2 (&x)[32]) {
   static_for<0, 4>([&](auto ac) {
     constexpr int a = decltype(ac)::value;
     static_for<0, 8>([&](auto jc) {
       constexpr int jj = decltype(jc)::value;
-      x[8 * a + brev<3>(jj)] = c.ld(e1_bytes(l, j + 8 * a, jj));
+      x[8 * a + brev<3>(jj)] = c.template ld<128 * (a >> 1) + 256 * jj>(m.B ^ (uint32_t)(64 * (a & 1)));
     });
   });
   static_for<0, 4>([&](auto ac) { DitF<8, 1, false>::run(x + 8 * decltype(ac)::value); });
 }
-PDEOPT_CF_FN void line_fwd(const Ctx& c, const float2* __restrict__ tw, int l, int j, float2 (&x)[32]) {
-  line_fwd_a(c, tw, l, j, x);
+PDEOPT_CF_FN void line_fwd(const Ctx& c, const float2* __restrict__ t, const LineMap& m, float2 (&x)[32]) {
+  line_fwd_a(c, t, m, x);
   line_sync();
-  line_fwd_b(c, l, j, x);
+  line_fwd_b(c, m, x);
 }
 
 // ---- inverse transform of a line: x[8 a + k0] frequency in -> x[n1] spatial out (times 256) ----------
-PDEOPT_CF_FN void line_inv_a(const Ctx& c, int l, int j, float2 (&x)[32]) {
-  // natural k0 order -> bit-reversed placement for the decimation-in-time inverse (register renaming)
+PDEOPT_CF_FN void line_inv_a(const Ctx& c, const LineMap& m, float2 (&x)[32]) {
+  line_sync();  // every thread of the line has read its inputs from the line's region
   static_for<0, 4>([&](auto ac) {
     constexpr int a = decltype(ac)::value;
+    // natural k0 order -> bit-reversed placement for the decimation-in-time inverse (register renaming)
     float2 t1 = x[8 * a + 1], t3 = x[8 * a + 3];
     x[8 * a + 1] = x[8 * a + 4];
     x[8 * a + 4] = t1;
     x[8 * a + 3] = x[8 * a + 6];
     x[8 * a + 6] = t3;
     DitF<8, 1, true>::run(x + 8 * a);  // x[8 a + jj]: value for thread jj of the line, k1 = j + 8 a
-  });
-  line_sync();  // every thread of the line has read its inputs from the line's region
-  static_for<0, 4>([&](auto ac) {
-    constexpr int a = decltype(ac)::value;
     static_for<0, 8>([&](auto jc) {
       constexpr int jj = decltype(jc)::value;
-      c.st(e1_bytes(l, j + 8 * a, jj), x[8 * a + jj]);
+      c.template st<128 * (a >> 1) + 256 * jj>(m.B ^ (uint32_t)(64 * (a & 1)), x[8 * a + jj]);
     });
   });
 }
-PDEOPT_CF_FN void line_inv_b(const Ctx& c, const float2* __restrict__ tw, int l, int j, float2 (&x)[32]) {
-  const float2* t = tw + j * 32;
+PDEOPT_CF_FN void line_inv_b(const Ctx& c, const float2* __restrict__ t, const LineMap& m, float2 (&x)[32]) {
   static_for<0, 32>([&](auto kc) {
     constexpr int k1 = decltype(kc)::value;
-    float2 v = c.ld(e1_bytes(l, k1, j));
+    float2 v = c.template ld<128 * (k1 >> 4)>(m.E ^ (uint32_t)(8 * (k1 & 15)));
     if constexpr (k1 > 0) v = cmulc(v, t[k1]);
     x[brev<5>(k1)] = v;
   });
   DitF<32, 1, true>::run(x);  // x[n1]
 }
-PDEOPT_CF_FN void line_inv(const Ctx& c, const float2* __restrict__ tw, int l, int j, float2 (&x)[32]) {
-  line_inv_a(c, l, j, x);
+PDEOPT_CF_FN void line_inv(const Ctx& c, const float2* __restrict__ t, const LineMap& m, float2 (&x)[32]) {
+  line_inv_a(c, m, x);
   line_sync();
-  line_inv_b(c, tw, l, j, x);
+  line_inv_b(c, t, m, x);
 }
 
 // ---- transposed stores: the row <-> column exchange across the cluster --------------------------------
-// frequency arrangement of line `gl` (global line index 0..255) -> the slab that owns position k as a line:
-// value k = j + 8 a + 32 k0 goes to CTA k >> 6, line k & 63, position gl
-PDEOPT_CF_FN void store_transposed_from_freq(const Ctx& c, int gl, int j, const float2 (&x)[32]) {
+// frequency arrangement of line gl -> the slab that owns position k as a line: value k = j + 8 a + 32 k0
+// goes to CTA k >> 6, line k & 63 = j + 8 (a + 4 (k0 & 1)), position gl
+PDEOPT_CF_FN void store_transposed_from_freq(const Ctx& c, const LineMap& m, const float2 (&x)[32]) {
   static_for<0, 32>([&](auto ic) {
     constexpr int i = decltype(ic)::value;
-    constexpr int a = i >> 3, k0 = i & 7;
-    const int line = j + 8 * a + 32 * (k0 & 1);
-    c.st_to(k0 >> 1, slot_bytes(line, gl), x[i]);
+    constexpr int a = i >> 3, k0 = i & 7, mm = a + 4 * (k0 & 1);
+    c.template st_to<16384 * mm>(k0 >> 1, m.Tp[k0 >> 1] ^ (uint32_t)(64 * (mm & 1)), x[i]);
   });
 }
-// spatial arrangement of line `gl` -> value n = 8 n1 + j goes to CTA n >> 6 = n1 >> 3, line 8 (n1 & 7) + j
-PDEOPT_CF_FN void store_transposed_from_spatial(const Ctx& c, int gl, int j, const float2 (&x)[32]) {
+// spatial arrangement of line gl -> value n = 8 n1 + j goes to CTA n1 >> 3, line 8 (n1 & 7) + j, position gl
+PDEOPT_CF_FN void store_transposed_from_spatial(const Ctx& c, const LineMap& m, const float2 (&x)[32]) {
   static_for<0, 32>([&](auto nc) {
     constexpr int n1 = decltype(nc)::value;
-    const int line = 8 * (n1 & 7) + j;
-    c.st_to(n1 >> 3, slot_bytes(line, gl), x[n1]);
-  });
-}
-// plain (non-transposed) store of the spatial arrangement into the own slab
-PDEOPT_CF_FN void store_spatial(const Ctx& c, int l, int j, const float2 (&x)[32]) {
-  static_for<0, 32>([&](auto nc) {
-    constexpr int n1 = decltype(nc)::value;
-    c.st(slot_bytes(l, 8 * n1 + j), x[n1]);
+    c.template st_to<16384 * (n1 & 7)>(n1 >> 3, m.Tp[n1 >> 3] ^ (uint32_t)(64 * (n1 & 1)), x[n1]);
   });
 }
 

@@ -50,24 +50,24 @@ def test_identity(lib):
 
 
 def test_layout_is_bank_conflict_free():
-    """Every access pattern of the passes hits 16 distinct 8-byte banks per half-warp (remote transposed stores are
-    checked at the destination)."""
-    g = lambda line: ((line & 1) << 3) | (line & 6)
-    slot = lambda line, pos: line * 256 + (pos ^ g(line))
-    e1 = lambda line, k1, j: line * 256 + 32 * j + (k1 ^ j ^ ((line & 1) << 3))
+    """Every access pattern of the passes hits 16 distinct 8-byte banks per half-warp (16 consecutive lines), and a
+    warp's transposed store is 32 consecutive positions of one destination line (256 contiguous bytes)."""
+    slot = lambda line, pos: line * 256 + (pos ^ (line & 15))
+    e1 = lambda line, k1, j: line * 256 + 32 * j + (k1 ^ (line & 15))
     ok = lambda s: len({int(v) % 16 for v in s}) == 16
-    for l0 in range(0, 64, 2):
-        half = [(l0 + (t >> 3), t & 7) for t in range(16)]
-        for n1 in range(32):
-            assert ok([slot(l, 8 * n1 + j) for l, j in half])                       # spatial load / store
-            assert ok([e1(l, n1, j) for l, j in half])                              # E1, thread j stores k1 = n1
-        for a in range(4):
-            for jj in range(8):
-                assert ok([e1(l, j + 8 * a, jj) for l, j in half])                  # E1, reads / inverse writes
-            for k0 in range(8):
-                assert ok([slot(l, j + 8 * a + 32 * k0) for l, j in half])          # frequency load
-                for q in range(4):
-                    assert ok([slot(j + 8 * a + 32 * (k0 & 1), 64 * q + l) for l, j in half])   # transposed store from freq
-        for n1 in range(32):
-            for q in range(4):
-                assert ok([slot(8 * (n1 & 7) + j, 64 * q + l) for l, j in half])    # transposed store from spatial
+    for l0 in range(0, 64, 16):
+        lines = range(l0, l0 + 16)
+        for j in range(8):
+            for n1 in range(32):
+                assert ok([slot(l, 8 * n1 + j) for l in lines])                      # spatial load / store
+                assert ok([e1(l, n1, j) for l in lines])                             # E1, own j
+            for a in range(4):
+                for jj in range(8):
+                    assert ok([e1(l, j + 8 * a, jj) for l in lines])                 # E1, the other threads' values
+                for k0 in range(8):
+                    assert ok([slot(l, j + 8 * a + 32 * k0) for l in lines])         # frequency load
+    for q in range(4):
+        for k in range(64):
+            for l0 in (0, 32):
+                s = sorted(slot(k, 64 * q + l) for l in range(l0, l0 + 32))
+                assert s == list(range(s[0], s[0] + 32)) and s[0] % 16 == 0          # transposed store: contiguous
