@@ -121,59 +121,191 @@ class PDEEnv(_EnvBase):
         return obs, reward, self._terminate(), False, self._get_info()
 
 
-class PDEVecEnv:
-    """B independent environments stepped by one fused launch per env-step.
+class NoiseReset:
+    """Batched device-side reset: clip(mean + std * N(0,1), lo, hi) for any number of environments in one
+    call (the distribution of the reference notebooks' reset functions, e.g. optimize_nn_script.py:40).
+    Called as reset_func(domain, seed=..., batch=n, device=...) -> [n, *points] float32 CUDA tensor."""
 
-    The control is the C-ABI control block (include/pdeopt_b200.h): `action_to_control(actions,
-    ctrl)` is a user callback that writes the [B, 8] float32 block (device tensor) from the
-    actions; observation (uint8, Box(0,255,(1,*points))) and reward (variance by default, the
-    reference notebooks' `np.var`; "mean"; or ("probe", i, j) for the value at one grid point) come from
-    the kernel epilogue.  Environments whose time
-    reaches `end_time` are reset automatically (pde_env.py:206-215 gives the criterion)."""
+    batched = True
+
+    def __init__(self, mean=0.5, std=0.01, lo=0.0, hi=1.0):
+        self.mean, self.std, self.lo, self.hi = float(mean), float(std), float(lo), float(hi)
+
+    def __call__(self, domain, seed=None, batch=1, device="cuda"):
+        g = torch.Generator(device=device)
+        if seed is not None:
+            g.manual_seed(int(seed))
+        else:
+            g.seed()
+        y = torch.randn((batch, *domain.points), device=device, generator=g, dtype=torch.float32)
+        return y.mul_(self.std).add_(self.mean).clamp_(self.lo, self.hi)
+
+
+class StateReset:
+    """Batched reset to (a perturbation of) a given state, e.g. the GPE ground state (pde_opt/data/ground_state.npy)."""
+
+    batched = True
+
+    def __init__(self, state, rel_noise=0.0):
+        self.state, self.rel_noise = np.asarray(state, dtype=np.float32), float(rel_noise)
+        self._dev = {}
+
+    def __call__(self, domain, seed=None, batch=1, device="cuda"):
+        k = str(device)
+        if k not in self._dev:
+            self._dev[k] = torch.from_numpy(self.state).to(device)
+        y = self._dev[k].unsqueeze(0).repeat(batch, *([1] * self.state.ndim)).contiguous()
+        if self.rel_noise:
+            g = torch.Generator(device=device)
+            g.manual_seed(int(seed)) if seed is not None else g.seed()
+            y.mul_(1.0 + self.rel_noise * torch.randn(y.shape, device=device, generator=g))
+        return y
+
+
+class PDEVecEnv:
+    """B independent environments stepped by one fused launch per env-step: the batched form of
+    PDEEnv.reset / PDEEnv.step (pde_env.py:217-317) with the gymnasium VectorEnv call signatures
+    (reset(seed, options) -> (obs, infos); step(actions) -> (obs, rewards, terminations, truncations, infos);
+    num_envs, single_observation_space / single_action_space).
+
+    Equations: CahnHilliard2DPeriodic / AllenCahn2DPeriodic with derivs='fd' (uint8 observation and (mean,
+    variance) reward from the kernel epilogue), GPE2DTSControl (Strang; observation = quantised density |psi|^2,
+    rewards "density_var" | "vortices" = -number of quantised vortices, rl_utils.py:19-84 on the batch |
+    ("probe", i, j)), AdvectionDiffusion2D (fused forward kernel).
+
+    Control: `action_to_control(actions, ctrl)` writes the C-ABI control block (include/pdeopt_b200.h: [B, 8] for
+    the phase-field and GPE kernels, [B, nseg, 4] = (cx, cy, p0, p1) for advection-diffusion) on the device.
+    Everything per environment lives on the device: state, control, time, termination and failure flags.
+    Environments whose time reaches `end_time` (pde_env.py:206-215) or whose state has become non-finite
+    (pdeopt_plan_set_nonfinite_flags / pdeopt_nonfinite_flags; `info["nonfinite"]`) are reset in one batched call
+    when `auto_reset` is on.  `reset_func(domain, seed=..., batch=n, device=...)` with attribute `batched = True`
+    (NoiseReset, StateReset) produces n initial states at once; a reference-style reset_func(domain[, seed]) is
+    still accepted and looped over."""
 
     def __init__(self, equation, solver, num_envs, end_time, step_dt, numeric_dt, reset_func,
                  action_to_control: Optional[Callable] = None, obs_range=(0.0, 1.0), reward="var",
-                 device="cuda", auto_reset=True):
-        if getattr(equation, "_kind", None) not in ("ch2d", "ac2d") or not getattr(equation, "fused", False) \
-                or getattr(equation, "derivs", "fd") != "fd":
-            # the fused observation / reward epilogue exists in the finite-difference phase-field kernels
-            # only; failing here is better than returning stale observation buffers
-            raise NotImplementedError(
-                "PDEVecEnv needs a Cahn-Hilliard / Allen-Cahn 2-D equation with derivs='fd' and enumerated closures; "
-                "use PDEEnv (one environment) for the other equation types"
-            )
+                 device="cuda", auto_reset=True, action_space=None, ad_segments=1):
+        kind = getattr(equation, "_kind", None)
+        name = type(equation).__name__
+        if kind in ("ch2d", "ac2d"):
+            if not getattr(equation, "fused", False) or getattr(equation, "derivs", "fd") != "fd":
+                raise NotImplementedError("PDEVecEnv: phase-field equations need derivs='fd' and enumerated closures")
+            self.kind = "phase"
+        elif name == "GPE2DTSControl":
+            if not getattr(equation, "fused", False):
+                raise NotImplementedError("PDEVecEnv: GPE needs an enumerated `lights` (None or GaussianLight); per-env spots go through the control block")
+            self.kind = "gpe"
+        elif name == "AdvectionDiffusion2D":
+            self.kind = "ad"
+        else:
+            raise NotImplementedError(f"PDEVecEnv: no batched stepper for {name}")
         self.eq, self.solver, self.B = equation, solver, int(num_envs)
+        self.num_envs = self.B
         self.end_time, self.step_dt, self.numeric_dt = end_time, step_dt, numeric_dt
         self.reset_func = reset_func
         self.action_to_control = action_to_control
         self.obs_range, self.reward_kind, self.auto_reset = obs_range, reward, auto_reset
         self.device = torch.device(device)
         nx, ny = equation.domain.points
-        self.observation_space = spaces.Box(low=0.0, high=255.0, shape=(1, nx, ny), dtype=np.uint8)
+        self.single_observation_space = spaces.Box(low=0.0, high=255.0, shape=(1, nx, ny), dtype=np.uint8)
+        self.observation_space = self.single_observation_space
+        self.single_action_space = action_space if action_space is not None else spaces.Box(low=-1.0, high=1.0, shape=(8,))
+        self.action_space = self.single_action_space
         self._times = constant_step_times(0.0, step_dt, numeric_dt, np.float32, 1_000_000)
         self._terms = ODETerm(equation)
-        self.state = torch.empty((self.B, nx, ny), dtype=torch.float32, device=self.device)
+        shape = (self.B, nx, ny, 2) if self.kind == "gpe" else (self.B, nx, ny)
+        self.state = torch.empty(shape, dtype=torch.float32, device=self.device)
         self._next = torch.empty_like(self.state)
         self.obs = torch.empty((self.B, 1, nx, ny), dtype=torch.uint8, device=self.device)
         self.stats = torch.empty((self.B, 2), dtype=torch.float32, device=self.device)
-        self.ctrl = torch.zeros((self.B, 8), dtype=torch.float32, device=self.device)
-        self.ctrl[:, 4] = 1.0
-        self.time = np.zeros(self.B, dtype=np.float64)
+        self.flags = torch.zeros(self.B, dtype=torch.int32, device=self.device)
+        if self.kind == "ad":
+            self.ctrl = torch.zeros((self.B, int(ad_segments), 4), dtype=torch.float32, device=self.device)
+        else:
+            self.ctrl = torch.zeros((self.B, 8), dtype=torch.float32, device=self.device)
+        self._ctrl_default()
+        self.time = torch.zeros(self.B, dtype=torch.float64, device=self.device)
+        self._episode = 0
 
-    def reset(self, seed: Optional[int] = None):
-        for b in range(self.B):
-            s = self.reset_func(self.eq.domain, seed=(None if seed is None else seed + b))
-            self.state[b] = torch.as_tensor(np.asarray(s, dtype=np.float32)).to(self.device)
-        self.time[:] = 0.0
-        self.ctrl.zero_()
-        self.ctrl[:, 4] = 1.0
+    # ---- helpers ----
+    def _ctrl_default(self, mask=None):
+        sel = slice(None) if mask is None else mask
+        self.ctrl[sel] = 0.0
+        if self.kind == "ad":
+            v = self.eq.velocity
+            self.ctrl[sel] = torch.tensor(v.control_row(), dtype=torch.float32, device=self.device)
+        else:
+            self.ctrl[sel, 4] = 1.0
+
+    def _initial_states(self, n, seed):
+        rf = self.reset_func
+        if getattr(rf, "batched", False):
+            return rf(self.eq.domain, seed=seed, batch=n, device=self.device).to(torch.float32)
+        out = []
+        for b in range(n):
+            s = rf(self.eq.domain, seed=(None if seed is None else seed + b)) if seed is not None else rf(self.eq.domain)
+            out.append(torch.as_tensor(np.asarray(s, dtype=np.float32)) if not torch.is_tensor(s) else s.to(torch.float32))
+        return torch.stack(out).to(self.device)
+
+    def reset(self, seed: Optional[int] = None, options: Optional[dict] = None):
+        self.state.copy_(self._initial_states(self.B, seed))
+        self.time.zero_()
+        self.flags.zero_()
+        self._ctrl_default()
         return self._observe(), {}
+
+    def _field(self):
+        if self.kind == "gpe":
+            return self.state[..., 0] ** 2 + self.state[..., 1] ** 2
+        return self.state
 
     def _observe(self):
         lo, hi = self.obs_range
-        q = torch.clamp((self.state - lo) / (hi - lo), 0.0, 1.0) * 255.0
+        q = torch.clamp((self._field() - lo) / (hi - lo), 0.0, 1.0) * 255.0
         self.obs[:, 0] = torch.round(q).to(torch.uint8)
         return self.obs
+
+    def _rollout(self, lo, hi):
+        y, out = self.state[lo:hi], self._next[lo:hi]
+        if self.kind == "phase":
+            self.solver.rollout(self._terms, self._times, y, ctrl=self.ctrl[lo:hi], obs=self.obs[lo:hi], obs_range=self.obs_range,
+                                reward=self.stats[lo:hi], out=out, nonfinite=self.flags[lo:hi])
+        elif self.kind == "gpe":
+            self.solver.rollout(self._terms, self._times, y, ctrl=self.ctrl[lo:hi], out=out)
+        else:
+            from .adjoint import ad_rollout
+
+            with torch.no_grad():
+                out.copy_(ad_rollout(self.eq, y, self.ctrl[lo:hi], self._times, A=float(getattr(self.solver, "A", 1.0))))
+
+    def _epilogue(self):
+        """Observation / reward / failure flags of the equations without a fused epilogue (device ops)."""
+        if self.kind == "phase":
+            return
+        import ctypes
+
+        from . import _lib
+
+        self._observe()
+        f = self._field()
+        self.stats[:, 0] = f.mean(dim=(1, 2))
+        self.stats[:, 1] = f.var(dim=(1, 2), unbiased=False)
+        n_per = int(self.state[0].numel())
+        with _lib.device_of(self.state):
+            _lib.check(_lib.load().pdeopt_nonfinite_flags(ctypes.c_void_p(self.state.data_ptr()), self.B, n_per,
+                                                          ctypes.c_void_p(self.flags.data_ptr()), _lib.stream_ptr(self.state)))
+
+    def _reward(self):
+        rk = self.reward_kind
+        if isinstance(rk, tuple) and rk[0] == "probe":
+            return self._field()[:, rk[1], rk[2]]  # point probe of the new state
+        if rk == "vortices":
+            from .rl_utils import vortex_counts
+
+            return -vortex_counts(self.state)[:, 0].to(torch.float32)
+        if rk in ("var", "density_var"):
+            return self.stats[:, 1]
+        return self.stats[:, 0]
 
     def step(self, actions, obs_host=None, stats_host=None, chunks=4):
         """One env step of all B environments.  With pinned host tensors `obs_host` [B, 1, nx, ny] uint8
@@ -182,43 +314,52 @@ class PDEVecEnv:
         call returns when everything has landed on the host."""
         if self.action_to_control is not None:
             self.action_to_control(actions, self.ctrl)
-        if obs_host is None:
-            self.solver.rollout(
-                self._terms, self._times, self.state, ctrl=self.ctrl, obs=self.obs, obs_range=self.obs_range,
-                reward=self.stats, out=self._next,
-            )
+        if obs_host is None or self.kind != "phase":
+            self._rollout(0, self.B)
+            self.state, self._next = self._next, self.state
+            self._epilogue()
+            if obs_host is not None:
+                obs_host.copy_(self.obs, non_blocking=True)
+                if stats_host is not None:
+                    stats_host.copy_(self.stats, non_blocking=True)
+                torch.cuda.current_stream(self.device).synchronize()
         else:
-            chunks = max(1, min(int(chunks), self.B // 2))
+            chunks = max(1, min(int(chunks), self.B))
             if not hasattr(self, "_streams") or len(self._streams) != chunks:
                 self._streams = [torch.cuda.Stream(device=self.device) for _ in range(chunks)]
             main = torch.cuda.current_stream(self.device)
-            step = 2 * ((self.B + 2 * chunks - 1) // (2 * chunks))  # even slices: two environments share a CTA
+            step = (self.B + chunks - 1) // chunks
             for c, st in enumerate(self._streams):
                 lo, hi = c * step, min(self.B, (c + 1) * step)
                 if lo >= hi:
                     break
                 st.wait_stream(main)
                 with torch.cuda.stream(st):
-                    self.solver.rollout(
-                        self._terms, self._times, self.state[lo:hi], ctrl=self.ctrl[lo:hi], obs=self.obs[lo:hi],
-                        obs_range=self.obs_range, reward=self.stats[lo:hi], out=self._next[lo:hi],
-                    )
+                    self._rollout(lo, hi)
                     obs_host[lo:hi].copy_(self.obs[lo:hi], non_blocking=True)
                     if stats_host is not None:
                         stats_host[lo:hi].copy_(self.stats[lo:hi], non_blocking=True)
             for st in self._streams:
                 main.wait_stream(st)
             main.synchronize()
-        self.state, self._next = self._next, self.state
+            self.state, self._next = self._next, self.state
         self.time += self.step_dt
-        if isinstance(self.reward_kind, tuple) and self.reward_kind[0] == "probe":
-            reward = self.state[:, self.reward_kind[1], self.reward_kind[2]]  # point probe of the new state
-        else:
-            reward = self.stats[:, 1] if self.reward_kind == "var" else self.stats[:, 0]
-        terminated = self.time >= self.end_time
-        if self.auto_reset and terminated.any():
-            for b in np.nonzero(terminated)[0]:
-                s = self.reset_func(self.eq.domain, seed=None)
-                self.state[b] = torch.as_tensor(np.asarray(s, dtype=np.float32)).to(self.device)
-                self.time[b] = 0.0
-        return self.obs, reward, terminated, np.zeros(self.B, dtype=bool), {}
+        reward = self._reward()
+        failed = self.flags != 0
+        terminated = (self.time >= self.end_time) | failed
+        truncated = torch.zeros_like(terminated)
+        info = {"nonfinite": failed}
+        if self.auto_reset:
+            self._auto_reset(terminated)
+        return self.obs, reward, terminated, truncated, info
+
+    def _auto_reset(self, mask):
+        """Resets the masked environments in one batched call; no host loop over B (one scalar sync for the count)."""
+        n = int(mask.sum().item())
+        if n == 0:
+            return
+        self._episode += 1
+        self.state[mask] = self._initial_states(n, None if self._episode is None else 7919 * self._episode)
+        self.time[mask] = 0.0
+        self.flags[mask] = 0
+        self._ctrl_default(mask)

@@ -184,7 +184,7 @@ class SemiImplicitFourierSpectral:
         dense_info = dict(y0=y0, y1=y1)
         return y1, y_error, dense_info, None, RESULTS.successful
 
-    def rollout(self, terms, times, y0, ctrl=None, obs=None, obs_range=(0.0, 1.0), reward=None, out=None):
+    def rollout(self, terms, times, y0, ctrl=None, obs=None, obs_range=(0.0, 1.0), reward=None, out=None, nonfinite=None):
         """All steps between consecutive entries of `times` (host array, working precision) in as
         few launches as possible: the K-fused form of the diffeqsolve loop body."""
         times = np.asarray(times, dtype=np.float32)
@@ -199,7 +199,7 @@ class SemiImplicitFourierSpectral:
         sym = self.symbol_on(y.device)
         if eq is not None:
             c = ctrl if ctrl is not None else eq.control
-            y1 = plan.step(y, dts, sym, ctrl=c, obs=obs, obs_range=obs_range, reward=reward, out=out)
+            y1 = plan.step(y, dts, sym, ctrl=c, obs=obs, obs_range=obs_range, reward=reward, out=out, nonfinite=nonfinite)
         else:
             y1 = y
             for k, dt in enumerate(dts):
