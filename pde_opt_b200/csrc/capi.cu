@@ -200,6 +200,7 @@ static pdeopt_status sifs_launch_impl(pdeopt_plan* plan, int mode, const float* 
   p.inv_hx2 = (float)(1.0 / (d.hx * d.hx));
   p.inv_hy2 = (float)(1.0 / (d.hy * d.hy));
   p.kappa = (float)d.kappa;
+  sifs_fill_rhs_consts(p, d.kind == PDEOPT_AC2D);
   p.lo_x = (float)d.lo_x;
   p.lo_y = (float)d.lo_y;
   p.hx = (float)d.hx;

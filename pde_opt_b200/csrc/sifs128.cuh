@@ -56,9 +56,25 @@ struct SifsParams {
   int mode;         // MODE_FUSED / MODE_RHS_ONLY / MODE_GIVEN_F
   float inv_hx, inv_hy, inv_hx2, inv_hy2, kappa;
   float lo_x, lo_y, hx, hy;
+  // sifs128r: loop-invariant constants of the RHS phase, both halves equal, filled on the host so that the
+  // packed instructions take them straight from the constant bank instead of holding them in registers.
+  // S = 1/(2 hx^2) (Cahn-Hilliard) or -1 (Allen-Cahn), see rhs_phase_r.
+  float2 rc_ax, rc_ay, rc_a0, rc_ln2p, rc_ln2m, rc_ratio, rc_S;
   PointwiseParams pw;
   float dt[kMaxK];
 };
+
+inline void sifs_fill_rhs_consts(SifsParams& p, bool allen_cahn) {
+  const float S = allen_cahn ? -1.0f : 0.5f * p.inv_hx * p.inv_hx;
+  auto two = [](float v) { return make_float2(v, v); };
+  p.rc_S = two(S);
+  p.rc_ax = two(-S * p.kappa * p.inv_hx2);
+  p.rc_ay = two(-S * p.kappa * p.inv_hy2);
+  p.rc_a0 = two(2.0f * S * p.kappa * (p.inv_hx2 + p.inv_hy2));
+  p.rc_ln2p = two(0.69314718055994531f * S);
+  p.rc_ln2m = two(-0.69314718055994531f * S);
+  p.rc_ratio = two((p.inv_hy * p.inv_hy) / (p.inv_hx * p.inv_hx));
+}
 
 // ---- TMEM parking of the state (64 x 32-bit columns per thread) --------------------------
 #ifndef PDEOPT_PARK_GLOBAL

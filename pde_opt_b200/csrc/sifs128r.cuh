@@ -100,44 +100,53 @@ __device__ __forceinline__ void rhs_phase_r(uint32_t wbase, const SifsParams& p,
     gyv[0] = make_float2(g4.x, g4.y);
     gyv[1] = make_float2(g4.z, g4.w);
   }
-  // -kappa lap(u) = ax (u[i+1] + u[i-1]) + ay (u[j+1] + u[j-1]) + a0 u  with ax = -kappa/hx^2, ay = -kappa/hy^2,
-  // a0 = 2 kappa (1/hx^2 + 1/hy^2): one packed add and three packed FMAs per pair, no hx == hy special
-  // case (derivatives.py:8-12 up to the summation order; the same value to a few ulp of the largest term)
-  const float2 ax = splat2(-p.kappa * p.inv_hx2), ay = splat2(-p.kappa * p.inv_hy2);
-  const float2 a0 = splat2(2.0f * p.kappa * (p.inv_hx2 + p.inv_hy2));
+  // Everything that feeds mu is pre-multiplied by one constant S so that the flux needs no trailing scale:
+  //   Cahn-Hilliard S = cx = 1/(2 hx^2):  f = (Gx - Gx_prev) + (cy/cx) (Gy - Gy_left),  G = (D + D_next)(S mu_next - S mu)
+  //   Allen-Cahn    S = -1:               f = R * (S mu)
+  // S mu = S ax (u[i+1] + u[i-1]) + S ay (u[j+1] + u[j-1]) + S a0 u + S mu_h with ax = -kappa/hx^2, ay = -kappa/hy^2,
+  // a0 = 2 kappa (1/hx^2 + 1/hy^2): one packed add and three packed FMAs per pair, the constants folded on the
+  // way in (derivatives.py:8-12 and cahn_hilliard.py:89-109 up to the summation order and a common factor; the
+  // same value to a few ulp of the largest term).  The control bump table gx is pre-scaled by S by the caller.
+  const float2 S2 = p.rc_S, ax = p.rc_ax, ay = p.rc_ay, a0 = p.rc_a0, ln2p = p.rc_ln2p, ln2m = p.rc_ln2m;
   const float2 woff2 = splat2(w_off);
-  // log family: mu_h = ln2 lg2(c) - ln2 lg2(1 - c) + w - 2 w c as three chained FMAs
+  // log family: S mu_h + S a0 c = (S a0 - 2 S w) c + S w + S ln2 lg2(c) - S ln2 lg2(1 - c): three chained FMAs
   const float wlog = p.pw.mu_coef[0] + w_off;
-  const float2 wl2 = splat2(wlog), m2wl2 = splat2(-2.0f * wlog);
+  const float2 wl2 = splat2(S2.x * wlog), lin2 = splat2(fmaf(-2.0f * S2.x, wlog, a0.x));
 
-  // mu and mobility of one row from its three-row neighbourhood
+  // S mu and the mobility of one row from its three-row neighbourhood
   auto mu_row = [&](int rho, const float2 (&um)[2], const float2 (&u0)[2], const float2 (&up)[2], float2 (&mu)[2],
                     float2 (&D)[2]) {
     const float uL = shf(u0[1].y, lm1), uR = shf(u0[0].x, lp1);
     float2 gxr = make_float2(0.f, 0.f);
     if (has_bump) gxr = splat2(gx[rho & (kRows - 1)]);
-    // left + right column neighbours: the operands straddle the aligned pairs, so the three shifted
-    // pairs (uL, c0), (c1, c2), (c3, uR) are assembled with register moves (ALU pipe, issued in the
-    // shadow of the packed instructions) and the sums stay packed
-    const float2 q = make_float2(u0[0].y, u0[1].x);
+    // left + right column neighbours: the operands straddle the aligned pairs.  Scalar adds cost the same
+    // FP32-pipe cycles as two packed adds and save the register moves that assembling the shifted pairs
+    // (uL, c0), (c1, c2), (c3, uR) would take (issue slots); PDEOPT_RHS_PACKED_SHIFTS keeps the packed form.
     float2 s[2];
+#ifdef PDEOPT_RHS_PACKED_SHIFTS
+    const float2 q = make_float2(u0[0].y, u0[1].x);
     s[0] = add2(make_float2(uL, u0[0].x), q);
     s[1] = add2(q, make_float2(u0[1].y, uR));
+#else
+    s[0] = make_float2(uL + u0[0].y, u0[0].x + u0[1].x);
+    s[1] = make_float2(u0[0].y + u0[1].y, u0[1].x + uR);
+#endif
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       float2 mh;
       if constexpr (MU == MU_LOG && (MOB == MOB_DEGENERATE || MOB == MOB_CONST)) {
         const float2 c = u0[j];
         const float2 sm = sub2(splat2(1.0f), c);
-        mh = fma2(c, m2wl2, wl2);
-        mh = fma2(make_float2(lg2_fast(sm.x), lg2_fast(sm.y)), splat2(-0.69314718055994531f), mh);
-        mh = fma2(make_float2(lg2_fast(c.x), lg2_fast(c.y)), splat2(0.69314718055994531f), mh);
+        mh = fma2(c, lin2, wl2);
+        mh = fma2(make_float2(lg2_fast(sm.x), lg2_fast(sm.y)), ln2m, mh);
+        mh = fma2(make_float2(lg2_fast(c.x), lg2_fast(c.y)), ln2p, mh);
         D[j] = (MOB == MOB_DEGENERATE) ? mul2(sm, c) : splat2(p.pw.mob_coef[0]);
       } else {
         mu_mob_pair<MU, MOB>(u0[j], p.pw, woff2, mh, D[j]);
+        mh = fma2(a0, u0[j], mul2(mh, S2));
       }
       if (has_bump) mh = fma2(gxr, gyv[j], mh);
-      mu[j] = fma2(ax, add2(up[j], um[j]), fma2(ay, s[j], fma2(a0, u0[j], mh)));
+      mu[j] = fma2(ax, add2(up[j], um[j]), fma2(ay, s[j], mh));
     }
   };
 
@@ -158,7 +167,7 @@ __device__ __forceinline__ void rhs_phase_r(uint32_t wbase, const SifsParams& p,
       float2 mu[2], R[2], f[2];
       mu_row(r0 + i, um, u0, up, mu, R);
 #pragma unroll
-      for (int j = 0; j < 2; ++j) f[j] = mul2(mul2(R[j], splat2(-1.0f)), mu[j]);
+      for (int j = 0; j < 2; ++j) f[j] = mul2(R[j], mu[j]);
       store_srow(wbase, r0 + i, lane, f);
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
@@ -170,7 +179,7 @@ __device__ __forceinline__ void rhs_phase_r(uint32_t wbase, const SifsParams& p,
   }
 
   // Cahn-Hilliard: f = div( D_face * grad_face(mu) )   (cahn_hilliard.py:89-109)
-  const float2 cx = splat2(0.5f * p.inv_hx * p.inv_hx), cy = splat2(0.5f * p.inv_hy * p.inv_hy);
+  const float2 ratio = p.rc_ratio;  // cy / cx
   float2 um[2], u0[2], up[2];
   float2 mu_p[2], D_p[2], gx_old[2], dy_p[2];
 #pragma unroll
@@ -193,7 +202,11 @@ __device__ __forceinline__ void rhs_phase_r(uint32_t wbase, const SifsParams& p,
       g[1] = mul2(add2(D[1], make_float2(D[1].y, DR)), sub2(make_float2(mu[1].y, muR), mu[1]));
       const float gL = shf(g[1].y, lm1);
       dy[0] = sub2(g[0], make_float2(gL, g[0].x));
+#ifdef PDEOPT_RHS_PACKED_SHIFTS
       dy[1] = sub2(g[1], make_float2(g[0].y, g[1].x));
+#else
+      dy[1] = make_float2(g[1].x - g[0].y, g[1].y - g[1].x);
+#endif
     }
     if (it >= 0) {
       float2 gxn[2];
@@ -202,7 +215,7 @@ __device__ __forceinline__ void rhs_phase_r(uint32_t wbase, const SifsParams& p,
       if (it >= 1) {
         float2 f[2];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) f[j] = fma2(sub2(gxn[j], gx_old[j]), cx, mul2(dy_p[j], cy));
+        for (int j = 0; j < 2; ++j) f[j] = fma2(dy_p[j], ratio, sub2(gxn[j], gx_old[j]));
         store_srow(wbase, r0 + it - 1, lane, f);
       }
 #pragma unroll
@@ -313,7 +326,9 @@ __global__ void __launch_bounds__(kThreadsR, 2) sifs128r_kernel(const __grid_con
       const float pos = isx ? (p.lo_x + (i + 0.5f) * p.hx) : (p.lo_y + (i + 0.5f) * p.hy);
       const float dd = pos - (isx ? ce[2] : ce[3]);
       const float iw = 0.5f / (ce[4] * ce[4]);
-      const float v = (ce[1] != 0.f ? expf(-dd * dd * iw) : 0.f) * (isx ? ce[1] : 1.0f);
+      // gx carries the amplitude and the constant S of rhs_phase_r (Cahn-Hilliard: 1/(2 hx^2); Allen-Cahn: -1)
+      const float sx = ce[1] * p.rc_S.x;
+      const float v = (ce[1] != 0.f ? expf(-dd * dd * iw) : 0.f) * (isx ? sx : 1.0f);
       if (isx) S.gx[i] = v; else S.gy[i] = v;
     }
     // ---- prologue: y0 -> natural layout (S map) ----
