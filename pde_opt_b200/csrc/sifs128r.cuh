@@ -313,6 +313,8 @@ __global__ void __launch_bounds__(kThreadsR, 2) sifs128r_kernel(const __grid_con
   // progress at the same rate (the warp scheduler favours one of them), so a static split would leave
   // the favoured CTA idle at the end of the launch while the other one finishes alone.
   for (int env = blockIdx.x; env < p.batch;) {
+    // the NEXT environment is claimed now, so that its state can be pulled into L2 while this one is stepped
+    if (tid == 0) S.next_env = (int)gridDim.x + atomicAdd(p.work_counter, 1);
     // ---- per-environment control (pde_env.py:274-286; our definition) ----
     float w_off = 0.f;
     bool has_bump = false;
@@ -344,6 +346,16 @@ __global__ void __launch_bounds__(kThreadsR, 2) sifs128r_kernel(const __grid_con
       }
     }
     __syncthreads();
+    const int next_env = S.next_env;
+#ifndef PDEOPT_NO_L2_PREFETCH
+    if (next_env < p.batch) {
+      // 64 KB = 512 lines of 128 B, two per thread: the prologue loads of the next environment hit L2, which
+      // matters when few steps are fused per launch (K = 1: load, step and store of a CTA do not overlap)
+      const char* nx = reinterpret_cast<const char*>(p.y0 + (size_t)next_env * kRows * kCols) + tid * 256;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 128));
+    }
+#endif
     float2 x[32];
     gather_nat(F, x);
 #pragma unroll
@@ -458,9 +470,8 @@ __global__ void __launch_bounds__(kThreadsR, 2) sifs128r_kernel(const __grid_con
         if (p.nonfinite != nullptr && tid == 0) p.nonfinite[env] = (fabsf(tot.x) <= 3.0e38f) ? 0 : 1;
       }
     }
-    if (tid == 0) S.next_env = (int)gridDim.x + atomicAdd(p.work_counter, 1);
     __syncthreads();  // the field buffer and the control tables are reused by the next environment
-    env = S.next_env;
+    env = next_env;
   }
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(S.tmem_base));
