@@ -30,7 +30,7 @@ _FFI = ctypes.CDLL(os.environ.get("PDEOPT_JAX_FFI_LIB", os.path.join(_HERE, "lib
 
 _TARGETS = {
     "pdeopt_sifs_step": "PdeoptSifsStep", "pdeopt_sifs_filter": "PdeoptSifsFilter", "pdeopt_rhs": "PdeoptRhs",
-    "pdeopt_pf_adjoint": "PdeoptPfAdjoint", "pdeopt_pf_tangent": "PdeoptPfTangent",
+    "pdeopt_pf_adjoint": "PdeoptPfAdjoint", "pdeopt_pf_tangent": "PdeoptPfTangent", "pdeopt_rollout_fwd": "PdeoptRolloutFwd",
     "pdeopt_strang_step": "PdeoptStrangStep", "pdeopt_ad_fwd": "PdeoptAdFwd", "pdeopt_ad_bwd": "PdeoptAdBwd",
 }
 for _name, _sym in _TARGETS.items():
@@ -107,11 +107,9 @@ def make_phasefield_rollout(plan_factory, symbol, dts):
 
     def fwd(y0, mu_coef, mob_coef):
         plan = plan_factory(np.asarray(mu_coef), np.asarray(mob_coef))
-        states, y = [], y0
-        for dt in dts:  # one launch per step: the adjoint needs the state before every step
-            states.append(y)
-            y = sifs_steps(plan, y, symbol, dts=[dt])[0]
-        return y, (states, plan, mu_coef.shape, mob_coef.shape)
+        out = (jax.ShapeDtypeStruct(y0.shape, jnp.float32), jax.ShapeDtypeStruct((len(dts),) + y0.shape, jnp.float32))
+        y, traj = jax.ffi.ffi_call("pdeopt_rollout_fwd", out)(y0, symbol, plan=np.int64(plan), dts=dts, save_every=np.int64(1))
+        return y, (list(traj), plan, mu_coef.shape, mob_coef.shape)  # the adjoint needs the state before every step
 
     def bwd(res, lam):
         states, plan, mu_shape, mob_shape = res

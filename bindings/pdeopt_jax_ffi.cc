@@ -19,7 +19,8 @@
 //   pdeopt_ad_fwd/_bwd : the advection-diffusion rollout and its hand-written adjoint (custom_vjp in place of
 //                        reverse-mode through diffeqsolve, pde_model.py:226-323)
 //   pdeopt_pf_adjoint  : discrete adjoint of one finite-difference Cahn-Hilliard / Allen-Cahn step
-//   pdeopt_pf_tangent  : forward-mode tangent of one such step (the ForwardMode adjoint that
+//   pdeopt_rollout_fwd : the forward rollout that keeps the step-start states (residuals of custom_vjp / custom_jvp)
+//   pdeopt_pf_tangent  : forward-mode tangents of such steps (the ForwardMode adjoint that
 //                        PDEModel.train(method="least_squares") asks diffrax for, pde_model.py:404-428)
 #if __has_include("xla/ffi/api/ffi.h")
 #include <cstdint>
@@ -89,14 +90,27 @@ ffi::Error PfAdjointImpl(void* stream, F32 u, F32 lam1, F32 symbol, F32 work, F6
                                                gmob->typed_data(), stream));
 }
 
-// Forward-mode tangent of one phase-field step for `ndir` parameter directions at once.
-ffi::Error PfTangentImpl(void* stream, F32 u, F32 v0, F32 dmu, F32 dmob, F32 symbol, int64_t plan, float dt,
-                         ffi::Result<F32> v1) {
-  const int32_t batch = static_cast<int32_t>(u.dimensions()[0]);
-  const int32_t ndir = static_cast<int32_t>(v0.dimensions()[0]);
-  return Status(pdeopt_phasefield_tangent_step(Plan(plan), u.typed_data(), v0.typed_data(), v1->typed_data(), batch,
-                                               ndir, dmu.typed_data(), dmob.typed_data(), dt, symbol.typed_data(),
-                                               stream));
+// Forward-mode tangents of K phase-field steps for `ndir` directions at once, in place on the tangent field
+// (aliased input -> output).  traj [K, B, nx, ny] are the step-start states kept by pdeopt_sifs_rollout_fwd.
+ffi::Error PfTangentImpl(void* stream, F32 traj, F32 v_in, F32 dmu, F32 dmob, F32 symbol, F32 work, int64_t plan,
+                         ffi::Span<const float> dts, ffi::Result<F32> v) {
+  (void)v_in;  // aliased onto v by input_output_aliases
+  const std::vector<float> dt = Dts(dts);
+  const int32_t ndir = static_cast<int32_t>(v->dimensions()[0]);
+  const int32_t batch = static_cast<int32_t>(v->dimensions()[1]);
+  return Status(pdeopt_phasefield_tangent_steps(Plan(plan), traj.typed_data(), v->typed_data(), batch, ndir,
+                                                static_cast<int32_t>(dt.size()), dt.data(), dmu.typed_data(), dmob.typed_data(),
+                                                symbol.typed_data(), const_cast<float*>(work.typed_data()), stream));
+}
+
+// K fused steps that also keep the state at the start of every save_every-th step (the forward half of the
+// differentiable rollout).  Results: y1 [B, nx, ny], traj [ceil(K / save_every), B, nx, ny].
+ffi::Error RolloutFwdImpl(void* stream, F32 y0, F32 symbol, int64_t plan, ffi::Span<const float> dts, int64_t save_every,
+                          ffi::Result<F32> y1, ffi::Result<F32> traj) {
+  const std::vector<float> dt = Dts(dts);
+  return Status(pdeopt_sifs_rollout_fwd(Plan(plan), y0.typed_data(), y1->typed_data(), static_cast<int32_t>(y0.dimensions()[0]),
+                                        static_cast<int32_t>(dt.size()), dt.data(), symbol.typed_data(), traj->typed_data(),
+                                        static_cast<int32_t>(save_every), stream));
 }
 
 // K fused Strang steps on 128 x 128 wavefunctions [B, n, n, 2].  a_term: the (kx >= 0, ky >= 0) quadrant of the
@@ -165,8 +179,12 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(PdeoptPfAdjoint, PfAdjointImpl,
                               ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F64>().Arg<F64>()
                                   .Attr<int64_t>("plan").Attr<float>("dt").Ret<F32>().Ret<F64>().Ret<F64>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(PdeoptPfTangent, PfTangentImpl,
-                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>()
-                                  .Attr<int64_t>("plan").Attr<float>("dt").Ret<F32>());
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>()
+                                  .Attr<int64_t>("plan").Attr<ffi::Span<const float>>("dts").Ret<F32>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(PdeoptRolloutFwd, RolloutFwdImpl,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<F32>()
+                                  .Attr<int64_t>("plan").Attr<ffi::Span<const float>>("dts").Attr<int64_t>("save_every")
+                                  .Ret<F32>().Ret<F32>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(PdeoptStrangStep, StrangStepImpl,
                               ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<F32>().Arg<F32>()
                                   .Attr<ffi::Span<const float>>("dts").Attr<ffi::Span<const double>>("geom")

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define PDEOPT_ABI_VERSION 3
+#define PDEOPT_ABI_VERSION 4
 #define PDEOPT_MAX_COEF 16
 #define PDEOPT_MAX_FUSED_STEPS 512 /* per launch; callers loop for longer rollouts */
 #define PDEOPT_NCTRL 8            /* floats per environment in the control block */
@@ -164,6 +164,30 @@ int64_t pdeopt_phasefield_adjoint_work_floats(const pdeopt_plan* plan, int32_t b
 pdeopt_status pdeopt_phasefield_adjoint_step(pdeopt_plan* plan, const float* u_dev, const float* lam1_dev, float* lam0_dev,
                                              int32_t batch, float dt, const float* symbol_dev, float* work_dev,
                                              double* gmu_dev, double* gmob_dev, void* stream);
+
+/* K fused steps like pdeopt_sifs_step_batched (no control, no epilogue) that also keep the state at the START of
+ * every save_every-th step: traj_dev [ceil(ksteps / save_every)][batch][nx][ny].  This is the forward half of the
+ * differentiable rollout (what diffrax's adjoints keep or recompute, pde_model.py:120-134 with
+ * RecursiveCheckpointAdjoint / ForwardMode): save_every = 1 feeds pdeopt_phasefield_adjoint_step /
+ * pdeopt_phasefield_tangent_steps directly; save_every = C > 1 keeps checkpoints from which the caller re-runs
+ * segments of C steps with save_every = 1 during the backward sweep.  Any ksteps (the library loops over launches
+ * of at most PDEOPT_MAX_FUSED_STEPS); the fused 128 x 128 kernel writes the checkpoints from shared memory. */
+pdeopt_status pdeopt_sifs_rollout_fwd(pdeopt_plan* plan, const float* y0_dev, float* y1_dev, int32_t batch,
+                                      int32_t ksteps, const float* dt_host, const float* symbol_dev, float* traj_dev,
+                                      int32_t save_every, void* stream);
+
+/* Forward-mode tangent (JVP) of ksteps semi-implicit steps of the finite-difference Cahn-Hilliard / Allen-Cahn
+ * equation of `plan` for ndir directions at once: the derivative optimistix's Levenberg-Marquardt takes through
+ * diffrax's ForwardMode adjoint in PDEModel.train(method="least_squares") (pde_model.py:334,404-428).
+ *   traj_dev : [ksteps][batch][nx][ny] state at the start of every step (pdeopt_sifs_rollout_fwd, save_every = 1)
+ *   v_dev    : [ndir][batch][nx][ny] tangent of the state, advanced IN PLACE by the ksteps steps
+ *   dmu_dev, dmob_dev : [ndir][PDEOPT_MAX_COEF] float32 directions in mu_coef / mob_coef (zeros for state-only tangents)
+ *   work_dev : pdeopt_phasefield_tangent_work_floats(plan, batch, ndir) floats of scratch
+ * The plan's coefficients are the point of linearisation. */
+int64_t pdeopt_phasefield_tangent_work_floats(const pdeopt_plan* plan, int32_t batch, int32_t ndir);
+pdeopt_status pdeopt_phasefield_tangent_steps(pdeopt_plan* plan, const float* traj_dev, float* v_dev, int32_t batch,
+                                              int32_t ndir, int32_t ksteps, const float* dt_host, const float* dmu_dev,
+                                              const float* dmob_dev, const float* symbol_dev, float* work_dev, void* stream);
 
 /* GPE2DTSControl (gross_pitaevskii.py:18-81) geometry and constants. */
 typedef struct {

@@ -116,6 +116,9 @@ EXPORTS = [
     "pdeopt_sifs_filter_batched",
     "pdeopt_phasefield_adjoint_work_floats",
     "pdeopt_phasefield_adjoint_step",
+    "pdeopt_sifs_rollout_fwd",
+    "pdeopt_phasefield_tangent_work_floats",
+    "pdeopt_phasefield_tangent_steps",
     "pdeopt_strang_step_batched",
     "pdeopt_gpe_detect_vortices",
     "pdeopt_ad_tables_len",
@@ -173,6 +176,12 @@ def load():
     lib.pdeopt_phasefield_adjoint_work_floats.restype = ctypes.c_int64
     lib.pdeopt_phasefield_adjoint_step.argtypes = [vp, vp, vp, vp, i32, f32, vp, vp, vp, vp, vp]
     lib.pdeopt_phasefield_adjoint_step.restype = ctypes.c_int
+    lib.pdeopt_sifs_rollout_fwd.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, i32, vp]
+    lib.pdeopt_sifs_rollout_fwd.restype = ctypes.c_int
+    lib.pdeopt_phasefield_tangent_work_floats.argtypes = [vp, i32, i32]
+    lib.pdeopt_phasefield_tangent_work_floats.restype = ctypes.c_int64
+    lib.pdeopt_phasefield_tangent_steps.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    lib.pdeopt_phasefield_tangent_steps.restype = ctypes.c_int
     lib.pdeopt_strang_step_batched.argtypes = [ctypes.POINTER(GpeDesc), vp, vp, i32, i32, vp, vp, f32, f32, vp, vp]
     lib.pdeopt_strang_step_batched.restype = ctypes.c_int
     lib.pdeopt_gpe_detect_vortices.argtypes = [vp, i32, i32, i32, f32, f32, vp, vp, vp]

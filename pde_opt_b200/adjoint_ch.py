@@ -1,5 +1,5 @@
 """Differentiable rollout of the finite-difference Cahn-Hilliard / Allen-Cahn equations: the fused
-forward kernels (one launch per step, the state before every step kept in HBM) and the adjoint step
+forward kernels (2-D: one launch per 512 steps that also writes the state before every step to HBM) and the adjoint step
 (pdeopt_phasefield_adjoint_step) behind a torch.autograd.Function — the custom_vjp of the north star
 for the reference's main training use case, fitting the coefficients of mu and D
 (docs/notebooks/optimization_3D.ipynb; pde_model.py:226-460).
@@ -28,16 +28,21 @@ class _PhaseFieldRollout(torch.autograd.Function):
         need_grad = y0.requires_grad or (mu_coef is not None and mu_coef.requires_grad) or (mob_coef is not None and mob_coef.requires_grad)
         if not need_grad:
             return plan.step(y, dts, sym)
-        traj = torch.empty((K + 1,) + tuple(y.shape), dtype=torch.float32, device=y.device)
-        traj[0].copy_(y)
-        for k in range(K):
-            plan.step(traj[k], dts[k : k + 1], sym, out=traj[k + 1])
+        if ctx.is3d:
+            traj = torch.empty((K + 1,) + tuple(y.shape), dtype=torch.float32, device=y.device)
+            traj[0].copy_(y)
+            for k in range(K):
+                plan.step(traj[k], dts[k : k + 1], sym, out=traj[k + 1])
+            y_end = traj[K].clone()
+        else:
+            # one fused launch per 512 steps; the kernel writes the step-start states itself (pdeopt_sifs_rollout_fwd)
+            y_end, traj = plan.rollout_fwd(y, dts, sym, save_every=1)
         ctx.plan, ctx.dts, ctx.sym = plan, dts, sym
         ctx.has_mu, ctx.has_mob = mu_coef is not None, mob_coef is not None
         ctx.n_mu = int(mu_coef.numel()) if mu_coef is not None else 0
         ctx.n_mob = int(mob_coef.numel()) if mob_coef is not None else 0
         ctx.save_for_backward(traj)
-        return traj[K].clone()
+        return y_end
 
     @staticmethod
     def backward(ctx, gy):

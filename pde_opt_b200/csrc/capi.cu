@@ -1,5 +1,6 @@
 // C ABI of libpdeopt_b200 (see include/pdeopt_b200.h for the contract and the reference
 // code each entry point replaces).
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <new>
@@ -10,6 +11,7 @@
 #include "sifs_generic.cuh"
 #include "sifs_small.cuh"
 #include "ch_adjoint.cuh"
+#include "ch_tangent.cuh"
 #include "fourier128.cuh"
 
 using namespace pdeopt;
@@ -32,6 +34,8 @@ struct pdeopt_plan {
   size_t park_bytes = 0;
   bool attr_set = false;
   int32_t* flags = nullptr;  // caller-owned [batch] non-finite flags (pdeopt_plan_set_nonfinite_flags)
+  float* traj = nullptr;     // set by pdeopt_sifs_rollout_fwd around its launch: checkpoint destination
+  int save_every = 1;
   // derivs='fourier': wavenumber tables and the per-CTA scratch line
   float* kxy = nullptr;
   float2* fscratch = nullptr;
@@ -195,6 +199,8 @@ static pdeopt_status sifs_launch_impl(pdeopt_plan* plan, int mode, const float* 
   p.mode = mode;
   p.f0 = f0_dev;
   p.nonfinite = (plan->flags && mode != MODE_RHS_ONLY) ? plan->flags + env_offset : nullptr;
+  p.traj = plan->traj;
+  p.save_every = plan->save_every > 0 ? plan->save_every : 1;
   p.inv_hx = (float)(1.0 / d.hx);
   p.inv_hy = (float)(1.0 / d.hy);
   p.inv_hx2 = (float)(1.0 / (d.hx * d.hx));
@@ -419,6 +425,94 @@ extern "C" pdeopt_status pdeopt_phasefield_adjoint_step(pdeopt_plan* plan, const
   if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("adjoint step: ") + cudaGetErrorString(e));
   g_launches.fetch_add(3);
   return PDEOPT_OK;
+}
+
+extern "C" pdeopt_status pdeopt_sifs_rollout_fwd(pdeopt_plan* plan, const float* y0_dev, float* y1_dev, int32_t batch,
+                                                 int32_t ksteps, const float* dt_host, const float* symbol_dev,
+                                                 float* traj_dev, int32_t save_every, void* stream) {
+  PdeoptDeviceGuard device_guard_(y0_dev);
+  if (!plan || !y0_dev || !y1_dev || !dt_host || !symbol_dev || !traj_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
+  if (batch <= 0 || ksteps <= 0) return fail(PDEOPT_ERR_INVALID, "batch and ksteps must be positive");
+  if (save_every <= 0 || save_every > PDEOPT_MAX_FUSED_STEPS) return fail(PDEOPT_ERR_INVALID, "save_every must be in [1, 512]");
+  const pdeopt_plan_desc& d = plan->d;
+  const size_t n = (size_t)batch * d.nx * d.ny;
+  const bool fused128 = d.nx == 128 && d.ny == 128 && d.derivs == PDEOPT_DERIVS_FD && !use_pair_kernel();
+  const float* cur = y0_dev;
+  pdeopt_status s = PDEOPT_OK;
+  if (fused128) {
+    // the fused kernel writes the checkpoints itself: one launch per 512 steps
+    const int chunk = (PDEOPT_MAX_FUSED_STEPS / save_every) * save_every;
+    for (int k0 = 0; k0 < ksteps && s == PDEOPT_OK; k0 += chunk) {
+      plan->traj = traj_dev + (size_t)(k0 / save_every) * n;
+      plan->save_every = save_every;
+      s = sifs_launch(plan, MODE_FUSED, nullptr, cur, y1_dev, batch, std::min(chunk, ksteps - k0), dt_host + k0, symbol_dev,
+                      nullptr, nullptr, 0.f, 1.f, nullptr, stream);
+      cur = y1_dev;
+    }
+    plan->traj = nullptr;
+    plan->save_every = 1;
+    return s;
+  }
+  for (int k0 = 0; k0 < ksteps; k0 += save_every) {
+    CUDA_TRY(cudaMemcpyAsync(traj_dev + (size_t)(k0 / save_every) * n, cur, n * sizeof(float), cudaMemcpyDeviceToDevice,
+                             (cudaStream_t)stream));
+    s = sifs_launch(plan, MODE_FUSED, nullptr, cur, y1_dev, batch, std::min((int)save_every, ksteps - k0), dt_host + k0,
+                    symbol_dev, nullptr, nullptr, 0.f, 1.f, nullptr, stream);
+    if (s != PDEOPT_OK) return s;
+    cur = y1_dev;
+  }
+  return s;
+}
+
+extern "C" int64_t pdeopt_phasefield_tangent_work_floats(const pdeopt_plan* plan, int32_t batch, int32_t ndir) {
+  if (!plan || batch <= 0 || ndir <= 0) return 0;
+  return (2 + 3 * (int64_t)ndir) * batch * plan->d.nx * plan->d.ny;
+}
+
+extern "C" pdeopt_status pdeopt_phasefield_tangent_steps(pdeopt_plan* plan, const float* traj_dev, float* v_dev, int32_t batch,
+                                                         int32_t ndir, int32_t ksteps, const float* dt_host,
+                                                         const float* dmu_dev, const float* dmob_dev, const float* symbol_dev,
+                                                         float* work_dev, void* stream) {
+  PdeoptDeviceGuard device_guard_(v_dev);
+  if (!plan || !traj_dev || !v_dev || !dt_host || !dmu_dev || !dmob_dev || !symbol_dev || !work_dev)
+    return fail(PDEOPT_ERR_INVALID, "null argument");
+  if (batch <= 0 || batch > 65535 || ndir <= 0 || ndir > 65535 || ksteps <= 0)
+    return fail(PDEOPT_ERR_INVALID, "batch, ndir in [1, 65535] and ksteps > 0 required");
+  const pdeopt_plan_desc& d = plan->d;
+  if (d.derivs != PDEOPT_DERIVS_FD) return fail(PDEOPT_ERR_UNSUPPORTED, "tangent: derivs='fd' only");
+  const int64_t npts = (int64_t)d.nx * d.ny, n = npts * batch;
+  ChTanParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.nx = d.nx; p.ny = d.ny; p.batch = batch; p.ndir = ndir; p.eq = d.kind == PDEOPT_AC2D ? 1 : 0;
+  p.v = v_dev; p.dmu = dmu_dev; p.dmob = dmob_dev;
+  p.mu = work_dev; p.dd = work_dev + n; p.mut = work_dev + 2 * n; p.ddt = p.mut + (int64_t)ndir * n; p.ft = p.ddt + (int64_t)ndir * n;
+  p.inv_hx = (float)(1.0 / d.hx); p.inv_hy = (float)(1.0 / d.hy);
+  p.inv_hx2 = (float)(1.0 / (d.hx * d.hx)); p.inv_hy2 = (float)(1.0 / (d.hy * d.hy));
+  p.kappa = (float)d.kappa;
+  p.pw.mu_family = d.mu_family; p.pw.mu_ncoef = d.mu_ncoef; p.pw.mob_family = d.mob_family; p.pw.mob_ncoef = d.mob_ncoef;
+  for (int i = 0; i < PDEOPT_MAX_COEF; ++i) { p.pw.mu_coef[i] = (float)d.mu_coef[i]; p.pw.mob_coef[i] = (float)d.mob_coef[i]; }
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)((npts + 255) / 256), batch, ndir);
+  int32_t* const flags = plan->flags;  // the caller's flag array is sized for `batch`, not for ndir * batch tangents
+  plan->flags = nullptr;
+  pdeopt_status s = PDEOPT_OK;
+  for (int k = 0; k < ksteps && s == PDEOPT_OK; ++k) {
+    p.u = traj_dev + (int64_t)k * n;
+    ch_tan_mu_kernel<<<grid, 256, 0, st>>>(p);
+    ch_tan_rhs_kernel<<<grid, 256, 0, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { s = fail(PDEOPT_ERR_CUDA, std::string("tangent step: ") + cudaGetErrorString(e)); break; }
+    g_launches.fetch_add(2);
+    // v <- v + dt G f~ : the filter of the forward step (solvers.py:62-63), ndir * batch fields at once
+    const int32_t total = batch * ndir;
+    for (int32_t b0 = 0; b0 < total && s == PDEOPT_OK; b0 += 32768) {
+      const int32_t nb = std::min(32768, total - b0);
+      s = sifs_launch(plan, MODE_GIVEN_F, p.ft + (int64_t)b0 * npts, v_dev + (int64_t)b0 * npts, v_dev + (int64_t)b0 * npts, nb, 1,
+                      dt_host + k, symbol_dev, nullptr, nullptr, 0.f, 1.f, nullptr, stream);
+    }
+  }
+  plan->flags = flags;
+  return s;
 }
 
 extern "C" pdeopt_status pdeopt_sifs_step_batched_host(pdeopt_plan* plan, const float* y0_host, float* y1_host,

@@ -53,6 +53,8 @@ struct SifsParams {
   const float* f0;  // MODE_GIVEN_F: externally evaluated vector field [batch][128][128]
   int32_t* nonfinite;  // [batch] or null: 1 where y1 of the environment holds a NaN / Inf
   int* work_counter;   // sifs128r: next environment index, zeroed before the launch (dynamic distribution)
+  float* traj;         // sifs128r: null, or [ceil(ksteps/save_every)][batch][128][128]: the state at the START of every
+  int save_every;      //           save_every-th step of this launch (residuals of the adjoint / tangent rollouts)
   int mode;         // MODE_FUSED / MODE_RHS_ONLY / MODE_GIVEN_F
   float inv_hx, inv_hy, inv_hx2, inv_hy2, kappa;
   float lo_x, lo_y, hx, hy;

@@ -381,6 +381,17 @@ __global__ void __launch_bounds__(kThreadsR, 2) sifs128r_kernel(const __grid_con
         dt_tab = dt;
         build_table_r(S.T, p.symbol, S.sc, dt);
       }
+      if (p.traj != nullptr && (k % p.save_every) == 0) {
+        // checkpoint for the adjoint / tangent rollouts: the natural layout holds the state at the start of the
+        // step; every warp copies the rows it is about to overwrite (no extra barrier)
+        float* te = p.traj + ((size_t)(k / p.save_every) * p.batch + env) * kRows * kCols;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float2 v[2];
+          load_srow(wbase, warp * 16 + i, lane, v);
+          *reinterpret_cast<float4*>(te + (warp * 16 + i) * kCols + 4 * lane) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+        }
+      }
       if (p.mode == MODE_GIVEN_F) {
         // unfused vector field (terms.vf evaluated by the caller, solvers.py:59): load f0 instead
         const float* fe = p.f0 + (size_t)env * kRows * kCols;

@@ -113,6 +113,38 @@ class SifsPlan:
                                                       _lib.stream_ptr(y0)))
         return y1
 
+    def rollout_fwd(self, y0, dts, symbol, save_every=1, out=None):
+        """len(dts) steps that also keep the state at the start of every `save_every`-th step
+        (pdeopt_sifs_rollout_fwd): returns (y1, traj [ceil(K / save_every), B, nx, ny])."""
+        lib = _lib.load()
+        assert y0.is_cuda and y0.dtype == torch.float32 and y0.is_contiguous()
+        dts = np.ascontiguousarray(np.asarray(dts, dtype=np.float32))
+        K, B = len(dts), y0.shape[0]
+        y1 = out if out is not None else torch.empty_like(y0)
+        traj = torch.empty((-(-K // save_every),) + tuple(y0.shape), dtype=torch.float32, device=y0.device)
+        with _lib.device_of(y0):
+            _lib.check(lib.pdeopt_plan_set_nonfinite_flags(self._h, None))
+            _lib.check(lib.pdeopt_sifs_rollout_fwd(self._h, _ptr(y0), _ptr(y1), B, K, _ptr(dts), _ptr(symbol), _ptr(traj),
+                                                   int(save_every), _lib.stream_ptr(y0)))
+        return y1, traj
+
+    def tangent_steps(self, traj, v, dts, dmu, dmob, symbol):
+        """Forward-mode tangents v [ndir, B, nx, ny] advanced IN PLACE through the len(dts) steps whose start
+        states are traj [K, B, nx, ny] (pdeopt_phasefield_tangent_steps); dmu / dmob [ndir, 16] float32."""
+        lib = _lib.load()
+        dts = np.ascontiguousarray(np.asarray(dts, dtype=np.float32))
+        ndir, B = v.shape[0], v.shape[1]
+        assert v.is_contiguous() and traj.is_contiguous() and traj.shape[0] == len(dts) and tuple(traj.shape[1:]) == tuple(v.shape[1:])
+        assert dmu.dtype == torch.float32 and dmob.dtype == torch.float32 and tuple(dmu.shape) == (ndir, _lib.MAX_COEF) == tuple(dmob.shape)
+        key = (B, ndir, str(v.device))
+        if getattr(self, "_tan_work_key", None) != key:
+            n = int(lib.pdeopt_phasefield_tangent_work_floats(self._h, B, ndir))
+            self._tan_work, self._tan_work_key = torch.empty(n, dtype=torch.float32, device=v.device), key
+        with _lib.device_of(v):
+            _lib.check(lib.pdeopt_phasefield_tangent_steps(self._h, _ptr(traj), _ptr(v), B, ndir, len(dts), _ptr(dts), _ptr(dmu.contiguous()),
+                                                           _ptr(dmob.contiguous()), _ptr(symbol), _ptr(self._tan_work), _lib.stream_ptr(v)))
+        return v
+
     def rhs(self, y, ctrl=None, out=None):
         lib = _lib.load()
         f = out if out is not None else torch.empty_like(y)

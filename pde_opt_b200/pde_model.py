@@ -3,8 +3,9 @@ differentiable-rollout objectives `residual_single` / `regularization` / `residu
 (:138-323).  Gradients come from the hand-written adjoint kernel (pde_opt_b200/adjoint.py) through
 torch.autograd, the role jax.grad + diffrax adjoints play in the reference.  `train(method="mse")`
 and `optimize` (:325-551) are host loops over those gradients (optimistix BFGS in the reference,
-torch.optim.LBFGS here: same quasi-Newton family, not the same iterates); the Levenberg-Marquardt
-`least_squares` method needs forward-mode JVPs and is not provided."""
+torch.optim.LBFGS here: same quasi-Newton family, not the same iterates); `train(method="least_squares")`,
+the reference's default, is a Levenberg-Marquardt loop over forward-mode Jacobians from the tangent kernels
+(pde_opt_b200/least_squares.py)."""
 from typing import Any, Dict
 
 import numpy as np
@@ -187,12 +188,26 @@ class PDEModel:
         return values - pred[1:]
 
     def regularization(self, parameters, weights, lambda_reg):
-        """lambda * sum_i w_i p_i^2 over the weighted parameters (pde_model.py:173-224)."""
+        """lambda * sum_i w_i p_i^2 over the weighted parameters (pde_model.py:173-224).  The reference reduces
+        leaf-wise over pytrees; here a parameter may be a tensor / number or a closure object, whose leaves are
+        its `tensor_leaves()` (weights: one array for a single leaf, or a sequence with one entry per leaf; None
+        entries are skipped)."""
         reg = 0.0
         for key, w in weights.items():
             if w is None:
                 continue
-            reg = reg + lambda_reg * (torch.as_tensor(w) * torch.as_tensor(parameters[key]) ** 2).sum()
+            p = parameters[key]
+            if hasattr(p, "tensor_leaves"):
+                leaves = p.tensor_leaves()
+                ws = [w] if (torch.is_tensor(w) or np.isscalar(w) or isinstance(w, np.ndarray)) else list(w)
+                if len(ws) != len(leaves):
+                    raise ValueError(f"weights[{key!r}] has {len(ws)} entries for {len(leaves)} parameter leaves")
+                for wi, leaf in zip(ws, leaves):
+                    if wi is not None:
+                        reg = reg + lambda_reg * (torch.as_tensor(wi, device=leaf.device) * leaf**2).sum()
+            else:
+                pt = torch.as_tensor(p)
+                reg = reg + lambda_reg * (torch.as_tensor(w, device=pt.device) * pt**2).sum()
         return reg
 
     def residuals(self, parameters, y0s__values, solver_parameters, ts, weights, lambda_reg, adjoint=None, dt0=0.000001):
@@ -243,19 +258,31 @@ class PDEModel:
         self.last_loss_history = history
         return history
 
-    def train(self, data, inds, opt_parameters, other_parameters, solver_parameters, weights, lambda_reg, method="mse",
+    def train(self, data, inds, opt_parameters, other_parameters, solver_parameters, weights, lambda_reg, method="least_squares",
               max_steps=100, dt0=0.000001, verbose=False):
-        """Fit `opt_parameters` to observed trajectories (pde_model.py:325-460), method "mse": minimise
-        PDEModel.mse with a quasi-Newton loop over the adjoint gradients.  `data = {"ys": [...], "ts":
-        [...]}`, `inds` = per trajectory [initial index, later indices...].  Returns the optimised
-        parameters merged with `other_parameters` (the tensors are updated in place)."""
-        if method != "mse":
-            raise NotImplementedError("only method='mse' (reverse-mode gradients through the adjoint kernel) is provided")
+        """Fit `opt_parameters` to observed trajectories (pde_model.py:325-460).  `data = {"ys": [...], "ts":
+        [...]}`, `inds` = per trajectory [initial index, later indices...].  method "least_squares" (the
+        reference's default): Levenberg-Marquardt over PDEModel.residuals with forward-mode Jacobians (tangent
+        kernels; closure coefficients of the finite-difference Cahn-Hilliard / Allen-Cahn equations); method
+        "mse": quasi-Newton minimisation of PDEModel.mse over the adjoint gradients (any differentiable
+        equation).  Returns the optimised parameters merged with `other_parameters` (tensors updated in place)."""
+        if method not in ("least_squares", "mse"):
+            raise ValueError(f"unknown method {method!r}: 'least_squares' or 'mse'")
         dev = "cuda"
         y0s = torch.stack([torch.as_tensor(data["ys"][ind[0]], dtype=torch.float32) for ind in inds]).to(dev)
         values = torch.stack([torch.stack([torch.as_tensor(data["ys"][i], dtype=torch.float32) for i in ind[1:]]) for ind in inds]).to(dev)
         ts = np.asarray([data["ts"][i] - data["ts"][inds[0][0]] for i in inds[0]], dtype=np.float32)
         leaves = self._leaves(opt_parameters)
+        if method == "least_squares":
+            from .functions import Closure
+            from .least_squares import levenberg_marquardt
+
+            if not all(isinstance(v, Closure) for v in opt_parameters.values()):
+                raise NotImplementedError("method='least_squares' optimises the tensor coefficients of mu / mobility closures "
+                                          "(forward-mode tangent kernels); use method='mse' for other parameters")
+            self.last_loss_history = levenberg_marquardt(self, {**opt_parameters, **other_parameters}, leaves, y0s, values, ts,
+                                                         solver_parameters, weights, lambda_reg, dt0, max_steps, verbose=verbose)
+            return {**opt_parameters, **other_parameters}
         self._minimise(lambda: self.mse({**opt_parameters, **other_parameters}, (y0s, values), solver_parameters, ts, weights,
                                         lambda_reg, dt0=dt0), leaves, max_steps, verbose)
         return {**opt_parameters, **other_parameters}

@@ -115,7 +115,7 @@ def test_c_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert set(_lib.EXPORTS) == declared
-    assert lib.pdeopt_abi_version() == 3
+    assert lib.pdeopt_abi_version() == 4
 
 
 def test_plan_validation_without_gpu():
