@@ -176,6 +176,18 @@ pdeopt_status pdeopt_sifs_rollout_fwd(pdeopt_plan* plan, const float* y0_dev, fl
                                       int32_t ksteps, const float* dt_host, const float* symbol_dev, float* traj_dev,
                                       int32_t save_every, void* stream);
 
+/* Discrete adjoint of the ksteps steps whose start states pdeopt_sifs_rollout_fwd kept (save_every = 1): the
+ * backward half of the differentiable rollout (the custom_vjp; replaces reverse-mode differentiation through
+ * diffeqsolve, pde_model.py:226-323).  128 x 128 grids run ONE fused kernel per 512 steps — the cotangent stays on
+ * chip, u of every step is the only HBM read, the coefficient cotangents are reduced in the CTA; other grids loop over
+ * pdeopt_phasefield_adjoint_step.
+ *   traj_dev : [ksteps][batch][nx][ny];  lam1_dev: cotangent after the last step;  lam0_dev: before the first (may alias)
+ *   work_dev : pdeopt_phasefield_adjoint_work_floats floats (may be NULL for 128 x 128 grids)
+ *   gmu_dev, gmob_dev : [batch][PDEOPT_MAX_COEF] float64, ACCUMULATED (+=) */
+pdeopt_status pdeopt_sifs_rollout_bwd(pdeopt_plan* plan, const float* traj_dev, const float* lam1_dev, float* lam0_dev,
+                                      int32_t batch, int32_t ksteps, const float* dt_host, const float* symbol_dev,
+                                      float* work_dev, double* gmu_dev, double* gmob_dev, void* stream);
+
 /* Forward-mode tangent (JVP) of ksteps semi-implicit steps of the finite-difference Cahn-Hilliard / Allen-Cahn
  * equation of `plan` for ndir directions at once: the derivative optimistix's Levenberg-Marquardt takes through
  * diffrax's ForwardMode adjoint in PDEModel.train(method="least_squares") (pde_model.py:334,404-428).

@@ -117,6 +117,7 @@ EXPORTS = [
     "pdeopt_phasefield_adjoint_work_floats",
     "pdeopt_phasefield_adjoint_step",
     "pdeopt_sifs_rollout_fwd",
+    "pdeopt_sifs_rollout_bwd",
     "pdeopt_phasefield_tangent_work_floats",
     "pdeopt_phasefield_tangent_steps",
     "pdeopt_strang_step_batched",
@@ -178,6 +179,8 @@ def load():
     lib.pdeopt_phasefield_adjoint_step.restype = ctypes.c_int
     lib.pdeopt_sifs_rollout_fwd.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, i32, vp]
     lib.pdeopt_sifs_rollout_fwd.restype = ctypes.c_int
+    lib.pdeopt_sifs_rollout_bwd.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
+    lib.pdeopt_sifs_rollout_bwd.restype = ctypes.c_int
     lib.pdeopt_phasefield_tangent_work_floats.argtypes = [vp, i32, i32]
     lib.pdeopt_phasefield_tangent_work_floats.restype = ctypes.c_int64
     lib.pdeopt_phasefield_tangent_steps.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]

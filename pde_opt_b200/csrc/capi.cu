@@ -12,6 +12,7 @@
 #include "sifs_small.cuh"
 #include "ch_adjoint.cuh"
 #include "ch_tangent.cuh"
+#include "sifs128r_adj.cuh"
 #include "fourier128.cuh"
 
 using namespace pdeopt;
@@ -108,6 +109,7 @@ cudaError_t pdeopt_sifs128_launch_a(int variant, const pdeopt::SifsParams& p, in
 cudaError_t pdeopt_sifs128_launch_b(int variant, const pdeopt::SifsParams& p, int grid, cudaStream_t st);
 cudaError_t pdeopt_sifs128r_launch_a(int variant, const pdeopt::SifsParams& p, cudaStream_t st);
 cudaError_t pdeopt_sifs128r_launch_b(int variant, const pdeopt::SifsParams& p, cudaStream_t st);
+cudaError_t pdeopt_sifs128r_adj_launch(const pdeopt::rf::AdjParams& p, cudaStream_t st);
 // PDEOPT_SIFS128_PAIR=1 selects the round-1 kernel (two environments per 512-thread CTA) for A/B
 // measurements; the default is the one-field-per-CTA kernel (sifs128r.cuh).
 static bool use_pair_kernel() {
@@ -462,6 +464,55 @@ extern "C" pdeopt_status pdeopt_sifs_rollout_fwd(pdeopt_plan* plan, const float*
     cur = y1_dev;
   }
   return s;
+}
+
+extern "C" pdeopt_status pdeopt_sifs_rollout_bwd(pdeopt_plan* plan, const float* traj_dev, const float* lam1_dev,
+                                                 float* lam0_dev, int32_t batch, int32_t ksteps, const float* dt_host,
+                                                 const float* symbol_dev, float* work_dev, double* gmu_dev, double* gmob_dev,
+                                                 void* stream) {
+  PdeoptDeviceGuard device_guard_(traj_dev);
+  if (!plan || !traj_dev || !lam1_dev || !lam0_dev || !dt_host || !symbol_dev || !gmu_dev || !gmob_dev)
+    return fail(PDEOPT_ERR_INVALID, "null argument");
+  if (batch <= 0 || ksteps <= 0) return fail(PDEOPT_ERR_INVALID, "batch and ksteps must be positive");
+  const pdeopt_plan_desc& d = plan->d;
+  if (d.derivs != PDEOPT_DERIVS_FD) return fail(PDEOPT_ERR_UNSUPPORTED, "adjoint: derivs='fd' only");
+  const size_t n = (size_t)batch * d.nx * d.ny;
+  if (!(d.nx == 128 && d.ny == 128)) {
+    // other grids: the streaming adjoint step, in reverse order
+    if (!work_dev) return fail(PDEOPT_ERR_INVALID, "work_dev is required for grids other than 128 x 128");
+    const float* lam = lam1_dev;
+    for (int k = ksteps - 1; k >= 0; --k) {
+      pdeopt_status s = pdeopt_phasefield_adjoint_step(plan, traj_dev + (size_t)k * n, lam, lam0_dev, batch, dt_host[k], symbol_dev,
+                                                       work_dev, gmu_dev, gmob_dev, stream);
+      if (s != PDEOPT_OK) return s;
+      lam = lam0_dev;
+    }
+    return PDEOPT_OK;
+  }
+  rf::AdjParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.lam0 = lam0_dev; p.gmu = gmu_dev; p.gmob = gmob_dev; p.symbol = symbol_dev;
+  p.batch = batch; p.eq = d.kind == PDEOPT_AC2D ? EQ_AC : EQ_CH;
+  p.inv_hx = (float)(1.0 / d.hx); p.inv_hy = (float)(1.0 / d.hy);
+  p.inv_hx2 = (float)(1.0 / (d.hx * d.hx)); p.inv_hy2 = (float)(1.0 / (d.hy * d.hy));
+  p.kappa = (float)d.kappa;
+  p.pw.mu_family = d.mu_family; p.pw.mu_ncoef = d.mu_ncoef; p.pw.mob_family = d.mob_family; p.pw.mob_ncoef = d.mob_ncoef;
+  for (int i = 0; i < PDEOPT_MAX_COEF; ++i) { p.pw.mu_coef[i] = (float)d.mu_coef[i]; p.pw.mob_coef[i] = (float)d.mob_coef[i]; }
+  const float* lam = lam1_dev;
+  // launches of at most 512 steps, last steps first
+  for (int k1 = ksteps; k1 > 0;) {
+    const int k0 = std::max(0, k1 - PDEOPT_MAX_FUSED_STEPS);
+    p.traj = traj_dev + (size_t)k0 * n;
+    p.lam1 = lam;
+    p.ksteps = k1 - k0;
+    for (int k = 0; k < p.ksteps; ++k) p.dt[k] = dt_host[k0 + k];
+    cudaError_t e = pdeopt_sifs128r_adj_launch(p, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("adjoint rollout: ") + cudaGetErrorString(e));
+    g_launches.fetch_add(1);
+    lam = lam0_dev;
+    k1 = k0;
+  }
+  return PDEOPT_OK;
 }
 
 extern "C" int64_t pdeopt_phasefield_tangent_work_floats(const pdeopt_plan* plan, int32_t batch, int32_t ndir) {

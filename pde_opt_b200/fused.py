@@ -128,6 +128,26 @@ class SifsPlan:
                                                    int(save_every), _lib.stream_ptr(y0)))
         return y1, traj
 
+    def rollout_bwd(self, traj, lam, dts, symbol, gmu, gmob):
+        """Discrete adjoint of the len(dts) steps whose start states are traj [K, B, nx, ny], IN PLACE on the
+        cotangent lam [B, nx, ny]; gmu / gmob [B, 16] float64 accumulate the coefficient cotangents
+        (pdeopt_sifs_rollout_bwd: one fused launch per 512 steps on 128 x 128 grids)."""
+        lib = _lib.load()
+        dts = np.ascontiguousarray(np.asarray(dts, dtype=np.float32))
+        B = lam.shape[0]
+        assert traj.is_contiguous() and lam.is_contiguous() and traj.shape[0] == len(dts) and tuple(traj.shape[1:]) == tuple(lam.shape)
+        work = None
+        if (self.nx, self.ny) != (128, 128):
+            key = (B, str(lam.device))
+            if getattr(self, "_adj_work_key", None) != key:
+                n = int(lib.pdeopt_phasefield_adjoint_work_floats(self._h, B))
+                self._adj_work, self._adj_work_key = torch.empty(n, dtype=torch.float32, device=lam.device), key
+            work = self._adj_work
+        with _lib.device_of(lam):
+            _lib.check(lib.pdeopt_sifs_rollout_bwd(self._h, _ptr(traj), _ptr(lam), _ptr(lam), B, len(dts), _ptr(dts), _ptr(symbol),
+                                                   _ptr(work), _ptr(gmu), _ptr(gmob), _lib.stream_ptr(lam)))
+        return lam
+
     def tangent_steps(self, traj, v, dts, dmu, dmob, symbol):
         """Forward-mode tangents v [ndir, B, nx, ny] advanced IN PLACE through the len(dts) steps whose start
         states are traj [K, B, nx, ny] (pdeopt_phasefield_tangent_steps); dmu / dmob [ndir, 16] float32."""

@@ -126,7 +126,7 @@ class PDEModel:
     def _solve_differentiable(self, equation, solver, y0, ts, dt0, max_steps, adjoint):
         """solve() on the differentiable paths (advection-diffusion; phase-field equations with tensor
         coefficients): same save-time semantics, every segment an autograd node whose backward is an
-        adjoint kernel.  `adjoint` may carry `checkpoint_every` (int, advection-diffusion only)."""
+        adjoint kernel.  `adjoint` may carry `checkpoint_every` (int): keep every C-th state and recompute in between."""
         from .adjoint import ad_rollout
         from .adjoint_ch import phasefield_rollout
 
@@ -148,8 +148,10 @@ class PDEModel:
             def roll(y_, seg_times, step0):
                 return ad_rollout(equation, y_, ctrl, seg_times, hold=hold, A=A, checkpoint_every=ck, step0=step0)
         else:
+            ck_pf = getattr(adjoint, "checkpoint_every", None)
+
             def roll(y_, seg_times, step0):
-                return phasefield_rollout(equation, solver, y_, seg_times)
+                return phasefield_rollout(equation, solver, y_, seg_times, checkpoint_every=ck_pf)
 
         out, i_cur = [], 0
         for s_ in ts:
