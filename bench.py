@@ -339,6 +339,39 @@ def run_ours(args):
         e2e_s = float(t.item())
     e2e_value = world * B * K_FUSED * e2e_steps / e2e_s
 
+    # ---- copy ceiling of this box: the SAME byte counts as one e2e step, nothing but concurrent H2D and D2H
+    # cudaMemcpyAsync calls (torch copy_ on pinned memory; one call per chunk, 8 chunks per direction, two streams),
+    # on every rank at once.  e2e can at best equal it: the ratio says how much of the gap to `value` is the box's
+    # PCIe / host-memory path and how much is the code's pipelining.
+    h2d_b = B * N * N * 4 + B * 8 * 4 + sym_host.nbytes
+    d2h_b = B * N * N * 4 + B * N * N + B * 2 * 4
+    hin, hout = torch.empty(h2d_b, dtype=torch.uint8).pin_memory(), torch.empty(d2h_b, dtype=torch.uint8).pin_memory()
+    din, dout = torch.empty(h2d_b, dtype=torch.uint8, device=dev), torch.empty(d2h_b, dtype=torch.uint8, device=dev)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def copy_step():
+        for c in range(8):
+            a0, a1 = c * h2d_b // 8, (c + 1) * h2d_b // 8
+            b0, b1 = c * d2h_b // 8, (c + 1) * d2h_b // 8
+            with torch.cuda.stream(s_in):
+                din[a0:a1].copy_(hin[a0:a1], non_blocking=True)
+            with torch.cuda.stream(s_out):
+                hout[b0:b1].copy_(dout[b0:b1], non_blocking=True)
+
+    copy_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        copy_step()
+    torch.cuda.synchronize()
+    copy_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([copy_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        copy_s = float(t.item())
+    copy_ceiling = world * B * K_FUSED * e2e_steps / copy_s
+    del hin, hout, din, dout
+
     # ---- env-API view: PDEEnv keeps its state on the device (pde_env.py:234-242, 305); per env step
     # the actions (control block) go host->device and the observation + reward come back ----
     # through the public class: PDEVecEnv.step(actions, obs_host, stats_host) steps the batch in slices on
@@ -412,6 +445,9 @@ def run_ours(args):
                     "api": "pdeopt_sifs_step_batched_host (pinned host state+control in, state+obs+reward out; "
                            "chunks pipelined over 3 streams)",
                     "steps": e2e_steps,
+                    "copy_ceiling": {"value": copy_ceiling, "unit": "env-steps/s", "GBs_per_gpu_both_directions": (h2d_b + d2h_b) * e2e_steps / copy_s / 1e9,
+                                     "what": "the same bytes per step as plain concurrent H2D + D2H cudaMemcpyAsync from / to pinned memory on all ranks at once, no kernels"},
+                    "frac_of_copy_ceiling": e2e_value / copy_ceiling,
                     "env_api": {"value": env_api_value, "unit": "env-steps/s", "h2d_bytes_per_step": B * 8 * 4,
                                 "d2h_bytes_per_step": B * N * N + B * 2 * 4, "steps": env_steps,
                                 "what": "PDEVecEnv.step(actions, obs_host, stats_host): state resident on the device as in PDEEnv (pde_env.py:305); pinned actions in, uint8 observation + reward out on the host before the call returns (4 slices on 4 streams overlap copy and compute)"}},

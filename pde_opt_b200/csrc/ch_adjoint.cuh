@@ -49,15 +49,18 @@ __device__ __forceinline__ float legendre_deriv(const float* __restrict__ coef, 
   float p_prev = 1.0f, p_curr = x;      // P_0, P_1
   float dp_prev = 0.0f, dp_curr = 1.0f; // P_0', P_1'
   if (ncoef > 1) d = coef[1];
-  for (int n = 2; n < ncoef; ++n) {
-    const float p_next = (float(2 * n - 1) * x * p_curr - float(n - 1) * p_prev) / float(n);
-    const float dp_next = dp_prev + float(2 * n - 1) * p_curr;
-    d = fmaf(coef[n], dp_next, d);
-    p_prev = p_curr;
-    p_curr = p_next;
-    dp_prev = dp_curr;
-    dp_curr = dp_next;
-  }
+  static_for<2, 16>([&](auto nc) {
+    constexpr int n = decltype(nc)::value;
+    if (n < ncoef) {
+      const float p_next = LegC<n>::a * x * p_curr - LegC<n>::b * p_prev;
+      const float dp_next = dp_prev + float(2 * n - 1) * p_curr;
+      d = fmaf(coef[n], dp_next, d);
+      p_prev = p_curr;
+      p_curr = p_next;
+      dp_prev = dp_curr;
+      dp_curr = dp_next;
+    }
+  });
   return d;
 }
 

@@ -21,18 +21,51 @@ struct PointwiseParams {
   float mob_coef[16];
 };
 
-// functions/legendre.py:19-34: three-term recurrence on x in [-1,1].
+// Legendre recurrence constants: P_n = a_n x P_{n-1} - b_n P_{n-2} with a_n = (2n-1)/n, b_n = (n-1)/n.  The reference
+// divides by n (functions/legendre.py:27-31); multiplying by the rounded reciprocal constants differs from that by
+// an ulp or two per term and saves an IEEE division (about twenty instructions) per term and grid point.
+template <int N>
+struct LegC {
+  static constexpr float a = float(double(2 * N - 1) / double(N));
+  static constexpr float b = float(double(N - 1) / double(N));
+};
+
+// functions/legendre.py:19-34: three-term recurrence on x in [-1,1] (at most 16 coefficients).
 __device__ __forceinline__ float legendre_eval(const float* __restrict__ coef, int ncoef, float x) {
   float result = coef[0];
   if (ncoef > 1) result = fmaf(coef[1], x, result);
   float p_prev = 1.0f, p_curr = x;
-  for (int n = 2; n < ncoef; ++n) {
-    float p_next = (float(2 * n - 1) * x * p_curr - float(n - 1) * p_prev) / float(n);
-    result = fmaf(coef[n], p_next, result);
-    p_prev = p_curr;
-    p_curr = p_next;
-  }
+  static_for<2, 16>([&](auto nc) {
+    constexpr int n = decltype(nc)::value;
+    if (n < ncoef) {
+      const float p_next = LegC<n>::a * x * p_curr - LegC<n>::b * p_prev;
+      result = fmaf(coef[n], p_next, result);
+      p_prev = p_curr;
+      p_curr = p_next;
+    }
+  });
   return result;
+}
+
+// sum_n a[n] P_n(x) and sum_n b[n] P_n(x) over ONE pass of the recurrence (mu and the mobility of the same point)
+__device__ __forceinline__ void legendre_eval2(const float* __restrict__ a, int na, const float* __restrict__ b, int nb, float x,
+                                               float& ra, float& rb) {
+  ra = na > 0 ? a[0] : 0.0f;
+  rb = nb > 0 ? b[0] : 0.0f;
+  if (na > 1) ra = fmaf(a[1], x, ra);
+  if (nb > 1) rb = fmaf(b[1], x, rb);
+  const int nmax = na > nb ? na : nb;
+  float p_prev = 1.0f, p_curr = x;
+  static_for<2, 16>([&](auto nc) {
+    constexpr int n = decltype(nc)::value;
+    if (n < nmax) {
+      const float p_next = LegC<n>::a * x * p_curr - LegC<n>::b * p_prev;
+      if (n < na) ra = fmaf(a[n], p_next, ra);
+      if (n < nb) rb = fmaf(b[n], p_next, rb);
+      p_prev = p_curr;
+      p_curr = p_next;
+    }
+  });
 }
 
 // log(c/(1-c)): one MUFU.RCP-based division and one MUFU.LG2.
@@ -91,8 +124,22 @@ __device__ __forceinline__ void mu_mob_pair(float2 c, const PointwiseParams& pw,
     mu = sub2(mul2(c2, c), c);  // c^3 - c
     D = (MOB == MOB_CONST) ? splat2(pw.mob_coef[0]) : add2(splat2(1.0f), c2);
   } else {
-    mu = make_float2(mu_h<MU>(c.x, pw, w_off.x), mu_h<MU>(c.y, pw, w_off.y));
-    D = make_float2(mob<MOB>(c.x, pw), mob<MOB>(c.y, pw));
+    const int mf = (MU == MU_RUNTIME) ? pw.mu_family : MU, df = (MOB == MOB_RUNTIME) ? pw.mob_family : MOB;
+    if ((mf == MU_LEGENDRE || mf == MU_LEGENDRE_LOGPRIOR) && df == MOB_LEGENDRE_EXP) {
+      // the training closures (legendre.py:37-74): mu and D of a point share one pass over the Legendre basis
+      float m0, d0, m1, d1;
+      legendre_eval2(pw.mu_coef, pw.mu_ncoef, pw.mob_coef, pw.mob_ncoef, 2.0f * c.x - 1.0f, m0, d0);
+      legendre_eval2(pw.mu_coef, pw.mu_ncoef, pw.mob_coef, pw.mob_ncoef, 2.0f * c.y - 1.0f, m1, d1);
+      if (mf == MU_LEGENDRE_LOGPRIOR) {
+        m0 += logit(c.x);
+        m1 += logit(c.y);
+      }
+      mu = make_float2(m0, m1);
+      D = make_float2(__expf(d0), __expf(d1));
+    } else {
+      mu = make_float2(mu_h<MU>(c.x, pw, w_off.x), mu_h<MU>(c.y, pw, w_off.y));
+      D = make_float2(mob<MOB>(c.x, pw), mob<MOB>(c.y, pw));
+    }
   }
 }
 

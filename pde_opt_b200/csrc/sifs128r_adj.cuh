@@ -73,30 +73,75 @@ __device__ __forceinline__ void col_nbrs(const float (&a)[4], int lm1, int lp1, 
   R[0] = a[1]; R[1] = a[2]; R[2] = a[3]; R[3] = aR;
 }
 
+// mu_h(c), D(c) and their derivatives in one pass over the Legendre basis (one recurrence serves all four)
+__device__ __forceinline__ void pw_eval(float c, const PointwiseParams& pw, float& mu, float& D, float& mup, float& Dp) {
+  const bool mleg = pw.mu_family == MU_LEGENDRE || pw.mu_family == MU_LEGENDRE_LOGPRIOR;
+  const bool dleg = pw.mob_family == MOB_LEGENDRE_EXP;
+  float sm = 0.f, dsm = 0.f, sd = 0.f, dsd = 0.f;
+  if (mleg || dleg) {
+    const float x = 2.0f * c - 1.0f;
+    const int nm = mleg ? pw.mu_ncoef : 0, nd = dleg ? pw.mob_ncoef : 0;
+    const int nmax = nm > nd ? nm : nd;
+    float pp = 1.0f, pc = x, dpp = 0.0f, dpc = 1.0f;
+    if (nm > 0) sm = pw.mu_coef[0];
+    if (nd > 0) sd = pw.mob_coef[0];
+    if (nm > 1) { sm = fmaf(pw.mu_coef[1], x, sm); dsm = pw.mu_coef[1]; }
+    if (nd > 1) { sd = fmaf(pw.mob_coef[1], x, sd); dsd = pw.mob_coef[1]; }
+    static_for<2, 16>([&](auto nc) {
+      constexpr int n = decltype(nc)::value;
+      if (n < nmax) {
+        const float pn = LegC<n>::a * x * pc - LegC<n>::b * pp;
+        const float dpn = fmaf(float(2 * n - 1), pc, dpp);  // P_n' = P_{n-2}' + (2n-1) P_{n-1}
+        if (n < nm) { sm = fmaf(pw.mu_coef[n], pn, sm); dsm = fmaf(pw.mu_coef[n], dpn, dsm); }
+        if (n < nd) { sd = fmaf(pw.mob_coef[n], pn, sd); dsd = fmaf(pw.mob_coef[n], dpn, dsd); }
+        pp = pc; pc = pn; dpp = dpc; dpc = dpn;
+      }
+    });
+  }
+  const float omc = 1.0f - c;
+  switch (pw.mu_family) {
+    case MU_DOUBLE_WELL: mu = c * c * c - c; mup = 3.0f * c * c - 1.0f; break;
+    case MU_LOG:
+      mu = __logf(__fdividef(c, omc)) + pw.mu_coef[0] * (1.0f - 2.0f * c);
+      mup = __fdividef(1.0f, c * omc) - 2.0f * pw.mu_coef[0];
+      break;
+    case MU_LEGENDRE: mu = sm; mup = 2.0f * dsm; break;
+    default: mu = sm + __logf(__fdividef(c, omc)); mup = 2.0f * dsm + __fdividef(1.0f, c * omc); break;
+  }
+  switch (pw.mob_family) {
+    case MOB_CONST: D = pw.mob_coef[0]; Dp = 0.0f; break;
+    case MOB_DEGENERATE: D = omc * c; Dp = 1.0f - 2.0f * c; break;
+    case MOB_ONE_PLUS_SQ: D = 1.0f + c * c; Dp = 2.0f * c; break;
+    default: D = __expf(sd); Dp = D * 2.0f * dsd; break;
+  }
+}
+
 // d mu_h / d theta_n (c) * s accumulated into acc[0..15], d D / d theta_n (c) * t into acc[16..31]
 __device__ __forceinline__ void accumulate_coef(float (&acc)[32], float c, float Dval, float s, float t, const PointwiseParams& pw) {
-  const float x = 2.0f * c - 1.0f;
   const bool mleg = pw.mu_family == MU_LEGENDRE || pw.mu_family == MU_LEGENDRE_LOGPRIOR;
   const bool dleg = pw.mob_family == MOB_LEGENDRE_EXP;
   if (pw.mu_family == MU_LOG) acc[0] = fmaf(1.0f - 2.0f * c, s, acc[0]);
   if (pw.mob_family == MOB_CONST) acc[16] += t;
   if (mleg || dleg) {
+    const float x = 2.0f * c - 1.0f;
+    const int nm = mleg ? pw.mu_ncoef : 0, nd = dleg ? pw.mob_ncoef : 0;
+    const int nmax = nm > nd ? nm : nd;
     const float tD = Dval * t;
     float pp = 1.0f, pc = x;
-    if (mleg) acc[0] += s;
-    if (dleg) acc[16] += tD;
-    if (mleg && pw.mu_ncoef > 1) acc[1] = fmaf(x, s, acc[1]);
-    if (dleg && pw.mob_ncoef > 1) acc[17] = fmaf(x, tD, acc[17]);
-#pragma unroll
-    for (int n = 2; n < 16; ++n) {
-      if (n < pw.mu_ncoef || n < pw.mob_ncoef) {
-        const float pn = (float(2 * n - 1) * x * pc - float(n - 1) * pp) / float(n);
-        if (mleg && n < pw.mu_ncoef) acc[n] = fmaf(pn, s, acc[n]);
-        if (dleg && n < pw.mob_ncoef) acc[16 + n] = fmaf(pn, tD, acc[16 + n]);
+    if (nm > 0) acc[0] += s;
+    if (nd > 0) acc[16] += tD;
+    if (nm > 1) acc[1] = fmaf(x, s, acc[1]);
+    if (nd > 1) acc[17] = fmaf(x, tD, acc[17]);
+    static_for<2, 16>([&](auto nc) {
+      constexpr int n = decltype(nc)::value;
+      if (n < nmax) {
+        const float pn = LegC<n>::a * x * pc - LegC<n>::b * pp;
+        if (n < nm) acc[n] = fmaf(pn, s, acc[n]);
+        if (n < nd) acc[16 + n] = fmaf(pn, tD, acc[16 + n]);
         pp = pc;
         pc = pn;
       }
-    }
+    });
   }
 }
 
@@ -200,6 +245,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) sifs128r_adj_kernel(const __grid
       {
         float um[4], u0[4], up[4];
         float mu_m[4], mu_0[4], mu_p[4], D_m[4], D_0[4], D_p[4], w_m[4], w_0[4], w_p[4], uc[4];
+        float mq_0[4], mq_p[4], dq_0[4], dq_p[4];  // mu_h'(u), D'(u) of the window rows
         float t1g[4][4];
         load_grow4(ue, r0 - 2 + kRows, lane, um);
         load_grow4(ue, r0 - 1 + kRows, lane, u0);
@@ -213,8 +259,9 @@ __global__ void __launch_bounds__(kThreadsR, 1) sifs128r_adj_kernel(const __grid
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float lap = ((up[j] - 2.0f * u0[j]) + um[j]) * hx2 + ((uR[j] - 2.0f * u0[j]) + uL[j]) * hy2;
-            mu_p[j] = mu_h<MU_RUNTIME>(u0[j], p.pw, 0.0f) - p.kappa * lap;
-            D_p[j] = mob<MOB_RUNTIME>(u0[j], p.pw);
+            float mh;
+            pw_eval(u0[j], p.pw, mh, D_p[j], mq_p[j], dq_p[j]);
+            mu_p[j] = mh - p.kappa * lap;
           }
           load_row4(wbase, r0 + it + kRows, lane, w_p);
           if constexpr (EMIT >= 0) {
@@ -245,7 +292,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) sifs128r_adj_kernel(const __grid
             store_row4(mbase, r0 + it - 1, lane, mb);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              t1g[EMIT][j] = mu_h_prime(uc[j], p.pw) * mb[j] + mob_prime(uc[j], D_0[j], p.pw) * db[j];
+              t1g[EMIT][j] = mq_0[j] * mb[j] + dq_0[j] * db[j];
               accumulate_coef(acc, uc[j], D_0[j], mb[j], db[j], p.pw);
             }
           }
@@ -254,6 +301,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) sifs128r_adj_kernel(const __grid
             mu_m[j] = mu_0[j]; mu_0[j] = mu_p[j];
             D_m[j] = D_0[j];   D_0[j] = D_p[j];
             w_m[j] = w_0[j];   w_0[j] = w_p[j];
+            mq_0[j] = mq_p[j]; dq_0[j] = dq_p[j];
             uc[j] = u0[j];
             um[j] = u0[j];     u0[j] = up[j];
           }

@@ -123,6 +123,67 @@ def c4_ad(envs=512, K=500, peak_tf=None):
     ]
 
 
+def c2_variants(peak_tf=None, envs=4096):
+    """The headline equation at K = 1 (the launch-per-step path PDEModel.solve with dense SaveAt, PID stepping and the
+    unfused `given f0` route use; HBM view) and its differentiable rollout: fused forward that keeps every state +
+    fused adjoint (pdeopt_sifs_rollout_fwd / _bwd), Legendre closures, 512 environments x 256 steps."""
+    from . import Domain
+    from .equations import CahnHilliard2DPeriodic
+    from .functions import ChemicalPotentialLegendrePolynomials, DegenerateMobility, DiffusionLegendrePolynomials, LogRegular
+    from .solvers import SemiImplicitFourierSpectral
+
+    N, H = 128, 0.01
+    dom = Domain((N, N), ((-N * H / 2, N * H / 2),) * 2, "dimensionless")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    out = []
+    # ---- K = 1 ----
+    eq = CahnHilliard2DPeriodic(dom, 0.002, LogRegular(3.0), DegenerateMobility())
+    solver = SemiImplicitFourierSpectral(0.5, eq.fourier_symbol, eq.fft, eq.ifft)
+    plan, sym = eq.plan(), solver.symbol_on("cuda")
+    y = (0.5 + 0.01 * torch.randn((envs, N, N), device="cuda", generator=g)).clamp_(0, 1).contiguous()
+    buf = torch.empty_like(y)
+    dts = np.full(1, 1e-6, np.float32)
+    t = _timed(lambda: plan.step(y, dts, sym, out=buf), 3, 10)
+    out.append({"config": "C2 Cahn-Hilliard 128x128, K = 1 (one launch per numeric step: state read + written every step)",
+                "envs_per_gpu": envs, "value": envs / t, "unit": "env-steps/s",
+                "roofline": {**_roof_hbm(2 * 4 * N * N * envs, t), "how": "2*4*128*128 B per env-step (SURVEY 8d K=1 view)",
+                             "fp32_frac": (108 * N * N * envs / t / 1e12) / peak_tf if peak_tf else None,
+                             "note": "compute-bound even at K = 1: the step itself needs envs / (K>=16 rate) of the time"}})
+    del y, buf
+    # ---- forward with kept states + fused adjoint ----
+    B, K = 512, 256
+    eq = CahnHilliard2DPeriodic(dom, 0.002, ChemicalPotentialLegendrePolynomials([0.1, -2.2, 0.3, 0.25], "log"),
+                                DiffusionLegendrePolynomials([-0.3, 0.2, -0.1]))
+    solver = SemiImplicitFourierSpectral(0.5, eq.fourier_symbol, eq.fft, eq.ifft)
+    plan, sym = eq.plan(), solver.symbol_on("cuda")
+    y = (0.5 + 0.05 * torch.randn((B, N, N), device="cuda", generator=g)).clamp_(0.1, 0.9).contiguous()
+    dts = np.full(K, 1e-6, np.float32)
+    lam = torch.randn((B, N, N), device="cuda", generator=g)
+    gmu = torch.zeros((B, 16), dtype=torch.float64, device="cuda")
+    gmob = torch.zeros_like(gmu)
+    y1 = torch.empty_like(y)
+    state = {}
+
+    def fwd():
+        state["traj"] = plan.rollout_fwd(y, dts, sym, save_every=1, out=y1)[1]
+
+    t_f = _timed(fwd, 1, 2)
+    t_b = _timed(lambda: plan.rollout_bwd(state["traj"], lam.clone(), dts, sym, gmu, gmob), 1, 2)
+    f_fwd, f_bwd = 108 + 40, 70 + 95  # per grid point and step: forward with Legendre closures; adjoint = filter + 3-level stencil
+    out.append({"config": "C2 Cahn-Hilliard 128x128 differentiable rollout: fused forward keeping every state + fused K-step adjoint "
+                          "(Legendre mu with log prior, exp-Legendre mobility; gradients of 7 coefficients and y0)",
+                "envs_per_gpu": B, "steps": K, "value": B * K / (t_f + t_b), "unit": "env-steps/s (forward + adjoint)",
+                "forward_env_steps_per_s": B * K / t_f, "adjoint_env_steps_per_s": B * K / t_b,
+                "trajectory_GiB": B * K * N * N * 4 / 2**30,
+                "roofline": {**_roof_fp32((f_fwd + f_bwd) * N * N * B * K, t_f + t_b, peak_tf),
+                             "how": f"{f_fwd} (forward) + {f_bwd} (adjoint: 2 real FFTs = 70, recomputed mu/D, flux transposes, lap, closure derivatives ~ 95) "
+                                    "algorithmic flop per grid point and step",
+                             "hbm_GBs": (2 * 4 * N * N * B * K) / (t_f + t_b) / 1e9}})
+    del state, y, lam, y1
+    torch.cuda.empty_cache()
+    return out
+
+
 def _ch3d_problem(n, rank=0, world=1):
     from . import Domain
     from .equations import CahnHilliard3DPeriodic
@@ -204,7 +265,7 @@ def c5_slab(n=512):
              "finite": finite}]
 
 
-def run_all(peak_tf, world=1, budget_s=90.0):
+def run_all(peak_tf, world=1, budget_s=120.0):
     """The `secondary` block.  On one GPU: C3, C4, C5.  Under torchrun: C3 at 128 environments per GPU and the
     slab-decomposed 512^3 step over all ranks (every rank participates; rank 0 reports)."""
     import time
@@ -213,7 +274,7 @@ def run_all(peak_tf, world=1, budget_s=90.0):
     out = []
     steps = [lambda: c3_gpe(128, 16, peak_tf, world)]
     if world == 1:
-        steps += [lambda: c4_ad(512, 500, peak_tf), lambda: c5_ch3d(512)]
+        steps += [lambda: c2_variants(peak_tf), lambda: c4_ad(512, 500, peak_tf), lambda: c5_ch3d(512)]
     else:
         steps += [lambda: c5_slab(512)]
     for fn in steps:
