@@ -145,6 +145,17 @@ pdeopt_status pdeopt_nonfinite_flags(const float* y_dev, int32_t batch, int64_t 
 pdeopt_status pdeopt_rhs_batched(pdeopt_plan* plan, const float* y_dev, float* f_dev, int32_t batch,
                                  const float* ctrl_dev, void* stream);
 
+/* eq.rhs(state, t) of the finite-difference Cahn-Hilliard / Allen-Cahn equation of `plan` with the homogeneous
+ * chemical potential mu_h(u) — and optionally the mobility D(u) / rate R(u) — evaluated by the CALLER on the whole
+ * batch: the unfused-but-batched path for closures that are not pointwise families, i.e. the reference's neural
+ * closures PeriodicCNN / Mixer2d (pde_opt/numerics/functions/cnn.py:46-102, mixer_mlp.py:40-86) or any other
+ * callable.  The stencils of cahn_hilliard.py:89-109 / allen_cahn.py:81-84 run here; feed f_dev to
+ * pdeopt_sifs_filter_batched for the step.  The plan's mu family is ignored; its mobility family is used when
+ * mob_dev is NULL.
+ *   u_dev, muh_dev, mob_dev (or NULL), f_dev : [batch][nx][ny];  work_dev : 2 * batch * nx * ny floats */
+pdeopt_status pdeopt_rhs_given_mu_batched(pdeopt_plan* plan, const float* u_dev, const float* muh_dev,
+                                          const float* mob_dev, float* f_dev, int32_t batch, float* work_dev, void* stream);
+
 /* One SemiImplicitFourierSpectral.step (solvers.py:56-70) with an externally evaluated vector
  * field f0 = terms.vf(t0, y0, args) (the unfused path for mu/D closures outside the enumerated
  * families): y1 = y0 + dt * Re ifft( fft(f0) / (1 + dt*A*symbol) ). */

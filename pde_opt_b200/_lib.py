@@ -116,6 +116,7 @@ EXPORTS = [
     "pdeopt_sifs_filter_batched",
     "pdeopt_phasefield_adjoint_work_floats",
     "pdeopt_phasefield_adjoint_step",
+    "pdeopt_rhs_given_mu_batched",
     "pdeopt_sifs_rollout_fwd",
     "pdeopt_sifs_rollout_bwd",
     "pdeopt_phasefield_tangent_work_floats",
@@ -179,6 +180,8 @@ def load():
     lib.pdeopt_phasefield_adjoint_step.restype = ctypes.c_int
     lib.pdeopt_sifs_rollout_fwd.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, i32, vp]
     lib.pdeopt_sifs_rollout_fwd.restype = ctypes.c_int
+    lib.pdeopt_rhs_given_mu_batched.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp]
+    lib.pdeopt_rhs_given_mu_batched.restype = ctypes.c_int
     lib.pdeopt_sifs_rollout_bwd.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.pdeopt_sifs_rollout_bwd.restype = ctypes.c_int
     lib.pdeopt_phasefield_tangent_work_floats.argtypes = [vp, i32, i32]

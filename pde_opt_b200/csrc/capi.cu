@@ -12,6 +12,7 @@
 #include "sifs_small.cuh"
 #include "ch_adjoint.cuh"
 #include "ch_tangent.cuh"
+#include "ch_given_mu.cuh"
 #include "sifs128r_adj.cuh"
 #include "fourier128.cuh"
 
@@ -426,6 +427,37 @@ extern "C" pdeopt_status pdeopt_phasefield_adjoint_step(pdeopt_plan* plan, const
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("adjoint step: ") + cudaGetErrorString(e));
   g_launches.fetch_add(3);
+  return PDEOPT_OK;
+}
+
+extern "C" pdeopt_status pdeopt_rhs_given_mu_batched(pdeopt_plan* plan, const float* u_dev, const float* muh_dev,
+                                                     const float* mob_dev, float* f_dev, int32_t batch, float* work_dev,
+                                                     void* stream) {
+  PdeoptDeviceGuard device_guard_(u_dev);
+  if (!plan || !u_dev || !muh_dev || !f_dev || !work_dev) return fail(PDEOPT_ERR_INVALID, "null argument");
+  if (batch <= 0 || batch > 65535) return fail(PDEOPT_ERR_INVALID, "batch must be in [1, 65535]");
+  const pdeopt_plan_desc& d = plan->d;
+  const int64_t npts = (int64_t)d.nx * d.ny, n = npts * batch;
+  GivenMuParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.nx = d.nx; p.ny = d.ny; p.batch = batch; p.eq = d.kind == PDEOPT_AC2D ? 1 : 0;
+  p.u = u_dev; p.muh = muh_dev; p.mob = mob_dev; p.mu = work_dev; p.dd = work_dev + n; p.f = f_dev;
+  p.inv_hx = (float)(1.0 / d.hx); p.inv_hy = (float)(1.0 / d.hy);
+  p.inv_hx2 = (float)(1.0 / (d.hx * d.hx)); p.inv_hy2 = (float)(1.0 / (d.hy * d.hy));
+  p.kappa = (float)d.kappa;
+  p.pw.mu_family = d.mu_family; p.pw.mu_ncoef = d.mu_ncoef; p.pw.mob_family = d.mob_family; p.pw.mob_ncoef = d.mob_ncoef;
+  for (int i = 0; i < PDEOPT_MAX_COEF; ++i) { p.pw.mu_coef[i] = (float)d.mu_coef[i]; p.pw.mob_coef[i] = (float)d.mob_coef[i]; }
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)((npts + 255) / 256), batch);
+  given_mu_pass1_kernel<<<grid, 256, 0, st>>>(p);
+  int launches = 1;
+  if (p.eq == 0) {
+    given_mu_pass2_kernel<<<grid, 256, 0, st>>>(p);
+    ++launches;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("rhs (given mu): ") + cudaGetErrorString(e));
+  g_launches.fetch_add(launches);
   return PDEOPT_OK;
 }
 

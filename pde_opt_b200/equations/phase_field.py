@@ -122,6 +122,35 @@ class _PhaseField2D(BaseEquation):
             )
         return self._plan
 
+    def _rhs_given_mu(self, y):
+        """rhs_fd for closures outside the enumerated families (PeriodicCNN / Mixer2d of functions_nn, or any callable
+        on torch tensors): mu_h (and the mobility, unless it is an enumerated family) evaluated by the closure on the
+        whole batch, the stencils by pdeopt_rhs_given_mu_batched (cahn_hilliard.py:89-109, allen_cahn.py:81-84)."""
+        import ctypes
+
+        import torch
+
+        from .. import _lib
+        from ..fused import SifsPlan
+
+        mob_fn = self.D if self._kind == "ch2d" else self.R
+        if getattr(self, "_gm_plan", None) is None:
+            nx, ny = self.domain.points
+            mob = self._mob_c.descriptor() if self._mob_c is not None else ("const", (1.0,))
+            self._gm_plan = SifsPlan(self._kind, nx, ny, (self.domain.box[0][0], self.domain.box[1][0]), self.domain.dx, self.kappa,
+                                     ("double_well", ()), mob, "fd")
+        with torch.no_grad():
+            muh = self.mu(y).to(torch.float32).contiguous()
+            mob_v = None if self._mob_c is not None else mob_fn(y).to(torch.float32).contiguous()
+        assert muh.shape == y.shape, "mu must map [B, nx, ny] to [B, nx, ny]"
+        f = torch.empty_like(y)
+        work = torch.empty((2,) + tuple(y.shape), dtype=torch.float32, device=y.device)
+        vp = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p()
+        with _lib.device_of(y):
+            _lib.check(_lib.load().pdeopt_rhs_given_mu_batched(self._gm_plan._h, vp(y), vp(muh), vp(mob_v), vp(f), y.shape[0], vp(work),
+                                                               _lib.stream_ptr(y)))
+        return f
+
     def rhs(self, state, t=0.0):
         """eq.rhs(state, t) on CUDA float32 tensors, [nx,ny] or [B,nx,ny]."""
         import ctypes
@@ -141,6 +170,9 @@ class _PhaseField2D(BaseEquation):
                 f = spectral_rhs_ac(self, y, k2)
             else:
                 f = spectral_rhs_ch(self, y, [_on(y.device, self.two_pi_i_kx, c, "qx"), _on(y.device, self.two_pi_i_ky, c, "qy")], k2)
+            return f[0] if single else f
+        if self.derivs == "fd" and not self.fused:
+            f = self._rhs_given_mu(y)
             return f[0] if single else f
         out = torch.empty_like(y)
         plan = self.plan()

@@ -226,6 +226,8 @@ def recognize(fn, kind):
     Closure object is the explicit form; auto-recognition emits a one-time warning naming the family."""
     if isinstance(fn, Closure):
         return fn
+    if getattr(fn, "is_field_closure", False) or type(fn).__module__.startswith("torch"):
+        return None  # closures of the whole field (PeriodicCNN, Mixer2d, any torch module): the unfused path
     c = _recognize(fn, kind)
     if c is not None:
         import warnings
@@ -265,3 +267,12 @@ def _recognize(fn, kind):
     if np.allclose(y, 1 + x**2, rtol=1e-9) and np.allclose(yo, 1 + xo**2, rtol=1e-9):
         return OnePlusSquare()
     return None
+
+
+def __getattr__(name):
+    # the neural closures live in functions_nn (they need torch at import time; this module does not)
+    if name in ("PeriodicCNN", "PeriodicConvBlock", "Mixer2d", "MixerBlock"):
+        from . import functions_nn
+
+        return getattr(functions_nn, name)
+    raise AttributeError(name)
