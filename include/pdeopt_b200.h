@@ -212,6 +212,27 @@ pdeopt_status pdeopt_phasefield_tangent_steps(pdeopt_plan* plan, const float* tr
                                               int32_t ndir, int32_t ksteps, const float* dt_host, const float* dmu_dev,
                                               const float* dmob_dev, const float* symbol_dev, float* work_dev, void* stream);
 
+/* ---- smoothed-boundary equations (cahn_hilliard.py:203-289, allen_cahn.py:87-159) ------------------------------- */
+typedef struct {
+  int32_t kind;   /* PDEOPT_CH2D or PDEOPT_AC2D */
+  int32_t nx, ny;
+  double hx, hy, kappa;
+} pdeopt_sbm_desc;
+
+/* eq.rhs(state, t) of CahnHilliard2DSmoothedBoundary.rhs_fd (cahn_hilliard.py:261-289) /
+ * AllenCahn2DSmoothedBoundary.rhs_fd (allen_cahn.py:142-159) for `batch` states.  The reference integrates these
+ * with explicit diffrax solvers, so there is no fused step: an RHS entry point.  The closures f, mu and D / R are
+ * arbitrary callables in the reference; the caller evaluates them on the whole batch.
+ *   u_dev, f_dev (free-energy density f(u)), mu_dev (mu(u)), mob_dev (D(u) or R(u)), out_dev : [batch][nx][ny]
+ *   psi_dev (domain.geometry.smooth), ngp_dev (|grad psi| / psi, centred differences), side_dev (the `left_half`
+ *   mask of the contact-angle term) : [nx][ny]
+ *   cos_theta = cos(theta(t)), cos_pi_minus_theta = cos(pi - theta(t)) (Cahn-Hilliard only), flux = flux(t) (CH only)
+ *   work_dev : batch * nx * ny floats (Cahn-Hilliard; may be NULL for Allen-Cahn) */
+pdeopt_status pdeopt_sbm_rhs_batched(const pdeopt_sbm_desc* desc, const float* u_dev, const float* f_dev, const float* mu_dev,
+                                     const float* mob_dev, const float* psi_dev, const float* ngp_dev, const float* side_dev,
+                                     float cos_theta, float cos_pi_minus_theta, float flux, float* work_dev, float* out_dev,
+                                     int32_t batch, void* stream);
+
 /* GPE2DTSControl (gross_pitaevskii.py:18-81) geometry and constants. */
 typedef struct {
   int32_t nx, ny;

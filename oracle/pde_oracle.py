@@ -513,3 +513,45 @@ def integrate_adaptive(step_err_fn, y0, t0, t1, dt0, rtol, atol, save_ts=None, o
                 si += 1
         y, t = y1, tn
     return (y[None] if save_ts is None else out), acc, rej
+
+
+# --------------------------------------------------------------------------------------
+# Smoothed-boundary equations  (reference: cahn_hilliard.py:203-289, allen_cahn.py:87-159)
+# --------------------------------------------------------------------------------------
+
+
+def grad_c(a, h, ax):  # derivatives.py:69-81 (centred first derivative)
+    return a.dtype.type(0.5) * (np.roll(a, -1, ax) - np.roll(a, 1, ax)) / a.dtype.type(h)
+
+
+def sbm_setup(psi, h):
+    """norm_grad_psi = |grad psi| / psi with centred differences (cahn_hilliard.py:248-254, allen_cahn.py:129-135)."""
+    return np.sqrt(grad_c(psi, h[0], 0) ** 2 + grad_c(psi, h[1], 1) ** 2) / psi
+
+
+def _sbm_lap(state, psi, h):
+    """div(psi_face grad_face(u)): cahn_hilliard.py:268-271."""
+    ax_, ay_ = avg_c2f(psi, 0), avg_c2f(psi, 1)
+    return div_f2c(ax_ * grad_c2f(state, h[0], 0), h[0], 0) + div_f2c(ay_ * grad_c2f(state, h[1], 1), h[1], 1)
+
+
+def sbm_rhs_ch(state, t, psi, h, kappa, f, mu, D, theta, flux, left_half):
+    """CahnHilliard2DSmoothedBoundary.rhs_fd, cahn_hilliard.py:261-289."""
+    tt = state.dtype.type
+    ngp = sbm_setup(psi, h)
+    inner = (mu(state) - (tt(kappa) / psi) * _sbm_lap(state, psi, h)
+             - tt(np.sqrt(kappa)) * ngp * np.sqrt(tt(2.0) * f(state))
+             * (tt(np.cos(theta(t))) * left_half + tt(np.cos(np.pi - theta(t))) * (tt(1.0) - left_half)))
+    Du = D(state)
+    Fx = avg_c2f(psi, 0) * avg_c2f(Du, 0) * grad_c2f(inner, h[0], 0)
+    Fy = avg_c2f(psi, 1) * avg_c2f(Du, 1) * grad_c2f(inner, h[1], 1)
+    return (div_f2c(Fx, h[0], 0) + div_f2c(Fy, h[1], 1)) / psi + ngp * tt(flux(t))
+
+
+def sbm_rhs_ac(state, t, psi, h, kappa, f, mu, R, theta, left_half):
+    """AllenCahn2DSmoothedBoundary.rhs_fd, allen_cahn.py:142-159."""
+    tt = state.dtype.type
+    ngp = sbm_setup(psi, h)
+    m = (mu(state) - (tt(kappa) / psi) * _sbm_lap(state, psi, h)
+         - tt(np.sqrt(kappa)) * ngp * np.sqrt(tt(2.0) * f(state)) * tt(np.cos(theta(t))) * left_half)
+    return -R(state) * m

@@ -38,6 +38,11 @@ class PlanDesc(ctypes.Structure):
     ]
 
 
+class SbmDesc(ctypes.Structure):  # pdeopt_sbm_desc
+    _fields_ = [("kind", ctypes.c_int32), ("nx", ctypes.c_int32), ("ny", ctypes.c_int32), ("hx", ctypes.c_double), ("hy", ctypes.c_double),
+                ("kappa", ctypes.c_double)]
+
+
 class GpeDesc(ctypes.Structure):
     _fields_ = [
         ("nx", ctypes.c_int32),
@@ -117,6 +122,7 @@ EXPORTS = [
     "pdeopt_phasefield_adjoint_work_floats",
     "pdeopt_phasefield_adjoint_step",
     "pdeopt_rhs_given_mu_batched",
+    "pdeopt_sbm_rhs_batched",
     "pdeopt_sifs_rollout_fwd",
     "pdeopt_sifs_rollout_bwd",
     "pdeopt_phasefield_tangent_work_floats",
@@ -180,6 +186,8 @@ def load():
     lib.pdeopt_phasefield_adjoint_step.restype = ctypes.c_int
     lib.pdeopt_sifs_rollout_fwd.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, i32, vp]
     lib.pdeopt_sifs_rollout_fwd.restype = ctypes.c_int
+    lib.pdeopt_sbm_rhs_batched.argtypes = [ctypes.POINTER(SbmDesc), vp, vp, vp, vp, vp, vp, vp, f32, f32, f32, vp, vp, i32, vp]
+    lib.pdeopt_sbm_rhs_batched.restype = ctypes.c_int
     lib.pdeopt_rhs_given_mu_batched.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp]
     lib.pdeopt_rhs_given_mu_batched.restype = ctypes.c_int
     lib.pdeopt_sifs_rollout_bwd.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]

@@ -1,6 +1,7 @@
 // C ABI of libpdeopt_b200 (see include/pdeopt_b200.h for the contract and the reference
 // code each entry point replaces).
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <new>
@@ -13,6 +14,7 @@
 #include "ch_adjoint.cuh"
 #include "ch_tangent.cuh"
 #include "ch_given_mu.cuh"
+#include "sbm.cuh"
 #include "sifs128r_adj.cuh"
 #include "fourier128.cuh"
 
@@ -457,6 +459,40 @@ extern "C" pdeopt_status pdeopt_rhs_given_mu_batched(pdeopt_plan* plan, const fl
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("rhs (given mu): ") + cudaGetErrorString(e));
+  g_launches.fetch_add(launches);
+  return PDEOPT_OK;
+}
+
+extern "C" pdeopt_status pdeopt_sbm_rhs_batched(const pdeopt_sbm_desc* desc, const float* u_dev, const float* f_dev,
+                                                const float* mu_dev, const float* mob_dev, const float* psi_dev,
+                                                const float* ngp_dev, const float* side_dev, float cos_theta,
+                                                float cos_pi_minus_theta, float flux, float* work_dev, float* out_dev,
+                                                int32_t batch, void* stream) {
+  PdeoptDeviceGuard device_guard_(u_dev);
+  if (!desc || !u_dev || !f_dev || !mu_dev || !mob_dev || !psi_dev || !ngp_dev || !side_dev || !out_dev)
+    return fail(PDEOPT_ERR_INVALID, "null argument");
+  if (desc->nx <= 0 || desc->ny <= 0 || batch <= 0 || batch > 65535) return fail(PDEOPT_ERR_INVALID, "bad sizes");
+  if (desc->kind != PDEOPT_CH2D && desc->kind != PDEOPT_AC2D) return fail(PDEOPT_ERR_INVALID, "kind must be CH2D or AC2D");
+  if (desc->kind == PDEOPT_CH2D && !work_dev) return fail(PDEOPT_ERR_INVALID, "work_dev is required for Cahn-Hilliard");
+  SbmParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.nx = desc->nx; p.ny = desc->ny; p.batch = batch; p.eq = desc->kind == PDEOPT_AC2D ? 1 : 0;
+  p.u = u_dev; p.fval = f_dev; p.muval = mu_dev; p.mob = mob_dev; p.psi = psi_dev; p.ngp = ngp_dev; p.lh = side_dev;
+  p.inner = work_dev; p.out = out_dev;
+  p.inv_hx = (float)(1.0 / desc->hx); p.inv_hy = (float)(1.0 / desc->hy);
+  p.kappa = (float)desc->kappa; p.sqrt_kappa = (float)std::sqrt(desc->kappa);
+  p.cos_a = cos_theta; p.cos_b = cos_pi_minus_theta; p.flux = flux;
+  const int64_t npts = (int64_t)desc->nx * desc->ny;
+  dim3 grid((unsigned)((npts + 255) / 256), batch);
+  cudaStream_t st = (cudaStream_t)stream;
+  sbm_pass1_kernel<<<grid, 256, 0, st>>>(p);
+  int launches = 1;
+  if (p.eq == 0) {
+    sbm_pass2_kernel<<<grid, 256, 0, st>>>(p);
+    ++launches;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("smoothed-boundary rhs: ") + cudaGetErrorString(e));
   g_launches.fetch_add(launches);
   return PDEOPT_OK;
 }

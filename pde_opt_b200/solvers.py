@@ -370,3 +370,79 @@ class StrangSplitting:
         del solver_state, made_jump
         y1 = self.rollout(terms, np.asarray([t0, t1], dtype=np.float32), y0)
         return y1, None, dict(y0=y0, y1=y1), None, RESULTS.successful
+
+
+# ---- explicit solvers for equations without a linear symbol (the smoothed-boundary equations) ---------------------
+# The reference passes diffrax solver classes straight through PDEModel (docs/notebooks/
+# solving_pde_smoothed_boundary.ipynb: PDEModel(AllenCahn2DSmoothedBoundary, domain, dfx.Tsit5) with a PIDController).
+# diffrax is not installable here; these are the same kind of object for this package's PDEModel: no required
+# equation attributes, `step` returns the embedded error estimate.  The stages are evaluated by `terms.vf` (the
+# equation's CUDA RHS); the stage combinations are torch axpy calls (host-orchestrated, off the semi-implicit hot
+# path).  Tsit5's tableau is not reproduced from memory: Dopri5 (diffrax has it too) is the 5(4) pair provided.
+
+class Euler:
+    """Forward Euler (diffrax.Euler): order 1, no error estimate."""
+
+    required_equation_attrs = []
+    term_structure = ODETerm
+    interpolation_cls = LocalLinearInterpolation
+
+    def __init__(self):
+        pass
+
+    def order(self, terms):
+        return 1
+
+    def init(self, terms, t0, t1, y0, args):
+        return None
+
+    def func(self, terms, t0, y0, args):
+        return terms.vf(t0, y0, args)
+
+    def step(self, terms, t0, t1, y0, args=None, solver_state=None, made_jump=False):
+        dt = float(np.float32(np.float32(t1) - np.float32(t0)))
+        y1 = y0 + dt * terms.vf(t0, y0, args)
+        return y1, None, dict(y0=y0, y1=y1), None, RESULTS.successful
+
+    def rollout(self, terms, times, y0, out=None, **_):
+        times = np.asarray(times, dtype=np.float32)
+        y = y0
+        for k in range(len(times) - 1):
+            y = self.step(terms, times[k], times[k + 1], y)[0]
+        if out is not None:
+            out.copy_(y)
+            return out
+        return y
+
+
+class Dopri5(Euler):
+    """Dormand-Prince 5(4) (diffrax.Dopri5): seven stages, fifth-order solution, embedded fourth-order error estimate."""
+
+    _C = (0.0, 1 / 5, 3 / 10, 4 / 5, 8 / 9, 1.0, 1.0)
+    _A = ((), (1 / 5,), (3 / 40, 9 / 40), (44 / 45, -56 / 15, 32 / 9), (19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729),
+          (9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656), (35 / 384, 0.0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84))
+    _B4 = (5179 / 57600, 0.0, 7571 / 16695, 393 / 640, -92097 / 339200, 187 / 2100, 1 / 40)
+
+    with_error = True
+
+    def order(self, terms):
+        return 5
+
+    def step(self, terms, t0, t1, y0, args=None, solver_state=None, made_jump=False):
+        t0f = float(np.float32(t0))
+        dt = float(np.float32(np.float32(t1) - np.float32(t0)))
+        k = []
+        for s in range(7):
+            ys = y0
+            for a, ki in zip(self._A[s], k):
+                if a != 0.0:
+                    ys = ys + (dt * a) * ki
+            k.append(terms.vf(t0f + self._C[s] * dt, ys, args))
+        y1 = ys  # the seventh stage point is the fifth-order solution (first-same-as-last)
+        b5 = self._A[6] + (0.0,)
+        err = None
+        for b, bs, ki in zip(b5, self._B4, k):
+            if b != bs:
+                term = (dt * (b - bs)) * ki
+                err = term if err is None else err + term
+        return y1, err, dict(y0=y0, y1=y1), None, RESULTS.successful
