@@ -348,6 +348,14 @@ pdeopt_status pdeopt_fft_lines_to_peers(const void* in_dev, int32_t n, const pde
                                         int64_t src_off, const float* sym_dev, const pdeopt_line_geom* gsym, float dt,
                                         float scale, void* stream);
 
+/* The slab transpose as a dedicated push kernel: block p (block_bytes, contiguous) of src_dev is stored into peer p's
+ * buffer at dst_off_bytes (P2P stores over NVLink into peer-mapped memory; peer_ptrs_host includes this rank's own
+ * buffer).  first_peer rotates the order in which the blocks are sent (pass the rank).  This is the default transport of
+ * the slab-decomposed 3-D step: plain coalesced stores reach 650-700 GB/s per rank, the stores fused into the transform
+ * kernels (pdeopt_fft_lines_to_peers) 270-390 GB/s.  The caller orders the consumers with a cross-rank barrier. */
+pdeopt_status pdeopt_push_blocks_to_peers(const void* src_dev, void* const* peer_ptrs_host, int32_t n_peers,
+                                          int64_t block_bytes, int64_t dst_off_bytes, int32_t first_peer, void* stream);
+
 /* Inverse transform of the last axis fused with the update y1 = y0 + dt * Re(.) (solvers.py:63). */
 pdeopt_status pdeopt_fft_lines_inv_update(const void* spec_dev, int32_t n, const pdeopt_line_geom* gin,
                                           const float* y0_dev, float* y1_dev, const pdeopt_line_geom* gout, float dt,

@@ -88,6 +88,58 @@ extern "C" pdeopt_status pdeopt_fft_lines_to_peers(const void* in_dev, int32_t n
   return PDEOPT_OK;
 }
 
+// Slab transpose as a dedicated push: block p of a contiguous send buffer goes to peer p's buffer (P2P stores over
+// NVLink, 16 bytes per thread, fully coalesced).  Measured on this pool (tools/p2p_store_bench.cu): plain SM stores into
+// peer memory reach 650-700 GB/s, while the same bytes stored from inside the last stage of a line-FFT kernel
+// (pdeopt_fft_lines_to_peers) reach 270-390 GB/s — the remote stores back up the kernel's load / compute phases.
+struct PushParams {
+  const float4* src;
+  float4* dst[8];
+  long long block_vec4;    // float4 elements per block
+  long long dst_off_vec4;  // offset inside every peer buffer
+  int n_peers, first;      // block order starts at `first` so that the ranks do not all hit the same peer at once
+};
+
+static __global__ void __launch_bounds__(256) push_blocks_kernel(const __grid_constant__ PushParams p) {
+  const long long total = p.block_vec4 * p.n_peers;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int k = (int)(i / p.block_vec4);
+    const long long w = i - (long long)k * p.block_vec4;
+    const int peer = (p.first + k) % p.n_peers;
+    p.dst[peer][p.dst_off_vec4 + w] = __ldg(p.src + (long long)peer * p.block_vec4 + w);
+  }
+}
+
+extern "C" pdeopt_status pdeopt_push_blocks_to_peers(const void* src_dev, void* const* peer_ptrs_host, int32_t n_peers,
+                                                     int64_t block_bytes, int64_t dst_off_bytes, int32_t first_peer,
+                                                     void* stream) {
+  PdeoptDeviceGuard device_guard_(src_dev);
+  if (!src_dev || !peer_ptrs_host) return fail(PDEOPT_ERR_INVALID, "null argument");
+  if (n_peers < 1 || n_peers > 8) return fail(PDEOPT_ERR_INVALID, "1..8 peers");
+  if (block_bytes <= 0 || (block_bytes & 15) || (dst_off_bytes & 15) || dst_off_bytes < 0)
+    return fail(PDEOPT_ERR_INVALID, "block_bytes and dst_off_bytes must be multiples of 16");
+  PushParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.src = (const float4*)src_dev;
+  for (int i = 0; i < n_peers; ++i) {
+    if (!peer_ptrs_host[i]) return fail(PDEOPT_ERR_INVALID, "null peer pointer");
+    p.dst[i] = (float4*)peer_ptrs_host[i];
+  }
+  p.block_vec4 = block_bytes / 16;
+  p.dst_off_vec4 = dst_off_bytes / 16;
+  p.n_peers = n_peers;
+  p.first = ((first_peer % n_peers) + n_peers) % n_peers;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  push_blocks_kernel<<<sms * 8, 256, 0, (cudaStream_t)stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("push_blocks_to_peers: ") + cudaGetErrorString(e));
+  g_launches.fetch_add(1);
+  return PDEOPT_OK;
+}
+
 extern "C" pdeopt_status pdeopt_fft_lines_inv_update(const void* spec_dev, int32_t n, const pdeopt_line_geom* gin,
                                                      const float* y0_dev, float* y1_dev, const pdeopt_line_geom* gout,
                                                      float dt, void* stream) {

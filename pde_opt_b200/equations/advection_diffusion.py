@@ -71,16 +71,18 @@ class AdvectionDiffusion2D(BaseEquation):
         return self.velocity.control_block(batch, nseg, device)
 
     def rhs(self, state, t=0.0):
-        """f = -div(v u) + D lap(u) on CUDA float32 tensors ([nx,ny] or [B,nx,ny]), evaluated with the
-        fused kernel as (y1 - y0)/dt of one explicit step (A = 0 makes the IMEX filter the identity)."""
+        """f = -div(v u) + D lap(u) on CUDA float32 tensors ([nx,ny] or [B,nx,ny]), evaluated with the fused kernel as
+        y1 - y0 of ONE explicit step of length 1 (A = 0 makes the IMEX filter the identity, so y1 = y0 + f exactly as the
+        kernel forms it).  With dt = 1 the subtraction loses at most an ulp of max(|y0|, |f|) — a step of length 2^-10,
+        as used before, amplified the rounding of y1 by 1/dt.  Not differentiable (no autograd node)."""
         import torch
 
         from ..adjoint import ad_rollout
 
         single = state.dim() == 2
         y = (state.unsqueeze(0) if single else state).contiguous()
-        dt = np.float32(2.0**-10)
-        ctrl = self.control_block(y.shape[0], y.device)
-        y1 = ad_rollout(self, y, ctrl, np.asarray([0.0, dt], dtype=np.float32), A=0.0)
-        f = (y1 - y) / float(dt)
+        with torch.no_grad():
+            ctrl = self.control_block(y.shape[0], y.device)
+            y1 = ad_rollout(self, y.detach(), ctrl.detach(), np.asarray([0.0, 1.0], dtype=np.float32), A=0.0)
+            f = y1 - y
         return f[0] if single else f

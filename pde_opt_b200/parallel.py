@@ -92,6 +92,15 @@ class _DeviceBackend:
             ctypes.c_void_p(sym.data_ptr()) if sym is not None else None, ctypes.byref(gsym) if gsym is not None else None,
             float(dt), float(scale), self._stream(src)))
 
+    def push_blocks(self, src, peer_ptrs, block_bytes, dst_off_bytes, first):
+        import ctypes
+
+        from . import _lib
+
+        arr = (ctypes.c_void_p * len(peer_ptrs))(*[ctypes.c_void_p(int(p)) for p in peer_ptrs])
+        _lib.check(_lib.load().pdeopt_push_blocks_to_peers(ctypes.c_void_p(src.data_ptr()), arr, len(peer_ptrs), int(block_bytes),
+                                                           int(dst_off_bytes), int(first), self._stream(src)))
+
     def fft_lines_imex(self, buf, n, g, sym, gsym, dt, scale):
         import ctypes
 
@@ -171,13 +180,18 @@ class SlabCahnHilliard3D:
         self.g_y_packed = geom(nxl * Hz, Hz, C * Hz, 1, Ny, Hz, chunk=C, hi=nxl * C * Hz)
         self.g_x = geom(C * Hz, C * Hz, 0, 1, Nx, C * Hz)
         self._bufs = None
-        if transport not in ("auto", "peer", "nccl"):
-            raise ValueError("transport must be 'auto', 'peer' or 'nccl'")
+        import os as _os
+
+        self._timing = [] if _os.environ.get("PDEOPT_SLAB_TIMING") == "1" else None
+        if transport not in ("auto", "push", "peer", "nccl"):
+            raise ValueError("transport must be 'auto', 'push', 'peer' or 'nccl'")
         on_gpu = isinstance(self.backend, _DeviceBackend) and device is not None and torch.device(device).type == "cuda"
-        if transport == "auto":  # peer stores on the GPUs of one box, collectives otherwise (CPU emulation, one rank)
-            transport = "peer" if (on_gpu and self.world > 1) else "nccl"
+        if transport == "auto":  # P2P pushes on the GPUs of one box, collectives otherwise (CPU emulation, one rank)
+            # (two ranks: half of every buffer stays local, and the stores fused into the transform kernels win — 1.58 vs
+            # 1.67 ms at 512^3; from four ranks on the dedicated push kernel does — 0.57 vs 0.65 ms on eight)
+            transport = ("push" if self.world > 2 else "peer") if (on_gpu and self.world > 1) else "nccl"
         self.transport = transport if self.world > 1 else "nccl"
-        if self.transport == "peer":
+        if self.transport in ("peer", "push"):
             import torch.distributed._symmetric_memory as symm_mem
 
             n = nxl * Ny * Hz  # complex elements per rank in either packed layout
@@ -191,6 +205,14 @@ class SlabCahnHilliard3D:
             # destination geometries inside one peer's buffer (hi = 0: the chunk index selects the peer)
             self.g_y_to_peers = geom(nxl * Hz, Hz, C * Hz, 1, Ny, Hz, chunk=C, hi=0)
             self.g_x_to_peers = geom(C * Hz, C * Hz, 0, 1, Nx, C * Hz, chunk=nxl, hi=0)
+            # halo planes by P2P stores as well: [lo: planes -2, -1 | hi: planes nxl, nxl+1] of THIS rank, written by its
+            # two ring neighbours straight into this symmetric buffer (no collective; one symmetric-memory barrier)
+            self._sym_halo = symm_mem.empty(4 * Ny * Nz, dtype=torch.float32, device=device)
+            self._h0 = symm_mem.rendezvous(self._sym_halo, grp)
+            up, down = (self.rank + 1) % P, (self.rank - 1) % P
+            self._halo_up_lo = self._h0.get_buffer(up, (2, Ny, Nz), torch.float32, 0)              # my last planes -> up.lo
+            self._halo_down_hi = self._h0.get_buffer(down, (2, Ny, Nz), torch.float32, 2 * Ny * Nz)  # my first planes -> down.hi
+            self._halo_mine = self._sym_halo.view(2, 2, Ny, Nz)
 
     def _buffers(self, like):
         if self._bufs is None:
@@ -208,6 +230,19 @@ class SlabCahnHilliard3D:
             b["lo"].copy_(u[-2:])
             b["hi"].copy_(u[:2])
             return b["lo"], b["hi"]
+        if self.transport in ("peer", "push"):
+            # the planes the neighbours need go straight into their halo buffers; the barrier orders the stores before
+            # the right-hand side reads them, and the two transpose barriers of the step order those reads before the
+            # next step's stores
+            if isinstance(self.backend, _DeviceBackend):
+                nb = 2 * self.Ny * self.Nz * 4
+                self.backend.push_blocks(u[-2:], [self._h0.buffer_ptrs[(self.rank + 1) % self.world]], nb, 0, 0)
+                self.backend.push_blocks(u[:2], [self._h0.buffer_ptrs[(self.rank - 1) % self.world]], nb, nb, 0)
+            else:
+                self._halo_up_lo.copy_(u[-2:])
+                self._halo_down_hi.copy_(u[:2])
+            self._h0.barrier(channel=2)
+            return self._halo_mine[0], self._halo_mine[1]
         # one small all-gather of the four boundary planes of every rank (4 x Ny x Nz floats each);
         # cheap next to the slab transposes and identical on NCCL and gloo
         mine = torch.cat([u[:2], u[-2:]], 0).contiguous()
@@ -225,24 +260,75 @@ class SlabCahnHilliard3D:
         else:
             dist.all_to_all_single(torch.view_as_real(dst), torch.view_as_real(src), group=self.group)
 
+    def _mark(self, name):
+        """PDEOPT_SLAB_TIMING=1: CUDA events between the phases of a step (tools/bench_configs.py prints the averages)."""
+        if self._timing is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._timing.append((name, ev))
+
+    def phase_times_ms(self):
+        """Average time of every phase over the steps recorded since the last call (needs PDEOPT_SLAB_TIMING=1)."""
+        torch.cuda.synchronize()
+        acc, cnt = {}, {}
+        for (n0, e0), (n1, e1) in zip(self._timing[:-1], self._timing[1:]):
+            if n1 != "start":
+                acc[n1] = acc.get(n1, 0.0) + e0.elapsed_time(e1)
+                cnt[n1] = cnt.get(n1, 0) + 1
+        self._timing = []
+        return {k: acc[k] / cnt[k] for k in acc}
+
     def step(self, u, dt, out=None):
         """u: this rank's slab [nxl, Ny, Nz] float32; returns the slab after one step of length dt."""
         be, b = self.backend, self._buffers(u)
         y1 = out if out is not None else torch.empty_like(u)
+        self._mark("start")
         lo, hi = self.exchange_halos(u)
+        self._mark("halo")
         f = be.rhs(u, lo, hi)
+        self._mark("rhs")
         be.fft_r2c(f, b["W"], self.Nz, self.nxl * self.Ny)
+        self._mark("r2c_z")
         if self.transport == "peer":
             blk = self.rank * self.nxl * self.C * self.Hz
             r1 = torch.view_as_complex(self._sym_recv1.view(-1, 2))
             r2 = torch.view_as_complex(self._sym_recv2.view(-1, 2))
             # y pass -> peers' x-line buffers; barrier; x pass (fwd * m * inv) -> peers' packed y buffers; barrier
             be.fft_lines_to_peers(b["W"], self.Ny, self.g_y, self._peers1, self.g_y_to_peers, blk)
+            self._mark("y_fwd_to_peers")
             self._h1.barrier(channel=0)
+            self._mark("barrier1")
             be.fft_lines_to_peers(r1, self.Nx, self.g_x, self._peers2, self.g_x_to_peers, blk, self.sym, self.g_x, dt, self.scale)
+            self._mark("x_imex_to_peers")
             self._h2.barrier(channel=1)
+            self._mark("barrier2")
             be.fft_lines(r2, b["W"], self.Ny, self.g_y_packed, self.g_y, True, False, 1.0)
+            self._mark("y_inv")
             be.fft_c2r_update(b["W"], self.Nz, self.nxl * self.Ny, u, y1, dt)
+            self._mark("c2r_z_update")
+            return y1
+        if self.transport == "push":
+            # transforms write packed local buffers at HBM speed; each transpose is one push kernel (P2P stores, block p ->
+            # peer p) followed by a symmetric-memory barrier
+            blk_bytes = self.nxl * self.C * self.Hz * 8
+            r1 = torch.view_as_complex(self._sym_recv1.view(-1, 2))
+            r2 = torch.view_as_complex(self._sym_recv2.view(-1, 2))
+            be.fft_lines(b["W"], b["send"], self.Ny, self.g_y, self.g_y_packed, False, False, 1.0)
+            self._mark("y_fwd")
+            be.push_blocks(b["send"], self._peers1, blk_bytes, self.rank * blk_bytes, self.rank + 1)
+            self._mark("push1")
+            self._h1.barrier(channel=0)
+            self._mark("barrier1")
+            be.fft_lines_imex(r1, self.Nx, self.g_x, self.sym, self.g_x, dt, self.scale)
+            self._mark("x_imex")
+            be.push_blocks(r1, self._peers2, blk_bytes, self.rank * blk_bytes, self.rank + 1)
+            self._mark("push2")
+            self._h2.barrier(channel=1)
+            self._mark("barrier2")
+            be.fft_lines(r2, b["W"], self.Ny, self.g_y_packed, self.g_y, True, False, 1.0)
+            self._mark("y_inv")
+            be.fft_c2r_update(b["W"], self.Nz, self.nxl * self.Ny, u, y1, dt)
+            self._mark("c2r_z_update")
             return y1
         be.fft_lines(b["W"], b["send"], self.Ny, self.g_y, self.g_y_packed, False, False, 1.0)
         self._all_to_all(b["recv"], b["send"])

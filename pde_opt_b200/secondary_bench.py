@@ -256,10 +256,12 @@ def c5_slab(n=512):
     pk, _ = hbm_peak()
     target = max(alg_local / (pk * 1e9), a2a / (NVLINK_GBS * 1e9))
     finite = bool(torch.isfinite(out).all())
+    transport = slab.transport
     del u, out, sym, slab
     torch.cuda.empty_cache()
     return [{"config": f"C5 Cahn-Hilliard 3D {n}^3 slab-decomposed over {world} GPUs, one semi-implicit step", "n_gpus": world,
              "value": vol / t, "unit": "grid-point-steps/s", "ms_per_step": t * 1e3, "transposed_MB_per_rank_per_step": a2a / 1e6,
+             "transport": transport,
              "roofline": {"bound": "hbm+nvlink", "achieved": 1.0 / t, "peak": 1.0 / target, "unit": "steps/s", "frac": target / t,
                           "how": f"target = max(local algorithmic bytes {alg_local / 1e9:.2f} GB / measured HBM, {a2a / 1e6:.0f} MB per rank over NVLink / {NVLINK_GBS:.0f} GB/s)"},
              "finite": finite}]

@@ -213,6 +213,8 @@ def c5slab(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    if slab._timing is not None:
+        slab._timing = []  # drop the warm-up steps
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     iters = 5
     e0.record()
@@ -223,6 +225,8 @@ def c5slab(args):
     t = torch.tensor([e0.elapsed_time(e1) / iters * 1e-3], device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if slab._timing is not None and rank == 0:
+        print(json.dumps({"phase_ms_rank0": {k: round(v, 4) for k, v in slab.phase_times_ms().items()}}))
     chk = out.double().sum()
     if world > 1:
         dist.all_reduce(chk)
@@ -259,7 +263,7 @@ if __name__ == "__main__":
     ap.add_argument("--envs3", type=int, default=128)
     ap.add_argument("--envs4", type=int, default=512)
     ap.add_argument("--check", action="store_true")
-    ap.add_argument("--transport", default="auto", choices=["auto", "nccl", "peer"])
+    ap.add_argument("--transport", default="auto", choices=["auto", "nccl", "peer", "push"])
     a = ap.parse_args()
     todo = [a.only] if a.only else ["c1", "c3", "c3b", "c4", "c5"]
     for name in todo:
