@@ -356,6 +356,13 @@ pdeopt_status pdeopt_fft_lines_to_peers(const void* in_dev, int32_t n, const pde
 pdeopt_status pdeopt_push_blocks_to_peers(const void* src_dev, void* const* peer_ptrs_host, int32_t n_peers,
                                           int64_t block_bytes, int64_t dst_off_bytes, int32_t first_peer, void* stream);
 
+/* The same push for a PART of every block (the pipelined slab step pushes chunks while the transforms of the next
+ * chunk run): for peer p, n_rows runs of run_bytes, row_stride_bytes apart, starting at src_dev + p * src_block_bytes,
+ * are stored at the same row offsets from dst_off_bytes inside peer p's buffer. */
+pdeopt_status pdeopt_push_rows_to_peers(const void* src_dev, void* const* peer_ptrs_host, int32_t n_peers,
+                                        int64_t src_block_bytes, int64_t dst_off_bytes, int32_t n_rows, int64_t run_bytes,
+                                        int64_t row_stride_bytes, int32_t first_peer, void* stream);
+
 /* Inverse transform of the last axis fused with the update y1 = y0 + dt * Re(.) (solvers.py:63). */
 pdeopt_status pdeopt_fft_lines_inv_update(const void* spec_dev, int32_t n, const pdeopt_line_geom* gin,
                                           const float* y0_dev, float* y1_dev, const pdeopt_line_geom* gout, float dt,

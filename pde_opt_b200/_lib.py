@@ -138,6 +138,7 @@ EXPORTS = [
     "pdeopt_fft_lines_inv_update",
     "pdeopt_fft_lines_to_peers",
     "pdeopt_push_blocks_to_peers",
+    "pdeopt_push_rows_to_peers",
     "pdeopt_fft_lines_r2c",
     "pdeopt_fft_lines_c2r_update",
     "pdeopt_ch3d_rhs",
@@ -191,6 +192,8 @@ def load():
     lib.pdeopt_sbm_rhs_batched.restype = ctypes.c_int
     lib.pdeopt_push_blocks_to_peers.argtypes = [vp, vp, i32, ctypes.c_int64, ctypes.c_int64, i32, vp]
     lib.pdeopt_push_blocks_to_peers.restype = ctypes.c_int
+    lib.pdeopt_push_rows_to_peers.argtypes = [vp, vp, i32, ctypes.c_int64, ctypes.c_int64, i32, ctypes.c_int64, ctypes.c_int64, i32, vp]
+    lib.pdeopt_push_rows_to_peers.restype = ctypes.c_int
     lib.pdeopt_rhs_given_mu_batched.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp]
     lib.pdeopt_rhs_given_mu_batched.restype = ctypes.c_int
     lib.pdeopt_sifs_rollout_bwd.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]

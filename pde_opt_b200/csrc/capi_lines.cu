@@ -1,4 +1,6 @@
 // C ABI: line-FFT engine, 3-D Cahn-Hilliard, Strang on large grids (see include/pdeopt_b200.h).
+#include <algorithm>
+
 #include "capi_common.h"
 #include "capi_lines_common.h"
 #include "ch3d.cuh"
@@ -95,30 +97,37 @@ extern "C" pdeopt_status pdeopt_fft_lines_to_peers(const void* in_dev, int32_t n
 struct PushParams {
   const float4* src;
   float4* dst[8];
-  long long block_vec4;    // float4 elements per block
-  long long dst_off_vec4;  // offset inside every peer buffer
-  int n_peers, first;      // block order starts at `first` so that the ranks do not all hit the same peer at once
+  long long src_block_vec4;  // distance between the blocks of consecutive peers in src (float4 elements)
+  long long dst_off_vec4;    // offset inside every peer buffer
+  long long run_vec4;        // contiguous run per row
+  long long row_stride_vec4; // distance between rows (same in src and dst)
+  int n_rows;
+  int n_peers, first;        // block order starts at `first` so that the ranks do not all hit the same peer at once
 };
 
 static __global__ void __launch_bounds__(256) push_blocks_kernel(const __grid_constant__ PushParams p) {
-  const long long total = p.block_vec4 * p.n_peers;
+  const long long per_block = p.run_vec4 * p.n_rows;
+  const long long total = per_block * p.n_peers;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int k = (int)(i / p.block_vec4);
-    const long long w = i - (long long)k * p.block_vec4;
+    const int k = (int)(i / per_block);
+    const long long w = i - (long long)k * per_block;
+    const long long row = w / p.run_vec4, col = w - row * p.run_vec4;
     const int peer = (p.first + k) % p.n_peers;
-    p.dst[peer][p.dst_off_vec4 + w] = __ldg(p.src + (long long)peer * p.block_vec4 + w);
+    const long long o = row * p.row_stride_vec4 + col;
+    p.dst[peer][p.dst_off_vec4 + o] = __ldg(p.src + (long long)peer * p.src_block_vec4 + o);
   }
 }
 
-extern "C" pdeopt_status pdeopt_push_blocks_to_peers(const void* src_dev, void* const* peer_ptrs_host, int32_t n_peers,
-                                                     int64_t block_bytes, int64_t dst_off_bytes, int32_t first_peer,
-                                                     void* stream) {
+static pdeopt_status push_launch(const void* src_dev, void* const* peer_ptrs_host, int32_t n_peers, int64_t src_block_bytes,
+                                 int64_t dst_off_bytes, int32_t n_rows, int64_t run_bytes, int64_t row_stride_bytes,
+                                 int32_t first_peer, void* stream) {
   PdeoptDeviceGuard device_guard_(src_dev);
   if (!src_dev || !peer_ptrs_host) return fail(PDEOPT_ERR_INVALID, "null argument");
   if (n_peers < 1 || n_peers > 8) return fail(PDEOPT_ERR_INVALID, "1..8 peers");
-  if (block_bytes <= 0 || (block_bytes & 15) || (dst_off_bytes & 15) || dst_off_bytes < 0)
-    return fail(PDEOPT_ERR_INVALID, "block_bytes and dst_off_bytes must be multiples of 16");
+  if (n_rows < 1 || run_bytes <= 0 || ((run_bytes | dst_off_bytes | src_block_bytes | row_stride_bytes) & 15) || dst_off_bytes < 0 ||
+      src_block_bytes < 0 || row_stride_bytes < 0 || ((uintptr_t)src_dev & 15))
+    return fail(PDEOPT_ERR_INVALID, "push: sizes, strides, offsets and the source pointer must be multiples of 16 bytes");
   PushParams p;
   std::memset(&p, 0, sizeof(p));
   p.src = (const float4*)src_dev;
@@ -126,18 +135,38 @@ extern "C" pdeopt_status pdeopt_push_blocks_to_peers(const void* src_dev, void* 
     if (!peer_ptrs_host[i]) return fail(PDEOPT_ERR_INVALID, "null peer pointer");
     p.dst[i] = (float4*)peer_ptrs_host[i];
   }
-  p.block_vec4 = block_bytes / 16;
+  p.src_block_vec4 = src_block_bytes / 16;
   p.dst_off_vec4 = dst_off_bytes / 16;
+  p.run_vec4 = run_bytes / 16;
+  p.row_stride_vec4 = row_stride_bytes / 16;
+  p.n_rows = n_rows;
   p.n_peers = n_peers;
   p.first = ((first_peer % n_peers) + n_peers) % n_peers;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  push_blocks_kernel<<<sms * 8, 256, 0, (cudaStream_t)stream>>>(p);
+  const long long total = p.run_vec4 * n_rows * n_peers;
+  const long long want = (total + 255) / 256;
+  const int grid = (int)std::min<long long>((long long)sms * 8, std::max<long long>(want, 1));
+  push_blocks_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("push_blocks_to_peers: ") + cudaGetErrorString(e));
   g_launches.fetch_add(1);
   return PDEOPT_OK;
+}
+
+extern "C" pdeopt_status pdeopt_push_blocks_to_peers(const void* src_dev, void* const* peer_ptrs_host, int32_t n_peers,
+                                                     int64_t block_bytes, int64_t dst_off_bytes, int32_t first_peer,
+                                                     void* stream) {
+  return push_launch(src_dev, peer_ptrs_host, n_peers, block_bytes, dst_off_bytes, 1, block_bytes, 0, first_peer, stream);
+}
+
+extern "C" pdeopt_status pdeopt_push_rows_to_peers(const void* src_dev, void* const* peer_ptrs_host, int32_t n_peers,
+                                                   int64_t src_block_bytes, int64_t dst_off_bytes, int32_t n_rows,
+                                                   int64_t run_bytes, int64_t row_stride_bytes, int32_t first_peer,
+                                                   void* stream) {
+  return push_launch(src_dev, peer_ptrs_host, n_peers, src_block_bytes, dst_off_bytes, n_rows, run_bytes, row_stride_bytes,
+                     first_peer, stream);
 }
 
 extern "C" pdeopt_status pdeopt_fft_lines_inv_update(const void* spec_dev, int32_t n, const pdeopt_line_geom* gin,

@@ -101,6 +101,20 @@ class _DeviceBackend:
         _lib.check(_lib.load().pdeopt_push_blocks_to_peers(ctypes.c_void_p(src.data_ptr()), arr, len(peer_ptrs), int(block_bytes),
                                                            int(dst_off_bytes), int(first), self._stream(src)))
 
+    def push_rows(self, src, peer_ptrs, src_block_bytes, dst_off_bytes, n_rows, run_bytes, row_stride_bytes, first):
+        import ctypes
+
+        from . import _lib
+
+        key = tuple(int(p) for p in peer_ptrs)
+        cache = self.__dict__.setdefault("_arr_cache", {})
+        arr = cache.get(key)
+        if arr is None:
+            arr = cache[key] = (ctypes.c_void_p * len(peer_ptrs))(*[ctypes.c_void_p(p) for p in key])
+        _lib.check(_lib.load().pdeopt_push_rows_to_peers(ctypes.c_void_p(src.data_ptr()), arr, len(peer_ptrs), int(src_block_bytes),
+                                                         int(dst_off_bytes), int(n_rows), int(run_bytes), int(row_stride_bytes), int(first),
+                                                         self._stream(src)))
+
     def fft_lines_imex(self, buf, n, g, sym, gsym, dt, scale):
         import ctypes
 
@@ -183,13 +197,23 @@ class SlabCahnHilliard3D:
         import os as _os
 
         self._timing = [] if _os.environ.get("PDEOPT_SLAB_TIMING") == "1" else None
+        # chunks of the pipelined push transport (1 = transforms and pushes strictly in turn); the chunk boundaries must keep
+        # every pushed run a multiple of 16 bytes: even chunk sizes along the local y range
+        self._chunks = int(_os.environ.get("PDEOPT_SLAB_CHUNKS", "4" if big else "1"))
+        while self._chunks > 1 and (nxl % self._chunks or C % (2 * self._chunks)):
+            self._chunks //= 2
+        self._side = None
+        self._pipe_geoms = None
         if transport not in ("auto", "push", "peer", "nccl"):
             raise ValueError("transport must be 'auto', 'push', 'peer' or 'nccl'")
         on_gpu = isinstance(self.backend, _DeviceBackend) and device is not None and torch.device(device).type == "cuda"
-        if transport == "auto":  # P2P pushes on the GPUs of one box, collectives otherwise (CPU emulation, one rank)
-            # (two ranks: half of every buffer stays local, and the stores fused into the transform kernels win — 1.58 vs
-            # 1.67 ms at 512^3; from four ranks on the dedicated push kernel does — 0.57 vs 0.65 ms on eight)
-            transport = ("push" if self.world > 2 else "peer") if (on_gpu and self.world > 1) else "nccl"
+        big = nxl * Ny * (Nz // 2 + 1) >= (1 << 24)  # complex elements per rank and transpose
+        if transport == "auto":
+            # P2P pushes on the GPUs of one box, collectives otherwise (CPU emulation, one rank).  Measured at 512^3
+            # (profiles/slab_multigpu_r2_*.log): 2 ranks — push pipelined in 4 chunks 1.48 ms, fused peer stores 1.58, push
+            # unpipelined 1.63; 8 ranks — push 0.57, fused peer stores 0.65, NCCL 0.70 (pipelining: no gain, the chunks are
+            # launch-bound).  Small slabs on two ranks (half of every buffer stays local): fused peer stores.
+            transport = ("push" if (self.world > 2 or big) else "peer") if (on_gpu and self.world > 1) else "nccl"
         self.transport = transport if self.world > 1 else "nccl"
         if self.transport in ("peer", "push"):
             import torch.distributed._symmetric_memory as symm_mem
@@ -287,8 +311,9 @@ class SlabCahnHilliard3D:
         self._mark("halo")
         f = be.rhs(u, lo, hi)
         self._mark("rhs")
-        be.fft_r2c(f, b["W"], self.Nz, self.nxl * self.Ny)
-        self._mark("r2c_z")
+        if not (self.transport == "push" and self._chunks > 1):
+            be.fft_r2c(f, b["W"], self.Nz, self.nxl * self.Ny)
+            self._mark("r2c_z")
         if self.transport == "peer":
             blk = self.rank * self.nxl * self.C * self.Hz
             r1 = torch.view_as_complex(self._sym_recv1.view(-1, 2))
@@ -307,6 +332,8 @@ class SlabCahnHilliard3D:
             be.fft_c2r_update(b["W"], self.Nz, self.nxl * self.Ny, u, y1, dt)
             self._mark("c2r_z_update")
             return y1
+        if self.transport == "push" and self._chunks > 1:
+            return self._step_pipelined(u, f, dt, y1)
         if self.transport == "push":
             # transforms write packed local buffers at HBM speed; each transpose is one push kernel (P2P stores, block p ->
             # peer p) followed by a symmetric-memory barrier
@@ -336,6 +363,62 @@ class SlabCahnHilliard3D:
         self._all_to_all(b["send"], b["recv"])
         be.fft_lines(b["send"], b["W"], self.Ny, self.g_y_packed, self.g_y, True, False, 1.0)
         be.fft_c2r_update(b["W"], self.Nz, self.nxl * self.Ny, u, y1, dt)
+        return y1
+
+    def _step_pipelined(self, u, f, dt, y1):
+        """transport="push" with the transposes pipelined against the transforms (PDEOPT_SLAB_CHUNKS chunks, two side
+        streams): transpose #1 is cut along the slab's planes — z transform, y transform and push of chunk q+1 run while
+        chunk q is on the wire; transpose #2 is cut along the local y range — x transform (fwd * m * inv) of chunk q+1 under
+        the push of chunk q.  One symmetric-memory barrier per transpose, as before; same arithmetic, bit for bit."""
+        from .linefft import geom
+
+        be, b = self.backend, self._buffers(u)
+        nxl, C, Hz, Ny, Nx, Nz, Q = self.nxl, self.C, self.Hz, self.Ny, self.Nx, self.Nz, self._chunks
+        blk = nxl * C * Hz  # complex elements per destination block
+        main = torch.cuda.current_stream(u.device)
+        if self._side is None:
+            self._side = [torch.cuda.Stream(u.device), torch.cuda.Stream(u.device)]
+        r1 = torch.view_as_complex(self._sym_recv1.view(-1, 2))
+        r2 = torch.view_as_complex(self._sym_recv2.view(-1, 2))
+        W, send, symf = b["W"], b["send"], self.sym.view(-1)
+        if self._pipe_geoms is None:
+            self._pipe_geoms = ([(geom((nxl // Q) * Hz, Hz, Ny * Hz, 1, Ny, Hz), geom((nxl // Q) * Hz, Hz, C * Hz, 1, Ny, Hz, chunk=C, hi=blk))
+                                 for _ in range(Q)],
+                                [geom((C // Q) * Hz, (C // Q) * Hz, 0, 1, Nx, C * Hz) for _ in range(Q)])
+        ev = main.record_event()
+        for q in range(Q):
+            x0, x1 = q * nxl // Q, (q + 1) * nxl // Q
+            st = self._side[q % 2]
+            st.wait_event(ev)
+            with torch.cuda.stream(st):
+                be.fft_r2c(f[x0:x1], W[x0 * Ny * Hz:], Nz, (x1 - x0) * Ny)
+                be.fft_lines(W[x0 * Ny * Hz:], send[x0 * C * Hz:], Ny, self._pipe_geoms[0][q][0], self._pipe_geoms[0][q][1], False, False, 1.0)
+                be.push_rows(send[x0 * C * Hz:], self._peers1, blk * 8, (self.rank * blk + x0 * C * Hz) * 8, 1, (x1 - x0) * C * Hz * 8, 0,
+                             self.rank + 1)
+        for st in self._side:
+            main.wait_stream(st)
+        self._mark("z_y_push1")
+        self._h1.barrier(channel=0)
+        self._mark("barrier1")
+        ev = main.record_event()
+        for q in range(Q):
+            c0, c1 = q * C // Q, (q + 1) * C // Q
+            st = self._side[q % 2]
+            st.wait_event(ev)
+            with torch.cuda.stream(st):
+                g = self._pipe_geoms[1][q]
+                be.fft_lines_imex(r1[c0 * Hz:], Nx, g, symf[c0 * Hz:], g, dt, self.scale)
+                be.push_rows(r1[c0 * Hz:], self._peers2, blk * 8, (self.rank * blk + c0 * Hz) * 8, nxl, (c1 - c0) * Hz * 8, C * Hz * 8,
+                             self.rank + 1)
+        for st in self._side:
+            main.wait_stream(st)
+        self._mark("x_imex_push2")
+        self._h2.barrier(channel=1)
+        self._mark("barrier2")
+        be.fft_lines(r2, W, Ny, self.g_y_packed, self.g_y, True, False, 1.0)
+        self._mark("y_inv")
+        be.fft_c2r_update(W, Nz, nxl * Ny, u, y1, dt)
+        self._mark("c2r_z_update")
         return y1
 
     def rollout(self, u, dts):
