@@ -194,6 +194,7 @@ class SlabCahnHilliard3D:
         self.g_y_packed = geom(nxl * Hz, Hz, C * Hz, 1, Ny, Hz, chunk=C, hi=nxl * C * Hz)
         self.g_x = geom(C * Hz, C * Hz, 0, 1, Nx, C * Hz)
         self._bufs = None
+        big = nxl * Ny * (Nz // 2 + 1) >= (1 << 24)  # complex elements per rank and transpose
         import os as _os
 
         self._timing = [] if _os.environ.get("PDEOPT_SLAB_TIMING") == "1" else None
@@ -207,7 +208,6 @@ class SlabCahnHilliard3D:
         if transport not in ("auto", "push", "peer", "nccl"):
             raise ValueError("transport must be 'auto', 'push', 'peer' or 'nccl'")
         on_gpu = isinstance(self.backend, _DeviceBackend) and device is not None and torch.device(device).type == "cuda"
-        big = nxl * Ny * (Nz // 2 + 1) >= (1 << 24)  # complex elements per rank and transpose
         if transport == "auto":
             # P2P pushes on the GPUs of one box, collectives otherwise (CPU emulation, one rank).  Measured at 512^3
             # (profiles/slab_multigpu_r2_*.log): 2 ranks — push pipelined in 4 chunks 1.48 ms, fused peer stores 1.58, push
