@@ -156,6 +156,20 @@ pdeopt_status pdeopt_rhs_batched(pdeopt_plan* plan, const float* y_dev, float* f
 pdeopt_status pdeopt_rhs_given_mu_batched(pdeopt_plan* plan, const float* u_dev, const float* muh_dev,
                                           const float* mob_dev, float* f_dev, int32_t batch, float* work_dev, void* stream);
 
+/* Discrete adjoint of one semi-implicit step whose mu_h (and optionally mobility) was evaluated by the caller
+ * (pdeopt_rhs_given_mu_batched + pdeopt_sifs_filter_batched), up to the closure's own vector-Jacobian product: with
+ * w = dt G lam1 the kernels return
+ *   mubar = d loss / d mu_h  (CH: div(D_f grad_f w); AC: -D w),   dbar = d loss / d D  (CH: -1/2 sum grad_f w grad_f mu; AC: -w mu),
+ *   lam0_base = lam1 - kappa lap(mubar),
+ * and the caller adds  J_{mu_h}(u)^T mubar + J_D(u)^T dbar  (back-propagation through the network in its own framework;
+ * the same two cotangents give the gradients of the network's parameters).  This is what jax.grad through
+ * diffeqsolve does for the reference's neural closures (docs/notebooks/optimization_neural_network.ipynb).
+ *   u_dev, muh_dev, mob_dev (or NULL: the plan's mobility family), lam1_dev, lam0_base_dev, mubar_dev, dbar_dev : [batch][nx][ny]
+ *   work_dev : 4 * batch * nx * ny floats */
+pdeopt_status pdeopt_phasefield_adjoint_given_mu(pdeopt_plan* plan, const float* u_dev, const float* muh_dev, const float* mob_dev,
+                                                 const float* lam1_dev, float* lam0_base_dev, float* mubar_dev, float* dbar_dev,
+                                                 int32_t batch, float dt, const float* symbol_dev, float* work_dev, void* stream);
+
 /* One SemiImplicitFourierSpectral.step (solvers.py:56-70) with an externally evaluated vector
  * field f0 = terms.vf(t0, y0, args) (the unfused path for mu/D closures outside the enumerated
  * families): y1 = y0 + dt * Re ifft( fft(f0) / (1 + dt*A*symbol) ). */

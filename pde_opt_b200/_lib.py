@@ -122,6 +122,7 @@ EXPORTS = [
     "pdeopt_phasefield_adjoint_work_floats",
     "pdeopt_phasefield_adjoint_step",
     "pdeopt_rhs_given_mu_batched",
+    "pdeopt_phasefield_adjoint_given_mu",
     "pdeopt_sbm_rhs_batched",
     "pdeopt_sifs_rollout_fwd",
     "pdeopt_sifs_rollout_bwd",
@@ -194,6 +195,8 @@ def load():
     lib.pdeopt_push_blocks_to_peers.restype = ctypes.c_int
     lib.pdeopt_push_rows_to_peers.argtypes = [vp, vp, i32, ctypes.c_int64, ctypes.c_int64, i32, ctypes.c_int64, ctypes.c_int64, i32, vp]
     lib.pdeopt_push_rows_to_peers.restype = ctypes.c_int
+    lib.pdeopt_phasefield_adjoint_given_mu.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, f32, vp, vp, vp]
+    lib.pdeopt_phasefield_adjoint_given_mu.restype = ctypes.c_int
     lib.pdeopt_rhs_given_mu_batched.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp]
     lib.pdeopt_rhs_given_mu_batched.restype = ctypes.c_int
     lib.pdeopt_sifs_rollout_bwd.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]

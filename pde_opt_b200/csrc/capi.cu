@@ -463,6 +463,50 @@ extern "C" pdeopt_status pdeopt_rhs_given_mu_batched(pdeopt_plan* plan, const fl
   return PDEOPT_OK;
 }
 
+extern "C" pdeopt_status pdeopt_phasefield_adjoint_given_mu(pdeopt_plan* plan, const float* u_dev, const float* muh_dev,
+                                                            const float* mob_dev, const float* lam1_dev, float* lam0_base_dev,
+                                                            float* mubar_dev, float* dbar_dev, int32_t batch, float dt,
+                                                            const float* symbol_dev, float* work_dev, void* stream) {
+  PdeoptDeviceGuard device_guard_(u_dev);
+  if (!plan || !u_dev || !muh_dev || !lam1_dev || !lam0_base_dev || !mubar_dev || !dbar_dev || !symbol_dev || !work_dev)
+    return fail(PDEOPT_ERR_INVALID, "null argument");
+  if (batch <= 0 || batch > 65535) return fail(PDEOPT_ERR_INVALID, "batch must be in [1, 65535]");
+  const pdeopt_plan_desc& d = plan->d;
+  const int64_t npts = (int64_t)d.nx * d.ny, n = npts * batch;
+  float* zeros = work_dev;
+  float* w = work_dev + n;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemsetAsync(zeros, 0, sizeof(float) * n, st));
+  int32_t* const flags = plan->flags;
+  plan->flags = nullptr;
+  pdeopt_status s = sifs_launch(plan, MODE_GIVEN_F, lam1_dev, zeros, w, batch, 1, &dt, symbol_dev, nullptr, nullptr, 0.f, 1.f,
+                                nullptr, stream);  // w = dt G lam1
+  plan->flags = flags;
+  if (s != PDEOPT_OK) return s;
+  GivenMuParams g;
+  std::memset(&g, 0, sizeof(g));
+  g.nx = d.nx; g.ny = d.ny; g.batch = batch; g.eq = d.kind == PDEOPT_AC2D ? 1 : 0; g.keep_mu = 1;
+  g.u = u_dev; g.muh = muh_dev; g.mob = mob_dev; g.mu = work_dev + 2 * n; g.dd = work_dev + 3 * n; g.f = nullptr;
+  g.inv_hx = (float)(1.0 / d.hx); g.inv_hy = (float)(1.0 / d.hy);
+  g.inv_hx2 = (float)(1.0 / (d.hx * d.hx)); g.inv_hy2 = (float)(1.0 / (d.hy * d.hy));
+  g.kappa = (float)d.kappa;
+  g.pw.mu_family = d.mu_family; g.pw.mu_ncoef = d.mu_ncoef; g.pw.mob_family = d.mob_family; g.pw.mob_ncoef = d.mob_ncoef;
+  for (int i = 0; i < PDEOPT_MAX_COEF; ++i) { g.pw.mu_coef[i] = (float)d.mu_coef[i]; g.pw.mob_coef[i] = (float)d.mob_coef[i]; }
+  ChAdjParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.nx = d.nx; p.ny = d.ny; p.batch = batch; p.eq = g.eq;
+  p.u = u_dev; p.w = w; p.mu = g.mu; p.dd = g.dd; p.mub = mubar_dev; p.db = dbar_dev;
+  p.inv_hx = g.inv_hx; p.inv_hy = g.inv_hy; p.inv_hx2 = g.inv_hx2; p.inv_hy2 = g.inv_hy2; p.kappa = g.kappa;
+  dim3 grid((unsigned)((npts + 255) / 256), batch);
+  given_mu_pass1_kernel<<<grid, 256, 0, st>>>(g);
+  ch_adj_bar_kernel<<<grid, 256, 0, st>>>(p);
+  sub_kappa_lap_kernel<<<grid, 256, 0, st>>>(lam1_dev, mubar_dev, lam0_base_dev, d.nx, d.ny, g.inv_hx2, g.inv_hy2, g.kappa);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("adjoint (given mu): ") + cudaGetErrorString(e));
+  g_launches.fetch_add(3);
+  return PDEOPT_OK;
+}
+
 extern "C" pdeopt_status pdeopt_sbm_rhs_batched(const pdeopt_sbm_desc* desc, const float* u_dev, const float* f_dev,
                                                 const float* mu_dev, const float* mob_dev, const float* psi_dev,
                                                 const float* ngp_dev, const float* side_dev, float cos_theta,

@@ -16,6 +16,7 @@ namespace pdeopt {
 
 struct GivenMuParams {
   int nx, ny, batch, eq;  // eq: 0 = Cahn-Hilliard, 1 = Allen-Cahn
+  int keep_mu;            // adjoint use: always write mu and D (Allen-Cahn normally finishes in pass 1)
   const float* u;    // [B][nx][ny]
   const float* muh;  // [B][nx][ny] mu_h(u) evaluated by the caller
   const float* mob;  // [B][nx][ny] D(u) / R(u) evaluated by the caller, or null: the plan's family
@@ -40,12 +41,29 @@ static __global__ void __launch_bounds__(256) given_mu_pass1_kernel(const __grid
                     ((u[r * p.ny + cp] - 2.0f * u0) + u[r * p.ny + cm]) * p.inv_hy2;
   const float mu = p.muh[o + i] - p.kappa * lap;
   const float D = p.mob ? p.mob[o + i] : mob<MOB_RUNTIME>(u0, p.pw);
-  if (p.eq == 1) {
+  if (p.eq == 1 && !p.keep_mu) {
     p.f[o + i] = -D * mu;  // allen_cahn.py:84
   } else {
     p.mu[o + i] = mu;
     p.dd[o + i] = D;
   }
+}
+
+// adjoint helper: out = a - kappa lap(b)
+static __global__ void __launch_bounds__(256) sub_kappa_lap_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                                   float* __restrict__ out, int nx, int ny, float inv_hx2, float inv_hy2,
+                                                                   float kappa) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int npts = nx * ny;
+  if (i >= npts) return;
+  const size_t o = (size_t)blockIdx.y * npts;
+  const int r = i / ny, c = i - r * ny;
+  const int rp = (r + 1 == nx) ? 0 : r + 1, rm = (r == 0) ? nx - 1 : r - 1;
+  const int cp = (c + 1 == ny) ? 0 : c + 1, cm = (c == 0) ? ny - 1 : c - 1;
+  const float* bb = b + o;
+  const float b0 = bb[i];
+  const float lap = ((bb[rp * ny + c] - 2.0f * b0) + bb[rm * ny + c]) * inv_hx2 + ((bb[r * ny + cp] - 2.0f * b0) + bb[r * ny + cm]) * inv_hy2;
+  out[o + i] = a[o + i] - kappa * lap;
 }
 
 static __global__ void __launch_bounds__(256) given_mu_pass2_kernel(const __grid_constant__ GivenMuParams p) {

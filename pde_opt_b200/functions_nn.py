@@ -65,8 +65,9 @@ class PeriodicCNN(nn.Module):
     def forward(self, x):
         single = x.dim() == 2
         y = (x[None] if single else x)[:, None]  # [B, 1, nx, ny]
-        for layer in self.layers:
-            y = layer(y)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):  # float32 convolutions: parity, not TF32 speed
+            for layer in self.layers:
+                y = layer(y)
         y = y[:, 0]
         return y[0] if single else y
 

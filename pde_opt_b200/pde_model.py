@@ -40,6 +40,8 @@ class PDEModel:
             return self._solve_differentiable(equation, solver, y0, ts, dt0, max_steps, adjoint)
         if self._wants_phasefield_grad(equation, y0):
             return self._solve_differentiable(equation, solver, y0, ts, dt0, max_steps, adjoint)
+        if self._wants_closure_grad(equation, y0):
+            return self._solve_differentiable(equation, solver, y0, ts, dt0, max_steps, adjoint, unfused=True)
         terms = ODETerm(equation)
         ts = np.asarray([float(t) for t in ts], dtype=np.float32)
         times = constant_step_times(ts[0], ts[-1], dt0, np.float32, max_steps)
@@ -123,7 +125,19 @@ class PDEModel:
         leaves = equation._mu_c.tensor_leaves() + equation._mob_c.tensor_leaves()
         return any(t.requires_grad for t in leaves) or (torch.is_tensor(y0) and y0.requires_grad)
 
-    def _solve_differentiable(self, equation, solver, y0, ts, dt0, max_steps, adjoint):
+    @staticmethod
+    def _wants_closure_grad(equation, y0):
+        """Cahn-Hilliard / Allen-Cahn 2-D (derivs='fd') with a torch closure of the whole field (PeriodicCNN, Mixer2d, ...)
+        whose parameters require grad, or with an initial state that does: the unfused differentiable rollout."""
+        if getattr(equation, "_kind", None) not in ("ch2d", "ac2d") or getattr(equation, "derivs", "") != "fd":
+            return False
+        if getattr(equation, "fused", True) or getattr(equation, "control", None) is not None:
+            return False
+        from .adjoint_nn import closure_parameters
+
+        return bool(closure_parameters(equation)) or (torch.is_tensor(y0) and y0.requires_grad)
+
+    def _solve_differentiable(self, equation, solver, y0, ts, dt0, max_steps, adjoint, unfused=False):
         """solve() on the differentiable paths (advection-diffusion; phase-field equations with tensor
         coefficients): same save-time semantics, every segment an autograd node whose backward is an
         adjoint kernel.  `adjoint` may carry `checkpoint_every` (int): keep every C-th state and recompute in between."""
@@ -147,6 +161,11 @@ class PDEModel:
 
             def roll(y_, seg_times, step0):
                 return ad_rollout(equation, y_, ctrl, seg_times, hold=hold, A=A, checkpoint_every=ck, step0=step0)
+        elif unfused:
+            from .adjoint_nn import given_mu_rollout
+
+            def roll(y_, seg_times, step0):
+                return given_mu_rollout(equation, solver, y_, seg_times)
         else:
             ck_pf = getattr(adjoint, "checkpoint_every", None)
 
@@ -235,6 +254,8 @@ class PDEModel:
                 leaves.append(v)
             elif hasattr(v, "tensor_leaves"):
                 leaves.extend(v.tensor_leaves())
+            elif isinstance(v, torch.nn.Module):  # neural closures: every parameter is a leaf
+                leaves.extend(v.parameters())
         leaves = [t for t in leaves if t.is_floating_point()]
         if not leaves:
             raise ValueError("opt_parameters holds no floating-point tensors to optimise")

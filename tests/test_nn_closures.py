@@ -76,3 +76,76 @@ def test_unfused_step_with_neural_mu_matches_oracle(n, kind, closure):
             assert err <= 1e-5, (K, b, err)  # north star: 1e-5 after one step (held here after 16 as well)
             inc = np.linalg.norm((got[b] - y0[b]) - (y - y0[b])) / np.linalg.norm(y - y0[b])
             assert inc <= 2e-3, (K, b, inc)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["ch", "ac"])
+def test_gradients_through_neural_mu_match_float64_autograd(kind):
+    """d loss / d (network parameters, y0) through 8 unfused steps: CUDA adjoint stencils + torch back-propagation through
+    the network against torch.autograd on the float64 twin of the whole rollout (the same network in double)."""
+    import copy
+
+    from oracle import ch_torch_oracle as TO
+    from pde_opt_b200 import Domain
+    from pde_opt_b200.adjoint_nn import given_mu_rollout
+    from pde_opt_b200.equations import AllenCahn2DPeriodic, CahnHilliard2DPeriodic
+    from pde_opt_b200.functions import ConstantMobility
+    from pde_opt_b200.solvers import SemiImplicitFourierSpectral
+
+    n, B, K = 64, 2, 8
+    net = PeriodicCNN(1, (6, 6), kernel_size=3, key=2).cuda()
+    net64 = copy.deepcopy(net).cpu().double()
+    box = ((-n * H / 2, n * H / 2),) * 2
+    dom = Domain((n, n), box, "dimensionless")
+    if kind == "ch":
+        eq, A, dt = CahnHilliard2DPeriodic(dom, KAPPA, net, ConstantMobility(0.15)), 0.5, 1e-6
+    else:
+        eq, A, dt = AllenCahn2DPeriodic(dom, KAPPA, net, ConstantMobility(0.15)), 1.0, 5e-6
+    solver = SemiImplicitFourierSpectral(A, eq.fourier_symbol, eq.fft, eq.ifft)
+    rng = np.random.default_rng(4)
+    y0 = np.clip(0.5 + 0.1 * rng.normal(size=(B, n, n)), 0.05, 0.95).astype(np.float32)
+    wgt = rng.normal(size=(B, n, n)).astype(np.float32)
+    times = (np.arange(K + 1, dtype=np.float64) * dt).astype(np.float32)
+    yg = torch.from_numpy(y0).cuda().requires_grad_(True)
+    y1 = given_mu_rollout(eq, solver, yg, times)
+    (y1 * torch.from_numpy(wgt).cuda()).sum().backward()
+
+    y64 = torch.from_numpy(y0.astype(np.float64)).requires_grad_(True)
+    dts = [float(d) for d in (times[1:] - times[:-1])]
+    yr = TO.rollout(y64, dts, (n, n), box, KAPPA, A, lambda c: net64(c), lambda c: 0.15 * torch.ones_like(c), kind)
+    (yr * torch.from_numpy(wgt.astype(np.float64))).sum().backward()
+    rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
+    assert rel(y1.detach().cpu().numpy(), yr.detach().numpy()) <= 1e-5
+    assert rel(yg.grad.cpu().numpy(), y64.grad.numpy()) <= 1e-4  # north star: gradients to relative 1e-4
+    got = np.concatenate([p.grad.detach().cpu().numpy().ravel() for p in net.parameters()])
+    want = np.concatenate([p.grad.detach().numpy().ravel() for p in net64.parameters()])
+    assert rel(got, want) <= 1e-4
+
+
+@pytest.mark.gpu
+def test_train_mse_with_neural_mu_reduces_the_loss():
+    """PDEModel.train(method="mse") with a PeriodicCNN as mu (optimization_neural_network.ipynb's set-up in miniature):
+    data generated with the log potential from a smooth large-amplitude state (so that mu_h, not the gradient-energy term,
+    drives the dynamics), a small pointwise network fitted to it; the loss goes down."""
+    from pde_opt_b200 import Domain
+    from pde_opt_b200.equations import CahnHilliard2DPeriodic
+    from pde_opt_b200.functions import ConstantMobility, LogRegular
+    from pde_opt_b200.pde_model import PDEModel
+    from pde_opt_b200.solvers import SemiImplicitFourierSpectral
+
+    n = 64
+    dom = Domain((n, n), ((-n * H / 2, n * H / 2),) * 2, "dimensionless")
+    model = PDEModel(CahnHilliard2DPeriodic, dom, SemiImplicitFourierSpectral)
+    X, Y = dom.mesh()
+    L = n * H
+    y0 = (0.5 + 0.25 * np.sin(2 * np.pi * X / L) * np.cos(4 * np.pi * Y / L) + 0.05 * np.cos(6 * np.pi * X / L)).astype(np.float32)[None]
+    y0 = torch.from_numpy(y0).cuda()
+    ts = np.array([0.0, 5e-4, 1e-3], np.float32)
+    sol = model.solve({"kappa": KAPPA, "mu": LogRegular(3.0), "D": ConstantMobility(0.15)}, y0, ts, {"A": 0.5}, dt0=2e-5)
+    assert float((sol[-1] - sol[0]).norm() / sol[0].norm()) > 5e-3  # the data carry a signal
+    data = {"ys": [sol[t, 0].cpu().numpy() for t in range(3)], "ts": [float(t) for t in ts]}
+    net = PeriodicCNN(1, (8,), kernel_size=1, key=1).cuda()  # pointwise network: the target is a pointwise function
+    model.train(data, [[0, 1, 2]], {"mu": net}, {"kappa": KAPPA, "D": ConstantMobility(0.15)}, {"A": 0.5}, {}, 0.0, method="mse",
+                max_steps=25, dt0=2e-5)
+    h = model.last_loss_history
+    assert h[-1] < 0.7 * h[0], h
