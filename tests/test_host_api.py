@@ -193,6 +193,53 @@ def test_compute_entry_points_reject_bad_arguments_before_touching_the_gpu():
     assert lib.pdeopt_gpe_detect_vortices(fake, 0, 64, 64, 0.0, 0.5, None, fake, None) == _lib.ERR_INVALID
 
 
+def test_round2_entry_points_reject_bad_arguments_before_touching_the_gpu():
+    """Same contract for the entry points added in round 2 (rollouts that keep states, fused adjoint, tangents, given-mu
+    right-hand side and adjoint, smoothed-boundary right-hand side, slab pushes)."""
+    lib = _lib.load()
+    fake = ctypes.c_void_p(0x1000)
+    dts = (ctypes.c_float * 8)(*([1e-6] * 8))
+    d = _lib.PlanDesc()
+    d.kind, d.derivs, d.nx, d.ny, d.hx, d.hy, d.kappa = _lib.KIND_CH2D, _lib.DERIVS_FD, 128, 128, 0.01, 0.01, 0.002
+    h = ctypes.c_void_p()
+    assert lib.pdeopt_plan_create(ctypes.byref(d), ctypes.byref(h)) == _lib.OK
+    fwd = lib.pdeopt_sifs_rollout_fwd
+    assert fwd(h, fake, fake, 1, 4, dts, fake, None, 1, None) == _lib.ERR_INVALID       # no trajectory buffer
+    assert fwd(h, fake, fake, 1, 4, dts, fake, fake, 0, None) == _lib.ERR_INVALID        # save_every < 1
+    assert fwd(h, fake, fake, 1, 4, dts, fake, fake, 513, None) == _lib.ERR_INVALID      # > PDEOPT_MAX_FUSED_STEPS
+    assert fwd(h, fake, fake, 0, 4, dts, fake, fake, 1, None) == _lib.ERR_INVALID
+    bwd = lib.pdeopt_sifs_rollout_bwd
+    assert bwd(h, None, fake, fake, 1, 4, dts, fake, None, fake, fake, None) == _lib.ERR_INVALID
+    assert bwd(h, fake, fake, fake, 1, 0, dts, fake, None, fake, fake, None) == _lib.ERR_INVALID
+    tan = lib.pdeopt_phasefield_tangent_steps
+    assert tan(h, fake, fake, 1, 0, 4, dts, fake, fake, fake, fake, None) == _lib.ERR_INVALID  # ndir < 1
+    assert tan(h, fake, None, 1, 2, 4, dts, fake, fake, fake, fake, None) == _lib.ERR_INVALID
+    assert lib.pdeopt_phasefield_tangent_work_floats(h, 3, 2) == (2 + 3 * 2) * 3 * 128 * 128
+    assert lib.pdeopt_phasefield_tangent_work_floats(h, 0, 2) == 0
+    assert lib.pdeopt_rhs_given_mu_batched(h, fake, None, None, fake, 1, fake, None) == _lib.ERR_INVALID
+    assert lib.pdeopt_rhs_given_mu_batched(h, fake, fake, None, fake, 0, fake, None) == _lib.ERR_INVALID
+    assert lib.pdeopt_phasefield_adjoint_given_mu(h, fake, fake, None, fake, fake, fake, None, 1, 1e-6, fake, fake, None) == _lib.ERR_INVALID
+    lib.pdeopt_plan_destroy(h)
+    d.derivs = _lib.DERIVS_FOURIER
+    assert lib.pdeopt_plan_create(ctypes.byref(d), ctypes.byref(h)) == _lib.OK
+    assert tan(h, fake, fake, 1, 1, 4, dts, fake, fake, fake, fake, None) == _lib.ERR_UNSUPPORTED  # tangents: derivs='fd' only
+    assert bwd(h, fake, fake, fake, 1, 4, dts, fake, None, fake, fake, None) == _lib.ERR_UNSUPPORTED
+    lib.pdeopt_plan_destroy(h)
+
+    sd = _lib.SbmDesc(kind=_lib.KIND_CH2D, nx=64, ny=64, hx=0.01, hy=0.01, kappa=0.002)
+    sbm = lib.pdeopt_sbm_rhs_batched
+    assert sbm(ctypes.byref(sd), fake, fake, fake, fake, fake, fake, fake, 0.0, 0.0, 0.0, None, fake, 1, None) == _lib.ERR_INVALID  # CH needs work
+    assert sbm(ctypes.byref(sd), fake, fake, fake, fake, None, fake, fake, 0.0, 0.0, 0.0, fake, fake, 1, None) == _lib.ERR_INVALID
+    sd.kind = 3
+    assert sbm(ctypes.byref(sd), fake, fake, fake, fake, fake, fake, fake, 0.0, 0.0, 0.0, fake, fake, 1, None) == _lib.ERR_INVALID
+
+    peers = (ctypes.c_void_p * 2)(fake, fake)
+    assert lib.pdeopt_push_blocks_to_peers(fake, peers, 2, 24, 0, 0, None) == _lib.ERR_INVALID   # not a multiple of 16 bytes
+    assert lib.pdeopt_push_blocks_to_peers(fake, peers, 9, 32, 0, 0, None) == _lib.ERR_INVALID   # > 8 peers
+    assert lib.pdeopt_push_rows_to_peers(fake, peers, 2, 64, 0, 0, 32, 64, 0, None) == _lib.ERR_INVALID  # n_rows < 1
+    assert lib.pdeopt_push_rows_to_peers(None, peers, 2, 64, 0, 1, 32, 64, 0, None) == _lib.ERR_INVALID
+
+
 def test_pid_controller_matches_oracle_restatement_on_a_scalar_ode():
     """pde_opt_b200.stepsize.PIDController against oracle.integrate_adaptive on y' = -50 y with an
     implicit/explicit Euler pair (the error estimate of solvers.py:61-65): same accept / reject
