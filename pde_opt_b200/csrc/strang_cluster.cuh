@@ -41,6 +41,18 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Execution-only cluster barrier: orders a write-after-read hazard (every thread of every CTA has FINISHED READING its
+// shared memory — the loaded values were consumed before the arrive — so peers may overwrite it).  No release fence: this CTA
+// has no remote stores in flight at such a point, and the release variant stalls on a membar anyway (10 % of the
+// kinetic kernel's stall samples).
+__device__ __forceinline__ void cluster_sync_exec() {
+#ifndef PDEOPT_CLUSTER_SYNC_RELAXED  // default until the relaxed form has been validated on the GPU
+  cluster_sync_all();
+#else
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+#endif
+}
 __device__ __forceinline__ void st_cluster_f32(uint32_t local_saddr, uint32_t rank, float v) {
   uint32_t raddr;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(local_saddr), "r"(rank));

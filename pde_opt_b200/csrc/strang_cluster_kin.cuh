@@ -70,7 +70,7 @@ __device__ __forceinline__ void kinetic_half(const Ctx& c, const LineMap& m, con
     float2 y[32];
     static_for<0, 32>([&](auto nc) { y[brev<5>(decltype(nc)::value)] = x[decltype(nc)::value]; });
     line_fwd(c, tw, m, y);
-    cluster_sync_all();  // A: every CTA is done with its slab (loads and in-line exchanges)
+    cluster_sync_exec();  // A: every CTA is done with its slab (loads and in-line exchanges)
     store_transposed_from_freq(c, m, y);
   }
   cluster_sync_all();  // B: the column slabs have arrived
@@ -83,15 +83,23 @@ __device__ __forceinline__ void kinetic_half(const Ctx& c, const LineMap& m, con
   line_fwd(c, tw, m, x);
   {
     // trow = table + 256 gl + j: kc = gl, kr = j + 8 a + 32 k0
-    static_for<0, 32>([&](auto ic) {
-      constexpr int i = decltype(ic)::value;
-      float2 m = __ldg(trow + 8 * (i >> 3) + 32 * (i & 7));
-      m = make_float2(m.x * scale, m.y * scale);
-      x[i] = cmul(x[i], m);
+    // in groups of eight: all 32 table loads in flight at once would need 64 more registers next to the 64 of x
+    static_for<0, 4>([&](auto gc) {
+      constexpr int g0 = 8 * decltype(gc)::value;
+      float2 mm[8];
+      static_for<0, 8>([&](auto ic) {
+        constexpr int i = g0 + decltype(ic)::value;
+        mm[i - g0] = __ldg(trow + 8 * (i >> 3) + 32 * (i & 7));
+      });
+      static_for<0, 8>([&](auto ic) {
+        constexpr int i = g0 + decltype(ic)::value;
+        x[i] = cmul(x[i], make_float2(mm[i - g0].x * scale, mm[i - g0].y * scale));
+      });
+      asm volatile("" ::: "memory");
     });
   }
   line_inv(c, tw, m, x);
-  cluster_sync_all();  // A
+  cluster_sync_exec();  // A
   store_transposed_from_spatial(c, m, x);
   cluster_sync_all();  // B: the row slabs (frequency along the row) have arrived
   load_freq(c, m, x);
