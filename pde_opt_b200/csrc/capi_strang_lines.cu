@@ -81,6 +81,8 @@ extern "C" pdeopt_status pdeopt_strang_lines_step_batched_light(const pdeopt_gpe
     static bool kattr[kPdeoptMaxDevices] = {};
     if (pdeopt_first_use_on_device(kattr)) {
       CUDA_TRY(cudaFuncSetAttribute(cf::strang_cluster_kin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(cf::KinSmem) + 2048));
+      // two CTAs (of different clusters) per SM need the full shared-memory carve-out
+      CUDA_TRY(cudaFuncSetAttribute(cf::strang_cluster_kin_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
     const int64_t np = (int64_t)cf::kN * cf::kN;
     const int max_tabs = batch < cf::kMaxTabs ? (batch < 1 ? 1 : batch) : cf::kMaxTabs;  // tables live in the W area
@@ -125,6 +127,16 @@ extern "C" pdeopt_status pdeopt_strang_lines_step_batched_light(const pdeopt_gpe
       attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
+      static const bool dbg_occ = [] { const char* e = std::getenv("PDEOPT_DEBUG_OCC"); return e && e[0] == '1'; }();
+      if (dbg_occ) {
+        int ncl = -1, nblk = -1;
+        cudaOccupancyMaxActiveClusters(&ncl, cf::strang_cluster_kin_kernel, &cfg);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, cf::strang_cluster_kin_kernel, cf::kThreadsC, cfg.dynamicSmemBytes);
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, cf::strang_cluster_kin_kernel);
+        fprintf(stderr, "strang_cluster_kin: max active clusters %d (x %d CTAs), CTAs per SM by resources %d, smem %zu B, regs %d, static smem %zu, local %zu, carveout %d, maxdyn %d\n", ncl, cf::kCtas,
+                nblk, (size_t)cfg.dynamicSmemBytes, fa.numRegs, fa.sharedSizeBytes, fa.localSizeBytes, fa.preferredShmemCarveout, fa.maxDynamicSharedSizeBytes);
+      }
       cudaError_t le = cudaLaunchKernelEx(&cfg, cf::strang_cluster_kin_kernel, kp);
       if (le != cudaSuccess) return fail(PDEOPT_ERR_CUDA, std::string("strang kinetic cluster launch: ") + cudaGetErrorString(le));
       g_launches.fetch_add(1);

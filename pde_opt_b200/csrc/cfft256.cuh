@@ -1,4 +1,4 @@
-// 256 x 256 complex FFT of ONE field distributed over a thread-block cluster of 4 CTAs (sm_100a),
+// 256 x 256 complex FFT of ONE field distributed over a thread-block cluster of 8 (or 4) CTAs (sm_100a),
 // host-emulable: the building block of the kinetic Strang step of GPE2DTSControl on BASELINE config 3
 // (replaces the jnp.fft.fftn / ifftn calls of StrangSplitting.step, solvers.py:107-114).
 //
@@ -30,17 +30,27 @@ namespace pdeopt {
 namespace cf {
 
 constexpr int kN = 256;
-constexpr int kCtas = 4;
-constexpr int kLines = kN / kCtas;  // lines per CTA
-constexpr int kThreadsC = 512;      // 8 threads per line
-constexpr uint32_t kSlabBytes = kLines * kN * 8;  // 128 KB
+// Cluster shape.  4 CTAs x 512 threads (64 lines, 128 KB per CTA, one CTA per SM) is the default.  PDEOPT_CF_CTAS=8 builds
+// 8 CTAs x 256 threads (32 lines, 64 KB per CTA): two CTAs of DIFFERENT clusters then share an SM and one environment's
+// exchanges and barriers overlap the other's arithmetic — measured: 30 environments resident take 51 us per step against 32 us for
+// 15 (+27 % per SM) — but only 15 clusters of 8 fit the GPCs of a B200 per layer (120 of 148 SMs; 37 clusters of 4 use all of
+// them), so both shapes end at 630 k env-steps/s for 128 environments.  Both are checked by the host emulation.
+#ifndef PDEOPT_CF_CTAS
+#define PDEOPT_CF_CTAS 4
+#endif
+constexpr int kCtas = PDEOPT_CF_CTAS;
+static_assert(kCtas == 4 || kCtas == 8, "cluster of 4 or 8 CTAs");
+constexpr int kLines = kN / kCtas;  // lines per CTA (64 or 32)
+constexpr int kThreadsC = 8 * kLines;  // 8 threads per line
+constexpr uint32_t kSlabBytes = kLines * kN * 8;  // 128 KB or 64 KB
+constexpr int kLineGroups = kLines / 8;  // destination lines j + 8 m, m < kLineGroups
 
 PDEOPT_HD int g_of(int line) { return line & 15; }
 PDEOPT_HD uint32_t slot_bytes(int line, int pos) { return (uint32_t)((line * kN + (pos ^ g_of(line))) * 8); }
 // exchange E1 inside a line's region: value (k1, j) at 32 j + (k1 ^ (line & 15))
 PDEOPT_HD uint32_t e1_bytes(int line, int k1, int j) { return (uint32_t)((line * kN + 32 * j + (k1 ^ (line & 15))) * 8); }
-PDEOPT_HD int thread_line(int t) { return (t & 31) + 32 * ((t >> 5) & 1); }
-PDEOPT_HD int thread_j(int t) { return t >> 6; }
+PDEOPT_HD int thread_line(int t) { return t % kLines; }  // the lanes of a warp are 32 consecutive lines
+PDEOPT_HD int thread_j(int t) { return t / kLines; }
 
 // ---- memory access: device = shared-window addresses (+ mapa for peers); host = emulated slabs ----
 // All accesses are [register + compile-time immediate]; the slab is 2048-byte aligned so that the swizzle
@@ -105,12 +115,34 @@ struct Ctx {
 //   slot(j + 8 m, gl) in CTA r                                      = (Tp[r] ^ 64 (m & 1)) + 16384 m
 // with B = slab + 2048 l + 8 (j ^ (l & 15)), E = slab + 2048 l + 256 j + 8 (l & 15), Tp[r] = peer r's slab + 2048 j + 8 (gl ^ j).
 struct LineMap {
-  uint32_t B, E, Tp[kCtas];
-  PDEOPT_CF_FN LineMap(const Ctx& c, int l, int j, int gl) {
+  uint32_t B, E;
+#if defined(__CUDACC__)
+  // The kCtas transposed-store bases live in shared memory (one row per thread, written once): eight more live
+  // registers would be spilled to local memory, whose L1 lines every cluster barrier invalidates.
+  uint32_t tp_row;  // shared-window address of this thread's row of kCtas bases
+  __device__ __forceinline__ LineMap(const Ctx& c, int l, int j, int gl, uint32_t tp_table, int tid) {
+    B = c.local((uint32_t)(2048 * l + 8 * (j ^ (l & 15))));
+    E = c.local((uint32_t)(2048 * l + 256 * j + 8 * (l & 15)));
+    tp_row = tp_table + (uint32_t)tid * (uint32_t)(kCtas * 4);
+    for (int r = 0; r < kCtas; ++r) {
+      const uint32_t v = c.remote(r, (uint32_t)(2048 * j + 8 * (gl ^ j)));
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(tp_row + 4u * (uint32_t)r), "r"(v) : "memory");
+    }
+  }
+  __device__ __forceinline__ uint32_t tp(const Ctx&, int r) const {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(tp_row + 4u * (uint32_t)r));
+    return v;
+  }
+#else
+  uint32_t Tp[kCtas];
+  LineMap(const Ctx& c, int l, int j, int gl) {
     B = c.local((uint32_t)(2048 * l + 8 * (j ^ (l & 15))));
     E = c.local((uint32_t)(2048 * l + 256 * j + 8 * (l & 15)));
     for (int r = 0; r < kCtas; ++r) Tp[r] = c.remote(r, (uint32_t)(2048 * j + 8 * (gl ^ j)));
   }
+  uint32_t tp(const Ctx&, int r) const { return Tp[r]; }
+#endif
 };
 
 // ---- loads of a line from the slab ------------------------------------------------------------------
@@ -206,15 +238,18 @@ PDEOPT_CF_FN void line_inv(const Ctx& c, const float2* __restrict__ t, const Lin
 PDEOPT_CF_FN void store_transposed_from_freq(const Ctx& c, const LineMap& m, const float2 (&x)[32]) {
   static_for<0, 32>([&](auto ic) {
     constexpr int i = decltype(ic)::value;
-    constexpr int a = i >> 3, k0 = i & 7, mm = a + 4 * (k0 & 1);
-    c.template st_to<16384 * mm>(k0 >> 1, m.Tp[k0 >> 1] ^ (uint32_t)(64 * (mm & 1)), x[i]);
+    constexpr int a = i >> 3, k0 = i & 7;
+    constexpr int k = 8 * a + 32 * k0;                       // position (without j): destination line = (j + k) % kLines
+    constexpr int rank = k / kLines, mm = (k % kLines) / 8;  // destination CTA and line group
+    c.template st_to<16384 * mm>(rank, m.tp(c, rank) ^ (uint32_t)(64 * (mm & 1)), x[i]);
   });
 }
-// spatial arrangement of line gl -> value n = 8 n1 + j goes to CTA n1 >> 3, line 8 (n1 & 7) + j, position gl
+// spatial arrangement of line gl -> value n = 8 n1 + j goes to CTA n / kLines, line 8 (n1 % kLineGroups) + j, position gl
 PDEOPT_CF_FN void store_transposed_from_spatial(const Ctx& c, const LineMap& m, const float2 (&x)[32]) {
   static_for<0, 32>([&](auto nc) {
     constexpr int n1 = decltype(nc)::value;
-    c.template st_to<16384 * (n1 & 7)>(n1 >> 3, m.Tp[n1 >> 3] ^ (uint32_t)(64 * (n1 & 1)), x[n1]);
+    constexpr int rank = n1 / kLineGroups, mm = n1 % kLineGroups;
+    c.template st_to<16384 * mm>(rank, m.tp(c, rank) ^ (uint32_t)(64 * (mm & 1)), x[n1]);
   });
 }
 

@@ -1,5 +1,5 @@
 // Fused K-step Strang split step of GPE2DTSControl WITH the kinetic term on 256x256 complex64 fields:
-// one thread-block CLUSTER of 4 CTAs per environment, the wavefunction resident in the cluster's
+// one thread-block CLUSTER of 4 CTAs x 512 threads per environment (8 x 256 with PDEOPT_CF_CTAS=8, see cfft256.cuh), the wavefunction resident in the cluster's
 // registers / shared memory / tensor memory for all K steps (sm_100a).
 //
 // Replaces K calls of StrangSplitting.step (pde_opt/numerics/solvers.py:99-122) with
@@ -45,6 +45,7 @@ struct __align__(2048) KinSmem {
   float gx[kLines], gy[kN];
   float red[kThreadsC / 32];
   float part[2][kCtas];
+  uint32_t tp[kThreadsC * kCtas];  // per-thread transposed-store bases (cfft256.cuh LineMap)
   uint32_t tmem_base;
 };
 
@@ -76,7 +77,9 @@ __device__ __forceinline__ void kinetic_half(const Ctx& c, const LineMap& m, con
   cluster_sync_all();  // B: the column slabs have arrived
   float scale = 1.0f;
   if (with_norm) {
-    const float tot = (part[0] + part[1]) + (part[2] + part[3]);
+    float tot = 0.f;
+#pragma unroll
+    for (int r = 0; r < kCtas; ++r) tot += part[r];
     scale = rsqrtf(tot * dx * dx);  // solvers.py:111, applied with the multiplier (the transforms are linear)
   }
   load_spatial(c, m, x);
@@ -106,7 +109,7 @@ __device__ __forceinline__ void kinetic_half(const Ctx& c, const LineMap& m, con
   line_inv(c, tw, m, x);
 }
 
-static __global__ void __launch_bounds__(kThreadsC, 1) strang_cluster_kin_kernel(const __grid_constant__ KinParams p) {
+static __global__ void __launch_bounds__(kThreadsC, kCtas == 8 ? 2 : 1) strang_cluster_kin_kernel(const __grid_constant__ KinParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // the slab must be 2048-byte aligned in the shared window (the swizzle XORs of cfft256.cuh commute with the base)
   const uint32_t raw_s = (uint32_t)__cvta_generic_to_shared(smem_raw);
@@ -118,11 +121,12 @@ static __global__ void __launch_bounds__(kThreadsC, 1) strang_cluster_kin_kernel
   const int gl = (int)q * kLines + l;  // global line index of this thread's line in either slab orientation
 
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(
-        (uint32_t)__cvta_generic_to_shared(&S.tmem_base)));
+    // psi0 of the step: 64 columns per thread, two warps per lane quadrant
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+        (uint32_t)__cvta_generic_to_shared(&S.tmem_base)), "n"(kThreadsC / 2));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  if (tid < 256) {
+  if (tid < 256) {  // kThreadsC >= 256
     float s, c;
     sincospif(-2.0f * float((tid >> 5) * (tid & 31)) / 256.0f, &s, &c);
     S.tw[tid] = make_float2(c, s);
@@ -153,7 +157,7 @@ static __global__ void __launch_bounds__(kThreadsC, 1) strang_cluster_kin_kernel
   for (int r = 0; r < kCtas; ++r) c.peer[r] = (r == (int)q) ? c.base : peer_addr(c.base, (uint32_t)r);
   c.self = (int)q;
   const uint32_t part_saddr = (uint32_t)__cvta_generic_to_shared(&S.part[0][0]);
-  const LineMap lm(c, l, j, gl);
+  const LineMap lm(c, l, j, gl, (uint32_t)__cvta_generic_to_shared(S.tp), tid);
 
   // ---- load: coalesced global reads of this CTA's 64 rows into the slab, then the spatial arrangement
   // (thread (l, j) holds columns 8 n1 + j of row gl) ----
@@ -257,7 +261,7 @@ static __global__ void __launch_bounds__(kThreadsC, 1) strang_cluster_kin_kernel
   }
   cluster_sync_all();  // no CTA exits while a peer may still write into its shared memory
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(S.tmem_base));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(S.tmem_base), "n"(kThreadsC / 2));
   }
 }
 

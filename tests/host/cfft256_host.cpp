@@ -24,9 +24,9 @@ void cfft256_roundtrip(const float* in, const float* mult, float* out, float* sp
   std::vector<float2> regs((size_t)kCtas * kThreadsC * 32);
   auto X = [&](int q, int t) -> float2(&)[32] { return *reinterpret_cast<float2(*)[32]>(&regs[((size_t)q * kThreadsC + t) * 32]); };
   auto ctx = [&](int q) { Ctx c; for (int r = 0; r < kCtas; ++r) c.slabs[r] = slab[r].data(); c.rank = q; return c; };
-#define FOR_ALL(...) for (int q = 0; q < kCtas; ++q) { Ctx c = ctx(q); (void)c; for (int t = 0; t < kThreadsC; ++t) { const int l = thread_line(t), j = thread_j(t); const LineMap m(c, l, j, 64 * q + l); const float2* tj = tw + 32 * j; (void)m; (void)tj; __VA_ARGS__; } }
+#define FOR_ALL(...) for (int q = 0; q < kCtas; ++q) { Ctx c = ctx(q); (void)c; for (int t = 0; t < kThreadsC; ++t) { const int l = thread_line(t), j = thread_j(t); const LineMap m(c, l, j, kLines * q + l); const float2* tj = tw + 32 * j; (void)m; (void)tj; __VA_ARGS__; } }
   // row slabs: CTA q, line l = row 64 q + l
-  FOR_ALL(static_for<0, 32>([&](auto nc) { constexpr int n1 = decltype(nc)::value; const int r = 64 * q + l, col = 8 * n1 + j;
+  FOR_ALL(static_for<0, 32>([&](auto nc) { constexpr int n1 = decltype(nc)::value; const int r = kLines * q + l, col = 8 * n1 + j;
                                              X(q, t)[brev<5>(n1)] = make_float2(in[(r * 256 + col) * 2], in[(r * 256 + col) * 2 + 1]); }))
   // row pass forward, transposed store -> column slabs
   FOR_ALL(line_fwd_a(c, tj, m, X(q, t)))
@@ -36,7 +36,7 @@ void cfft256_roundtrip(const float* in, const float* mult, float* out, float* sp
   FOR_ALL(load_spatial(c, m, X(q, t)))
   FOR_ALL(line_fwd_a(c, tj, m, X(q, t)))
   FOR_ALL(line_fwd_b(c, m, X(q, t)))
-  FOR_ALL(for (int i = 0; i < 32; ++i) { const int kr = j + 8 * (i >> 3) + 32 * (i & 7), kc = 64 * q + l;
+  FOR_ALL(for (int i = 0; i < 32; ++i) { const int kr = j + 8 * (i >> 3) + 32 * (i & 7), kc = kLines * q + l;
             if (spec) { spec[(kr * 256 + kc) * 2] = X(q, t)[i].x; spec[(kr * 256 + kc) * 2 + 1] = X(q, t)[i].y; }
             if (mult) X(q, t)[i] = cmul(X(q, t)[i], make_float2(mult[(kr * 256 + kc) * 2], mult[(kr * 256 + kc) * 2 + 1])); })
   FOR_ALL(line_inv_a(c, m, X(q, t)))
@@ -46,7 +46,7 @@ void cfft256_roundtrip(const float* in, const float* mult, float* out, float* sp
   FOR_ALL(load_freq(c, m, X(q, t)))
   FOR_ALL(line_inv_a(c, m, X(q, t)))
   FOR_ALL(line_inv_b(c, tj, m, X(q, t)))
-  FOR_ALL(for (int n1 = 0; n1 < 32; ++n1) { const int r = 64 * q + l, col = 8 * n1 + j;
+  FOR_ALL(for (int n1 = 0; n1 < 32; ++n1) { const int r = kLines * q + l, col = 8 * n1 + j;
             out[(r * 256 + col) * 2] = X(q, t)[n1].x; out[(r * 256 + col) * 2 + 1] = X(q, t)[n1].y; })
 #undef FOR_ALL
 }

@@ -1,5 +1,5 @@
-"""The cluster-distributed 256x256 complex FFT (pde_opt_b200/csrc/cfft256.cuh) executed on the host: four
-emulated CTAs x 512 threads, remote stores as writes into the peers' buffers, against numpy.fft."""
+"""The cluster-distributed 256x256 complex FFT (pde_opt_b200/csrc/cfft256.cuh) executed on the host: eight
+emulated CTAs x 256 threads (and the 4 x 512 variant), remote stores as writes into the peers' buffers, against numpy.fft."""
 import ctypes
 import os
 import subprocess
@@ -11,11 +11,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 N = 256
 
 
-@pytest.fixture(scope="module")
-def lib(tmp_path_factory):
-    out = tmp_path_factory.mktemp("cfft256") / "cfft256_host.so"
+@pytest.fixture(scope="module", params=[8, 4])
+def lib(request, tmp_path_factory):
+    out = tmp_path_factory.mktemp(f"cfft256_{request.param}") / "cfft256_host.so"
     src = os.path.join(HERE, "host", "cfft256_host.cpp")
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-x", "c++", src, "-o", str(out)])
+    subprocess.check_call(["g++", "-std=c++17", "-O1", f"-DPDEOPT_CF_CTAS={request.param}", "-shared", "-fPIC", "-x", "c++", src, "-o", str(out)])
     return ctypes.CDLL(str(out))
 
 
@@ -49,13 +49,16 @@ def test_identity(lib):
     assert np.abs(got - z).max() < 5e-6 * np.abs(z).max()
 
 
-def test_layout_is_bank_conflict_free():
+@pytest.mark.parametrize("ctas", [8, 4])
+def test_layout_is_bank_conflict_free(ctas):
     """Every access pattern of the passes hits 16 distinct 8-byte banks per half-warp (16 consecutive lines), and a
-    warp's transposed store is 32 consecutive positions of one destination line (256 contiguous bytes)."""
+    warp's transposed store is 32 consecutive positions of one destination line (256 contiguous bytes) — for the
+    8-CTA x 256-thread cluster (32 lines per CTA, the default) and the 4-CTA x 512-thread one."""
+    lines_per_cta = 256 // ctas
     slot = lambda line, pos: line * 256 + (pos ^ (line & 15))
     e1 = lambda line, k1, j: line * 256 + 32 * j + (k1 ^ (line & 15))
     ok = lambda s: len({int(v) % 16 for v in s}) == 16
-    for l0 in range(0, 64, 16):
+    for l0 in range(0, lines_per_cta, 16):
         lines = range(l0, l0 + 16)
         for j in range(8):
             for n1 in range(32):
@@ -66,8 +69,8 @@ def test_layout_is_bank_conflict_free():
                     assert ok([e1(l, j + 8 * a, jj) for l in lines])                 # E1, the other threads' values
                 for k0 in range(8):
                     assert ok([slot(l, j + 8 * a + 32 * k0) for l in lines])         # frequency load
-    for q in range(4):
-        for k in range(64):
-            for l0 in (0, 32):
-                s = sorted(slot(k, 64 * q + l) for l in range(l0, l0 + 32))
+    for q in range(ctas):
+        for k in range(lines_per_cta):
+            for l0 in range(0, lines_per_cta, 32):
+                s = sorted(slot(k, lines_per_cta * q + l) for l in range(l0, l0 + 32))
                 assert s == list(range(s[0], s[0] + 32)) and s[0] % 16 == 0          # transposed store: contiguous
