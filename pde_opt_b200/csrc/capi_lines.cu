@@ -1,5 +1,6 @@
 // C ABI: line-FFT engine, 3-D Cahn-Hilliard, Strang on large grids (see include/pdeopt_b200.h).
 #include <algorithm>
+#include <cstdlib>
 
 #include "capi_common.h"
 #include "capi_lines_common.h"
@@ -269,6 +270,9 @@ extern "C" pdeopt_status pdeopt_ch3d_rhs(const pdeopt_ch3d_desc* d, const float*
       xl = c;
       if (tiles * (d->nx / c) >= 3 * 148) break;
     }
+    // experiment hook: PDEOPT_CH3D_XL forces the chunk length (must divide nx)
+    static const int force_xl = [] { const char* e = std::getenv("PDEOPT_CH3D_XL"); return e ? std::atoi(e) : 0; }();
+    if (force_xl > 0 && d->nx % force_xl == 0) xl = force_xl;
   }
   auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
   const bool aligned = aligned16(u_dev) && aligned16(f_dev) && aligned16(halo_lo_dev) && aligned16(halo_hi_dev);
