@@ -3,6 +3,7 @@ be checked without them: every C-ABI function the shim calls is declared in incl
 the built library, and every FFI target the Python wrapper registers is defined by the shim."""
 import os
 import re
+import subprocess
 
 from pde_opt_b200 import _lib
 
@@ -55,3 +56,13 @@ def test_argument_counts_match_the_header():
     protos = {m.group(1): arg_count(header, m.end() - 1) for m in re.finditer(r"pdeopt_status\s+(pdeopt_[a-z0-9_]+)\s*\(", header)}
     for m in re.finditer(r"Status\((pdeopt_[a-z0-9_]+)\s*\(", shim):
         assert arg_count(shim, m.end() - 1) == protos[m.group(1)], m.group(1)
+
+
+def test_shim_type_checks_against_the_header_with_a_mock_of_the_xla_ffi_api():
+    """g++ -fsyntax-only of bindings/pdeopt_jax_ffi.cc against include/pdeopt_b200.h and a MOCK xla/ffi/api/ffi.h
+    (tests/host/mock_xla: buffers, results, spans, errors, an unchecked binder): every call into the C ABI has the
+    right argument count and types.  The real jaxlib header is what a maintainer builds against."""
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I" + os.path.join(ROOT, "tests", "host", "mock_xla"),
+                        "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "bindings", "pdeopt_jax_ffi.cc")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
