@@ -33,7 +33,7 @@ class _GivenMuRollout(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y0, eq, solver, dts, sym, *params):
         y = y0.contiguous()
-        plan, _ = solver._plan_for(type("T", (), {"equation": None})(), tuple(y.shape[-2:]))
+        plan = solver.filter_plan(tuple(y.shape[-2:]))
         traj = torch.empty((len(dts),) + tuple(y.shape), dtype=torch.float32, device=y.device)
         for k, dt in enumerate(dts):
             traj[k].copy_(y)

@@ -141,14 +141,18 @@ class SemiImplicitFourierSpectral:
             y1 = out
         return y1[0] if single else y1
 
+    def filter_plan(self, shape):
+        """The plan of the unfused path (caller-evaluated vector field + pdeopt_sifs_filter_batched) for a grid."""
+        if self._filter_plan is None:
+            nx, ny = shape
+            self._filter_plan = SifsPlan("ch2d", nx, ny, (0.0, 0.0), (1.0, 1.0), 0.0)
+        return self._filter_plan
+
     def _plan_for(self, terms, shape):
         eq = getattr(terms, "equation", None)
         if eq is not None and getattr(eq, "fused", False):
             return eq.plan(), eq
-        if self._filter_plan is None:
-            nx, ny = shape
-            self._filter_plan = SifsPlan("ch2d", nx, ny, (0.0, 0.0), (1.0, 1.0), 0.0)
-        return self._filter_plan, None
+        return self.filter_plan(shape), None
 
     def step(self, terms, t0, t1, y0, args=None, solver_state=None, made_jump=False):
         del solver_state, made_jump
