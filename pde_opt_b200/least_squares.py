@@ -108,39 +108,23 @@ def residuals_and_jacobian(model, parameters, leaves, y0s, values, ts, solver_pa
     return res.reshape(-1), J, float(reg.detach()) if torch.is_tensor(reg) else float(reg), dreg, theta
 
 
-def levenberg_marquardt(model, parameters, leaves, y0s, values, ts, solver_parameters, weights, lambda_reg, dt0, max_steps=100,
-                        rtol=1e-8, atol=1e-8, verbose=False):
-    """Minimise 1/2 (|values - pred[1:]|^2 + reg^2) over the entries of `leaves` (updated in place)."""
-    history = []
-
-    def evaluate():
-        with torch.enable_grad():
-            r, J, reg, dreg, theta = residuals_and_jacobian(model, parameters, leaves, y0s, values, ts, solver_parameters, weights,
-                                                            lambda_reg, dt0)
-        f = 0.5 * (float((r.double() ** 2).sum()) + reg**2)
-        Jd = J.double()
-        JtJ = Jd @ Jd.T + torch.outer(dreg, dreg).to(Jd.device)
-        Jtr = Jd @ r.double() + (dreg * reg).to(Jd.device)
-        return f, JtJ.cpu(), Jtr.cpu(), theta.cpu()
-
-    def assign(theta):
-        o = 0
-        with torch.no_grad():
-            for t in leaves:
-                t.copy_(theta[o:o + t.numel()].reshape(t.shape).to(t.dtype))
-                o += t.numel()
-
-    f, JtJ, Jtr, theta = evaluate()
-    history.append(f)
+def lm_iterate(evaluate, theta0, max_steps=100, rtol=1e-8, atol=1e-8, verbose=False):
+    """The Levenberg-Marquardt iteration itself, independent of where residuals and Jacobians come from (host logic,
+    unit-tested on the CPU): `evaluate(theta) -> (f, JtJ, Jtr)` with f = 1/2 |r|^2, float64 CPU tensors.  Damped
+    Gauss-Newton step (J^T J + I / step_size) delta = -J^T r; classical trust-region update of step_size from the ratio of
+    actual to predicted reduction (accept above 0.01, grow x 3.5 above 0.99, shrink x 0.25 on rejection); Cauchy
+    termination on both the step and the loss.  Returns (theta, loss history)."""
+    theta = theta0.clone()
+    f, JtJ, Jtr = evaluate(theta)
+    history = [f]
     step_size = 1.0
     for it in range(int(max_steps)):
         lam = 1.0 / step_size
         delta = -torch.linalg.solve(JtJ + lam * torch.eye(JtJ.shape[0], dtype=torch.float64), Jtr)
         predicted = float(Jtr @ delta + 0.5 * delta @ (JtJ @ delta))  # model reduction (negative)
-        assign(theta + delta)
-        f_new, JtJ_new, Jtr_new, _ = evaluate()
+        f_new, JtJ_new, Jtr_new = evaluate(theta + delta)
         ratio = (f_new - f) / predicted if predicted < 0 else -1.0
-        accept = np.isfinite(f_new) and ratio > 0.01
+        accept = bool(np.isfinite(f_new)) and ratio > 0.01
         if verbose:
             print(f"LM step {it}: loss {f:.6e} -> {f_new:.6e}  step_size {step_size:.3g}  {'accepted' if accept else 'rejected'}")
         if accept:
@@ -153,9 +137,35 @@ def levenberg_marquardt(model, parameters, leaves, y0s, values, ts, solver_param
             if small_y and small_f:
                 break
         else:
-            assign(theta)
             step_size *= 0.25
             if step_size < 1e-30:
                 break
+    return theta, history
+
+
+def levenberg_marquardt(model, parameters, leaves, y0s, values, ts, solver_parameters, weights, lambda_reg, dt0, max_steps=100,
+                        rtol=1e-8, atol=1e-8, verbose=False):
+    """Minimise 1/2 (|values - pred[1:]|^2 + reg^2) over the entries of `leaves` (updated in place)."""
+
+    def assign(theta):
+        o = 0
+        with torch.no_grad():
+            for t in leaves:
+                t.copy_(theta[o:o + t.numel()].reshape(t.shape).to(t.dtype))
+                o += t.numel()
+
+    def evaluate(theta):
+        assign(theta)
+        with torch.enable_grad():
+            r, J, reg, dreg, _ = residuals_and_jacobian(model, parameters, leaves, y0s, values, ts, solver_parameters, weights,
+                                                        lambda_reg, dt0)
+        f = 0.5 * (float((r.double() ** 2).sum()) + reg**2)
+        Jd = J.double()
+        JtJ = Jd @ Jd.T + torch.outer(dreg, dreg).to(Jd.device)
+        Jtr = Jd @ r.double() + (dreg * reg).to(Jd.device)
+        return f, JtJ.cpu(), Jtr.cpu()
+
+    theta0 = torch.cat([t.detach().reshape(-1) for t in leaves]).to(torch.float64).cpu()
+    theta, history = lm_iterate(evaluate, theta0, max_steps, rtol, atol, verbose)
     assign(theta)
     return history

@@ -274,3 +274,45 @@ def test_pid_controller_matches_oracle_restatement_on_a_scalar_ode():
                 r2 += 1
         assert (a2, r2) == (acc, rej) and acc > 5
         np.testing.assert_allclose(y, np.exp(-lam * 0.2) * y0, atol=2e-3)
+
+
+def test_levenberg_marquardt_iteration_on_analytic_problems():
+    """pde_opt_b200.least_squares.lm_iterate (the host loop behind PDEModel.train(method="least_squares"), optimistix's
+    LevenbergMarquardt restated) on problems with known answers: a linear least-squares problem is solved to machine
+    precision; Rosenbrock in residual form converges to (1, 1); the loss never increases along accepted steps."""
+    import torch
+
+    from pde_opt_b200.least_squares import lm_iterate
+
+    rng = np.random.default_rng(0)
+    A = torch.from_numpy(rng.normal(size=(20, 3)))
+    b = torch.from_numpy(rng.normal(size=20))
+
+    def lin(theta):
+        r = A @ theta - b
+        return 0.5 * float(r @ r), A.T @ A, A.T @ r
+
+    theta, hist = lm_iterate(lin, torch.zeros(3, dtype=torch.float64), max_steps=200)
+    want = torch.linalg.lstsq(A, b[:, None]).solution[:, 0]
+    assert torch.allclose(theta, want, atol=1e-7) and all(h1 <= h0 for h0, h1 in zip(hist, hist[1:]))
+
+    def rosen(theta):
+        x, y = float(theta[0]), float(theta[1])
+        r = torch.tensor([10.0 * (y - x * x), 1.0 - x], dtype=torch.float64)
+        J = torch.tensor([[-20.0 * x, 10.0], [-1.0, 0.0]], dtype=torch.float64)
+        return 0.5 * float(r @ r), J.T @ J, J.T @ r
+
+    theta, hist = lm_iterate(rosen, torch.tensor([-1.2, 1.0], dtype=torch.float64), max_steps=200)
+    assert torch.allclose(theta, torch.ones(2, dtype=torch.float64), atol=1e-6), theta
+    assert hist[-1] < 1e-12 and all(h1 <= h0 for h0, h1 in zip(hist, hist[1:]))
+
+    # a non-finite trial point is rejected and the step size shrinks until a finite one is found
+    def wall(theta):
+        x = float(theta[0])
+        if x > 2.0:
+            return float("nan"), torch.eye(1, dtype=torch.float64), torch.zeros(1, dtype=torch.float64)
+        r = torch.tensor([x - 1.9], dtype=torch.float64)
+        return 0.5 * float(r @ r), torch.ones((1, 1), dtype=torch.float64) * 1e-6, torch.tensor([(x - 1.9) * 1e-3], dtype=torch.float64)
+
+    theta, hist = lm_iterate(wall, torch.tensor([0.0], dtype=torch.float64), max_steps=50)
+    assert np.isfinite(hist[-1]) and float(theta[0]) <= 2.0
