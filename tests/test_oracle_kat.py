@@ -244,3 +244,28 @@ def test_detect_vortices_oracle_counts_known_windings():
     assert r["positions"].shape == (4, 2) and np.allclose(r["positions"] % 1.0, 0.5)
     # without the mask the periodic plaquette sum vanishes identically (Stokes on a torus)
     assert O.detect_vortices(psi)["total_topological_charge"] == 0
+
+
+def test_smoothed_boundary_oracle_reduces_to_the_periodic_equations_for_a_trivial_geometry():
+    """With psi == 1 (no boundary: |grad psi| = 0) the smoothed-boundary right-hand sides (cahn_hilliard.py:261-289,
+    allen_cahn.py:142-159) must equal the periodic ones (cahn_hilliard.py:89-109, allen_cahn.py:81-84), which the
+    reference's own known-answer tests pin: a consistency check of the restatement in oracle/pde_oracle.py."""
+    n, h, kappa = 32, 0.01, 0.002
+    dom = O.Domain((n, n), ((0.0, n * h),) * 2)
+    rng = np.random.default_rng(3)
+    u = np.clip(0.5 + 0.2 * rng.normal(size=(n, n)), 0.05, 0.95)
+    psi = np.ones((n, n))
+    side = np.zeros((n, n)); side[: n // 2] = 1
+    f = lambda c: c * np.log(c) + (1 - c) * np.log(1 - c) + 3.0 * c * (1 - c) + 0.059
+    mu = lambda c: O.mu_log(c, 3.0)
+    D = lambda c: (1 - c) * c
+    ch = O.CahnHilliardPeriodic(dom, kappa, mu, D, "fd", np.float64)
+    got = O.sbm_rhs_ch(u, 0.3, psi, dom.dx, kappa, f, mu, D, lambda t: 1.0, lambda t: 0.7, side)
+    assert np.allclose(got, ch.rhs_fd(u), rtol=1e-10, atol=1e-8 * np.abs(got).max())
+    ac = O.AllenCahn2DPeriodic(dom, kappa, mu, D, "fd", np.float64)
+    got = O.sbm_rhs_ac(u, 0.3, psi, dom.dx, kappa, f, mu, D, lambda t: 1.0, side)
+    assert np.allclose(got, ac.rhs_fd(u), rtol=1e-10, atol=1e-8 * np.abs(got).max())
+    # and the boundary terms switch on with the geometry: a non-trivial psi changes the answer
+    x = np.linspace(-1, 1, n)
+    psi2 = np.clip(0.5 * (1 + np.tanh((0.6 - np.abs(x)) / 0.1))[:, None] * np.ones((1, n)), 0.001, 1.0)
+    assert not np.allclose(O.sbm_rhs_ac(u, 0.3, psi2, dom.dx, kappa, f, mu, D, lambda t: 1.0, side), ac.rhs_fd(u))
