@@ -74,6 +74,9 @@ __device__ __forceinline__ void col_nbrs(const float (&a)[4], int lm1, int lp1, 
 }
 
 // mu_h(c), D(c) and their derivatives in one pass over the Legendre basis (one recurrence serves all four)
+// NC: compile-time bound on the number of Legendre coefficients (the unrolled recurrence stops there: the sweep is
+// instruction-fetch bound when all 16 terms are unrolled for every point, profiles/ncu_full_r2_sifs128r_adj_512x256.txt)
+template <int NC>
 __device__ __forceinline__ void pw_eval(float c, const PointwiseParams& pw, float& mu, float& D, float& mup, float& Dp) {
   const bool mleg = pw.mu_family == MU_LEGENDRE || pw.mu_family == MU_LEGENDRE_LOGPRIOR;
   const bool dleg = pw.mob_family == MOB_LEGENDRE_EXP;
@@ -87,7 +90,7 @@ __device__ __forceinline__ void pw_eval(float c, const PointwiseParams& pw, floa
     if (nd > 0) sd = pw.mob_coef[0];
     if (nm > 1) { sm = fmaf(pw.mu_coef[1], x, sm); dsm = pw.mu_coef[1]; }
     if (nd > 1) { sd = fmaf(pw.mob_coef[1], x, sd); dsd = pw.mob_coef[1]; }
-    static_for<2, 16>([&](auto nc) {
+    static_for<2, (NC > 2 ? NC : 2)>([&](auto nc) {
       constexpr int n = decltype(nc)::value;
       if (n < nmax) {
         const float pn = LegC<n>::a * x * pc - LegC<n>::b * pp;
@@ -117,6 +120,7 @@ __device__ __forceinline__ void pw_eval(float c, const PointwiseParams& pw, floa
 }
 
 // d mu_h / d theta_n (c) * s accumulated into acc[0..15], d D / d theta_n (c) * t into acc[16..31]
+template <int NC>
 __device__ __forceinline__ void accumulate_coef(float (&acc)[32], float c, float Dval, float s, float t, const PointwiseParams& pw) {
   const bool mleg = pw.mu_family == MU_LEGENDRE || pw.mu_family == MU_LEGENDRE_LOGPRIOR;
   const bool dleg = pw.mob_family == MOB_LEGENDRE_EXP;
@@ -132,7 +136,7 @@ __device__ __forceinline__ void accumulate_coef(float (&acc)[32], float c, float
     if (nd > 0) acc[16] += tD;
     if (nm > 1) acc[1] = fmaf(x, s, acc[1]);
     if (nd > 1) acc[17] = fmaf(x, tD, acc[17]);
-    static_for<2, 16>([&](auto nc) {
+    static_for<2, (NC > 2 ? NC : 2)>([&](auto nc) {
       constexpr int n = decltype(nc)::value;
       if (n < nmax) {
         const float pn = LegC<n>::a * x * pc - LegC<n>::b * pp;
@@ -145,7 +149,7 @@ __device__ __forceinline__ void accumulate_coef(float (&acc)[32], float c, float
   }
 }
 
-template <int EQ>
+template <int EQ, int NC>
 __global__ void __launch_bounds__(kThreadsR, 1) sifs128r_adj_kernel(const __grid_constant__ AdjParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   ASmem& S = *reinterpret_cast<ASmem*>(smem_raw);
@@ -260,7 +264,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) sifs128r_adj_kernel(const __grid
           for (int j = 0; j < 4; ++j) {
             const float lap = ((up[j] - 2.0f * u0[j]) + um[j]) * hx2 + ((uR[j] - 2.0f * u0[j]) + uL[j]) * hy2;
             float mh;
-            pw_eval(u0[j], p.pw, mh, D_p[j], mq_p[j], dq_p[j]);
+            pw_eval<NC>(u0[j], p.pw, mh, D_p[j], mq_p[j], dq_p[j]);
             mu_p[j] = mh - p.kappa * lap;
           }
           load_row4(wbase, r0 + it + kRows, lane, w_p);
@@ -293,7 +297,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) sifs128r_adj_kernel(const __grid
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               t1g[EMIT][j] = mq_0[j] * mb[j] + dq_0[j] * db[j];
-              accumulate_coef(acc, uc[j], D_0[j], mb[j], db[j], p.pw);
+              accumulate_coef<NC>(acc, uc[j], D_0[j], mb[j], db[j], p.pw);
             }
           }
 #pragma unroll

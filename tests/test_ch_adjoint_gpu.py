@@ -228,3 +228,46 @@ def test_long_rollout_gradients_vs_float64_oracle(checkpoint):
     assert _rel(yg.grad.cpu().numpy(), y64.grad.numpy()) <= 1e-4
     assert _rel(mu_t.grad.cpu().numpy()[1:], pm.grad.numpy()[1:]) <= 1e-4  # [0]: the constant does not enter the dynamics
     assert _rel(mob_t.grad.cpu().numpy(), pd.grad.numpy()) <= 1e-4
+
+
+@pytest.mark.parametrize("ncoef", [6, 11])
+def test_fused_adjoint_with_more_coefficients_matches_streaming_steps(ncoef):
+    """The fused adjoint kernel is instantiated for at most 4, 8 and 16 Legendre coefficients (the unrolled recurrence
+    stops at the bound); 6 and 11 coefficients take the 8- and 16-term instantiations."""
+    import ctypes
+
+    from pde_opt_b200 import Domain, _lib
+    from pde_opt_b200.equations import CahnHilliard2DPeriodic
+    from pde_opt_b200.functions import ChemicalPotentialLegendrePolynomials, DiffusionLegendrePolynomials
+    from pde_opt_b200.solvers import SemiImplicitFourierSpectral
+
+    n, B, K = 128, 3, 5
+    rng = np.random.default_rng(ncoef)
+    mu_c = (0.3 * rng.normal(size=ncoef) / (1 + np.arange(ncoef))).astype(np.float32)
+    mu_c[1] = 2.0
+    d_c = (0.2 * rng.normal(size=ncoef - 1) / (1 + np.arange(ncoef - 1))).astype(np.float32)
+    dom = Domain((n, n), ((0.0, n * H), (0.0, n * H)), "dimensionless")
+    eq = CahnHilliard2DPeriodic(dom, KAPPA, ChemicalPotentialLegendrePolynomials(mu_c, "log"), DiffusionLegendrePolynomials(d_c))
+    solver = SemiImplicitFourierSpectral(0.5, eq.fourier_symbol, eq.fft, eq.ifft)
+    y0 = torch.from_numpy(np.clip(0.5 + 0.05 * rng.normal(size=(B, n, n)), 0.1, 0.9).astype(np.float32)).cuda()
+    lam_T = torch.from_numpy(rng.normal(size=(B, n, n)).astype(np.float32)).cuda()
+    dts = np.full(K, 1e-6, np.float32)
+    plan, sym = eq.plan(), solver.symbol_on("cuda")
+    _, traj = plan.rollout_fwd(y0, dts, sym, save_every=1)
+    lam_f = lam_T.clone()
+    gmu_f = torch.zeros((B, 16), dtype=torch.float64, device="cuda")
+    gmob_f = torch.zeros_like(gmu_f)
+    plan.rollout_bwd(traj, lam_f, dts, sym, gmu_f, gmob_f)
+    lib = _lib.load()
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    lam_s = lam_T.clone()
+    gmu_s, gmob_s = torch.zeros_like(gmu_f), torch.zeros_like(gmu_f)
+    work = torch.empty(int(lib.pdeopt_phasefield_adjoint_work_floats(plan._h, B)), dtype=torch.float32, device="cuda")
+    for k in range(K - 1, -1, -1):
+        _lib.check(lib.pdeopt_phasefield_adjoint_step(plan._h, vp(traj[k]), vp(lam_s), vp(lam_s), B, float(dts[k]), vp(sym), vp(work),
+                                                      vp(gmu_s), vp(gmob_s), _lib.stream_ptr(lam_s)))
+    assert _rel(lam_f.cpu().numpy(), lam_s.cpu().numpy()) <= 2e-5
+    for a, b in ((gmu_f, gmu_s), (gmob_f, gmob_s)):
+        a, b = a.cpu().numpy(), b.cpu().numpy()
+        assert np.abs(a - b).max() <= 2e-4 * np.abs(b).max(), (a, b)
+        assert np.abs(b[:, ncoef - 2]).max() > 0  # the high coefficients do receive gradients
